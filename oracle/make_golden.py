@@ -1,0 +1,197 @@
+#!/usr/bin/env python
+"""Generate golden input/output vectors from the UNMODIFIED reference (test infrastructure only).
+
+Runs in the authoring container only: imports lab-emi/OpenDPD from /root/reference (read-only),
+builds every hot-path backbone through the reference's own constructors, runs
+forward + nn.MSELoss + backward on CPU in fp32 (and in fp64 as arbiter) on frames cut from the
+reference's APA_200MHz dataset, and writes small .npz fixtures under tests/golden/.
+
+The fixtures travel to the GPU box; /root/reference does not.  Nothing in the product imports
+this file.  Re-run:  python oracle/make_golden.py
+"""
+import os, sys, json, hashlib
+os.environ.setdefault("PYTHONDONTWRITEBYTECODE", "1")
+sys.dont_write_bytecode = True
+REF = "/root/reference"
+sys.path.insert(0, REF)
+import numpy as np
+import torch
+import torch.nn as nn
+
+import quant  # noqa: E402  (reference package)
+from quant.modules.ops import Sqrt, Pow  # qgru.py:7 import bug shim
+quant.Sqrt, quant.Pow = Sqrt, Pow
+import models  # noqa: E402  reference models.py
+from backbones.pgjanet import PGJANET  # CoreModel('pgjanet') raises TypeError (models.py:111-114)
+
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+torch.set_num_threads(4)
+
+
+def load_apa():
+    import pandas as pd
+    d = os.path.join(REF, "datasets", "APA_200MHz")
+    X = pd.read_csv(os.path.join(d, "train_input.csv")).to_numpy(dtype=np.float64)
+    Y = pd.read_csv(os.path.join(d, "train_output.csv")).to_numpy(dtype=np.float64)
+    return X, Y
+
+
+def frames(X, Y, B, T, seed):
+    """Frames exactly as IQFrameDataset makes them (data_collector.py:240-247): rows [k,k+T), f64->f32."""
+    g = torch.Generator().manual_seed(seed)
+    n = X.shape[0] - T + 1
+    idx = torch.randperm(n, generator=g)[:B].tolist()
+    x = np.stack([X[k:k + T] for k in idx]).astype(np.float32)
+    y = np.stack([Y[k:k + T] for k in idx]).astype(np.float32)
+    return x, y
+
+
+def build(kind, H, seed, thx=0.0, thh=0.0, K=3):
+    torch.manual_seed(seed)
+    if kind == "pgjanet":
+        bb = PGJANET(hidden_size=H, output_size=2, bias=True)
+        bb.reset_parameters()
+        net = models.CoreModel.__new__(models.CoreModel)
+        nn.Module.__init__(net)
+        net.num_layers, net.hidden_size, net.backbone = 1, H, bb
+        return net
+    return models.CoreModel(input_size=2, hidden_size=H, num_layers=1, backbone_type=kind,
+                            num_dvr_units=K, thx=thx, thh=thh)
+
+
+def flat_params(net):
+    return np.concatenate([p.detach().cpu().numpy().reshape(-1).astype(np.float64)
+                           for _, p in net.backbone.named_parameters()])
+
+
+def param_index(net):
+    return [(n, list(p.shape)) for n, p in net.backbone.named_parameters()]
+
+
+class MaskTap:
+    """Record the delta keep-masks of the reference's DeltaGRULayer.compute_deltas without editing it."""
+
+    def __init__(self, layer_cls):
+        self.cls, self.mx, self.mh = layer_cls, [], []
+        self.orig = layer_cls.__dict__["compute_deltas"].__func__
+
+    def __enter__(self):
+        tap = self
+
+        def wrapped(x, x_p, h, h_p, th_x, th_h):
+            r = tap.orig(x, x_p, h, h_p, th_x, th_h)
+            tap.mx.append((r[2] >= th_x).numpy().copy())
+            tap.mh.append((r[3] >= th_h).numpy().copy())
+            return r
+        self.cls.compute_deltas = staticmethod(wrapped)
+        return self
+
+    def __exit__(self, *a):
+        self.cls.compute_deltas = staticmethod(self.orig)
+
+    def packed(self):
+        def pack(lst):  # list over t of (B, n) bool -> (B, T) uint64 bitfield, bit k = unit k kept
+            a = np.stack(lst, axis=1)
+            w = (1 << np.arange(a.shape[-1], dtype=np.uint64))
+            return (a.astype(np.uint64) * w).sum(-1).astype(np.uint64)
+        return pack(self.mx), pack(self.mh)
+
+
+def run(net, x, y, dtype, tap_cls=None):
+    # CoreModel.forward (models.py:154-155) and GMP (gmp.py:21,26) allocate default-dtype tensors, so the
+    # fp64 arbiter run switches the default dtype instead of editing the reference.
+    torch.set_default_dtype(dtype)
+    try:
+        return _run(net, x, y, dtype, tap_cls)
+    finally:
+        torch.set_default_dtype(torch.float32)
+
+
+def _run(net, x, y, dtype, tap_cls=None):
+    net = net.to(dtype)
+    xt = torch.tensor(x, dtype=dtype, requires_grad=True)
+    yt = torch.tensor(y, dtype=dtype)
+    for p in net.parameters():
+        p.grad = None
+    res = {}
+    if tap_cls is not None:
+        net.backbone.set_debug(1)
+        with MaskTap(tap_cls) as tap:
+            out = net(xt)
+        res["mask_x"], res["mask_h"] = tap.packed()
+        st = net.backbone.rnn.statistics
+        res["stats"] = np.array([float(st["num_dx_zeros"]), float(st["num_dx_numel"]),
+                                 float(st["num_dh_zeros"]), float(st["num_dh_numel"])], dtype=np.float64)
+    else:
+        out = net(xt)
+    loss = nn.MSELoss()(out, yt)
+    loss.backward()
+    res["out"] = out.detach().numpy()
+    res["loss"] = np.array(loss.item(), dtype=np.float64)
+    res["gx"] = xt.grad.numpy()
+    res["gparams"] = np.concatenate([p.grad.numpy().reshape(-1) for _, p in net.backbone.named_parameters()])
+    return res
+
+
+# (name, kind, H, B, T, data seed, thx, thh)
+CASES = [
+    ("gru_h32_b8_t128",      "gru",  32, 8, 128, 1, 0, 0),
+    ("gru_h23_b3_t17",       "gru",  23, 3, 17, 2, 0, 0),
+    ("gru_h8_b1_t1",         "gru",   8, 1, 1, 3, 0, 0),
+    ("dgru_h13_b8_t256",     "dgru", 13, 8, 256, 4, 0, 0),
+    ("dgru_h13_b4_t48",      "dgru", 13, 4, 48, 5, 0, 0),
+    ("dgru_h8_b3_t33",       "dgru",  8, 3, 33, 6, 0, 0),
+    ("dgru_h23_b2_t65",      "dgru", 23, 2, 65, 7, 0, 0),
+    ("lstm_h9_b4_t64",       "lstm",  9, 4, 64, 8, 0, 0),
+    ("lstm_h16_b2_t33",      "lstm", 16, 2, 33, 9, 0, 0),
+    ("deltagru_h15_b4_t96",  "deltagru", 15, 4, 96, 10, 0.01, 0.05),
+    ("deltagru_h15_b2_t40_th0", "deltagru", 15, 2, 40, 11, 0.0, 0.0),
+    ("deltagru_h10_b3_t33",  "deltagru", 10, 3, 33, 12, 0.02, 0.02),
+    ("tres_h15_b4_t96",      "deltagru_tcnskip", 15, 4, 96, 13, 0.01, 0.05),
+    ("tres_h15_b2_t200",     "deltagru_tcnskip", 15, 2, 200, 14, 0.01, 0.05),
+    ("tres_h15_b3_t20",      "deltagru_tcnskip", 15, 3, 20, 15, 0.0, 0.0),
+    ("pgjanet_h15_b4_t64",   "pgjanet", 15, 4, 64, 16, 0, 0),
+    ("pgjanet_h10_b2_t33",   "pgjanet", 10, 2, 33, 17, 0, 0),
+    ("dvrjanet_h15_b4_t64",  "dvrjanet", 15, 4, 64, 18, 0, 0),
+    ("dvrjanet_h10_b2_t33",  "dvrjanet", 10, 2, 33, 19, 0, 0),
+    ("gmp_b4_t64",           "gmp", 0, 4, 64, 20, 0, 0),
+    ("gmp_b2_t7",            "gmp", 0, 2, 7, 21, 0, 0),
+    ("qgru_h10_b4_t50",      "qgru", 10, 4, 50, 22, 0, 0),
+    ("qgru_amp1_h10_b4_t50", "qgru_amp1", 10, 4, 50, 23, 0, 0),
+]
+
+
+def main():
+    X, Y = load_apa()
+    os.makedirs(OUT, exist_ok=True)
+    manifest = {}
+    for name, kind, H, B, T, seed, thx, thh in CASES:
+        x, y = frames(X, Y, B, T, seed)
+        net = build(kind, max(H, 1), seed, thx, thh)
+        tap_cls = None
+        if kind == "deltagru":
+            from backbones.deltagru import DeltaGRULayer as tap_cls
+        elif kind == "deltagru_tcnskip":
+            from backbones.deltagru_tcnskip import DeltaGRULayer as tap_cls
+        params = flat_params(net)
+        r32 = run(net, x, y, torch.float32, tap_cls)
+        r64 = run(net, x, y, torch.float64, tap_cls)
+        net.float()
+        rec = dict(x=x, y=y, params=params.astype(np.float32), kind=np.array(kind), H=np.array(H),
+                   thx=np.array(thx, dtype=np.float64), thh=np.array(thh, dtype=np.float64),
+                   K=np.array(3), param_index=np.array(json.dumps(param_index(net))))
+        for k, v in r32.items():
+            rec[k] = v
+        for k, v in r64.items():
+            rec[k + "64"] = v
+        path = os.path.join(OUT, name + ".npz")
+        np.savez_compressed(path, **rec)
+        manifest[name] = dict(kind=kind, H=H, B=B, T=T, n_params=int(params.size), loss=float(r32["loss"]),
+                              bytes=os.path.getsize(path))
+        print(name, manifest[name], flush=True)
+    with open(os.path.join(OUT, "MANIFEST.json"), "w") as f:
+        json.dump(manifest, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()

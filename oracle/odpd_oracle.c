@@ -1,0 +1,775 @@
+/*
+ * odpd_oracle.c — CPU ORACLE (test infrastructure, NOT product code).
+ *
+ * Plain-C restatement of the reference's recurrent-backbone forward + I/Q MSE + backward
+ * (lab-emi/OpenDPD).  Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may load this library.  The product (opendpd_b200/) never does.
+ *
+ * Parity pin: the reference holds NO golden vectors or numeric tests for this path,
+ * so this oracle is pinned against outputs of the reference itself, generated in the authoring
+ * container by oracle/make_golden.py (fixtures in tests/golden/, checked by tests/test_oracle_golden.py).
+ *
+ * Every function cites the reference file:line it restates.  The arithmetic of nn.GRU / nn.LSTM lives in
+ * PyTorch ATen (third-party, torch>=2.4 per pyproject.toml:34; container has 2.11.0):
+ *   GRU cell  (aten/src/ATen/native/RNN.cpp, GRUCell):  r=σ(Wir x+bir+Whr h+bhr), z=σ(...),
+ *             n=tanh(Win x+bin + r*(Whn h+bhn)), h'=(h-n)*z+n      gate order r,z,n
+ *   LSTM cell (LSTMCell): gates i,f,g,o ; c'=f*c+i*g ; h'=o*tanh(c')
+ *
+ * Compiled twice (REAL=float / REAL=double) into one shared object, see oracle/Makefile.
+ * Flat parameter layout = named_parameters() order of the reference module (documented in include/odpd.h).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#ifndef REAL
+#define REAL float
+#endif
+#define CAT_(a, b) a##b
+#define CAT(a, b) CAT_(a, b)
+#ifdef REAL_IS_DOUBLE
+#define SUF(n) CAT(n, _f64)
+#define R_EXP exp
+#define R_TANH tanh
+#define R_SQRT sqrt
+#define R_FABS fabs
+#define R_ATAN2 atan2
+#define R_SIN sin
+#define R_COS cos
+#define R_POW pow
+#else
+#define SUF(n) CAT(n, _f32)
+#define R_EXP expf
+#define R_TANH tanhf
+#define R_SQRT sqrtf
+#define R_FABS fabsf
+#define R_ATAN2 atan2f
+#define R_SIN sinf
+#define R_COS cosf
+#define R_POW powf
+#endif
+
+enum { CELL_GRU = 0, CELL_LSTM = 1, CELL_DGRU = 2, CELL_DELTAGRU = 3, CELL_TRES = 4, CELL_PGJANET = 5,
+       CELL_DVRJANET = 6, CELL_GMP = 7, CELL_QGRU = 8, CELL_QGRU_AMP1 = 9 };
+
+typedef struct {
+    int cell, B, T, H, K;
+    REAL thx, thh;
+    const REAL *params;
+    int want_gx, want_gp;
+} Ctx;
+
+static inline REAL sigm(REAL v) { return (REAL)1 / ((REAL)1 + R_EXP(-v)); }
+
+/* y[r] (+)= sum_c W[r*ld+c]*v[c] */
+static inline REAL dotv(const REAL *w, const REAL *v, int n) {
+    REAL s = 0;
+    for (int i = 0; i < n; ++i) s += w[i] * v[i];
+    return s;
+}
+
+/* ---------------------------------------------------------------- features
+ * gru.py:45 (raw I,Q) · dgru.py:61-68 (I,Q,a,a^3,sin,cos) · deltagru.py:61-72 (same order)
+ * qgru.py:61-66 (I,Q,a^2,a^4) · qgru_amp1.py:61-70 (I,Q,a,a^3) · deltagru_tcnskip.py:91-100 (I,Q,a,a^3,I_nxt,Q_nxt)
+ * ATen pow(x,2)=x*x, pow(x,3)=(x*x)*x, each op separately rounded (no FMA). */
+static int n_features(int cell) {
+    switch (cell) {
+    case CELL_GRU: case CELL_LSTM: return 2;
+    case CELL_QGRU: case CELL_QGRU_AMP1: return 4;
+    default: return 6;
+    }
+}
+
+static void features_fwd(int cell, const REAL *x, int T, int t, REAL *f) {
+    volatile REAL i = x[2 * t], q = x[2 * t + 1];
+    volatile REAL ii = i * i, qq = q * q;
+    volatile REAL a2 = ii + qq;
+    f[0] = i; f[1] = q;
+    if (cell == CELL_GRU || cell == CELL_LSTM) return;
+    if (cell == CELL_QGRU) { volatile REAL a4 = a2 * a2; f[2] = a2; f[3] = a4; return; }
+    volatile REAL a = R_SQRT(a2);
+    volatile REAL aa = a * a;
+    volatile REAL a3 = aa * a;
+    f[2] = a; f[3] = a3;
+    if (cell == CELL_QGRU_AMP1) return;
+    if (cell == CELL_TRES) { int tn = (t + 1) % T; f[4] = x[2 * tn]; f[5] = x[2 * tn + 1]; return; }
+    f[4] = q / a; /* sin */
+    f[5] = i / a; /* cos */
+}
+
+/* accumulate d(loss)/dx from d(loss)/dfeatures; gx is the whole (T,2) row because TRES rolls. */
+static void features_bwd(int cell, const REAL *x, int T, int t, const REAL *gf, REAL *gx) {
+    REAL i = x[2 * t], q = x[2 * t + 1];
+    REAL gi = gf[0], gq = gf[1];
+    if (cell == CELL_GRU || cell == CELL_LSTM) { gx[2 * t] += gi; gx[2 * t + 1] += gq; return; }
+    REAL a2 = i * i + q * q;
+    if (cell == CELL_QGRU) {
+        REAL ga2 = gf[2] + (REAL)2 * a2 * gf[3];
+        gx[2 * t] += gi + (REAL)2 * i * ga2; gx[2 * t + 1] += gq + (REAL)2 * q * ga2; return;
+    }
+    REAL a = R_SQRT(a2);
+    REAL ga = gf[2] + (REAL)3 * a * a * gf[3];
+    if (cell == CELL_DGRU || cell == CELL_DELTAGRU) {
+        REAL gsin = gf[4], gcos = gf[5];
+        ga -= (q * gsin + i * gcos) / a2;
+        gi += gcos / a; gq += gsin / a;
+    } else if (cell == CELL_TRES) {
+        int tn = (t + 1) % T;
+        gx[2 * tn] += gf[4]; gx[2 * tn + 1] += gf[5];
+    }
+    gx[2 * t] += gi + ga * i / a; gx[2 * t + 1] += gq + ga * q / a;
+}
+
+/* ================================================================ GRU family: gru / dgru / qgru / qgru_amp1
+ * gru.py:45-48, dgru.py:59-74, qgru.py:59-71, qgru_amp1.py:59-76 + ATen GRUCell.
+ * params: W_ih(3H,F) W_hh(3H,H) b_ih(3H) b_hh(3H) fc_out.W(2,H[+6]) fc_out.b(2) [fc_hid.W(H,H) fc_hid.b(H)] */
+static void seq_gru_family(const Ctx *c, const REAL *x, const REAL *gout_or_null, REAL *out, REAL *gx, REAL *gp,
+                           int phase) {
+    const int H = c->H, T = c->T, F = n_features(c->cell), dg = (c->cell == CELL_DGRU);
+    const int O = dg ? H + F : H;
+    const REAL *Wih = c->params, *Whh = Wih + 3 * H * F, *bih = Whh + 3 * H * H, *bhh = bih + 3 * H;
+    const REAL *Wo = bhh + 3 * H, *bo = Wo + 2 * O, *Wh = bo + 2, *bh = Wh + H * H;
+    /* saved per step: f(F) r z n hgn h g  */
+    static __thread REAL *sv = NULL; static __thread size_t sv_n = 0;
+    const int S = F + 6 * H;
+    size_t need = (size_t)T * S;
+    if (sv_n < need) { free(sv); sv = (REAL *)malloc(need * sizeof(REAL)); sv_n = need; }
+    if (phase == 0) {
+        REAL h[64] = {0}, cat[64 + 8];
+        for (int t = 0; t < T; ++t) {
+            REAL *s = sv + (size_t)t * S, *f = s, *r = s + F, *z = r + H, *n = z + H, *hgn = n + H, *hs = hgn + H,
+                 *g = hs + H;
+            features_fwd(c->cell, x, T, t, f);
+            REAL hn[64];
+            for (int j = 0; j < H; ++j) {
+                REAL xr = dotv(Wih + (size_t)j * F, f, F) + bih[j];
+                REAL xz = dotv(Wih + (size_t)(H + j) * F, f, F) + bih[H + j];
+                REAL xn = dotv(Wih + (size_t)(2 * H + j) * F, f, F) + bih[2 * H + j];
+                REAL hr = dotv(Whh + (size_t)j * H, h, H) + bhh[j];
+                REAL hz = dotv(Whh + (size_t)(H + j) * H, h, H) + bhh[H + j];
+                REAL hnn = dotv(Whh + (size_t)(2 * H + j) * H, h, H) + bhh[2 * H + j];
+                r[j] = sigm(hr + xr); z[j] = sigm(hz + xz); hgn[j] = hnn;
+                n[j] = R_TANH(xn + hnn * r[j]);
+                hn[j] = (h[j] - n[j]) * z[j] + n[j];
+            }
+            memcpy(h, hn, sizeof(REAL) * H); memcpy(hs, h, sizeof(REAL) * H);
+            if (dg) {
+                for (int j = 0; j < H; ++j) { REAL p = dotv(Wh + (size_t)j * H, h, H) + bh[j]; g[j] = p > 0 ? p : 0; cat[j] = g[j]; }
+                for (int k = 0; k < F; ++k) cat[H + k] = f[k];
+            } else memcpy(cat, h, sizeof(REAL) * H);
+            out[2 * t] = dotv(Wo, cat, O) + bo[0];
+            out[2 * t + 1] = dotv(Wo + O, cat, O) + bo[1];
+        }
+        return;
+    }
+    /* backward */
+    REAL *gWih = gp, *gWhh = gWih + 3 * H * F, *gbih = gWhh + 3 * H * H, *gbhh = gbih + 3 * H;
+    REAL *gWo = gbhh + 3 * H, *gbo = gWo + 2 * O, *gWh = gbo + 2, *gbh = gWh + H * H;
+    REAL gH[64] = {0};
+    for (int t = T - 1; t >= 0; --t) {
+        REAL *s = sv + (size_t)t * S, *f = s, *r = s + F, *z = r + H, *n = z + H, *hgn = n + H, *hs = hgn + H, *g = hs + H;
+        const REAL *hp = t ? (sv + (size_t)(t - 1) * S + F + 4 * H) : NULL;
+        const REAL go0 = gout_or_null[2 * t], go1 = gout_or_null[2 * t + 1];
+        REAL gf[8] = {0};
+        if (dg) {
+            REAL dpre[64];
+            for (int j = 0; j < H; ++j) {
+                REAL dgj = Wo[j] * go0 + Wo[O + j] * go1;
+                dpre[j] = g[j] > 0 ? dgj : 0;
+                gWo[j] += go0 * g[j]; gWo[O + j] += go1 * g[j];
+            }
+            for (int k = 0; k < F; ++k) {
+                gf[k] += Wo[H + k] * go0 + Wo[O + H + k] * go1;
+                gWo[H + k] += go0 * f[k]; gWo[O + H + k] += go1 * f[k];
+            }
+            for (int j = 0; j < H; ++j) {
+                gbh[j] += dpre[j];
+                for (int k = 0; k < H; ++k) { gWh[j * H + k] += dpre[j] * hs[k]; gH[k] += Wh[j * H + k] * dpre[j]; }
+            }
+        } else {
+            for (int j = 0; j < H; ++j) {
+                gH[j] += Wo[j] * go0 + Wo[O + j] * go1;
+                gWo[j] += go0 * hs[j]; gWo[O + j] += go1 * hs[j];
+            }
+        }
+        gbo[0] += go0; gbo[1] += go1;
+        REAL dx3[192], dh3[192], ghp[64];
+        for (int j = 0; j < H; ++j) {
+            REAL hpj = hp ? hp[j] : 0;
+            REAL gz = gH[j] * (hpj - n[j]), gn = gH[j] * ((REAL)1 - z[j]);
+            ghp[j] = gH[j] * z[j];
+            REAL an = gn * ((REAL)1 - n[j] * n[j]);
+            REAL az = gz * z[j] * ((REAL)1 - z[j]);
+            REAL ar = an * hgn[j] * r[j] * ((REAL)1 - r[j]);
+            dx3[j] = ar; dx3[H + j] = az; dx3[2 * H + j] = an;
+            dh3[j] = ar; dh3[H + j] = az; dh3[2 * H + j] = an * r[j];
+        }
+        for (int k = 0; k < 3 * H; ++k) {
+            gbih[k] += dx3[k]; gbhh[k] += dh3[k];
+            for (int q = 0; q < F; ++q) { gWih[k * F + q] += dx3[k] * f[q]; gf[q] += Wih[k * F + q] * dx3[k]; }
+            for (int q = 0; q < H; ++q) { gWhh[k * H + q] += dh3[k] * (hp ? hp[q] : 0); ghp[q] += Whh[k * H + q] * dh3[k]; }
+        }
+        memcpy(gH, ghp, sizeof(REAL) * H);
+        if (gx) features_bwd(c->cell, x, T, t, gf, gx);
+    }
+}
+
+/* ================================================================ LSTM: lstm.py:45-48 + ATen LSTMCell, (h0,c0)=(0,0)
+ * params: W_ih(4H,2) W_hh(4H,H) b_ih(4H) b_hh(4H) fc_out.W(2,H) fc_out.b(2) */
+static void seq_lstm(const Ctx *c, const REAL *x, const REAL *gout, REAL *out, REAL *gx, REAL *gp, int phase) {
+    const int H = c->H, T = c->T, F = 2;
+    const REAL *Wih = c->params, *Whh = Wih + 4 * H * F, *bih = Whh + 4 * H * H, *bhh = bih + 4 * H;
+    const REAL *Wo = bhh + 4 * H, *bo = Wo + 2 * H;
+    static __thread REAL *sv = NULL; static __thread size_t sv_n = 0;
+    const int S = 7 * H; /* i f g o c h tanh(c) */
+    size_t need = (size_t)T * S;
+    if (sv_n < need) { free(sv); sv = (REAL *)malloc(need * sizeof(REAL)); sv_n = need; }
+    if (phase == 0) {
+        REAL h[64] = {0}, cc[64] = {0};
+        for (int t = 0; t < T; ++t) {
+            REAL *s = sv + (size_t)t * S; const REAL *f = x + 2 * t; REAL hn[64];
+            for (int j = 0; j < H; ++j) {
+                REAL a[4];
+                for (int g = 0; g < 4; ++g)
+                    a[g] = (dotv(Wih + (size_t)(g * H + j) * F, f, F) + bih[g * H + j]) +
+                           (dotv(Whh + (size_t)(g * H + j) * H, h, H) + bhh[g * H + j]);
+                REAL ig = sigm(a[0]), fg = sigm(a[1]), gg = R_TANH(a[2]), og = sigm(a[3]);
+                REAL cn = fg * cc[j] + ig * gg, tc = R_TANH(cn);
+                s[j] = ig; s[H + j] = fg; s[2 * H + j] = gg; s[3 * H + j] = og; s[4 * H + j] = cn; s[6 * H + j] = tc;
+                cc[j] = cn; hn[j] = og * tc;
+            }
+            memcpy(h, hn, sizeof(REAL) * H); memcpy(s + 5 * H, h, sizeof(REAL) * H);
+            out[2 * t] = dotv(Wo, h, H) + bo[0]; out[2 * t + 1] = dotv(Wo + H, h, H) + bo[1];
+        }
+        return;
+    }
+    REAL *gWih = gp, *gWhh = gWih + 4 * H * F, *gbih = gWhh + 4 * H * H, *gbhh = gbih + 4 * H, *gWo = gbhh + 4 * H,
+         *gbo = gWo + 2 * H;
+    REAL gH[64] = {0}, gC[64] = {0};
+    for (int t = T - 1; t >= 0; --t) {
+        REAL *s = sv + (size_t)t * S; const REAL *f = x + 2 * t;
+        const REAL *sp = t ? sv + (size_t)(t - 1) * S : NULL;
+        REAL go0 = gout[2 * t], go1 = gout[2 * t + 1], d[256], ghp[64] = {0};
+        for (int j = 0; j < H; ++j) {
+            gH[j] += Wo[j] * go0 + Wo[H + j] * go1;
+            gWo[j] += go0 * s[5 * H + j]; gWo[H + j] += go1 * s[5 * H + j];
+        }
+        gbo[0] += go0; gbo[1] += go1;
+        for (int j = 0; j < H; ++j) {
+            REAL ig = s[j], fg = s[H + j], gg = s[2 * H + j], og = s[3 * H + j], tc = s[6 * H + j];
+            REAL cp = sp ? sp[4 * H + j] : 0;
+            REAL go = gH[j] * tc;
+            REAL gc = gC[j] + gH[j] * og * ((REAL)1 - tc * tc);
+            d[j] = gc * gg * ig * ((REAL)1 - ig);
+            d[H + j] = gc * cp * fg * ((REAL)1 - fg);
+            d[2 * H + j] = gc * ig * ((REAL)1 - gg * gg);
+            d[3 * H + j] = go * og * ((REAL)1 - og);
+            gC[j] = gc * fg;
+        }
+        REAL gf[2] = {0, 0};
+        for (int k = 0; k < 4 * H; ++k) {
+            gbih[k] += d[k]; gbhh[k] += d[k];
+            for (int q = 0; q < F; ++q) { gWih[k * F + q] += d[k] * f[q]; gf[q] += Wih[k * F + q] * d[k]; }
+            for (int q = 0; q < H; ++q) { gWhh[k * H + q] += d[k] * (sp ? sp[5 * H + q] : 0); ghp[q] += Whh[k * H + q] * d[k]; }
+        }
+        memcpy(gH, ghp, sizeof(REAL) * H);
+        if (gx) { gx[2 * t] += gf[0]; gx[2 * t + 1] += gf[1]; }
+    }
+}
+
+/* ================================================================ Delta GRU cells
+ * deltagru.py:60-77,149-266 (biases folded into M_0, :164-170) and deltagru_tcnskip.py:89-103,232-304
+ * (bias-free x2h/h2h, TCN skip :32-49, out=fc_out(h)+skip :102).  Backward: SURVEY.md §8a-D.
+ * deltagru params: W_ih(3H,6) W_hh(3H,H) b_ih(3H) b_hh(3H) fc_out.W(2,H) fc_out.b(2)
+ * tres     params: x2h.W(3H,6) h2h.W(3H,H) fc_out.W(2,H) tcn.0.W(3,2,3) tcn.2.W(2,3,1) */
+static inline REAL hardswish(REAL v) {
+    REAL t = v + (REAL)3; t = t < 0 ? 0 : (t > 6 ? 6 : t);
+    return v * t / (REAL)6;
+}
+static inline REAL hardswish_grad(REAL v) { /* ATen hardswish_backward */
+    return v < (REAL)-3 ? 0 : (v <= (REAL)3 ? v / (REAL)3 + (REAL)0.5 : (REAL)1);
+}
+
+static void seq_delta(const Ctx *c, const REAL *x, const REAL *gout, REAL *out, REAL *gx, REAL *gp, int phase,
+                      uint64_t *mask_x, uint64_t *mask_h, int64_t *stats) {
+    const int H = c->H, T = c->T, F = 6, tres = (c->cell == CELL_TRES);
+    const REAL *Wih = c->params, *Whh = Wih + 3 * H * F;
+    const REAL *bih = tres ? NULL : Whh + 3 * H * H, *bhh = tres ? NULL : bih + 3 * H;
+    const REAL *Wo = tres ? Whh + 3 * H * H : bhh + 3 * H;
+    const REAL *bo = tres ? NULL : Wo + 2 * H;
+    const REAL *w0 = tres ? Wo + 2 * H : NULL, *w2 = tres ? w0 + 18 : NULL;
+    /* saved per step: f(6) dx(6) dh(H) r z n Mnh h c1(3) c2(2) + masks */
+    static __thread REAL *sv = NULL; static __thread size_t sv_n = 0;
+    static __thread uint64_t *mk = NULL; static __thread size_t mk_n = 0;
+    const int S = 12 + 6 * H + 5;
+    size_t need = (size_t)T * S;
+    if (sv_n < need) { free(sv); sv = (REAL *)malloc(need * sizeof(REAL)); sv_n = need; }
+    if (mk_n < (size_t)2 * T) { free(mk); mk = (uint64_t *)malloc(sizeof(uint64_t) * 2 * T); mk_n = 2 * T; }
+    if (phase == 0) {
+        REAL h[64] = {0}, hp[64] = {0}, xp[6] = {0}, M[192], Mnh[64];
+        for (int j = 0; j < H; ++j) {
+            M[j] = tres ? 0 : bih[j] + bhh[j]; M[H + j] = tres ? 0 : bih[H + j] + bhh[H + j];
+            M[2 * H + j] = tres ? 0 : bih[2 * H + j]; Mnh[j] = tres ? 0 : bhh[2 * H + j];
+        }
+        int64_t zx = 0, zh = 0;
+        for (int t = 0; t < T; ++t) {
+            REAL *s = sv + (size_t)t * S, *f = s, *dx = s + 6, *dh = s + 12, *r = dh + H, *z = r + H, *n = z + H,
+                 *mn = n + H, *hs = mn + H, *cv = hs + H;
+            features_fwd(c->cell, x, T, t, f);
+            uint64_t mx = 0, mh = 0;
+            for (int k = 0; k < F; ++k) {
+                REAL d = f[k] - xp[k], a = R_FABS(d);
+                if (a < c->thx) d = 0;
+                if (a >= c->thx) { xp[k] = f[k]; mx |= (uint64_t)1 << k; }
+                dx[k] = d; zx += (d == 0);
+            }
+            for (int j = 0; j < H; ++j) {
+                REAL d = h[j] - hp[j], a = R_FABS(d);
+                if (a < c->thh) d = 0;
+                if (a >= c->thh) { hp[j] = h[j]; mh |= (uint64_t)1 << j; }
+                dh[j] = d; zh += (d == 0);
+            }
+            mk[2 * t] = mx; mk[2 * t + 1] = mh;
+            if (mask_x) mask_x[t] = mx;
+            if (mask_h) mask_h[t] = mh;
+            REAL hn[64];
+            for (int j = 0; j < H; ++j) {
+                REAL mxr = dotv(Wih + (size_t)j * F, dx, F) + M[j];
+                REAL mxz = dotv(Wih + (size_t)(H + j) * F, dx, F) + M[H + j];
+                REAL mxn = dotv(Wih + (size_t)(2 * H + j) * F, dx, F) + M[2 * H + j];
+                M[j] = mxr + dotv(Whh + (size_t)j * H, dh, H);
+                M[H + j] = mxz + dotv(Whh + (size_t)(H + j) * H, dh, H);
+                M[2 * H + j] = mxn;
+                Mnh[j] = dotv(Whh + (size_t)(2 * H + j) * H, dh, H) + Mnh[j];
+                r[j] = sigm(M[j]); z[j] = sigm(M[H + j]);
+                n[j] = R_TANH(M[2 * H + j] + r[j] * Mnh[j]);
+                mn[j] = Mnh[j];
+                hn[j] = ((REAL)1 - z[j]) * n[j] + z[j] * h[j];
+            }
+            memcpy(h, hn, sizeof(REAL) * H); memcpy(hs, h, sizeof(REAL) * H);
+            REAL o0 = dotv(Wo, h, H), o1 = dotv(Wo + H, h, H);
+            if (tres) {
+                for (int co = 0; co < 3; ++co) {
+                    REAL a = 0;
+                    for (int ci = 0; ci < 2; ++ci)
+                        for (int k = 0; k < 3; ++k) {
+                            int tt = t + (k - 1) * 16;
+                            if (tt >= 0 && tt < T) a += w0[(co * 2 + ci) * 3 + k] * x[2 * tt + ci];
+                        }
+                    cv[co] = a;
+                }
+                for (int o = 0; o < 2; ++o) {
+                    REAL a = 0;
+                    for (int ch = 0; ch < 3; ++ch) a += w2[o * 3 + ch] * hardswish(cv[ch]);
+                    cv[3 + o] = a;
+                }
+                o0 += hardswish(cv[3]); o1 += hardswish(cv[4]);
+            } else { o0 += bo[0]; o1 += bo[1]; }
+            out[2 * t] = o0; out[2 * t + 1] = o1;
+        }
+        if (stats) { stats[0] = zx; stats[1] = (int64_t)T * F; stats[2] = zh; stats[3] = (int64_t)T * H; }
+        return;
+    }
+    REAL *gWih = gp, *gWhh = gWih + 3 * H * F;
+    REAL *gbih = tres ? NULL : gWhh + 3 * H * H, *gbhh = tres ? NULL : gbih + 3 * H;
+    REAL *gWo = tres ? gWhh + 3 * H * H : gbhh + 3 * H;
+    REAL *gbo = tres ? NULL : gWo + 2 * H;
+    REAL *gw0 = tres ? gWo + 2 * H : NULL, *gw2 = tres ? gw0 + 18 : NULL;
+    REAL gH[64] = {0}, gM[192] = {0}, gMnh[64] = {0}, gxp[6] = {0}, ghp[64] = {0};
+    for (int t = T - 1; t >= 0; --t) {
+        REAL *s = sv + (size_t)t * S, *f = s, *dx = s + 6, *dh = s + 12, *r = dh + H, *z = r + H, *n = z + H, *mn = n + H,
+             *hs = mn + H, *cv = hs + H;
+        const REAL *hprev = t ? sv + (size_t)(t - 1) * S + 12 + 5 * H : NULL;
+        REAL go0 = gout[2 * t], go1 = gout[2 * t + 1];
+        for (int j = 0; j < H; ++j) {
+            gH[j] += Wo[j] * go0 + Wo[H + j] * go1;
+            gWo[j] += go0 * hs[j]; gWo[H + j] += go1 * hs[j];
+        }
+        if (tres) {
+            REAL g2[2] = {go0 * hardswish_grad(cv[3]), go1 * hardswish_grad(cv[4])};
+            REAL ga1[3] = {0, 0, 0};
+            for (int o = 0; o < 2; ++o)
+                for (int ch = 0; ch < 3; ++ch) { gw2[o * 3 + ch] += g2[o] * hardswish(cv[ch]); ga1[ch] += w2[o * 3 + ch] * g2[o]; }
+            for (int co = 0; co < 3; ++co) {
+                REAL gc1 = ga1[co] * hardswish_grad(cv[co]);
+                for (int ci = 0; ci < 2; ++ci)
+                    for (int k = 0; k < 3; ++k) {
+                        int tt = t + (k - 1) * 16;
+                        if (tt >= 0 && tt < T) {
+                            gw0[(co * 2 + ci) * 3 + k] += gc1 * x[2 * tt + ci];
+                            if (gx) gx[2 * tt + ci] += w0[(co * 2 + ci) * 3 + k] * gc1;
+                        }
+                    }
+            }
+        } else { gbo[0] += go0; gbo[1] += go1; }
+        REAL ghprev[64];
+        for (int j = 0; j < H; ++j) {
+            REAL hpj = hprev ? hprev[j] : 0;
+            REAL gz = gH[j] * (hpj - n[j]), gn = gH[j] * ((REAL)1 - z[j]);
+            ghprev[j] = gH[j] * z[j];
+            REAL ga = gn * ((REAL)1 - n[j] * n[j]);
+            gM[j] += ga * mn[j] * r[j] * ((REAL)1 - r[j]);
+            gM[H + j] += gz * z[j] * ((REAL)1 - z[j]);
+            gM[2 * H + j] += ga;
+            gMnh[j] += ga * r[j];
+        }
+        REAL gdx[6] = {0}, gdh[64] = {0};
+        for (int k = 0; k < 3 * H; ++k) {
+            REAL gk = gM[k], gk_h = (k < 2 * H) ? gM[k] : gMnh[k - 2 * H];
+            for (int q = 0; q < F; ++q) { gWih[k * F + q] += gk * dx[q]; gdx[q] += Wih[k * F + q] * gk; }
+            for (int q = 0; q < H; ++q) { gWhh[k * H + q] += gk_h * dh[q]; gdh[q] += Whh[k * H + q] * gk_h; }
+        }
+        uint64_t mx = mk[2 * t], mh = mk[2 * t + 1];
+        REAL gf[6];
+        for (int k = 0; k < F; ++k) {
+            if ((mx >> k) & 1) { gf[k] = gxp[k] + gdx[k]; gxp[k] = -gdx[k]; } else gf[k] = 0;
+        }
+        for (int j = 0; j < H; ++j) {
+            if ((mh >> j) & 1) { ghprev[j] += ghp[j] + gdh[j]; ghp[j] = -gdh[j]; }
+        }
+        memcpy(gH, ghprev, sizeof(REAL) * H);
+        if (gx) features_bwd(c->cell, x, T, t, gf, gx);
+    }
+    if (!tres)
+        for (int j = 0; j < H; ++j) {
+            gbih[j] += gM[j]; gbhh[j] += gM[j]; gbih[H + j] += gM[H + j]; gbhh[H + j] += gM[H + j];
+            gbih[2 * H + j] += gM[2 * H + j]; gbhh[2 * H + j] += gMnh[j];
+        }
+}
+
+/* ================================================================ PGJANET: pgjanet.py:24-77, h = h_0[0] = 0
+ * params: W_a(H,H+1) b_a W_p1(H,H+1) b_p1 W_p2(H,H+1) b_p2 W_f(H,2H) b_f W_g(H,2H) b_g W_o(2,H) b_o(2) */
+static void seq_pgjanet(const Ctx *c, const REAL *x, const REAL *gout, REAL *out, REAL *gx, REAL *gp, int phase) {
+    const int H = c->H, T = c->T, H1 = H + 1, H2 = 2 * H;
+    const REAL *Wa = c->params, *ba = Wa + H * H1, *Wp1 = ba + H, *bp1 = Wp1 + H * H1, *Wp2 = bp1 + H, *bp2 = Wp2 + H * H1;
+    const REAL *Wf = bp2 + H, *bf = Wf + H * H2, *Wg = bf + H, *bg = Wg + H * H2, *Wo = bg + H, *bo = Wo + 2 * H;
+    static __thread REAL *sv = NULL; static __thread size_t sv_n = 0;
+    const int S = 4 + 7 * H; /* a cos sin pad | an p1 p2 u f g h */
+    size_t need = (size_t)T * S;
+    if (sv_n < need) { free(sv); sv = (REAL *)malloc(need * sizeof(REAL)); sv_n = need; }
+    if (phase == 0) {
+        REAL h[64] = {0};
+        for (int t = 0; t < T; ++t) {
+            REAL *s = sv + (size_t)t * S, *an = s + 4, *p1 = an + H, *p2 = p1 + H, *u = p2 + H, *fg = u + H, *gg = fg + H,
+                 *hs = gg + H;
+            REAL i = x[2 * t], q = x[2 * t + 1];
+            REAL a = R_SQRT(i * i + q * q), th = R_ATAN2(q, i), ct = R_COS(th), st = R_SIN(th);
+            s[0] = a; s[1] = ct; s[2] = st;
+            for (int j = 0; j < H; ++j) {
+                an[j] = R_TANH(dotv(Wa + (size_t)j * H1, h, H) + Wa[j * H1 + H] * a + ba[j]);
+                p1[j] = R_TANH(dotv(Wp1 + (size_t)j * H1, h, H) + Wp1[j * H1 + H] * ct + bp1[j]);
+                p2[j] = R_TANH(dotv(Wp2 + (size_t)j * H1, h, H) + Wp2[j * H1 + H] * st + bp2[j]);
+                u[j] = an[j] * p1[j] * p2[j] * ((REAL)1 - an[j]) * ((REAL)1 - p1[j]) * ((REAL)1 - p2[j]);
+            }
+            REAL hn[64];
+            for (int j = 0; j < H; ++j) {
+                fg[j] = sigm(dotv(Wf + (size_t)j * H2, h, H) + dotv(Wf + (size_t)j * H2 + H, u, H) + bf[j]);
+                gg[j] = R_TANH(dotv(Wg + (size_t)j * H2, h, H) + dotv(Wg + (size_t)j * H2 + H, u, H) + bg[j]);
+                hn[j] = fg[j] * h[j] + ((REAL)1 - fg[j]) * gg[j];
+            }
+            memcpy(h, hn, sizeof(REAL) * H); memcpy(hs, h, sizeof(REAL) * H);
+            out[2 * t] = dotv(Wo, h, H) + bo[0]; out[2 * t + 1] = dotv(Wo + H, h, H) + bo[1];
+        }
+        return;
+    }
+    REAL *gWa = gp, *gba = gWa + H * H1, *gWp1 = gba + H, *gbp1 = gWp1 + H * H1, *gWp2 = gbp1 + H, *gbp2 = gWp2 + H * H1;
+    REAL *gWf = gbp2 + H, *gbf = gWf + H * H2, *gWg = gbf + H, *gbg = gWg + H * H2, *gWo = gbg + H, *gbo = gWo + 2 * H;
+    REAL gH[64] = {0};
+    for (int t = T - 1; t >= 0; --t) {
+        REAL *s = sv + (size_t)t * S, *an = s + 4, *p1 = an + H, *p2 = p1 + H, *u = p2 + H, *fg = u + H, *gg = fg + H, *hs = gg + H;
+        REAL hp[64];
+        for (int j = 0; j < H; ++j) hp[j] = t ? (sv + (size_t)(t - 1) * S + 4 + 6 * H)[j] : 0;
+        REAL go0 = gout[2 * t], go1 = gout[2 * t + 1];
+        for (int j = 0; j < H; ++j) {
+            gH[j] += Wo[j] * go0 + Wo[H + j] * go1;
+            gWo[j] += go0 * hs[j]; gWo[H + j] += go1 * hs[j];
+        }
+        gbo[0] += go0; gbo[1] += go1;
+        REAL ghp[64], gu[64] = {0};
+        REAL af[64], ag[64];
+        for (int j = 0; j < H; ++j) {
+            REAL gf_ = gH[j] * (hp[j] - gg[j]), gg_ = gH[j] * ((REAL)1 - fg[j]);
+            ghp[j] = gH[j] * fg[j];
+            af[j] = gf_ * fg[j] * ((REAL)1 - fg[j]); ag[j] = gg_ * ((REAL)1 - gg[j] * gg[j]);
+        }
+        for (int j = 0; j < H; ++j) {
+            gbf[j] += af[j]; gbg[j] += ag[j];
+            for (int k = 0; k < H; ++k) {
+                gWf[j * H2 + k] += af[j] * hp[k]; gWf[j * H2 + H + k] += af[j] * u[k];
+                gWg[j * H2 + k] += ag[j] * hp[k]; gWg[j * H2 + H + k] += ag[j] * u[k];
+                ghp[k] += Wf[j * H2 + k] * af[j] + Wg[j * H2 + k] * ag[j];
+                gu[k] += Wf[j * H2 + H + k] * af[j] + Wg[j * H2 + H + k] * ag[j];
+            }
+        }
+        REAL ga = 0, gc = 0, gs = 0;
+        for (int j = 0; j < H; ++j) {
+            REAL A = an[j] * ((REAL)1 - an[j]), P1 = p1[j] * ((REAL)1 - p1[j]), P2 = p2[j] * ((REAL)1 - p2[j]);
+            REAL gan = gu[j] * ((REAL)1 - (REAL)2 * an[j]) * P1 * P2;
+            REAL gp1_ = gu[j] * A * ((REAL)1 - (REAL)2 * p1[j]) * P2;
+            REAL gp2_ = gu[j] * A * P1 * ((REAL)1 - (REAL)2 * p2[j]);
+            REAL aa = gan * ((REAL)1 - an[j] * an[j]), a1 = gp1_ * ((REAL)1 - p1[j] * p1[j]), a2 = gp2_ * ((REAL)1 - p2[j] * p2[j]);
+            gba[j] += aa; gbp1[j] += a1; gbp2[j] += a2;
+            for (int k = 0; k < H; ++k) {
+                gWa[j * H1 + k] += aa * hp[k]; gWp1[j * H1 + k] += a1 * hp[k]; gWp2[j * H1 + k] += a2 * hp[k];
+                ghp[k] += Wa[j * H1 + k] * aa + Wp1[j * H1 + k] * a1 + Wp2[j * H1 + k] * a2;
+            }
+            gWa[j * H1 + H] += aa * s[0]; gWp1[j * H1 + H] += a1 * s[1]; gWp2[j * H1 + H] += a2 * s[2];
+            ga += Wa[j * H1 + H] * aa; gc += Wp1[j * H1 + H] * a1; gs += Wp2[j * H1 + H] * a2;
+        }
+        memcpy(gH, ghp, sizeof(REAL) * H);
+        if (gx) {
+            REAL i = x[2 * t], q = x[2 * t + 1], a = s[0], a2 = a * a;
+            REAL gth = -s[2] * gc + s[1] * gs;
+            gx[2 * t] += ga * i / a - gth * q / a2;
+            gx[2 * t + 1] += ga * q / a + gth * i / a2;
+        }
+    }
+}
+
+/* ================================================================ DVRJANET: dvrjanet.py:43-102, dvr_block :32-41
+ * params: cs(K) W_ph(H,H) W_pth(H,1) W_ah(H,H) W_ax(H,1) W_f(H,H) b_f W_ccos(H,2H) b W_csin(H,2H) b W_o1(1,H) b W_o2(1,H) b */
+static void seq_dvrjanet(const Ctx *c, const REAL *x, const REAL *gout, REAL *out, REAL *gx, REAL *gp, int phase) {
+    const int H = c->H, T = c->T, K = c->K, H2 = 2 * H;
+    const REAL *cs = c->params, *Wph = cs + K, *Wpt = Wph + H * H, *Wah = Wpt + H, *Wax = Wah + H * H, *Wf = Wax + H, *bf = Wf + H * H;
+    const REAL *Wc = bf + H, *bc = Wc + H * H2, *Ws = bc + H, *bs = Ws + H * H2, *Wo1 = bs + H, *bo1 = Wo1 + H, *Wo2 = bo1 + 1,
+               *bo2 = Wo2 + H;
+    static __thread REAL *sv = NULL; static __thread size_t sv_n = 0;
+    const int S = 4 + 10 * H; /* a th | pa at ct st f gc gs hI hQ tht */
+    size_t need = (size_t)T * S;
+    if (sv_n < need) { free(sv); sv = (REAL *)malloc(need * sizeof(REAL)); sv_n = need; }
+    if (phase == 0) {
+        REAL hI[64] = {0}, hQ[64] = {0};
+        for (int t = 0; t < T; ++t) {
+            REAL *s = sv + (size_t)t * S, *pa = s + 4, *at = pa + H, *ct = at + H, *st = ct + H, *fg = st + H, *gc = fg + H,
+                 *gs = gc + H, *sI = gs + H, *sQ = sI + H;
+            REAL i = x[2 * t], q = x[2 * t + 1];
+            REAL a = R_SQRT(i * i + q * q), th = R_ATAN2(q, i);
+            s[0] = a; s[1] = th;
+            REAL sm[64], vc[64], vs[64];
+            for (int j = 0; j < H; ++j) sm[j] = hI[j] + hQ[j];
+            for (int j = 0; j < H; ++j) {
+                REAL tht = Wpt[j] * th + dotv(Wph + (size_t)j * H, sm, H);
+                pa[j] = Wax[j] * a + dotv(Wah + (size_t)j * H, sm, H);
+                REAL acc = 0;
+                for (int k = 1; k <= K; ++k) acc = acc + R_FABS(pa[j] - (REAL)((double)k / K)) * cs[k - 1];
+                at[j] = acc; ct[j] = R_COS(tht); st[j] = R_SIN(tht);
+                fg[j] = sigm(dotv(Wf + (size_t)j * H, sm, H) + bf[j]);
+                vc[j] = at[j] * ct[j]; vs[j] = at[j] * st[j];
+            }
+            REAL nI[64], nQ[64];
+            for (int j = 0; j < H; ++j) {
+                gc[j] = R_TANH(dotv(Wc + (size_t)j * H2, hI, H) + dotv(Wc + (size_t)j * H2 + H, vc, H) + bc[j]);
+                gs[j] = R_TANH(dotv(Ws + (size_t)j * H2, hQ, H) + dotv(Ws + (size_t)j * H2 + H, vs, H) + bs[j]);
+                nI[j] = fg[j] * hI[j] + ((REAL)1 - fg[j]) * gc[j];
+                nQ[j] = fg[j] * hQ[j] + ((REAL)1 - fg[j]) * gs[j];
+            }
+            memcpy(hI, nI, sizeof(REAL) * H); memcpy(hQ, nQ, sizeof(REAL) * H);
+            memcpy(sI, hI, sizeof(REAL) * H); memcpy(sQ, hQ, sizeof(REAL) * H);
+            out[2 * t] = dotv(Wo1, hI, H) + bo1[0]; out[2 * t + 1] = dotv(Wo2, hQ, H) + bo2[0];
+        }
+        return;
+    }
+    REAL *gcs = gp, *gWph = gcs + K, *gWpt = gWph + H * H, *gWah = gWpt + H, *gWax = gWah + H * H, *gWf = gWax + H, *gbf = gWf + H * H;
+    REAL *gWc = gbf + H, *gbc = gWc + H * H2, *gWs = gbc + H, *gbs = gWs + H * H2, *gWo1 = gbs + H, *gbo1 = gWo1 + H, *gWo2 = gbo1 + 1,
+         *gbo2 = gWo2 + H;
+    REAL gI[64] = {0}, gQ[64] = {0};
+    for (int t = T - 1; t >= 0; --t) {
+        REAL *s = sv + (size_t)t * S, *pa = s + 4, *at = pa + H, *ct = at + H, *st = ct + H, *fg = st + H, *gc = fg + H, *gs = gc + H,
+             *sI = gs + H, *sQ = sI + H;
+        REAL hI[64], hQ[64], sm[64], vc[64], vs[64];
+        for (int j = 0; j < H; ++j) {
+            hI[j] = t ? (sv + (size_t)(t - 1) * S + 4 + 7 * H)[j] : 0;
+            hQ[j] = t ? (sv + (size_t)(t - 1) * S + 4 + 8 * H)[j] : 0;
+            sm[j] = hI[j] + hQ[j]; vc[j] = at[j] * ct[j]; vs[j] = at[j] * st[j];
+        }
+        REAL go0 = gout[2 * t], go1 = gout[2 * t + 1];
+        for (int j = 0; j < H; ++j) {
+            gI[j] += Wo1[j] * go0; gQ[j] += Wo2[j] * go1;
+            gWo1[j] += go0 * sI[j]; gWo2[j] += go1 * sQ[j];
+        }
+        gbo1[0] += go0; gbo2[0] += go1;
+        REAL gIp[64], gQp[64], af[64], ac[64], as_[64], gvc[64] = {0}, gvs[64] = {0};
+        for (int j = 0; j < H; ++j) {
+            REAL gf_ = gI[j] * (hI[j] - gc[j]) + gQ[j] * (hQ[j] - gs[j]);
+            af[j] = gf_ * fg[j] * ((REAL)1 - fg[j]);
+            ac[j] = gI[j] * ((REAL)1 - fg[j]) * ((REAL)1 - gc[j] * gc[j]);
+            as_[j] = gQ[j] * ((REAL)1 - fg[j]) * ((REAL)1 - gs[j] * gs[j]);
+            gIp[j] = gI[j] * fg[j]; gQp[j] = gQ[j] * fg[j];
+        }
+        for (int j = 0; j < H; ++j) {
+            gbc[j] += ac[j]; gbs[j] += as_[j]; gbf[j] += af[j];
+            for (int k = 0; k < H; ++k) {
+                gWc[j * H2 + k] += ac[j] * hI[k]; gWc[j * H2 + H + k] += ac[j] * vc[k];
+                gWs[j * H2 + k] += as_[j] * hQ[k]; gWs[j * H2 + H + k] += as_[j] * vs[k];
+                gIp[k] += Wc[j * H2 + k] * ac[j]; gvc[k] += Wc[j * H2 + H + k] * ac[j];
+                gQp[k] += Ws[j * H2 + k] * as_[j]; gvs[k] += Ws[j * H2 + H + k] * as_[j];
+            }
+        }
+        REAL gsm[64] = {0}, gth = 0, ga = 0;
+        for (int j = 0; j < H; ++j) {
+            REAL gat = gvc[j] * ct[j] + gvs[j] * st[j];
+            REAL gtht = -gvc[j] * at[j] * st[j] + gvs[j] * at[j] * ct[j];
+            REAL gpa = 0;
+            for (int k = 1; k <= K; ++k) {
+                REAL d = pa[j] - (REAL)((double)k / K);
+                gcs[k - 1] += gat * R_FABS(d);
+                gpa += cs[k - 1] * (d > 0 ? (REAL)1 : (d < 0 ? (REAL)-1 : (REAL)0));
+            }
+            gpa *= gat;
+            gWpt[j] += gtht * s[1]; gWax[j] += gpa * s[0];
+            gth += Wpt[j] * gtht; ga += Wax[j] * gpa;
+            for (int k = 0; k < H; ++k) {
+                gWph[j * H + k] += gtht * sm[k]; gWah[j * H + k] += gpa * sm[k]; gWf[j * H + k] += af[j] * sm[k];
+                gsm[k] += Wph[j * H + k] * gtht + Wah[j * H + k] * gpa + Wf[j * H + k] * af[j];
+            }
+        }
+        for (int j = 0; j < H; ++j) { gI[j] = gIp[j] + gsm[j]; gQ[j] = gQp[j] + gsm[j]; }
+        if (gx) {
+            REAL i = x[2 * t], q = x[2 * t + 1], a = s[0], a2 = a * a;
+            gx[2 * t] += ga * i / a - gth * q / a2;
+            gx[2 * t + 1] += ga * q / a + gth * i / a2;
+        }
+    }
+}
+
+/* ================================================================ GMP: gmp.py:18-51 (M=11 taps, degree 5; real weights)
+ * y[j] = sum_m w[m] x[j+m-10] + sum_{p<4,k<11,m<11} w[11+p*121+k*11+m] x[j+m-10] |x[j+k+m-20]|^(p+1), x[n<0]=0 */
+static void seq_gmp(const Ctx *c, const REAL *x, const REAL *gout, REAL *out, REAL *gx, REAL *gp, int phase) {
+    const int T = c->T; const REAL *w = c->params;
+    for (int j = 0; j < T; ++j) {
+        REAL yr = 0, yi = 0;
+        REAL g0 = phase ? gout[2 * j] : 0, g1 = phase ? gout[2 * j + 1] : 0;
+        for (int m = 0; m < 11; ++m) {
+            int a = j + m - 10; if (a < 0) continue;
+            REAL ar = x[2 * a], ai = x[2 * a + 1];
+            if (!phase) { yr += w[m] * ar; yi += w[m] * ai; }
+            else { gp[m] += g0 * ar + g1 * ai; if (gx) { gx[2 * a] += g0 * w[m]; gx[2 * a + 1] += g1 * w[m]; } }
+        }
+        for (int p = 0; p < 4; ++p)
+            for (int k = 0; k < 11; ++k)
+                for (int m = 0; m < 11; ++m) {
+                    int a = j + m - 10, cc = j + k + m - 20, idx = 11 + p * 121 + k * 11 + m;
+                    if (a < 0) continue;           /* x[a]=0 -> term and all its gradients vanish */
+                    REAL ar = x[2 * a], ai = x[2 * a + 1];
+                    REAL cr = cc >= 0 ? x[2 * cc] : 0, ci = cc >= 0 ? x[2 * cc + 1] : 0;
+                    REAL amp = R_SQRT(cr * cr + ci * ci);
+                    REAL pw = amp; for (int e = 0; e < p; ++e) pw *= amp;   /* amp^(p+1) */
+                    if (!phase) { yr += w[idx] * ar * pw; yi += w[idx] * ai * pw; continue; }
+                    gp[idx] += (g0 * ar + g1 * ai) * pw;
+                    if (gx) {
+                        gx[2 * a] += g0 * w[idx] * pw; gx[2 * a + 1] += g1 * w[idx] * pw;
+                        if (cc >= 0 && amp > 0) {
+                            REAL pm = 1; for (int e = 0; e < p; ++e) pm *= amp;   /* amp^p */
+                            REAL coef = w[idx] * (g0 * ar + g1 * ai) * (REAL)(p + 1) * pm / amp;
+                            gx[2 * cc] += coef * cr; gx[2 * cc + 1] += coef * ci;
+                        }
+                    }
+                }
+        if (!phase) { out[2 * j] = yr; out[2 * j + 1] = yi; }
+    }
+}
+
+static size_t n_params(int cell, int H, int K) {
+    switch (cell) {
+    case CELL_GRU: return (size_t)3 * H * 2 + 3 * H * H + 6 * H + 2 * H + 2;
+    case CELL_QGRU: case CELL_QGRU_AMP1: return (size_t)3 * H * 4 + 3 * H * H + 6 * H + 2 * H + 2;
+    case CELL_DGRU: return (size_t)3 * H * 6 + 3 * H * H + 6 * H + 2 * (H + 6) + 2 + H * H + H;
+    case CELL_LSTM: return (size_t)4 * H * 2 + 4 * H * H + 8 * H + 2 * H + 2;
+    case CELL_DELTAGRU: return (size_t)3 * H * 6 + 3 * H * H + 6 * H + 2 * H + 2;
+    case CELL_TRES: return (size_t)3 * H * 6 + 3 * H * H + 2 * H + 18 + 6;
+    case CELL_PGJANET: return (size_t)3 * (H * (H + 1) + H) + 2 * (2 * H * H + H) + 2 * H + 2;
+    case CELL_DVRJANET: return (size_t)K + 3 * H * H + 2 * H + H + 2 * (2 * H * H + H) + 2 * (H + 1);
+    case CELL_GMP: return 495;
+    }
+    return 0;
+}
+
+static void seq_dispatch(const Ctx *c, const REAL *x, const REAL *gout, REAL *out, REAL *gx, REAL *gp, int phase,
+                         uint64_t *mx, uint64_t *mh, int64_t *st) {
+    switch (c->cell) {
+    case CELL_GRU: case CELL_DGRU: case CELL_QGRU: case CELL_QGRU_AMP1: seq_gru_family(c, x, gout, out, gx, gp, phase); break;
+    case CELL_LSTM: seq_lstm(c, x, gout, out, gx, gp, phase); break;
+    case CELL_DELTAGRU: case CELL_TRES: seq_delta(c, x, gout, out, gx, gp, phase, mx, mh, st); break;
+    case CELL_PGJANET: seq_pgjanet(c, x, gout, out, gx, gp, phase); break;
+    case CELL_DVRJANET: seq_dvrjanet(c, x, gout, out, gx, gp, phase); break;
+    case CELL_GMP: seq_gmp(c, x, gout, out, gx, gp, phase); break;
+    }
+}
+
+/*
+ * One full pass: forward (+ MSE vs target, nn.MSELoss mean over `loss_count` scalars, project.py:262-272)
+ * and, when gx/gparams are requested, backward.  train_funcs.py:33-39 (fwd, criterion, backward).
+ *   x,target,out,gx : (B,T,2) contiguous;  gout_in (B,T,2) used instead of the MSE gradient when target==NULL
+ *   loss            : sum of squared errors / loss_count  (double)
+ *   mask_x, mask_h  : (B,T) uint64 keep-bitfields (delta cells) or NULL;  stats: 4 x int64 accumulated (+=)
+ * Returns 0, or -1 on bad arguments.
+ */
+int SUF(odpd_oracle_run)(int cell, int B, int T, int H, int K, double thx, double thh, const REAL *x, const REAL *target,
+                         const REAL *gout_in, const REAL *params, REAL *out, double *loss, double loss_count, REAL *gx,
+                         REAL *gparams, uint64_t *mask_x, uint64_t *mask_h, int64_t *stats, int nthreads) {
+    if (B < 0 || T < 0 || H > 64 || (cell != CELL_GMP && H < 1)) return -1;
+    const size_t P = n_params(cell, H, K);
+    Ctx c = {cell, B, T, H, K, (REAL)thx, (REAL)thh, params, gx != NULL, gparams != NULL};
+    const int bwd = (gx || gparams);
+    if (nthreads < 1) nthreads = 1;
+    double lsum = 0;
+    REAL *gp_all = bwd ? (REAL *)calloc((size_t)nthreads * P, sizeof(REAL)) : NULL;
+    int64_t st_all[4] = {0, 0, 0, 0};
+    if (gx) memset(gx, 0, sizeof(REAL) * (size_t)B * T * 2);
+#ifdef _OPENMP
+#pragma omp parallel num_threads(nthreads) reduction(+ : lsum)
+#endif
+    {
+        int tid = 0;
+#ifdef _OPENMP
+        tid = omp_get_thread_num();
+#endif
+        REAL *gtmp = (REAL *)malloc(sizeof(REAL) * (size_t)(T > 0 ? T : 1) * 2);
+        int64_t st_loc[4] = {0, 0, 0, 0};
+#ifdef _OPENMP
+#pragma omp for schedule(static)
+#endif
+        for (int b = 0; b < B; ++b) {
+            const REAL *xb = x + (size_t)b * T * 2;
+            REAL *ob = out + (size_t)b * T * 2;
+            int64_t st[4] = {0, 0, 0, 0};
+            seq_dispatch(&c, xb, NULL, ob, NULL, NULL, 0, mask_x ? mask_x + (size_t)b * T : NULL,
+                         mask_h ? mask_h + (size_t)b * T : NULL, st);
+            for (int k = 0; k < 4; ++k) st_loc[k] += st[k];
+            const REAL *g = NULL;
+            if (target) {
+                const REAL *yb = target + (size_t)b * T * 2;
+                for (int i = 0; i < 2 * T; ++i) {
+                    REAL d = ob[i] - yb[i];
+                    lsum += (double)d * (double)d;
+                    gtmp[i] = (REAL)((double)2 * (double)d / loss_count);
+                }
+                g = gtmp;
+            } else if (gout_in) g = gout_in + (size_t)b * T * 2;
+            if (bwd && g)
+                seq_dispatch(&c, xb, g, ob, gx ? gx + (size_t)b * T * 2 : NULL, gp_all + (size_t)tid * P, 1, NULL, NULL, NULL);
+        }
+        free(gtmp);
+#ifdef _OPENMP
+#pragma omp critical
+#endif
+        for (int k = 0; k < 4; ++k) st_all[k] += st_loc[k];
+    }
+    if (loss) *loss = target ? lsum / loss_count : 0.0;
+    if (gparams) {
+        memset(gparams, 0, sizeof(REAL) * P);
+        for (int t = 0; t < nthreads; ++t)
+            for (size_t i = 0; i < P; ++i) gparams[i] += gp_all[(size_t)t * P + i];
+    }
+    if (stats) for (int k = 0; k < 4; ++k) stats[k] += st_all[k];
+    free(gp_all);
+    return 0;
+}
+
+#ifndef REAL_IS_DOUBLE
+size_t odpd_oracle_n_params(int cell, int H, int K) { return n_params(cell, H, K); }
+#endif

@@ -1,0 +1,37 @@
+import glob, json, os
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def golden_cases(kinds=None):
+    out = []
+    for f in sorted(glob.glob(os.path.join(GOLDEN, "*.npz"))):
+        name = os.path.basename(f)[:-4]
+        if kinds is None or any(name.startswith(k) for k in kinds):
+            out.append(name)
+    return out
+
+
+def load_golden(name):
+    d = np.load(os.path.join(GOLDEN, name + ".npz"))
+    g = {k: d[k] for k in d.files}
+    g["kind"] = str(g["kind"]); g["H"] = int(g["H"]); g["K"] = int(g["K"])
+    g["thx"] = float(g["thx"]); g["thh"] = float(g["thh"])
+    g["param_index"] = json.loads(str(g["param_index"]))
+    return g
+
+
+def rel_err(a, b):
+    """max|a-b| / max|b| — the relative-fp32 figure of merit used throughout (north_star: <=1e-5)."""
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / (np.max(np.abs(b)) + 1e-300))
+
+
+def tol_for(g, key, base=1e-5):
+    """Tolerance for comparing an fp32 implementation with the fp32 reference: the north-star 1e-5, widened only
+    where the reference's own fp32-vs-fp64 disagreement shows the case is ill-conditioned (e.g. DVRJANET's
+    cos/sin of an unbounded learned phase)."""
+    cond = rel_err(g[key], g[key + "64"])
+    return max(base, 20.0 * cond)
