@@ -1,0 +1,131 @@
+/*
+ * odpd.h — C ABI of libodpd.so: B200-native (sm_100a) recurrent-backbone forward / backward for OpenDPD.
+ *
+ * This is the drop-in boundary for ONE hot path of lab-emi/OpenDPD: the backbone forward/backward (+ I/Q MSE)
+ * that `net_train` executes per step (reference: modules/train_funcs.py:28-48 -> models.py:150-176 ->
+ * backbones/<name>.py forward).  The reference has no FFI of its own (it is pure PyTorch); the entry points
+ * below are what a ctypes/cffi binding added to the reference's backbones/*.py would call — one call replaces
+ * one `Backbone.forward` (or its autograd backward).  INTEGRATION.md shows that binding.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer owned by the caller (PyTorch), valid until the
+ *     stream work completes; the library keeps no reference after the call returns and never allocates
+ *     device memory.  All tensors are contiguous fp32 unless stated.
+ *   - launches are enqueued on `stream` (a cudaStream_t passed as void*); no host or device synchronisation.
+ *   - return 0 on success, <0 on error; odpd_last_error() returns a thread-local message. No C++ exceptions
+ *     cross the ABI and the library never calls exit().
+ *   - NaN/Inf propagate exactly as IEEE arithmetic dictates (the reference divides by amp=0 unguarded,
+ *     backbones/dgru.py:66-67).
+ *
+ * Flat parameter layout (`params`, `gparams`): the reference module's named_parameters() order, each tensor
+ * row-major, concatenated (H hidden, F features, K dvr units):
+ *   GRU       (gru.py:17-25)        rnn.weight_ih_l0(3H,2) weight_hh_l0(3H,H) bias_ih_l0(3H) bias_hh_l0(3H) fc_out.weight(2,H) fc_out.bias(2)
+ *   LSTM      (lstm.py:17-25)       rnn.weight_ih_l0(4H,2) weight_hh_l0(4H,H) bias_ih_l0(4H) bias_hh_l0(4H) fc_out.weight(2,H) fc_out.bias(2)
+ *   DGRU      (dgru.py:22-33)       rnn.* as GRU with F=6, fc_out.weight(2,H+6) fc_out.bias(2) fc_hid.weight(H,H) fc_hid.bias(H)
+ *   QGRU/QGRU_AMP1 (qgru.py:22-31)  rnn.* as GRU with F=4, fc_out.weight(2,H) fc_out.bias(2)
+ *   DELTAGRU  (deltagru.py:23-30)   rnn.weight_ih_l0(3H,6) weight_hh_l0(3H,H) bias_ih_l0(3H) bias_hh_l0(3H) fc_out.weight(2,H) fc_out.bias(2)
+ *   TRES      (deltagru_tcnskip.py:24-49) rnn.x2h.weight(3H,6) rnn.h2h.weight(3H,H) fc_out.weight(2,H) tcn.0.weight(3,2,3) tcn.2.weight(2,3,1)
+ *   PGJANET   (pgjanet.py:13-22)    W_a.weight(H,H+1) W_a.bias(H) W_p1.* W_p2.* W_f.weight(H,2H) W_f.bias(H) W_g.* W_o.weight(2,H) W_o.bias(2)
+ *   DVRJANET  (dvrjanet.py:14-30)   cs(K) W_ph.weight(H,H) W_ptheta.weight(H,1) W_ah.weight(H,H) W_ax.weight(H,1) W_f.weight(H,H) W_f.bias(H)
+ *                                   W_ccos.weight(H,2H) W_ccos.bias(H) W_csin.* W_o1.weight(1,H) W_o1.bias(1) W_o2.weight(1,H) W_o2.bias(1)
+ *   GMP       (gmp.py:11)           Weight(1,495)
+ */
+#ifndef ODPD_H_
+#define ODPD_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ODPD_VERSION 100
+
+/* cell families == reference backbones (models.py:26-141 names them) */
+enum {
+    ODPD_CELL_GRU = 0,       /* backbones/gru.py:45-48 */
+    ODPD_CELL_LSTM = 1,      /* backbones/lstm.py:45-48 */
+    ODPD_CELL_DGRU = 2,      /* backbones/dgru.py:59-74 */
+    ODPD_CELL_DELTAGRU = 3,  /* backbones/deltagru.py:60-77, 208-266 */
+    ODPD_CELL_TRES = 4,      /* backbones/deltagru_tcnskip.py:89-103, 244-304 */
+    ODPD_CELL_PGJANET = 5,   /* backbones/pgjanet.py:24-77 */
+    ODPD_CELL_DVRJANET = 6,  /* backbones/dvrjanet.py:43-102 */
+    ODPD_CELL_GMP = 7,       /* backbones/gmp.py:18-51 */
+    ODPD_CELL_QGRU = 8,      /* backbones/qgru.py:59-71 */
+    ODPD_CELL_QGRU_AMP1 = 9, /* backbones/qgru_amp1.py:59-76 */
+    ODPD_CELL_COUNT = 10
+};
+
+/* flags */
+#define ODPD_F_NEED_DX 1u    /* backward emits gx   (frozen-PA input gradient, models.py:169-171) */
+#define ODPD_F_NEED_DW 2u    /* backward emits gparams */
+#define ODPD_F_SAVE 4u       /* forward stores activations for a later odpd_backbone_bwd */
+
+typedef struct OdpdDims {
+    int32_t cell;   /* ODPD_CELL_* */
+    int32_t B;      /* sequences in this call (>=0)                        */
+    int32_t T;      /* frame length (>=0)                                  */
+    int32_t H;      /* hidden size (1..32 on the fused path; ignored by GMP) */
+    int32_t K;      /* DVRJANET num_dvr_units (dvrjanet.py:6)              */
+    uint32_t flags; /* ODPD_F_*                                            */
+    float thx, thh; /* delta thresholds (deltagru.py:216-217)              */
+} OdpdDims;
+
+int odpd_version(void);
+const char *odpd_last_error(void);
+
+/* number of fp32 parameters of a backbone == reference count_net_params (utils/util.py) of `backbone` */
+int64_t odpd_n_params(int32_t cell, int32_t H, int32_t K);
+/* bytes of the caller-allocated `saved` buffer a forward with ODPD_F_SAVE fills for the matching backward */
+int64_t odpd_saved_bytes(const OdpdDims *d);
+/* bytes of the caller-allocated scratch `workspace` odpd_backbone_bwd needs (per-sequence grad partials) */
+int64_t odpd_bwd_workspace_bytes(const OdpdDims *d);
+
+/*
+ * Forward: replaces `backbone.forward(x, h_0)` with h_0 == 0 (models.py:154-155) and, when `target` is given,
+ * the `nn.MSELoss()(out, target)` that follows it (train_funcs.py:35-37, project.py:262-272).
+ *   x       (B,T,2)   in
+ *   target  (B,T,2)   in, or NULL
+ *   params  flat      in  (layout above; must be 16-byte aligned)
+ *   out     (B,T,2)   out
+ *   loss    double[1] in/out, or NULL: += sum((out-target)^2) * loss_scale  (caller zeroes it; loss_scale is
+ *                     1/(2*B_global*T) for MSELoss 'mean')
+ *   saved   odpd_saved_bytes(d) out when ODPD_F_SAVE, else may be NULL
+ *   stats   int64[4]  in/out, or NULL: += {dx_zeros, dx_numel, dh_zeros, dh_numel} (delta cells only;
+ *                     deltagru.py:241-247 keeps these in fp32 tensors, we count exactly in int64)
+ */
+int odpd_backbone_fwd(const OdpdDims *d, const float *x, const float *target, const float *params, float *out,
+                      double *loss, double loss_scale, void *saved, int64_t *stats, void *stream);
+
+/*
+ * Backward: replaces autograd's backward through the same backbone call.
+ *   gout            (B,T,2) dLoss/dout, or NULL to use the fused MSE gradient
+ *                   gscale * gscale_dev[0] * (out - target)   (gscale = 2/(2*B_global*T) for MSELoss 'mean';
+ *                   gscale_dev is an optional device scalar = the upstream dLoss, NULL == 1)
+ *   gx              (B,T,2) out (overwritten) when ODPD_F_NEED_DX, else may be NULL
+ *   gparams         flat fp32, ACCUMULATED (+=) when ODPD_F_NEED_DW, else may be NULL
+ *   workspace       odpd_bwd_workspace_bytes(d)
+ * The reduction of per-sequence gradient partials is ordered (no float atomics): results are bit-reproducible
+ * run to run for fixed (B,T).
+ */
+int odpd_backbone_bwd(const OdpdDims *d, const float *x, const float *params, const void *saved, const float *gout,
+                      const float *out, const float *target, double gscale, const float *gscale_dev, float *gx,
+                      float *gparams, void *workspace, void *stream);
+
+/*
+ * Optimiser step on the flat buffers: clip_grad_norm_(max_norm) over `grad` (train_funcs.py:41-42; global L2 norm,
+ * coefficient min(1, max_norm/(norm+1e-6)) as torch.nn.utils.clip_grad_norm_) followed by torch.optim.AdamW
+ * (project.py:283; decoupled weight decay, bias correction, eps outside the sqrt) — one launch.
+ *   step_dev  int64[1] device step counter, incremented by the kernel (keeps the call graph-capturable)
+ *   lr_dev    float[1] device learning rate (ReduceLROnPlateau updates it host-side, project.py:288-297)
+ *   gnorm_out float[1] or NULL: pre-clip gradient norm
+ *   max_norm <= 0 disables clipping (train_funcs.py:41).
+ */
+int odpd_clip_adamw(float *param, float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, const float *lr_dev,
+                    float beta1, float beta2, float eps, float weight_decay, float max_norm, int64_t *step_dev,
+                    float *gnorm_out, int zero_grad, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ODPD_H_ */

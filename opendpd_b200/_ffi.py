@@ -1,0 +1,64 @@
+"""ctypes binding of libodpd.so (include/odpd.h).  Raw device pointers in, no torch types across the boundary.
+
+Fails loudly when the library is missing: the product has no CPU path.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libodpd.so")
+
+CELLS = {"gru": 0, "lstm": 1, "dgru": 2, "deltagru": 3, "deltagru_tcnskip": 4, "pgjanet": 5, "dvrjanet": 6, "gmp": 7,
+         "qgru": 8, "qgru_amp1": 9}
+F_NEED_DX, F_NEED_DW, F_SAVE = 1, 2, 4
+
+
+class OdpdDims(ctypes.Structure):
+    _fields_ = [("cell", ctypes.c_int32), ("B", ctypes.c_int32), ("T", ctypes.c_int32), ("H", ctypes.c_int32),
+                ("K", ctypes.c_int32), ("flags", ctypes.c_uint32), ("thx", ctypes.c_float), ("thh", ctypes.c_float)]
+
+
+class OdpdError(RuntimeError):
+    pass
+
+
+_lib = None
+_vp, _i64, _i32, _dbl, _flt = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_double, ctypes.c_float
+_DP = ctypes.POINTER(OdpdDims)
+
+# every symbol include/odpd.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "odpd_version": (ctypes.c_int, []),
+    "odpd_last_error": (ctypes.c_char_p, []),
+    "odpd_n_params": (_i64, [_i32, _i32, _i32]),
+    "odpd_saved_bytes": (_i64, [_DP]),
+    "odpd_bwd_workspace_bytes": (_i64, [_DP]),
+    "odpd_backbone_fwd": (ctypes.c_int, [_DP, _vp, _vp, _vp, _vp, _vp, _dbl, _vp, _vp, _vp]),
+    "odpd_backbone_bwd": (ctypes.c_int, [_DP, _vp, _vp, _vp, _vp, _vp, _vp, _dbl, _vp, _vp, _vp, _vp, _vp]),
+    "odpd_clip_adamw": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _flt, _flt, _flt, _flt, _flt, _vp, _vp,
+                                       ctypes.c_int, _vp]),
+}
+
+
+def lib():
+    """Load libodpd.so once. Raises OdpdError if it has not been built (python -c 'import __graft_entry__ as g; g.build()')."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise OdpdError(f"{LIB_PATH} is missing: build it with `make -C opendpd_b200/csrc` "
+                            "(there is no CPU fallback for the native backbones)")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise OdpdError(f"libodpd error {rc}: {lib().odpd_last_error().decode()}")
+
+
+def n_params(cell, H, K=0):
+    return int(lib().odpd_n_params(CELLS[cell], int(H), int(K)))

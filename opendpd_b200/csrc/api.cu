@@ -1,0 +1,191 @@
+// api.cu — the extern "C" surface of libodpd.so (include/odpd.h): argument checking, dispatch, error strings,
+// the ordered gradient-partials reduction and the fused clip+AdamW step.
+#include <cstdarg>
+#include <cstdio>
+#include "cells.h"
+
+namespace odpd {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int check_launch(const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: CUDA launch failed: %s", what, cudaGetErrorString(e));
+        return -2;
+    }
+    return 0;
+}
+
+// g[p] += sum_{b=0..nrows-1} part[b][p], summed in row order (bit-reproducible)
+__global__ void reduce_partials_kernel(const float *__restrict__ part, int nrows, int64_t P, float *__restrict__ g) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int b = 0;
+    for (; b + 3 < nrows; b += 4) {
+        s0 += part[(int64_t)b * P + p];
+        s1 += part[(int64_t)(b + 1) * P + p];
+        s2 += part[(int64_t)(b + 2) * P + p];
+        s3 += part[(int64_t)(b + 3) * P + p];
+    }
+    for (; b < nrows; ++b) s0 += part[(int64_t)b * P + p];
+    g[p] += (s0 + s1) + (s2 + s3);
+}
+
+int reduce_partials(const float *part, int nrows, int64_t P, float *g, cudaStream_t st) {
+    if (P <= 0) return 0;
+    const int threads = 128;
+    reduce_partials_kernel<<<(unsigned)((P + threads - 1) / threads), threads, 0, st>>>(part, nrows, P, g);
+    return check_launch("reduce_partials_kernel");
+}
+
+// ---------------------------------------------------------------- fused clip_grad_norm_ + AdamW, single CTA (n is ~1e3)
+// train_funcs.py:41-44: nn.utils.clip_grad_norm_(params, max_norm) then optimizer.step() with torch.optim.AdamW
+// defaults (project.py:283): p *= 1-lr*wd;  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;
+// p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+__global__ void __launch_bounds__(1024) clip_adamw_kernel(float *__restrict__ p, float *__restrict__ g, float *__restrict__ m,
+                                                          float *__restrict__ v, int64_t n, const float *__restrict__ lr_dev, float b1,
+                                                          float b2, float eps, float wd, float max_norm, int64_t *step_dev,
+                                                          float *gnorm_out, int zero_grad) {
+    __shared__ float red[32];
+    __shared__ float s_coef;
+    float ss = 0.f;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) { const float x = g[i]; ss = fmaf(x, x, ss); }
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+        t = warp_sum(t);
+        if (threadIdx.x == 0) {
+            const float norm = sqrtf(t);
+            float coef = 1.f;
+            if (max_norm > 0.f) { coef = max_norm / (norm + 1e-6f); coef = coef < 1.f ? coef : 1.f; }
+            s_coef = coef;
+            if (gnorm_out) *gnorm_out = norm;
+        }
+    }
+    __syncthreads();
+    const float coef = s_coef;
+    const int64_t step = *step_dev + 1;
+    const float lr = *lr_dev;
+    const float bc1 = 1.f - powf(b1, (float)step), bc2 = 1.f - powf(b2, (float)step);
+    const float step_size = lr / bc1, bc2s = sqrtf(bc2);
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const float gi = g[i] * coef;
+        float pi = p[i] * (1.f - lr * wd);
+        const float mi = fmaf(b1, m[i], (1.f - b1) * gi);
+        const float vi = fmaf(b2, v[i], (1.f - b2) * gi * gi);
+        const float denom = sqrtf(vi) / bc2s + eps;
+        pi -= step_size * (mi / denom);
+        p[i] = pi; m[i] = mi; v[i] = vi;
+        if (zero_grad) g[i] = 0.f; else g[i] = gi;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *step_dev = step;
+}
+
+static int check_dims(const OdpdDims *d) {
+    ODPD_CHECK(d != nullptr, "dims is NULL");
+    ODPD_CHECK(d->cell >= 0 && d->cell < ODPD_CELL_COUNT, "unknown cell %d", d->cell);
+    ODPD_CHECK(d->B >= 0 && d->T >= 0, "negative B/T (%d,%d)", d->B, d->T);
+    if (d->cell != ODPD_CELL_GMP) ODPD_CHECK(d->H >= 1 && d->H <= 32, "hidden_size %d outside the fused range 1..32", d->H);
+    if (d->cell == ODPD_CELL_DVRJANET) ODPD_CHECK(d->K >= 1 && d->K <= 8, "num_dvr_units %d outside 1..8", d->K);
+    return 0;
+}
+
+static bool is_gru_family(int c) { return c == ODPD_CELL_GRU || c == ODPD_CELL_DGRU || c == ODPD_CELL_QGRU || c == ODPD_CELL_QGRU_AMP1; }
+
+}  // namespace odpd
+
+using namespace odpd;
+
+extern "C" {
+
+int odpd_version(void) { return ODPD_VERSION; }
+const char *odpd_last_error(void) { return g_err; }
+
+int64_t odpd_n_params(int32_t cell, int32_t H, int32_t K) {
+    if (is_gru_family(cell)) return gru_family_nparams(cell, H);
+    return other_nparams(cell, H, K);
+}
+
+int64_t odpd_saved_bytes(const OdpdDims *d) {
+    if (check_dims(d)) return -1;
+    if (is_gru_family(d->cell)) return 4 * gru_family_saved_floats(d->cell, d->B, d->T, d->H);
+    return other_saved_bytes(d);
+}
+
+int64_t odpd_bwd_workspace_bytes(const OdpdDims *d) {
+    if (check_dims(d)) return -1;
+    return 4 * (int64_t)(d->B > 0 ? d->B : 1) * odpd_n_params(d->cell, d->H, d->K) + 64;
+}
+
+int odpd_backbone_fwd(const OdpdDims *d, const float *x, const float *target, const float *params, float *out, double *loss,
+                      double loss_scale, void *saved, int64_t *stats, void *stream) {
+    if (check_dims(d)) return -1;
+    ODPD_CHECK(params && out, "params/out must not be NULL");
+    ODPD_CHECK(((uintptr_t)params & 15) == 0, "params must be 16-byte aligned");
+    const bool save = (d->flags & ODPD_F_SAVE) != 0;
+    ODPD_CHECK(!save || saved, "ODPD_F_SAVE set but saved==NULL");
+    if (d->B == 0 || d->T == 0) return 0;
+    ODPD_CHECK(x != nullptr, "x must not be NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (is_gru_family(d->cell)) {
+        GruArgs a{};
+        a.B = d->B; a.T = d->T; a.H = d->H; a.x = x; a.target = target; a.params = params; a.out = out; a.loss = loss;
+        a.loss_scale = (float)loss_scale; a.saved = (float *)saved; a.save = save;
+        return gru_family_run(d->cell, a, 0, false, st);
+    }
+    return other_fwd(d, x, target, params, out, loss, loss_scale, saved, stats, st);
+}
+
+int odpd_backbone_bwd(const OdpdDims *d, const float *x, const float *params, const void *saved, const float *gout, const float *out,
+                      const float *target, double gscale, const float *gscale_dev, float *gx, float *gparams, void *workspace,
+                      void *stream) {
+    if (check_dims(d)) return -1;
+    const bool dx = (d->flags & ODPD_F_NEED_DX) != 0, dw = (d->flags & ODPD_F_NEED_DW) != 0;
+    ODPD_CHECK(params != nullptr, "params must not be NULL");
+    ODPD_CHECK(((uintptr_t)params & 15) == 0, "params must be 16-byte aligned");
+    ODPD_CHECK(!dx || gx, "ODPD_F_NEED_DX set but gx==NULL");
+    ODPD_CHECK(!dw || (gparams && workspace), "ODPD_F_NEED_DW set but gparams/workspace==NULL");
+    ODPD_CHECK(gout || (out && target), "need gout, or out+target for the fused MSE gradient");
+    if (d->B == 0 || d->T == 0 || (!dx && !dw)) return 0;
+    ODPD_CHECK(x && (saved || d->cell == ODPD_CELL_GMP), "x/saved must not be NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t P = odpd_n_params(d->cell, d->H, d->K);
+    int rc;
+    if (is_gru_family(d->cell)) {
+        GruArgs a{};
+        a.B = d->B; a.T = d->T; a.H = d->H; a.x = x; a.params = params; a.saved = (float *)saved; a.gout = gout; a.out_in = out;
+        a.target = target; a.gscale = (float)gscale; a.gscale_dev = gscale_dev; a.gx = gx; a.partials = (float *)workspace;
+        a.need_dx = dx;
+        rc = gru_family_run(d->cell, a, 1, dw, st);
+    } else {
+        rc = other_bwd(d, x, params, saved, gout, out, target, gscale, gscale_dev, gx, (float *)workspace, st);
+    }
+    if (rc) return rc;
+    if (dw) return reduce_partials((const float *)workspace, d->B, P, gparams, st);
+    return 0;
+}
+
+int odpd_clip_adamw(float *param, float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, const float *lr_dev, float beta1,
+                    float beta2, float eps, float weight_decay, float max_norm, int64_t *step_dev, float *gnorm_out, int zero_grad,
+                    void *stream) {
+    ODPD_CHECK(param && grad && exp_avg && exp_avg_sq && lr_dev && step_dev, "odpd_clip_adamw: NULL buffer");
+    ODPD_CHECK(n >= 0, "odpd_clip_adamw: negative n");
+    if (n == 0) return 0;
+    clip_adamw_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr_dev, beta1, beta2, eps, weight_decay,
+                                                            max_norm, step_dev, gnorm_out, zero_grad);
+    return check_launch("clip_adamw_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,32 @@
+// cells.h — internal (non-ABI) interfaces between api.cu and the per-family kernel files.
+#pragma once
+#include "common.cuh"
+
+namespace odpd {
+
+struct GruArgs {
+    int B, T, H;
+    const float *x, *target, *params, *gout, *out_in, *gscale_dev;
+    float *out, *gx, *partials;
+    double *loss;
+    float *saved;
+    float loss_scale, gscale;
+    int save, need_dx;
+};
+
+// gru_family.cu : GRU / DGRU / QGRU / QGRU_AMP1
+int64_t gru_family_nparams(int cell, int H);
+int64_t gru_family_saved_floats(int cell, int B, int T, int H);
+int gru_family_run(int cell, const GruArgs &a, int dir, bool dw, cudaStream_t st);
+
+// remaining families (lstm.cu, delta.cu, janet.cu, gmp.cu) behind one dispatcher in others.cu
+int64_t other_nparams(int cell, int H, int K);
+int64_t other_saved_bytes(const OdpdDims *d);
+int other_fwd(const OdpdDims *d, const float *x, const float *target, const float *params, float *out, double *loss, double loss_scale,
+              void *saved, int64_t *stats, cudaStream_t st);
+int other_bwd(const OdpdDims *d, const float *x, const float *params, const void *saved, const float *gout, const float *out,
+              const float *target, double gscale, const float *gscale_dev, float *gx, float *partials, cudaStream_t st);
+
+int reduce_partials(const float *part, int nrows, int64_t P, float *g, cudaStream_t st);
+
+}  // namespace odpd

@@ -1,0 +1,143 @@
+// common.cuh — device helpers shared by the sm_100a backbone kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/odpd.h"
+
+#define ODPD_CHUNK 32           // timesteps per time-parallel phase (one per lane)
+#define ODPD_FULL 0xffffffffu
+
+namespace odpd {
+
+// ---------------------------------------------------------------- error plumbing (host)
+void set_error(const char *fmt, ...);
+#define ODPD_CHECK(cond, ...)                \
+    do {                                     \
+        if (!(cond)) {                       \
+            ::odpd::set_error(__VA_ARGS__);  \
+            return -1;                       \
+        }                                    \
+    } while (0)
+int check_launch(const char *what);
+
+// ---------------------------------------------------------------- math
+// Gate nonlinearities: 2 MUFU ops each (ex2 + rcp), |abs err| ~1e-7 — far inside the 1e-5 parity budget and
+// ~3x shorter dependent chain than expf()+IEEE divide; they sit on the serial critical path of every timestep.
+__device__ __forceinline__ float fast_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return fast_rcp(1.0f + fast_ex2(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float tanhf_(float x) {
+    // tanh(x) = 2*sigmoid(2x) - 1
+    return fmaf(2.0f, fast_rcp(1.0f + fast_ex2(-2.8853900817779268f * x)), -1.0f);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(ODPD_FULL, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------- features (bit-exact w.r.t. the reference's unfused ATen ops)
+// gru.py:45 | dgru.py:61-68 / deltagru.py:61-72 | qgru.py:61-66 | qgru_amp1.py:61-70 | deltagru_tcnskip.py:91-100
+enum { FM_RAW2 = 0, FM_DGRU6 = 1, FM_QGRU4 = 2, FM_AMP4 = 3, FM_TRES6 = 4 };
+template <int FM> struct FeatN { static constexpr int value = (FM == FM_RAW2) ? 2 : ((FM == FM_QGRU4 || FM == FM_AMP4) ? 4 : 6); };
+
+// f[0..F): features of sample (i,q); (in,qn) = next sample (TRES only).  No FMA contraction, IEEE sqrt/div:
+// the delta-x mask must match the CPU reference bit for bit (SURVEY.md §7 hard part 1).
+template <int FM>
+__device__ __forceinline__ void features_fwd(float i, float q, float in, float qn, float *f) {
+    f[0] = i;
+    f[1] = q;
+    if constexpr (FM == FM_RAW2) return;
+    const float a2 = __fadd_rn(__fmul_rn(i, i), __fmul_rn(q, q));
+    if constexpr (FM == FM_QGRU4) {
+        f[2] = a2;
+        f[3] = __fmul_rn(a2, a2);
+        return;
+    }
+    const float a = __fsqrt_rn(a2);
+    f[2] = a;
+    f[3] = __fmul_rn(__fmul_rn(a, a), a);
+    if constexpr (FM == FM_DGRU6) {
+        f[4] = __fdiv_rn(q, a);  // sin
+        f[5] = __fdiv_rn(i, a);  // cos
+    }
+    if constexpr (FM == FM_TRES6) {
+        f[4] = in;
+        f[5] = qn;
+    }
+}
+
+// d(loss)/d(i,q) from d(loss)/d(features).  For TRES the (I_next,Q_next) grads are returned separately.
+template <int FM>
+__device__ __forceinline__ void features_bwd(float i, float q, const float *gf, float &gi, float &gq) {
+    gi = gf[0];
+    gq = gf[1];
+    if constexpr (FM == FM_RAW2) return;
+    const float a2 = i * i + q * q;
+    if constexpr (FM == FM_QGRU4) {
+        const float ga2 = gf[2] + 2.0f * a2 * gf[3];
+        gi += 2.0f * i * ga2;
+        gq += 2.0f * q * ga2;
+        return;
+    }
+    const float a = sqrtf(a2);
+    float ga = gf[2] + 3.0f * a * a * gf[3];
+    if constexpr (FM == FM_DGRU6) {
+        ga -= (q * gf[4] + i * gf[5]) / a2;
+        gi += gf[5] / a;
+        gq += gf[4] / a;
+    }
+    gi += ga * i / a;
+    gq += ga * q / a;
+}
+
+// ---------------------------------------------------------------- parameter staging: global -> shared via the TMA bulk-copy engine
+// One elected thread issues cp.async.bulk (SASS: UBLKCP) on an mbarrier; everybody waits on the barrier phase.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void stage_params(float *sdst, const float *gsrc, int n, uint64_t *bar) {
+    const int n16 = (((uintptr_t)gsrc & 15) == 0) ? (n & ~3) : 0;  // bulk part: 16-byte granules
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (n16 > 0) {
+        if (threadIdx.x == 0) {
+            const uint32_t bytes = (uint32_t)n16 * 4u;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sdst)),
+                "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                : "memory");
+        }
+    }
+    for (int i = n16 + threadIdx.x; i < n; i += blockDim.x) sdst[i] = gsrc[i];
+    if (n16 > 0) {
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(smem_u32(bar)), "r"(0u)
+                : "memory");
+        }
+    }
+    __syncthreads();
+}
+
+// Deterministic second-stage reduction of per-sequence gradient partials:  g[p] += sum_b part[b][p]
+__global__ void reduce_partials_kernel(const float *__restrict__ part, int nrows, int64_t P, float *__restrict__ g);
+
+}  // namespace odpd

@@ -1,0 +1,121 @@
+"""Autograd bridge: one torch.autograd.Function that runs a whole backbone forward (optionally + fused I/Q MSE)
+and its backward through libodpd.so.  PyTorch is plumbing here (allocation, streams, autograd graph edges)."""
+import ctypes
+import torch
+from . import _ffi
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class CellSpec:
+    """Static description of one native backbone call."""
+
+    def __init__(self, cell, H, K=0, thx=0.0, thh=0.0):
+        self.cell, self.H, self.K, self.thx, self.thh = cell, int(H), int(K or 0), float(thx), float(thh)
+        self.cell_id = _ffi.CELLS[cell]
+
+    def dims(self, B, T, flags):
+        return _ffi.OdpdDims(self.cell_id, int(B), int(T), self.H, self.K, int(flags), self.thx, self.thh)
+
+
+def _check_x(x):
+    if not x.is_cuda:
+        raise _ffi.OdpdError("native backbones run on CUDA tensors only (no CPU fallback); got a CPU tensor")
+    if x.dtype != torch.float32 or x.dim() != 3 or x.size(-1) != 2:
+        raise _ffi.OdpdError(f"expected a float32 (B,T,2) tensor, got {tuple(x.shape)} {x.dtype}")
+    return x.contiguous()
+
+
+def backbone_forward_raw(spec, x, flat, target=None, loss_scale=0.0, save=True, stats=None):
+    """Launch the forward kernel.  Returns (out, loss_double_or_None, saved_or_None)."""
+    L = _ffi.lib()
+    B, T = x.shape[0], x.shape[1]
+    d = spec.dims(B, T, _ffi.F_SAVE if save else 0)
+    out = torch.empty_like(x)
+    saved = None
+    if save:
+        nbytes = L.odpd_saved_bytes(ctypes.byref(d))
+        if nbytes < 0:
+            _ffi.check(-1)
+        saved = torch.empty(max(int(nbytes) // 4, 1), dtype=torch.float32, device=x.device)
+    loss = torch.zeros(1, dtype=torch.float64, device=x.device) if target is not None else None
+    _ffi.check(L.odpd_backbone_fwd(ctypes.byref(d), _ptr(x), _ptr(target), _ptr(flat), _ptr(out), _ptr(loss),
+                                   ctypes.c_double(loss_scale), _ptr(saved), _ptr(stats), _stream()))
+    return out, loss, saved
+
+
+def backbone_backward_raw(spec, x, flat, saved, need_dx, need_dw, gout=None, out=None, target=None, gscale=0.0,
+                          gscale_dev=None, gflat=None):
+    """Launch the backward kernel (+ ordered partial reduction). gflat is accumulated into. Returns (gx, gflat)."""
+    L = _ffi.lib()
+    B, T = x.shape[0], x.shape[1]
+    flags = (_ffi.F_NEED_DX if need_dx else 0) | (_ffi.F_NEED_DW if need_dw else 0)
+    d = spec.dims(B, T, flags)
+    gx = torch.empty_like(x) if need_dx else None
+    ws = None
+    if need_dw:
+        if gflat is None:
+            gflat = torch.zeros_like(flat)
+        ws = torch.empty(int(L.odpd_bwd_workspace_bytes(ctypes.byref(d))) // 4, dtype=torch.float32, device=x.device)
+    _ffi.check(L.odpd_backbone_bwd(ctypes.byref(d), _ptr(x), _ptr(flat), _ptr(saved), _ptr(gout), _ptr(out), _ptr(target),
+                                   ctypes.c_double(gscale), _ptr(gscale_dev), _ptr(gx), _ptr(gflat), _ptr(ws), _stream()))
+    return gx, gflat
+
+
+class BackboneFn(torch.autograd.Function):
+    """out, loss = BackboneFn.apply(spec, layout, flat, stats, target, loss_count, x, *params)
+
+    `params` are the module's nn.Parameters (views into `flat`, see FlatParams) — passed so autograd routes their
+    gradients; the kernels read `flat`.  With `target` the I/Q MSE (nn.MSELoss 'mean' over loss_count scalars) is
+    fused into the forward and its gradient into the backward."""
+
+    @staticmethod
+    def forward(ctx, spec, layout, flat, stats, target, loss_count, x, *params):
+        x = _check_x(x)
+        if target is not None:
+            target = _check_x(target)
+        nig = ctx.needs_input_grad  # (spec, layout, flat, stats, target, loss_count, x, *params)
+        need_dx = bool(nig[6])
+        need_dw = any(nig[7:])
+        save = need_dx or need_dw
+        lc = float(loss_count) if loss_count else float(x.numel())
+        out, loss_d, saved = backbone_forward_raw(spec, x, flat, target, 1.0 / lc if target is not None else 0.0, save, stats)
+        ctx.spec, ctx.layout, ctx.flat, ctx.saved, ctx.lc = spec, layout, flat, saved, lc
+        ctx.need = (need_dx, need_dw, [bool(v) for v in nig[7:]])
+        ctx.save_for_backward(x, out, target)
+        ctx.set_materialize_grads(False)
+        loss = loss_d.to(torch.float32).reshape(()) if loss_d is not None else None
+        return out, loss
+
+    @staticmethod
+    def backward(ctx, g_out, g_loss):
+        x, out, target = ctx.saved_tensors
+        need_dx, need_dw, pmask = ctx.need
+        if ctx.saved is None:
+            raise _ffi.OdpdError("backward called but the forward ran without saving activations")
+        gout, gscale, gscale_dev = None, 0.0, None
+        if g_loss is not None and target is not None:
+            gscale = 2.0 / ctx.lc
+            gscale_dev = g_loss.to(torch.float32).contiguous()
+            if g_out is not None:  # rare: both heads used downstream -> materialise the sum
+                gout = (g_out + gscale_dev * gscale * (out - target)).contiguous()
+                gscale_dev = None
+        elif g_out is not None:
+            gout = g_out.contiguous()
+        else:
+            return (None,) * (7 + len(pmask))
+        gx, gflat = backbone_backward_raw(ctx.spec, x, ctx.flat, ctx.saved, need_dx, need_dw, gout=gout,
+                                          out=out if gout is None else None, target=target if gout is None else None,
+                                          gscale=gscale, gscale_dev=gscale_dev)
+        gparams = [None] * len(pmask)
+        if need_dw:
+            for i, (off, n, shape) in enumerate(ctx.layout):
+                if pmask[i]:
+                    gparams[i] = gflat[off:off + n].view(shape)
+        return (None, None, None, None, None, None, gx, *gparams)
