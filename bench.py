@@ -1,0 +1,290 @@
+#!/usr/bin/env python
+"""bench.py — the hot-path benchmark (BASELINE.json metric: IQ samples/sec/train-step, DGRU, APA_200MHz-shaped frames).
+
+    python bench.py [--gpus N --steps K --warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A "step" is one pass of the reference's net_train body (modules/train_funcs.py:33-48): forward + I/Q MSE + backward
++ clip_grad_norm_(200) + AdamW on one batch.  Workload at N=1 = BASELINE.json configs[1] (C2a in BASELINE.md):
+DGRU H=13 (1041 params), batch 64, frame length 2048, fp32, train_pa.  N>1: every rank runs its own 64 frames (weak
+scaling), one all-reduce of the flat 1041-float gradient (+loss) per step.
+Prints ONE JSON line (see DESIGN.md §Measurement for every key)."""
+import argparse, json, os, sys, threading, time
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(name="C2a: DGRU H=13 (1041 params) train_pa step, B=64 x T=2048 IQ frames, fp32", kind="dgru", H=13, B=64, T=2048)
+ALGO_BYTES_PER_SAMPLE_PER_KERNEL = 16  # fwd reads x(8)+target(8); bwd re-reads x(8)+target/dout(8)  => 32 B/sample/step
+
+
+def synth_batches(n, B, T, seed):
+    """SURVEY §8d synthetic fallback: x = clip(0.2*(N(0,1)+jN(0,1)), |x|<=1); target = x*(1-0.2|x|^2) rotated by 0.1 rad."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    x = 0.2 * torch.randn(n, B, T, 2, generator=g)
+    amp = x.pow(2).sum(-1, keepdim=True).sqrt().clamp_min(1e-12)
+    x = x * torch.clamp(1.0 / amp, max=1.0).where(amp > 1.0, torch.ones_like(amp))
+    a2 = x.pow(2).sum(-1, keepdim=True)
+    c, s = float(np.cos(0.1)), float(np.sin(0.1))
+    yr = (x[..., :1] * c - x[..., 1:] * s) * (1 - 0.2 * a2)
+    yi = (x[..., :1] * s + x[..., 1:] * c) * (1 - 0.2 * a2)
+    return x.contiguous(), torch.cat([yr, yi], -1).contiguous()
+
+
+class ClockSampler:
+    """SM clock / throttle-reason sampler (NVML, the library behind nvidia-smi) running during the timed regions."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.stop_flag, self.thread, self.ok = [], set(), False, None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # pragma: no cover
+            self.err = str(e)
+
+    def _loop(self):
+        nv = self.nv
+        names = {getattr(nv, k): k for k in dir(nv) if k.startswith("nvmlClocksThrottleReason") or k.startswith("nvmlClocksEventReason")}
+        while not self.stop_flag:
+            try:
+                clk = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                util = nv.nvmlDeviceGetUtilizationRates(self.h).gpu
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((clk, util))
+                for bit, name in names.items():
+                    if isinstance(bit, int) and bit and (mask & bit) and bit & (bit - 1) == 0:
+                        self.reasons.add(name.replace("nvmlClocksThrottleReason", "").replace("nvmlClocksEventReason", ""))
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def start(self):
+        if self.ok:
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join()
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        clk = [c for c, _ in self.samples]
+        bad = {"GpuIdle", "None", "All", "ApplicationsClocksSetting"}
+        return {"sm_mhz": float(np.median(clk)), "sm_max_mhz": float(self.max_sm), "samples": len(clk),
+                "reasons": sorted(r for r in self.reasons if r not in bad)}
+
+
+def cpu_port_leg(seconds=10.0, kind="dgru", H=13, B=64, T=2048, threads=None):
+    """CPU arm: the net_train body of the workload on the host cores.
+    Two restatements are timed: the PyTorch-ATen op sequence the reference executes (oracle/torch_port.py — the reference IS
+    PyTorch; this is what its CPU path costs) and the plain-C/OpenMP port (oracle/odpd_oracle.c, forward+MSE+backward)."""
+    import torch
+    from oracle import oracle
+    cores = threads or os.cpu_count() or 1
+    xs, ys = synth_batches(1, B, T, 123)
+    x, y = xs[0].numpy(), ys[0].numpy()
+    rng = np.random.default_rng(0)
+    P = oracle.n_params(kind, H)
+    params = (0.3 * rng.standard_normal(P)).astype(np.float32)
+    nthr = min(cores, B)
+    oracle.run(kind, x, params, target=y, H=H, nthreads=nthr)
+    t0, n = time.perf_counter(), 0
+    while time.perf_counter() - t0 < seconds / 2 or n < 3:
+        oracle.run(kind, x, params, target=y, H=H, nthreads=nthr)
+        n += 1
+    c_dt = (time.perf_counter() - t0) / n
+    res = {"c_port": {"value": B * T / c_dt, "unit": "IQ samples/s", "cores": nthr, "s_per_step": c_dt,
+                      "sample": f"{n} x (fwd+MSE+bwd) of the full {B}x{T} batch, C/OpenMP over sequences"}}
+    try:
+        from oracle import torch_port
+        torch.set_num_threads(cores)
+        step = torch_port.make_train_step(kind, H, seed=0)
+        xt, yt = xs[0], ys[0]
+        step(xt, yt)
+        t0, n = time.perf_counter(), 0
+        while time.perf_counter() - t0 < seconds / 2 or n < 3:
+            step(xt, yt)
+            n += 1
+        dt = (time.perf_counter() - t0) / n
+        res["torch_port"] = {"value": B * T / dt, "unit": "IQ samples/s", "cores": cores, "s_per_step": dt,
+                             "sample": f"{n} x full net_train body (fwd, MSE, bwd, clip 200, AdamW) of the {B}x{T} batch, "
+                                       f"PyTorch CPU ops, torch.set_num_threads({cores})"}
+    except Exception as e:  # torch port optional
+        res["torch_port_error"] = repr(e)
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    W = max(args.warmup, 3)
+    K = max(args.steps, 1)
+    wl = WORKLOAD
+    B, T = wl["B"], wl["T"]
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        r = cpu_port_leg(seconds=max(args.cpu_seconds, 6.0))
+        main_leg = r.get("torch_port") or r["c_port"]
+        kind = "port"
+        line = {"impl": "reference", "metric": "IQ samples/sec/train-step", "value": main_leg["value"], "unit": "IQ samples/s",
+                "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": main_leg["s_per_step"] * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": wl["name"], "global_batch": B, "frame_len": T},
+                "cpu_baseline": {"value": main_leg["value"], "unit": "IQ samples/s", "cores": main_leg["cores"], "kind": kind,
+                                 "sample": main_leg["sample"]},
+                "cpu_c_port": r["c_port"],
+                "e2e": {"value": main_leg["value"], "unit": "IQ samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        if "torch_port_error" in r:
+            line["torch_port_error"] = r["torch_port_error"]
+        print(json.dumps(line), flush=True)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from opendpd_b200 import models
+    from opendpd_b200.train import NativeTrainStep
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback on the native path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    pg = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        pg = dist.group.WORLD
+
+    torch.manual_seed(0)                               # same initial weights on every rank
+    net = models.CoreModel(2, wl["H"], 1, wl["kind"]).to(dev)
+    trainer = NativeTrainStep(net, lr=5e-4, grad_clip_val=200.0, process_group=pg, world_size=world)
+
+    # input pool larger than L2 (126 MB): POOL distinct batches, each 2 x 1 MiB
+    POOL = 80
+    xs, ys = synth_batches(POOL, B, T, 1000 + rank)
+    xs_pin, ys_pin = xs.pin_memory(), ys.pin_memory()
+    xd, yd = xs.to(dev), ys.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    # ---- warm-up
+    for i in range(W):
+        trainer.step(xd[i % POOL], yd[i % POOL])
+    flush.zero_()                                       # evict the pool from L2: every timed step reads a cold batch
+    barrier()
+    sampler.start()
+    # ---- timed region: exactly K steps, device-resident inputs
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        loss = trainer.step(xd[(W + i) % POOL], yd[(W + i) % POOL])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    final_loss = float(loss.item())
+
+    # ---- e2e: host (pinned) inputs, H2D inside the step, loss read back every step
+    for i in range(3):
+        trainer.step_host(xs_pin[i], ys_pin[i])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        trainer.step_host(xs_pin[(W + i) % POOL], ys_pin[(W + i) % POOL])
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+
+    # ---- per-kernel durations (CUDA events between launches on the launching stream) for the roofline of the dominant kernel
+    from opendpd_b200.functional import backbone_forward_raw, backbone_backward_raw
+    bb = net.backbone
+    flat, _ = bb._flat_sync()
+    spec = bb._spec()
+    nk = min(K, 50)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(nk)]
+    count = float(2 * B * T)
+    gflat = torch.empty_like(flat)
+    for i in range(nk):
+        xb, yb = xd[(i * 7 + 3) % POOL], yd[(i * 7 + 3) % POOL]
+        ev[i][0].record()
+        out, _, saved = backbone_forward_raw(spec, xb, flat, yb, 1.0 / count, True, None)
+        ev[i][1].record()
+        backbone_backward_raw(spec, xb, flat, saved, False, True, out=out, target=yb, gscale=2.0 / count, gflat=gflat)
+        ev[i][2].record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    fwd_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
+    bwd_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        dom = ("odpd::gru_bwd_kernel", bwd_ms) if bwd_ms >= fwd_ms else ("odpd::gru_fwd_kernel", fwd_ms)
+        achieved = ALGO_BYTES_PER_SAMPLE_PER_KERNEL * B * T / (dom[1] * 1e-3) / 1e9
+        line = {
+            "metric": "IQ samples/sec/train-step", "value": world * B * T * K / (ms * 1e-3), "unit": "IQ samples/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["name"], "global_batch": B * world, "per_gpu_batch": B, "frame_len": T,
+                       "parallelism": f"dp{world}", "optimizer": "clip_grad_norm_(200)+AdamW(lr=5e-4) fused on the flat buffer",
+                       "l2": f"inputs larger than L2: pool of {POOL} distinct 2x1MiB batches, L2 flushed (256 MiB write) after warm-up",
+                       "final_loss": final_loss},
+            "clocks": clocks,
+            "e2e": {"value": world * B * T * K / e2e_s, "unit": "IQ samples/s", "ms_per_step": e2e_s / K * 1e3,
+                    "h2d_bytes_per_step": 2 * B * T * 2 * 4, "d2h_bytes_per_step": 8,
+                    "path": "NativeTrainStep.step_host: pinned host (B,T,2) features+targets -> cudaMemcpyAsync -> fwd/bwd/optimizer kernels -> loss.item()"},
+            "gpu_launches": 4 * K,
+            "kernels_per_step": ["gru_fwd_kernel<13,DGRU6,1>", "gru_bwd_kernel<13,DGRU6,1,true>", "reduce_partials_kernel", "clip_adamw_kernel"],
+            "kernel_ms": {"fwd": fwd_ms, "bwd": bwd_ms},
+            "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                         "traffic": None,
+                         "latency_view": {"timesteps": T, "ns_per_timestep_fwd": fwd_ms * 1e6 / T, "ns_per_timestep_bwd": bwd_ms * 1e6 / T,
+                                          "note": "the path is a T-step serial recurrence per sequence: latency-bound, not bandwidth-bound (SURVEY §8d)"}},
+        }
+        if world == 1:
+            r = cpu_port_leg(seconds=args.cpu_seconds)
+            leg = r.get("torch_port") or r["c_port"]
+            line["cpu_baseline"] = {"value": leg["value"], "unit": "IQ samples/s", "cores": leg["cores"], "kind": "port", "sample": leg["sample"]}
+            line["cpu_c_port"] = r["c_port"]
+            if "torch_port_error" in r:
+                line["torch_port_error"] = r["torch_port_error"]
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

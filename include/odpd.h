@@ -60,6 +60,8 @@ enum {
 #define ODPD_F_NEED_DX 1u    /* backward emits gx   (frozen-PA input gradient, models.py:169-171) */
 #define ODPD_F_NEED_DW 2u    /* backward emits gparams */
 #define ODPD_F_SAVE 4u       /* forward stores activations for a later odpd_backbone_bwd */
+#define ODPD_F_OVERWRITE_DW 8u /* backward: gparams = sum instead of gparams += sum (saves the caller a memset) */
+#define ODPD_F_ZERO_LOSS 16u /* forward: the library clears *loss (cudaMemsetAsync on `stream`) before accumulating */
 
 typedef struct OdpdDims {
     int32_t cell;   /* ODPD_CELL_* */

@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(_HERE, "libodpd.so")
 
 CELLS = {"gru": 0, "lstm": 1, "dgru": 2, "deltagru": 3, "deltagru_tcnskip": 4, "pgjanet": 5, "dvrjanet": 6, "gmp": 7,
          "qgru": 8, "qgru_amp1": 9}
-F_NEED_DX, F_NEED_DW, F_SAVE = 1, 2, 4
+F_NEED_DX, F_NEED_DW, F_SAVE, F_OVERWRITE_DW, F_ZERO_LOSS = 1, 2, 4, 8, 16
 
 
 class OdpdDims(ctypes.Structure):

@@ -25,7 +25,7 @@ int check_launch(const char *what) {
 }
 
 // g[p] += sum_{b=0..nrows-1} part[b][p], summed in row order (bit-reproducible)
-__global__ void reduce_partials_kernel(const float *__restrict__ part, int nrows, int64_t P, float *__restrict__ g) {
+__global__ void reduce_partials_kernel(const float *__restrict__ part, int nrows, int64_t P, float *__restrict__ g, int overwrite) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P) return;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -37,13 +37,14 @@ __global__ void reduce_partials_kernel(const float *__restrict__ part, int nrows
         s3 += part[(int64_t)(b + 3) * P + p];
     }
     for (; b < nrows; ++b) s0 += part[(int64_t)b * P + p];
-    g[p] += (s0 + s1) + (s2 + s3);
+    const float s = (s0 + s1) + (s2 + s3);
+    g[p] = overwrite ? s : g[p] + s;
 }
 
-int reduce_partials(const float *part, int nrows, int64_t P, float *g, cudaStream_t st) {
+int reduce_partials(const float *part, int nrows, int64_t P, float *g, int overwrite, cudaStream_t st) {
     if (P <= 0) return 0;
     const int threads = 128;
-    reduce_partials_kernel<<<(unsigned)((P + threads - 1) / threads), threads, 0, st>>>(part, nrows, P, g);
+    reduce_partials_kernel<<<(unsigned)((P + threads - 1) / threads), threads, 0, st>>>(part, nrows, P, g, overwrite);
     return check_launch("reduce_partials_kernel");
 }
 
@@ -136,9 +137,13 @@ int odpd_backbone_fwd(const OdpdDims *d, const float *x, const float *target, co
     ODPD_CHECK(((uintptr_t)params & 15) == 0, "params must be 16-byte aligned");
     const bool save = (d->flags & ODPD_F_SAVE) != 0;
     ODPD_CHECK(!save || saved, "ODPD_F_SAVE set but saved==NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (loss && (d->flags & ODPD_F_ZERO_LOSS)) {
+        cudaError_t e = cudaMemsetAsync(loss, 0, sizeof(double), st);
+        ODPD_CHECK(e == cudaSuccess, "cudaMemsetAsync(loss): %s", cudaGetErrorString(e));
+    }
     if (d->B == 0 || d->T == 0) return 0;
     ODPD_CHECK(x != nullptr, "x must not be NULL");
-    cudaStream_t st = (cudaStream_t)stream;
     if (is_gru_family(d->cell)) {
         GruArgs a{};
         a.B = d->B; a.T = d->T; a.H = d->H; a.x = x; a.target = target; a.params = params; a.out = out; a.loss = loss;
@@ -173,7 +178,7 @@ int odpd_backbone_bwd(const OdpdDims *d, const float *x, const float *params, co
         rc = other_bwd(d, x, params, saved, gout, out, target, gscale, gscale_dev, gx, (float *)workspace, st);
     }
     if (rc) return rc;
-    if (dw) return reduce_partials((const float *)workspace, d->B, P, gparams, st);
+    if (dw) return reduce_partials((const float *)workspace, d->B, P, gparams, (d->flags & ODPD_F_OVERWRITE_DW) != 0, st);
     return 0;
 }
 

@@ -27,6 +27,6 @@ int other_fwd(const OdpdDims *d, const float *x, const float *target, const floa
 int other_bwd(const OdpdDims *d, const float *x, const float *params, const void *saved, const float *gout, const float *out,
               const float *target, double gscale, const float *gscale_dev, float *gx, float *partials, cudaStream_t st);
 
-int reduce_partials(const float *part, int nrows, int64_t P, float *g, cudaStream_t st);
+int reduce_partials(const float *part, int nrows, int64_t P, float *g, int overwrite, cudaStream_t st);
 
 }  // namespace odpd

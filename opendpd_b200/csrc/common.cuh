@@ -138,6 +138,6 @@ __device__ __forceinline__ void stage_params(float *sdst, const float *gsrc, int
 }
 
 // Deterministic second-stage reduction of per-sequence gradient partials:  g[p] += sum_b part[b][p]
-__global__ void reduce_partials_kernel(const float *__restrict__ part, int nrows, int64_t P, float *__restrict__ g);
+__global__ void reduce_partials_kernel(const float *__restrict__ part, int nrows, int64_t P, float *__restrict__ g, int overwrite);
 
 }  // namespace odpd

@@ -4,434 +4,593 @@
 // backbones/qgru_amp1.py:59-76 and the ATen GRU cell behind torch.nn.GRU (gate order r,z,n;
 // n = tanh(W_in x + b_in + r*(W_hn h + b_hn)); h' = (h-n)*z + n), plus nn.MSELoss (project.py:262-272).
 //
-// Mapping (B200): one warp per sequence, lane j owns hidden unit j.  The flat parameter block is staged once
-// into shared memory by a TMA bulk copy, each lane then keeps its weight rows in registers for the whole frame;
-// h_t lives in a register, is broadcast through a double-buffered shared-memory line (1 STS + H/4 LDS.128) and
-// the recurrent matvec is 3H register FMAs per lane.  Work that is not part of the serial chain (feature
-// extraction with IEEE sqrt/div, the 2-wide output reduction, the MSE, dX) is done time-parallel, 32 steps
-// at a time, one step per lane, with coalesced float2 loads/stores of the IQ stream.
+// Mapping (B200).  The path is a T-step serial recurrence per sequence, so everything is organised around the
+// length of ONE timestep's dependent chain.  One CTA = one sequence = three specialised warps that form a
+// software pipeline over 32-step chunks (double/triple-buffered in shared memory, one __syncthreads per chunk):
+//     warp 1 "pre"   : coalesced float2 loads of the IQ stream, feature extraction (IEEE sqrt/div), input
+//                      projection W_ih f_t + b for the whole chunk (no recurrence -> fully pipelined);
+//                      backward: TMA bulk load of the saved activations, dLoss/dout, fc_hid back-projection
+//     warp 0 "chain" : the recurrence only.  Lane j owns hidden unit j: weight rows/columns in registers, h in a
+//                      register, broadcast through shared memory (1 STS + H/4 LDS.128), 2 MUFU per gate
+//     warp 2 "post"  : output head + squared error + TMA bulk store of the activations (forward);
+//                      weight-gradient accumulation in registers, dL/dfeatures -> dL/dx (backward)
+// The flat parameter block is staged once per CTA into shared memory by a TMA bulk copy.
 #include "cells.h"
+#include "pipeline.cuh"
 
 namespace odpd {
-
 
 template <int FM, int HEAD>
 struct GruLayout {
     static constexpr int F = FeatN<FM>::value;
-    int H, O, oWih, oWhh, obih, obhh, oWo, obo, oWh, obh, P, NS;
+    int H, O, oWih, oWhh, obih, obhh, oWo, obo, oWh, obh, P;
     __host__ __device__ explicit GruLayout(int h) {
         H = h; O = HEAD ? h + F : h;
         oWih = 0; oWhh = 3 * h * F; obih = oWhh + 3 * h * h; obhh = obih + 3 * h; oWo = obhh + 3 * h;
         obo = oWo + 2 * O; oWh = obo + 2; obh = oWh + h * h; P = HEAD ? obh + h : obo + 2;
-        NS = HEAD ? 6 : 5;
     }
 };
 
-template <int HT> struct Pad4 { static constexpr int value = (HT + 3) & ~3; };
+// activation row saved per timestep: r | z | n | hgn(=W_hn h + b_hn) | h_t | g(=relu(fc_hid), DGRU only), each HP floats
+template <int HT, int HEAD> struct Row { static constexpr int NS = HEAD ? 6 : 5; static constexpr int value = NS * Pad4<HT>::value; };
 
-// shared memory: [mbarrier 16 B][params, padded to 4 floats][per warp scratch]
-template <int HT> __host__ __device__ constexpr int fwd_warp_floats() { return 32 * 8 + 2 * Pad4<HT>::value + 2 * 32 * 33; }
-template <int HT> __host__ __device__ constexpr int bwd_warp_floats() { return 32 * 8 + 32 * 2 + 32 * 8 + 2 * 4 * Pad4<HT>::value + 2 * Pad4<HT>::value; }
+// shared-memory carve-up (floats).  [0,16): 4 mbarriers (params + 3 activation slots)
+template <int HT, int HEAD>
+struct FwdSmem {
+    static constexpr int HP = Pad4<HT>::value, ROW = Row<HT, HEAD>::value;
+    static constexpr int XP = CH * 3 * HP;     // input projection of one chunk
+    static constexpr int FT = CH * 8;          // features of one chunk
+    static constexpr int ACT = CH * ROW;       // activation rows of one chunk
+    static constexpr int PO = CH * 33;
+    __host__ __device__ static constexpr int total(int Ppad) { return 16 + Ppad + HP + 2 * XP + 3 * FT + 2 * ACT + 2 * PO; }
+};
+template <int HT, int HEAD>
+struct BwdSmem {
+    static constexpr int HP = Pad4<HT>::value, ROW = Row<HT, HEAD>::value;
+    static constexpr int ACT = (CH + 1) * ROW;  // chunk rows + the row before the chunk
+    static constexpr int PRE = CH * 12;         // features(8) + dLoss/dout(2) + pad per step
+    static constexpr int DH = CH * HP;
+    static constexpr int G = CH * 4 * HP;       // ar | az | an*r | an
+    static constexpr int DF = CH * 8;
+    __host__ __device__ static constexpr int total(int Ppad) { return 16 + Ppad + 3 * ACT + 3 * PRE + 2 * DH + 3 * DH + 2 * G + DF; }
+};
 
 // ================================================================ forward
 template <int HT, int FM, int HEAD>
-__global__ void __launch_bounds__(128) gru_fwd_kernel(GruArgs a) {
-    constexpr int F = FeatN<FM>::value, HP = Pad4<HT>::value;
+__global__ void __launch_bounds__(96, 1) gru_fwd_kernel(GruArgs a) {
+    constexpr int F = FeatN<FM>::value, HP = Pad4<HT>::value, ROW = Row<HT, HEAD>::value;
+    using SM = FwdSmem<HT, HEAD>;
     const GruLayout<FM, HEAD> L(a.H);
-    const int H = a.H;
-    extern __shared__ __align__(16) float smem[];
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
-    float *sp = smem + 4;
+    const int H = a.H, T = a.T;
+    extern __shared__ __align__(128) float smem[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
+    float *sp = smem + 16;
     const int Ppad = (L.P + 3) & ~3;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
-    float *ws = sp + Ppad + warp * fwd_warp_floats<HT>();
-    float *sfeat = ws;                  // [32][8]
-    float *shb = sfeat + 32 * 8;        // [2][HP]
-    float *spo0 = shb + 2 * HP;         // [32][33]
-    float *spo1 = spo0 + 32 * 33;       // [32][33]
+    float *zero = sp + Ppad;                 // [HP] zeros: h_{-1}
+    float *sxp = zero + HP;                  // [2][CH][3*HP]
+    float *sft = sxp + 2 * SM::XP;           // [3][CH][8]
+    float *sact = sft + 3 * SM::FT;          // [2][CH][ROW]
+    float *spo = sact + 2 * SM::ACT;         // [2][CH][33]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x;
 
-    stage_params(sp, a.params, L.P, bar);
-    const int b = blockIdx.x * wpc + warp;
-    if (b >= a.B) return;
+    stage_params(sp, a.params, L.P, bars);
+    if (threadIdx.x < HP) zero[threadIdx.x] = 0.f;
+    __syncthreads();
 
     const bool act = lane < H;
     const int j = act ? lane : 0;
-    float whr[HT], whz[HT], whn[HT], wir[F], wiz[F], win[F], wh[HEAD ? HT : 1];
+    const int nchunks = (T + CH - 1) / CH;
+    const float2 *x2 = reinterpret_cast<const float2 *>(a.x) + (size_t)b * T;
+
+    if (warp == 1) {
+        // =============================== pre: features + input projection, one chunk ahead of the chain
+        float wir[F], wiz[F], win[F];
 #pragma unroll
-    for (int k = 0; k < HT; ++k) {
-        const bool ok = act && k < H;
-        whr[k] = ok ? sp[L.oWhh + (0 * H + j) * H + k] : 0.f;
-        whz[k] = ok ? sp[L.oWhh + (1 * H + j) * H + k] : 0.f;
-        whn[k] = ok ? sp[L.oWhh + (2 * H + j) * H + k] : 0.f;
-        if constexpr (HEAD) wh[k] = ok ? sp[L.oWh + j * H + k] : 0.f;
-    }
-#pragma unroll
-    for (int f = 0; f < F; ++f) {
-        wir[f] = act ? sp[L.oWih + (0 * H + j) * F + f] : 0.f;
-        wiz[f] = act ? sp[L.oWih + (1 * H + j) * F + f] : 0.f;
-        win[f] = act ? sp[L.oWih + (2 * H + j) * F + f] : 0.f;
-    }
-    const float b_r = act ? sp[L.obih + j] + sp[L.obhh + j] : 0.f;
-    const float b_z = act ? sp[L.obih + H + j] + sp[L.obhh + H + j] : 0.f;
-    const float b_in = act ? sp[L.obih + 2 * H + j] : 0.f;
-    const float b_hn = act ? sp[L.obhh + 2 * H + j] : 0.f;
-    const float wo0 = act ? sp[L.oWo + j] : 0.f, wo1 = act ? sp[L.oWo + L.O + j] : 0.f;
-    const float bh = (HEAD && act) ? sp[L.obh + j] : 0.f;
-    const float bo0 = sp[L.obo], bo1 = sp[L.obo + 1];
-
-    const float2 *x2 = reinterpret_cast<const float2 *>(a.x) + (size_t)b * a.T;
-    const float2 *y2 = a.target ? reinterpret_cast<const float2 *>(a.target) + (size_t)b * a.T : nullptr;
-    float2 *o2 = reinterpret_cast<float2 *>(a.out) + (size_t)b * a.T;
-    float *sv = a.save ? a.saved + (size_t)b * a.T * L.NS * H : nullptr;
-
-    float h = 0.f, lsum = 0.f;
-    int cur = 0;
-    if (lane < HP) { shb[lane] = 0.f; shb[HP + lane] = 0.f; }
-    __syncwarp();
-
-    for (int t0 = 0; t0 < a.T; t0 += ODPD_CHUNK) {
-        const int nt = min(ODPD_CHUNK, a.T - t0);
-        // ---- phase A: one timestep per lane — coalesced IQ load + feature extraction
-        if (lane < nt) {
-            const float2 v = __ldg(x2 + t0 + lane);
-            float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            features_fwd<FM>(v.x, v.y, 0.f, 0.f, f);
-            float4 *d = reinterpret_cast<float4 *>(sfeat + lane * 8);
-            d[0] = make_float4(f[0], f[1], f[2], f[3]);
-            d[1] = make_float4(f[4], f[5], f[6], f[7]);
+        for (int f = 0; f < F; ++f) {
+            wir[f] = act ? sp[L.oWih + (0 * H + j) * F + f] : 0.f;
+            wiz[f] = act ? sp[L.oWih + (1 * H + j) * F + f] : 0.f;
+            win[f] = act ? sp[L.oWih + (2 * H + j) * F + f] : 0.f;
         }
-        __syncwarp();
-        // ---- phase B: the serial recurrence
-        for (int tl = 0; tl < nt; ++tl) {
-            float feat[8];
-            {
-                const float4 *fp = reinterpret_cast<const float4 *>(sfeat + tl * 8);
-                const float4 f0 = fp[0];
-                feat[0] = f0.x; feat[1] = f0.y; feat[2] = f0.z; feat[3] = f0.w;
-                if (F > 4) { const float4 f1 = fp[1]; feat[4] = f1.x; feat[5] = f1.y; feat[6] = f1.z; feat[7] = f1.w; }
-            }
-            float xr = b_r, xz = b_z, xn = b_in;
+        const float b_r = act ? sp[L.obih + j] + sp[L.obhh + j] : 0.f;
+        const float b_z = act ? sp[L.obih + H + j] + sp[L.obhh + H + j] : 0.f;
+        const float b_in = act ? sp[L.obih + 2 * H + j] : 0.f;
+        for (int s = 0; s < nchunks + 2; ++s) {
+            if (s < nchunks) {
+                const int t0 = s * CH, nt = min(CH, T - t0);
+                float *ft = sft + (s % 3) * SM::FT, *xp = sxp + (s & 1) * SM::XP;
+                if (lane < nt) {
+                    const float2 v = __ldg(x2 + t0 + lane);
+                    float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    features_fwd<FM>(v.x, v.y, 0.f, 0.f, f);
+                    float4 *d = reinterpret_cast<float4 *>(ft + lane * 8);
+                    d[0] = make_float4(f[0], f[1], f[2], f[3]);
+                    d[1] = make_float4(f[4], f[5], f[6], f[7]);
+                }
+                __syncwarp();
+                if (lane < HP) {
+#pragma unroll 4
+                    for (int tl = 0; tl < nt; ++tl) {
+                        const float4 *fp = reinterpret_cast<const float4 *>(ft + tl * 8);
+                        const float4 f0 = fp[0];
+                        float feat[8] = {f0.x, f0.y, f0.z, f0.w, 0.f, 0.f, 0.f, 0.f};
+                        if (F > 4) { const float4 f1 = fp[1]; feat[4] = f1.x; feat[5] = f1.y; feat[6] = f1.z; feat[7] = f1.w; }
+                        float xr = b_r, xz = b_z, xn = b_in;
 #pragma unroll
-            for (int f = 0; f < F; ++f) { xr = fmaf(wir[f], feat[f], xr); xz = fmaf(wiz[f], feat[f], xz); xn = fmaf(win[f], feat[f], xn); }
-            float ar0 = xr, ar1 = 0.f, az0 = xz, az1 = 0.f, an0 = b_hn, an1 = 0.f;
-            const float4 *hb4 = reinterpret_cast<const float4 *>(shb + cur * HP);
-#pragma unroll
-            for (int k4 = 0; k4 < HP / 4; ++k4) {
-                const float4 hv = hb4[k4];
-                const float hk[4] = {hv.x, hv.y, hv.z, hv.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int k = k4 * 4 + e;
-                    if (k < HT) {
-                        if (k & 1) { ar1 = fmaf(whr[k], hk[e], ar1); az1 = fmaf(whz[k], hk[e], az1); an1 = fmaf(whn[k], hk[e], an1); }
-                        else       { ar0 = fmaf(whr[k], hk[e], ar0); az0 = fmaf(whz[k], hk[e], az0); an0 = fmaf(whn[k], hk[e], an0); }
+                        for (int f = 0; f < F; ++f) { xr = fmaf(wir[f], feat[f], xr); xz = fmaf(wiz[f], feat[f], xz); xn = fmaf(win[f], feat[f], xn); }
+                        float *o = xp + tl * 3 * HP + lane;
+                        o[0] = xr; o[HP] = xz; o[2 * HP] = xn;
                     }
                 }
             }
-            const float r = sigmoidf_(ar0 + ar1);
-            const float z = sigmoidf_(az0 + az1);
-            const float hgn = an0 + an1;
-            const float n = tanhf_(fmaf(r, hgn, xn));
-            h = fmaf(h - n, z, n);
-            cur ^= 1;
-            if (lane < HP) shb[cur * HP + lane] = h;
-            __syncwarp();
-            float g = h;
-            if constexpr (HEAD) {
-                float p0 = bh, p1 = 0.f;
-                const float4 *hn4 = reinterpret_cast<const float4 *>(shb + cur * HP);
+            __syncthreads();
+        }
+    } else if (warp == 0) {
+        // =============================== chain: the serial recurrence
+        float whr[HT], whz[HT], whn[HT];
 #pragma unroll
-                for (int k4 = 0; k4 < HP / 4; ++k4) {
-                    const float4 hv = hn4[k4];
-                    const float hk[4] = {hv.x, hv.y, hv.z, hv.w};
+        for (int k = 0; k < HT; ++k) {
+            const bool ok = act && k < H;
+            whr[k] = ok ? sp[L.oWhh + (0 * H + j) * H + k] : 0.f;
+            whz[k] = ok ? sp[L.oWhh + (1 * H + j) * H + k] : 0.f;
+            whn[k] = ok ? sp[L.oWhh + (2 * H + j) * H + k] : 0.f;
+        }
+        const float b_hn = act ? sp[L.obhh + 2 * H + j] : 0.f;
+        const int lp = lane < HP ? lane : 0;  // clamp: lanes >= HP read lane 0's slot and never write
+        float h = 0.f;
+        for (int s = 0; s < nchunks + 2; ++s) {
+            const int c = s - 1;
+            if (c >= 0 && c < nchunks) {
+                const int t0 = c * CH, nt = min(CH, T - t0);
+                const float *xp = sxp + (c & 1) * SM::XP + lp;
+                float *ac = sact + (c & 1) * SM::ACT;
+                const float *hrow = (c == 0) ? zero : sact + ((c - 1) & 1) * SM::ACT + (CH - 1) * ROW + 4 * HP;
+                float xr = xp[0], xz = xp[HP], xn = xp[2 * HP];
+                for (int tl = 0; tl < nt; ++tl) {
+                    // prefetch next step's input projection (independent of h)
+                    const int tn = (tl + 1 < nt) ? tl + 1 : tl;
+                    const float nxr = xp[tn * 3 * HP], nxz = xp[tn * 3 * HP + HP], nxn = xp[tn * 3 * HP + 2 * HP];
+                    float ar0 = xr, ar1 = 0.f, az0 = xz, az1 = 0.f, an0 = b_hn, an1 = 0.f;
+                    const float4 *hb4 = reinterpret_cast<const float4 *>(hrow);
+                    float4 hv[HP / 4];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int k = k4 * 4 + e;
-                        if (k < HT) { if (k & 1) p1 = fmaf(wh[k], hk[e], p1); else p0 = fmaf(wh[k], hk[e], p0); }
+                    for (int k4 = 0; k4 < HP / 4; ++k4) hv[k4] = hb4[k4];
+#pragma unroll
+                    for (int k4 = 0; k4 < HP / 4; ++k4) {
+                        const float hk[4] = {hv[k4].x, hv[k4].y, hv[k4].z, hv[k4].w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int k = k4 * 4 + e;
+                            if (k < HT) {
+                                if (k & 1) { ar1 = fmaf(whr[k], hk[e], ar1); az1 = fmaf(whz[k], hk[e], az1); an1 = fmaf(whn[k], hk[e], an1); }
+                                else       { ar0 = fmaf(whr[k], hk[e], ar0); az0 = fmaf(whz[k], hk[e], az0); an0 = fmaf(whn[k], hk[e], an0); }
+                            }
+                        }
+                    }
+                    const float r = sigmoidf_(ar0 + ar1);
+                    const float z = sigmoidf_(az0 + az1);
+                    const float hgn = an0 + an1;
+                    const float n = tanhf_(fmaf(r, hgn, xn));
+                    h = fmaf(h - n, z, n);
+                    float *row = ac + tl * ROW;
+                    if (lane < HP) {
+                        row[4 * HP + lane] = h;
+                        row[lane] = r; row[HP + lane] = z; row[2 * HP + lane] = n; row[3 * HP + lane] = hgn;
+                    }
+                    hrow = row + 4 * HP;
+                    xr = nxr; xz = nxz; xn = nxn;
+                    __syncwarp();
+                }
+                fence_async_smem();   // rows of this chunk are bulk-stored by the post warp next stage
+            }
+            __syncthreads();
+        }
+    } else {
+        // =============================== post: head, output, squared error, activation store
+        float wh[HEAD ? HT : 1];
+        if constexpr (HEAD) {
+#pragma unroll
+            for (int k = 0; k < HT; ++k) wh[k] = (act && k < H) ? sp[L.oWh + j * H + k] : 0.f;
+        }
+        const float wo0 = act ? sp[L.oWo + j] : 0.f, wo1 = act ? sp[L.oWo + L.O + j] : 0.f;
+        const float bh = (HEAD && act) ? sp[L.obh + j] : 0.f;
+        const float bo0 = sp[L.obo], bo1 = sp[L.obo + 1];
+        const float2 *y2 = a.target ? reinterpret_cast<const float2 *>(a.target) + (size_t)b * T : nullptr;
+        float2 *o2 = reinterpret_cast<float2 *>(a.out) + (size_t)b * T;
+        float *svg = a.save ? a.saved + (size_t)b * T * ROW : nullptr;
+        float *spo0 = spo, *spo1 = spo + SM::PO;
+        float lsum = 0.f;
+        for (int s = 0; s < nchunks + 2; ++s) {
+            const int c = s - 2;
+            if (c >= 0) {
+                const int t0 = c * CH, nt = min(CH, T - t0);
+                float *ac = sact + (c & 1) * SM::ACT;
+                const float *ft = sft + (c % 3) * SM::FT;
+#pragma unroll 2
+                for (int tl = 0; tl < nt; ++tl) {
+                    float *row = ac + tl * ROW;
+                    float g;
+                    if constexpr (HEAD) {
+                        float p0 = bh, p1 = 0.f;
+                        const float4 *hn4 = reinterpret_cast<const float4 *>(row + 4 * HP);
+#pragma unroll
+                        for (int k4 = 0; k4 < HP / 4; ++k4) {
+                            const float4 hv = hn4[k4];
+                            const float hk[4] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const int k = k4 * 4 + e;
+                                if (k < HT) { if (k & 1) p1 = fmaf(wh[k], hk[e], p1); else p0 = fmaf(wh[k], hk[e], p0); }
+                            }
+                        }
+                        g = fmaxf(p0 + p1, 0.f);
+                        if (lane < HP) row[5 * HP + lane] = g;
+                    } else {
+                        g = lane < HP ? row[4 * HP + lane] : 0.f;
+                    }
+                    spo0[tl * 33 + lane] = wo0 * g;
+                    spo1[tl * 33 + lane] = wo1 * g;
+                }
+                fence_async_smem();
+                __syncwarp();
+                if (svg && lane == 0) tma_store_1d(svg + (size_t)t0 * ROW, ac, (uint32_t)(nt * ROW * 4));
+                if (lane < nt) {
+                    float o0 = bo0, o1 = bo1;
+                    for (int k = 0; k < H; ++k) { o0 += spo0[lane * 33 + k]; o1 += spo1[lane * 33 + k]; }
+                    if constexpr (HEAD) {
+#pragma unroll
+                        for (int f = 0; f < F; ++f) {
+                            const float fv = ft[lane * 8 + f];
+                            o0 = fmaf(sp[L.oWo + H + f], fv, o0);
+                            o1 = fmaf(sp[L.oWo + L.O + H + f], fv, o1);
+                        }
+                    }
+                    o2[t0 + lane] = make_float2(o0, o1);
+                    if (y2) {
+                        const float2 y = __ldg(y2 + t0 + lane);
+                        const float d0 = o0 - y.x, d1 = o1 - y.y;
+                        lsum = fmaf(d0, d0, fmaf(d1, d1, lsum));
                     }
                 }
-                g = fmaxf(p0 + p1, 0.f);
+                if (svg && lane == 0) tma_store_wait_read();
+                __syncwarp();
             }
-            spo0[tl * 33 + lane] = wo0 * g;
-            spo1[tl * 33 + lane] = wo1 * g;
-            if (sv && act) {
-                float *s = sv + (size_t)(t0 + tl) * L.NS * H + lane;
-                s[0] = r; s[H] = z; s[2 * H] = n; s[3 * H] = hgn; s[4 * H] = h;
-                if constexpr (HEAD) s[5 * H] = g;
-            }
+            __syncthreads();
         }
-        __syncwarp();
-        // ---- phase C: one timestep per lane — output reduction, store, squared error
-        if (lane < nt) {
-            float o0 = bo0, o1 = bo1;
-            for (int k = 0; k < H; ++k) { o0 += spo0[lane * 33 + k]; o1 += spo1[lane * 33 + k]; }
-            if constexpr (HEAD) {
-#pragma unroll
-                for (int f = 0; f < F; ++f) {
-                    const float fv = sfeat[lane * 8 + f];
-                    o0 = fmaf(sp[L.oWo + H + f], fv, o0);
-                    o1 = fmaf(sp[L.oWo + L.O + H + f], fv, o1);
-                }
-            }
-            o2[t0 + lane] = make_float2(o0, o1);
-            if (y2) {
-                const float2 y = __ldg(y2 + t0 + lane);
-                const float d0 = o0 - y.x, d1 = o1 - y.y;
-                lsum = fmaf(d0, d0, fmaf(d1, d1, lsum));
-            }
+        if (a.loss && y2) {
+            lsum = warp_sum(lsum);
+            if (lane == 0) atomicAdd(a.loss, (double)lsum * (double)a.loss_scale);
         }
-        __syncwarp();
-    }
-    if (a.loss && y2) {
-        lsum = warp_sum(lsum);
-        if (lane == 0) atomicAdd(a.loss, (double)lsum * (double)a.loss_scale);
     }
 }
 
 // ================================================================ backward
-// SPLIT = the F "feature lanes" (which turn the broadcast gate gradients into dL/dfeatures) do not fit next to
-// the H unit lanes in one warp (H+F>32): lanes 0..F-1 then carry a second weight column.
+// SPLIT: the F "feature lanes" (which turn the gate gradients into dL/dfeatures) do not fit next to the H unit lanes in
+// one warp (H+F>32); lanes 0..F-1 then serve the features.
 template <int HT, int FM, int HEAD, bool DW>
-__global__ void __launch_bounds__(128) gru_bwd_kernel(GruArgs a) {
-    constexpr int F = FeatN<FM>::value, HP = Pad4<HT>::value;
+__global__ void __launch_bounds__(96, 1) gru_bwd_kernel(GruArgs a) {
+    constexpr int F = FeatN<FM>::value, HP = Pad4<HT>::value, ROW = Row<HT, HEAD>::value;
     constexpr bool SPLIT = (HT + F > 32);
+    using SM = BwdSmem<HT, HEAD>;
     const GruLayout<FM, HEAD> L(a.H);
-    const int H = a.H;
-    extern __shared__ __align__(16) float smem[];
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
-    float *sp = smem + 4;
+    const int H = a.H, T = a.T;
+    extern __shared__ __align__(128) float smem[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem);   // [0] params, [1..3] activation slots
+    float *sp = smem + 16;
     const int Ppad = (L.P + 3) & ~3;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
-    float *ws = sp + Ppad + warp * bwd_warp_floats<HT>();
-    float *sfeat = ws;               // [32][8]
-    float *sgo = sfeat + 32 * 8;     // [32][2]
-    float *sdf = sgo + 32 * 2;       // [32][8]
-    float *sG = sdf + 32 * 8;        // [2][4*HP]   ar | az | an*r | an
-    float *sdp = sG + 2 * 4 * HP;    // [2][HP]
+    float *sact = sp + Ppad;                 // [3][(CH+1)][ROW]   row 0 = step t0-1
+    float *spre = sact + 3 * SM::ACT;        // [3][CH][12]        feat(8) | go(2)
+    float *sdh = spre + 3 * SM::PRE;         // [2][CH][HP]        dL/dh_t from the head
+    float *sdp = sdh + 2 * SM::DH;           // [3][CH][HP]        dpre (DGRU head)
+    float *sG = sdp + 3 * SM::DH;            // [2][CH][4*HP]
+    float *sdf = sG + 2 * SM::G;             // [CH][8]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x;
 
-    stage_params(sp, a.params, L.P, bar);
-    const int b = blockIdx.x * wpc + warp;
-    if (b >= a.B) return;
+    if (threadIdx.x == 0) { mbar_init(bars + 1, 1); mbar_init(bars + 2, 1); mbar_init(bars + 3, 1); }
+    stage_params(sp, a.params, L.P, bars);   // contains the mbarrier-init fence + __syncthreads
 
     const bool act = lane < H;
     const int j = act ? lane : 0;
-    const int fl = SPLIT ? lane : lane - H;               // feature index this lane serves (if 0<=fl<F)
-    const bool isf = fl >= 0 && fl < F;
-    // weight columns
-    float wcol[3 * HT], wicol[SPLIT ? 3 * HT : 1], whT[HEAD ? HT : 1];
-#pragma unroll
-    for (int g = 0; g < 3; ++g)
-#pragma unroll
-        for (int k = 0; k < HT; ++k) {
-            float w = 0.f;
-            if (k < H) {
-                if (act) w = sp[L.oWhh + (g * H + k) * H + j];
-                else if (!SPLIT && isf) w = sp[L.oWih + (g * H + k) * F + fl];
-            }
-            wcol[g * HT + k] = w;
-            if constexpr (SPLIT) wicol[g * HT + k] = (k < H && isf) ? sp[L.oWih + (g * H + k) * F + fl] : 0.f;
-        }
-    if constexpr (HEAD) {
-#pragma unroll
-        for (int k = 0; k < HT; ++k) whT[k] = (act && k < H) ? sp[L.oWh + k * H + j] : 0.f;
-    }
-    const float wo0 = act ? sp[L.oWo + j] : 0.f, wo1 = act ? sp[L.oWo + L.O + j] : 0.f;
-    const float wof0 = (HEAD && isf) ? sp[L.oWo + H + fl] : 0.f, wof1 = (HEAD && isf) ? sp[L.oWo + L.O + H + fl] : 0.f;
+    const int lp = lane < HP ? lane : 0;
+    const int nchunks = (T + CH - 1) / CH;
+    const float2 *x2 = reinterpret_cast<const float2 *>(a.x) + (size_t)b * T;
+    const float *svg = a.saved + (size_t)b * T * ROW;
 
-    // gradient accumulators (registers)
-    float gwhh[DW ? 3 * HT : 1], gwih[DW ? 3 * F : 1], gwh[(DW && HEAD) ? HT : 1];
-    float gb_r = 0.f, gb_z = 0.f, gb_n = 0.f, gb_hn = 0.f, gwo0 = 0.f, gwo1 = 0.f, gbh = 0.f, gbo0 = 0.f, gbo1 = 0.f;
-    float gwof[(DW && HEAD) ? 2 * F : 1];
-    if constexpr (DW) {
-#pragma unroll
-        for (int k = 0; k < 3 * HT; ++k) gwhh[k] = 0.f;
-#pragma unroll
-        for (int k = 0; k < 3 * F; ++k) gwih[k] = 0.f;
+    // stage s: pre -> chunk index (nchunks-1-s), chain -> one stage later, post -> two stages later
+    if (warp == 1) {
+        // =============================== pre
+        float whT[HEAD ? HT : 1];
         if constexpr (HEAD) {
 #pragma unroll
-            for (int k = 0; k < HT; ++k) gwh[k] = 0.f;
-#pragma unroll
-            for (int k = 0; k < 2 * F; ++k) gwof[k] = 0.f;
+            for (int k = 0; k < HT; ++k) whT[k] = (act && k < H) ? sp[L.oWh + k * H + j] : 0.f;
         }
-    }
-
-    const float2 *x2 = reinterpret_cast<const float2 *>(a.x) + (size_t)b * a.T;
-    const float2 *go2 = a.gout ? reinterpret_cast<const float2 *>(a.gout) + (size_t)b * a.T : nullptr;
-    const float2 *oi2 = a.out_in ? reinterpret_cast<const float2 *>(a.out_in) + (size_t)b * a.T : nullptr;
-    const float2 *y2 = a.target ? reinterpret_cast<const float2 *>(a.target) + (size_t)b * a.T : nullptr;
-    float2 *gx2 = (a.need_dx && a.gx) ? reinterpret_cast<float2 *>(a.gx) + (size_t)b * a.T : nullptr;
-    const float *sv = a.saved + (size_t)b * a.T * L.NS * H;
-    const float gs = a.gscale * (a.gscale_dev ? __ldg(a.gscale_dev) : 1.0f);
-
-    float gH = 0.f;
-    int cur = 0;
-    const int nchunks = (a.T + ODPD_CHUNK - 1) / ODPD_CHUNK;
-    for (int c = nchunks - 1; c >= 0; --c) {
-        const int t0 = c * ODPD_CHUNK, nt = min(ODPD_CHUNK, a.T - t0);
-        // ---- phase A': per-lane timestep: features (recomputed) and dLoss/dout
-        float my_go0 = 0.f, my_go1 = 0.f;
-        if (lane < nt) {
-            const float2 v = __ldg(x2 + t0 + lane);
-            float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            features_fwd<FM>(v.x, v.y, 0.f, 0.f, f);
-            float4 *d = reinterpret_cast<float4 *>(sfeat + lane * 8);
-            d[0] = make_float4(f[0], f[1], f[2], f[3]);
-            d[1] = make_float4(f[4], f[5], f[6], f[7]);
-            if (go2) { const float2 g = __ldg(go2 + t0 + lane); my_go0 = g.x; my_go1 = g.y; }
-            else { const float2 o = __ldg(oi2 + t0 + lane), y = __ldg(y2 + t0 + lane); my_go0 = gs * (o.x - y.x); my_go1 = gs * (o.y - y.y); }
-            *reinterpret_cast<float2 *>(sgo + lane * 2) = make_float2(my_go0, my_go1);
-            if constexpr (DW) {
-                gbo0 += my_go0; gbo1 += my_go1;
+        const float wo0 = act ? sp[L.oWo + j] : 0.f, wo1 = act ? sp[L.oWo + L.O + j] : 0.f;
+        const float2 *go2 = a.gout ? reinterpret_cast<const float2 *>(a.gout) + (size_t)b * T : nullptr;
+        const float2 *oi2 = a.out_in ? reinterpret_cast<const float2 *>(a.out_in) + (size_t)b * T : nullptr;
+        const float2 *y2 = a.target ? reinterpret_cast<const float2 *>(a.target) + (size_t)b * T : nullptr;
+        const float gs = a.gscale * (a.gscale_dev ? __ldg(a.gscale_dev) : 1.0f);
+        for (int s = 0; s < nchunks + 2; ++s) {
+            if (s < nchunks) {
+                const int c = nchunks - 1 - s, t0 = c * CH, nt = min(CH, T - t0);
+                const int slot = s % 3;
+                float *ac = sact + slot * SM::ACT;
+                float *pr = spre + slot * SM::PRE;
+                float *dh = sdh + (s & 1) * SM::DH, *dp = sdp + slot * SM::DH;
+                uint64_t *bar = bars + 1 + slot;
+                if (lane == 0) {
+                    if (t0 > 0) {
+                        const uint32_t bytes = (uint32_t)((nt + 1) * ROW * 4);
+                        mbar_expect_tx(bar, bytes);
+                        tma_load_1d(ac, svg + (size_t)(t0 - 1) * ROW, bytes, bar);
+                    } else {
+                        const uint32_t bytes = (uint32_t)(nt * ROW * 4);
+                        mbar_expect_tx(bar, bytes);
+                        tma_load_1d(ac + ROW, svg, bytes, bar);
+                    }
+                }
+                if (t0 == 0) { for (int i = lane; i < ROW; i += 32) ac[i] = 0.f; }   // h_{-1} = 0
+                if (lane < nt) {
+                    const float2 v = __ldg(x2 + t0 + lane);
+                    float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    features_fwd<FM>(v.x, v.y, 0.f, 0.f, f);
+                    float g0, g1;
+                    if (go2) { const float2 g = __ldg(go2 + t0 + lane); g0 = g.x; g1 = g.y; }
+                    else { const float2 o = __ldg(oi2 + t0 + lane), y = __ldg(y2 + t0 + lane); g0 = gs * (o.x - y.x); g1 = gs * (o.y - y.y); }
+                    float4 *d = reinterpret_cast<float4 *>(pr + lane * 12);
+                    d[0] = make_float4(f[0], f[1], f[2], f[3]);
+                    d[1] = make_float4(f[4], f[5], f[6], f[7]);
+                    d[2] = make_float4(g0, g1, 0.f, 0.f);
+                }
+                __syncwarp();
+                mbar_wait(bar, (uint32_t)((s / 3) & 1));
+                if constexpr (HEAD) {
+                    if (lane < HP) {
+                        for (int tl = 0; tl < nt; ++tl) {
+                            const float2 go = *reinterpret_cast<const float2 *>(pr + tl * 12 + 8);
+                            const float g = ac[(tl + 1) * ROW + 5 * HP + lane];
+                            dp[tl * HP + lane] = g > 0.f ? fmaf(wo0, go.x, wo1 * go.y) : 0.f;
+                        }
+                    }
+                    __syncwarp();
+                    if (lane < HP) {
+#pragma unroll 2
+                        for (int tl = 0; tl < nt; ++tl) {
+                            float d0 = 0.f, d1 = 0.f;
+                            const float4 *dp4 = reinterpret_cast<const float4 *>(dp + tl * HP);
+#pragma unroll
+                            for (int k4 = 0; k4 < HP / 4; ++k4) {
+                                const float4 dv = dp4[k4];
+                                const float dk[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const int k = k4 * 4 + e;
+                                    if (k < HT) { if (k & 1) d1 = fmaf(whT[k], dk[e], d1); else d0 = fmaf(whT[k], dk[e], d0); }
+                                }
+                            }
+                            dh[tl * HP + lane] = d0 + d1;
+                        }
+                    }
+                } else {
+                    if (lane < HP) {
+                        for (int tl = 0; tl < nt; ++tl) {
+                            const float2 go = *reinterpret_cast<const float2 *>(pr + tl * 12 + 8);
+                            dh[tl * HP + lane] = fmaf(wo0, go.x, wo1 * go.y);
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    } else if (warp == 0) {
+        // =============================== chain: reverse-time recurrence of dL/dh
+        float wcol[3 * HT];   // column j of W_hh
+#pragma unroll
+        for (int g = 0; g < 3; ++g)
+#pragma unroll
+            for (int k = 0; k < HT; ++k) wcol[g * HT + k] = (act && k < H) ? sp[L.oWhh + (g * H + k) * H + j] : 0.f;
+        float gH = 0.f;
+        for (int s = 0; s < nchunks + 2; ++s) {
+            const int sc = s - 1;
+            if (sc >= 0 && sc < nchunks) {
+                const int c = nchunks - 1 - sc, t0 = c * CH, nt = min(CH, T - t0);
+                const float *ac = sact + (sc % 3) * SM::ACT + lp;
+                const float *dh = sdh + (sc & 1) * SM::DH + lp;
+                float *Gb = sG + (sc & 1) * SM::G;
+                // software-pipelined operand fetch (none of these depend on the recurrence)
+                const float *row = ac + nt * ROW;   // step t0+nt-1
+                float r = row[0], z = row[HP], n = row[2 * HP], hgn = row[3 * HP], hp = row[4 * HP - ROW], dht = dh[(nt - 1) * HP];
+                for (int tl = nt - 1; tl >= 0; --tl) {
+                    const int tp = tl > 0 ? tl - 1 : 0;
+                    const float *rown = ac + (tp + 1) * ROW;
+                    const float r_n = rown[0], z_n = rown[HP], n_n = rown[2 * HP], hgn_n = rown[3 * HP], hp_n = rown[4 * HP - ROW],
+                                dh_n = dh[tp * HP];
+                    gH += dht;
+                    const float gz = gH * (hp - n), gn = gH * (1.f - z), ghp = gH * z;
+                    const float an = gn * (1.f - n * n);
+                    const float az = gz * z * (1.f - z);
+                    const float anr = an * r;
+                    const float ar = anr * hgn * (1.f - r);
+                    float *G = Gb + tl * 4 * HP;
+                    if (lane < HP) { G[lane] = ar; G[HP + lane] = az; G[2 * HP + lane] = anr; G[3 * HP + lane] = an; }
+                    __syncwarp();
+                    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+                    const float4 *G4 = reinterpret_cast<const float4 *>(G);
+                    float4 gv[3 * (HP / 4)];
+#pragma unroll
+                    for (int q = 0; q < 3 * (HP / 4); ++q) gv[q] = G4[q];
+#pragma unroll
+                    for (int k4 = 0; k4 < HP / 4; ++k4) {
+                        const float kr[4] = {gv[k4].x, gv[k4].y, gv[k4].z, gv[k4].w};
+                        const float kz[4] = {gv[HP / 4 + k4].x, gv[HP / 4 + k4].y, gv[HP / 4 + k4].z, gv[HP / 4 + k4].w};
+                        const float kn[4] = {gv[2 * (HP / 4) + k4].x, gv[2 * (HP / 4) + k4].y, gv[2 * (HP / 4) + k4].z, gv[2 * (HP / 4) + k4].w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int k = k4 * 4 + e;
+                            if (k < HT) {
+                                if (k & 1) { acc1 = fmaf(wcol[k], kr[e], acc1); acc3 = fmaf(wcol[HT + k], kz[e], acc3); acc1 = fmaf(wcol[2 * HT + k], kn[e], acc1); }
+                                else       { acc0 = fmaf(wcol[k], kr[e], acc0); acc2 = fmaf(wcol[HT + k], kz[e], acc2); acc0 = fmaf(wcol[2 * HT + k], kn[e], acc0); }
+                            }
+                        }
+                    }
+                    gH = ghp + ((acc0 + acc1) + (acc2 + acc3));
+                    r = r_n; z = z_n; n = n_n; hgn = hgn_n; hp = hp_n; dht = dh_n;
+                }
+            }
+            __syncthreads();
+        }
+    } else {
+        // =============================== post: weight gradients (registers) and dL/dx
+        const int fl = SPLIT ? lane : lane - H;   // feature column served by this lane (if 0<=fl<F)
+        const bool isf = fl >= 0 && fl < F;
+        float wicol[3 * HT];                      // column fl of W_ih (feature lanes)
+#pragma unroll
+        for (int g = 0; g < 3; ++g)
+#pragma unroll
+            for (int k = 0; k < HT; ++k) wicol[g * HT + k] = (isf && k < H) ? sp[L.oWih + (g * H + k) * F + fl] : 0.f;
+        const float wof0 = (HEAD && isf) ? sp[L.oWo + H + fl] : 0.f, wof1 = (HEAD && isf) ? sp[L.oWo + L.O + H + fl] : 0.f;
+        float gwhh[DW ? 3 * HT : 1], gwih[DW ? 3 * F : 1], gwh[(DW && HEAD) ? HT : 1], gwof[(DW && HEAD) ? 2 * F : 1];
+        float gb_r = 0.f, gb_z = 0.f, gb_n = 0.f, gb_hn = 0.f, gwo0 = 0.f, gwo1 = 0.f, gbh = 0.f, gbo0 = 0.f, gbo1 = 0.f;
+        if constexpr (DW) {
+#pragma unroll
+            for (int k = 0; k < 3 * HT; ++k) gwhh[k] = 0.f;
+#pragma unroll
+            for (int k = 0; k < 3 * F; ++k) gwih[k] = 0.f;
+            if constexpr (HEAD) {
+#pragma unroll
+                for (int k = 0; k < HT; ++k) gwh[k] = 0.f;
+#pragma unroll
+                for (int k = 0; k < 2 * F; ++k) gwof[k] = 0.f;
+            }
+        }
+        float2 *gx2 = (a.need_dx && a.gx) ? reinterpret_cast<float2 *>(a.gx) + (size_t)b * T : nullptr;
+        for (int s = 0; s < nchunks + 2; ++s) {
+            const int sc = s - 2;
+            if (sc >= 0) {
+                const int c = nchunks - 1 - sc, t0 = c * CH, nt = min(CH, T - t0);
+                const float *ac = sact + (sc % 3) * SM::ACT;
+                const float *pr = spre + (sc % 3) * SM::PRE;
+                const float *dp = sdp + (sc % 3) * SM::DH;
+                const float *Gb = sG + (sc & 1) * SM::G;
+                for (int tl = 0; tl < nt; ++tl) {
+                    const float *G = Gb + tl * 4 * HP;
+                    const float4 *G4 = reinterpret_cast<const float4 *>(G);
+                    const float *row = ac + (tl + 1) * ROW;
+                    const float hp = row[4 * HP - ROW + lp], ht = row[4 * HP + lp];
+                    const float2 go = *reinterpret_cast<const float2 *>(pr + tl * 12 + 8);
+                    float feat[8];
+                    {
+                        const float4 *fp = reinterpret_cast<const float4 *>(pr + tl * 12);
+                        const float4 f0 = fp[0];
+                        feat[0] = f0.x; feat[1] = f0.y; feat[2] = f0.z; feat[3] = f0.w;
+                        if (F > 4) { const float4 f1 = fp[1]; feat[4] = f1.x; feat[5] = f1.y; feat[6] = f1.z; feat[7] = f1.w; }
+                    }
+                    if constexpr (DW) {
+                        const float ar = G[lp], az = G[HP + lp], anr = G[2 * HP + lp], an = G[3 * HP + lp];
+#pragma unroll
+                        for (int q = 0; q < F; ++q) {
+                            gwih[q] = fmaf(ar, feat[q], gwih[q]);
+                            gwih[F + q] = fmaf(az, feat[q], gwih[F + q]);
+                            gwih[2 * F + q] = fmaf(an, feat[q], gwih[2 * F + q]);
+                        }
+                        gb_r += ar; gb_z += az; gb_n += an; gb_hn += anr;
+                        if constexpr (HEAD) {
+                            const float g = row[5 * HP + lp];
+                            gwo0 = fmaf(go.x, g, gwo0); gwo1 = fmaf(go.y, g, gwo1);
+                            gbh += dp[tl * HP + lp];
+                            const float4 *dp4 = reinterpret_cast<const float4 *>(dp + tl * HP);
+#pragma unroll
+                            for (int k4 = 0; k4 < HP / 4; ++k4) {
+                                const float4 dv = dp4[k4];
+                                const float dk[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) { const int k = k4 * 4 + e; if (k < HT) gwh[k] = fmaf(dk[e], ht, gwh[k]); }
+                            }
+                        } else {
+                            gwo0 = fmaf(go.x, ht, gwo0); gwo1 = fmaf(go.y, ht, gwo1);
+                        }
+                    }
+                    float fa0 = 0.f, fa1 = 0.f;
+#pragma unroll
+                    for (int k4 = 0; k4 < HP / 4; ++k4) {
+                        const float4 v_r = G4[k4], v_z = G4[HP / 4 + k4], v_nh = G4[2 * (HP / 4) + k4], v_nx = G4[3 * (HP / 4) + k4];
+                        const float kr[4] = {v_r.x, v_r.y, v_r.z, v_r.w}, kz[4] = {v_z.x, v_z.y, v_z.z, v_z.w};
+                        const float knh[4] = {v_nh.x, v_nh.y, v_nh.z, v_nh.w}, knx[4] = {v_nx.x, v_nx.y, v_nx.z, v_nx.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int k = k4 * 4 + e;
+                            if (k < HT) {
+                                if (a.need_dx) {
+                                    fa0 = fmaf(wicol[k], kr[e], fa0);
+                                    fa1 = fmaf(wicol[HT + k], kz[e], fa1);
+                                    fa0 = fmaf(wicol[2 * HT + k], knx[e], fa0);
+                                }
+                                if constexpr (DW) {
+                                    gwhh[k] = fmaf(kr[e], hp, gwhh[k]);
+                                    gwhh[HT + k] = fmaf(kz[e], hp, gwhh[HT + k]);
+                                    gwhh[2 * HT + k] = fmaf(knh[e], hp, gwhh[2 * HT + k]);
+                                }
+                            }
+                        }
+                    }
+                    if (a.need_dx && isf) sdf[tl * 8 + fl] = (fa0 + fa1) + (HEAD ? fmaf(wof0, go.x, wof1 * go.y) : 0.f);
+                }
+                __syncwarp();
+                // time-parallel tail of the chunk: one timestep per lane
+                if (lane < nt) {
+                    const float *p = pr + lane * 12;
+                    if constexpr (DW) {
+                        gbo0 += p[8]; gbo1 += p[9];
+                        if constexpr (HEAD) {
+#pragma unroll
+                            for (int q = 0; q < F; ++q) { gwof[q] = fmaf(p[8], p[q], gwof[q]); gwof[F + q] = fmaf(p[9], p[q], gwof[F + q]); }
+                        }
+                    }
+                    if (gx2) {
+                        const float2 v = __ldg(x2 + t0 + lane);
+                        float gf[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) gf[q] = (q < F) ? sdf[lane * 8 + q] : 0.f;
+                        float gi, gq;
+                        features_bwd<FM>(v.x, v.y, gf, gi, gq);
+                        gx2[t0 + lane] = make_float2(gi, gq);
+                    }
+                }
+                __syncwarp();
+            }
+            __syncthreads();
+        }
+        if constexpr (DW) {
+            if (a.partials) {
+                float *prt = a.partials + (size_t)b * L.P;
+                if (act) {
+#pragma unroll
+                    for (int g = 0; g < 3; ++g) {
+#pragma unroll
+                        for (int q = 0; q < F; ++q) prt[L.oWih + (g * H + lane) * F + q] = gwih[g * F + q];
+#pragma unroll
+                        for (int k = 0; k < HT; ++k)
+                            if (k < H) prt[L.oWhh + (g * H + k) * H + lane] = gwhh[g * HT + k];
+                    }
+                    prt[L.obih + lane] = gb_r; prt[L.obih + H + lane] = gb_z; prt[L.obih + 2 * H + lane] = gb_n;
+                    prt[L.obhh + lane] = gb_r; prt[L.obhh + H + lane] = gb_z; prt[L.obhh + 2 * H + lane] = gb_hn;
+                    prt[L.oWo + lane] = gwo0; prt[L.oWo + L.O + lane] = gwo1;
+                    if constexpr (HEAD) {
+#pragma unroll
+                        for (int k = 0; k < HT; ++k)
+                            if (k < H) prt[L.oWh + k * H + lane] = gwh[k];
+                        prt[L.obh + lane] = gbh;
+                    }
+                }
+                gbo0 = warp_sum(gbo0); gbo1 = warp_sum(gbo1);
+                if (lane == 0) { prt[L.obo] = gbo0; prt[L.obo + 1] = gbo1; }
                 if constexpr (HEAD) {
 #pragma unroll
-                    for (int q = 0; q < F; ++q) { gwof[q] = fmaf(my_go0, f[q], gwof[q]); gwof[F + q] = fmaf(my_go1, f[q], gwof[F + q]); }
-                }
-            }
-        }
-        __syncwarp();
-        // ---- phase B': serial reverse-time recurrence
-        for (int tl = nt - 1; tl >= 0; --tl) {
-            const int t = t0 + tl;
-            float r = 0.f, z = 0.f, n = 0.f, hgn = 0.f, ht = 0.f, g = 0.f, hp = 0.f;
-            if (act) {
-                const float *s = sv + (size_t)t * L.NS * H + lane;
-                r = __ldg(s); z = __ldg(s + H); n = __ldg(s + 2 * H); hgn = __ldg(s + 3 * H); ht = __ldg(s + 4 * H);
-                if constexpr (HEAD) g = __ldg(s + 5 * H);
-                if (t > 0) hp = __ldg(s - (size_t)L.NS * H + 4 * H);
-            }
-            const float2 go = *reinterpret_cast<const float2 *>(sgo + tl * 2);
-            float feat[8];
-            {
-                const float4 *fp = reinterpret_cast<const float4 *>(sfeat + tl * 8);
-                const float4 f0 = fp[0];
-                feat[0] = f0.x; feat[1] = f0.y; feat[2] = f0.z; feat[3] = f0.w;
-                if (F > 4) { const float4 f1 = fp[1]; feat[4] = f1.x; feat[5] = f1.y; feat[6] = f1.z; feat[7] = f1.w; }
-            }
-            // head backward
-            if constexpr (HEAD) {
-                const float dg = fmaf(wo0, go.x, wo1 * go.y);
-                const float dpre = g > 0.f ? dg : 0.f;
-                if constexpr (DW) { gwo0 = fmaf(go.x, g, gwo0); gwo1 = fmaf(go.y, g, gwo1); gbh += dpre; }
-                if (lane < HP) sdp[cur * HP + lane] = dpre;
-                __syncwarp();
-                float dh0 = 0.f, dh1 = 0.f;
-                const float4 *dp4 = reinterpret_cast<const float4 *>(sdp + cur * HP);
-#pragma unroll
-                for (int k4 = 0; k4 < HP / 4; ++k4) {
-                    const float4 dv = dp4[k4];
-                    const float dk[4] = {dv.x, dv.y, dv.z, dv.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int k = k4 * 4 + e;
-                        if (k < HT) {
-                            if (k & 1) dh1 = fmaf(whT[k], dk[e], dh1); else dh0 = fmaf(whT[k], dk[e], dh0);
-                            if constexpr (DW) gwh[k] = fmaf(dk[e], ht, gwh[k]);
-                        }
+                    for (int q = 0; q < 2 * F; ++q) {
+                        const float sum = warp_sum(gwof[q]);
+                        if (lane == 0) prt[L.oWo + (q / F) * L.O + H + (q % F)] = sum;
                     }
                 }
-                gH += dh0 + dh1;
-            } else {
-                gH += fmaf(wo0, go.x, wo1 * go.y);
-                if constexpr (DW) { gwo0 = fmaf(go.x, ht, gwo0); gwo1 = fmaf(go.y, ht, gwo1); }
-            }
-            // cell backward
-            const float gz = gH * (hp - n), gn = gH * (1.f - z), ghp = gH * z;
-            const float an = gn * (1.f - n * n);
-            const float az = gz * z * (1.f - z);
-            const float anr = an * r;
-            const float ar = anr * hgn * (1.f - r);
-            if constexpr (DW) {
-#pragma unroll
-                for (int q = 0; q < F; ++q) {
-                    gwih[q] = fmaf(ar, feat[q], gwih[q]);
-                    gwih[F + q] = fmaf(az, feat[q], gwih[F + q]);
-                    gwih[2 * F + q] = fmaf(an, feat[q], gwih[2 * F + q]);
-                }
-                gb_r += ar; gb_z += az; gb_n += an; gb_hn += anr;
-            }
-            if (lane < HP) {
-                float *G = sG + cur * 4 * HP + lane;
-                G[0] = ar; G[HP] = az; G[2 * HP] = anr; G[3 * HP] = an;
-            }
-            __syncwarp();
-            float acc0 = 0.f, acc1 = 0.f, fa0 = 0.f, fa1 = 0.f;
-            const float4 *G4 = reinterpret_cast<const float4 *>(sG + cur * 4 * HP);
-#pragma unroll
-            for (int k4 = 0; k4 < HP / 4; ++k4) {
-                const float4 v_r = G4[k4], v_z = G4[HP / 4 + k4], v_nh = G4[2 * (HP / 4) + k4], v_nx = G4[3 * (HP / 4) + k4];
-                const float kr[4] = {v_r.x, v_r.y, v_r.z, v_r.w}, kz[4] = {v_z.x, v_z.y, v_z.z, v_z.w};
-                const float knh[4] = {v_nh.x, v_nh.y, v_nh.z, v_nh.w}, knx[4] = {v_nx.x, v_nx.y, v_nx.z, v_nx.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int k = k4 * 4 + e;
-                    if (k < HT) {
-                        const float vn = SPLIT ? knh[e] : (act ? knh[e] : knx[e]);
-                        acc0 = fmaf(wcol[k], kr[e], acc0);
-                        acc1 = fmaf(wcol[HT + k], kz[e], acc1);
-                        acc0 = fmaf(wcol[2 * HT + k], vn, acc0);
-                        if constexpr (SPLIT) {
-                            fa0 = fmaf(wicol[k], kr[e], fa0);
-                            fa1 = fmaf(wicol[HT + k], kz[e], fa1);
-                            fa0 = fmaf(wicol[2 * HT + k], knx[e], fa0);
-                        }
-                        if constexpr (DW) {
-                            gwhh[k] = fmaf(kr[e], hp, gwhh[k]);
-                            gwhh[HT + k] = fmaf(kz[e], hp, gwhh[HT + k]);
-                            gwhh[2 * HT + k] = fmaf(knh[e], hp, gwhh[2 * HT + k]);
-                        }
-                    }
-                }
-            }
-            const float acc = acc0 + acc1;
-            if (a.need_dx && isf) {
-                const float df = (SPLIT ? (fa0 + fa1) : acc) + (HEAD ? fmaf(wof0, go.x, wof1 * go.y) : 0.f);
-                sdf[tl * 8 + fl] = df;
-            }
-            gH = act ? ghp + acc : 0.f;
-            cur ^= 1;
-        }
-        __syncwarp();
-        // ---- phase C': per-lane timestep: dL/dfeatures -> dL/d(I,Q), coalesced store
-        if (gx2 && lane < nt) {
-            const float2 v = __ldg(x2 + t0 + lane);
-            float gf[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) gf[q] = (q < F) ? sdf[lane * 8 + q] : 0.f;
-            float gi, gq;
-            features_bwd<FM>(v.x, v.y, gf, gi, gq);
-            gx2[t0 + lane] = make_float2(gi, gq);
-        }
-        __syncwarp();
-    }
-
-    if constexpr (DW) if (a.partials) {
-        float *pr = a.partials + (size_t)b * L.P;
-        if (act) {
-#pragma unroll
-            for (int g = 0; g < 3; ++g) {
-#pragma unroll
-                for (int q = 0; q < F; ++q) pr[L.oWih + (g * H + lane) * F + q] = gwih[g * F + q];
-#pragma unroll
-                for (int k = 0; k < HT; ++k)
-                    if (k < H) pr[L.oWhh + (g * H + k) * H + lane] = gwhh[g * HT + k];
-            }
-            pr[L.obih + lane] = gb_r; pr[L.obih + H + lane] = gb_z; pr[L.obih + 2 * H + lane] = gb_n;
-            pr[L.obhh + lane] = gb_r; pr[L.obhh + H + lane] = gb_z; pr[L.obhh + 2 * H + lane] = gb_hn;
-            pr[L.oWo + lane] = gwo0; pr[L.oWo + L.O + lane] = gwo1;
-            if constexpr (HEAD) {
-#pragma unroll
-                for (int k = 0; k < HT; ++k)
-                    if (k < H) pr[L.oWh + k * H + lane] = gwh[k];
-                pr[L.obh + lane] = gbh;
-            }
-        }
-        gbo0 = warp_sum(gbo0); gbo1 = warp_sum(gbo1);
-        if (lane == 0) { pr[L.obo] = gbo0; pr[L.obo + 1] = gbo1; }
-        if constexpr (HEAD) {
-#pragma unroll
-            for (int q = 0; q < 2 * F; ++q) {
-                const float s = warp_sum(gwof[q]);
-                if (lane == 0) pr[L.oWo + (q / F) * L.O + H + (q % F)] = s;
             }
         }
     }
@@ -440,37 +599,39 @@ __global__ void __launch_bounds__(128) gru_bwd_kernel(GruArgs a) {
 // ================================================================ host dispatch
 template <int FM, int HEAD> static int64_t gru_nparams(int H) { return GruLayout<FM, HEAD>(H).P; }
 
-static int pick_wpc(int B) { return B > 148 * 16 ? 4 : 1; }
+// compiled hidden-size tiers: exact for the sizes the reference's scripts use, next-larger tier otherwise
+#define ODPD_GRU_TIERS(X, FM, HEAD) X(8, FM, HEAD) X(10, FM, HEAD) X(13, FM, HEAD) X(16, FM, HEAD) X(23, FM, HEAD) X(32, FM, HEAD)
+static int gru_tier(int H) {
+#define X(HTV, FMV, HEADV) if (H <= HTV) return HTV;
+    ODPD_GRU_TIERS(X, 0, 0)
+#undef X
+    return -1;
+}
 
 template <int HT, int FM, int HEAD>
 static int launch_fwd(const GruArgs &a, cudaStream_t st) {
     const GruLayout<FM, HEAD> L(a.H);
-    const int wpc = pick_wpc(a.B);
-    const size_t smem = (4 + ((L.P + 3) & ~3) + wpc * fwd_warp_floats<HT>()) * sizeof(float);
+    const size_t smem = (size_t)FwdSmem<HT, HEAD>::total((L.P + 3) & ~3) * sizeof(float);
     auto k = gru_fwd_kernel<HT, FM, HEAD>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<(a.B + wpc - 1) / wpc, wpc * 32, smem, st>>>(a);
+    k<<<a.B, 96, smem, st>>>(a);
     return check_launch("gru_fwd_kernel");
 }
 template <int HT, int FM, int HEAD>
 static int launch_bwd(const GruArgs &a, bool dw, cudaStream_t st) {
     const GruLayout<FM, HEAD> L(a.H);
-    const int wpc = pick_wpc(a.B);
-    const size_t smem = (4 + ((L.P + 3) & ~3) + wpc * bwd_warp_floats<HT>()) * sizeof(float);
+    const size_t smem = (size_t)BwdSmem<HT, HEAD>::total((L.P + 3) & ~3) * sizeof(float);
     if (dw) {
         auto k = gru_bwd_kernel<HT, FM, HEAD, true>;
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k<<<(a.B + wpc - 1) / wpc, wpc * 32, smem, st>>>(a);
+        k<<<a.B, 96, smem, st>>>(a);
     } else {
         auto k = gru_bwd_kernel<HT, FM, HEAD, false>;
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k<<<(a.B + wpc - 1) / wpc, wpc * 32, smem, st>>>(a);
+        k<<<a.B, 96, smem, st>>>(a);
     }
     return check_launch("gru_bwd_kernel");
 }
-
-// compiled hidden-size tiers: exact for the sizes the reference's scripts use, next-larger tier otherwise
-#define ODPD_GRU_TIERS(X, FM, HEAD) X(8, FM, HEAD) X(10, FM, HEAD) X(13, FM, HEAD) X(16, FM, HEAD) X(23, FM, HEAD) X(32, FM, HEAD)
 
 template <int FM, int HEAD>
 static int dispatch(const GruArgs &a, int dir, bool dw, cudaStream_t st) {
@@ -489,7 +650,11 @@ int64_t gru_family_nparams(int cell, int H) {
     default: return gru_nparams<FM_QGRU4, 0>(H);
     }
 }
-int64_t gru_family_saved_floats(int cell, int B, int T, int H) { return (int64_t)B * T * (cell == ODPD_CELL_DGRU ? 6 : 5) * H; }
+int64_t gru_family_saved_floats(int cell, int B, int T, int H) {
+    const int ht = gru_tier(H);
+    if (ht < 0) return -1;
+    return (int64_t)B * T * (cell == ODPD_CELL_DGRU ? 6 : 5) * ((ht + 3) & ~3);
+}
 
 int gru_family_run(int cell, const GruArgs &a, int dir, bool dw, cudaStream_t st) {
     switch (cell) {

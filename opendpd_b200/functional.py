@@ -32,37 +32,51 @@ def _check_x(x):
     return x.contiguous()
 
 
-def backbone_forward_raw(spec, x, flat, target=None, loss_scale=0.0, save=True, stats=None):
-    """Launch the forward kernel.  Returns (out, loss_double_or_None, saved_or_None)."""
+def backbone_forward_raw(spec, x, flat, target=None, loss_scale=0.0, save=True, stats=None, bufs=None):
+    """Launch the forward kernel.  Returns (out, loss_double_or_None, saved_or_None).
+    `bufs` (dict) caches out/saved/loss allocations across calls of identical shape (NativeTrainStep)."""
     L = _ffi.lib()
     B, T = x.shape[0], x.shape[1]
-    d = spec.dims(B, T, _ffi.F_SAVE if save else 0)
-    out = torch.empty_like(x)
-    saved = None
-    if save:
-        nbytes = L.odpd_saved_bytes(ctypes.byref(d))
-        if nbytes < 0:
-            _ffi.check(-1)
-        saved = torch.empty(max(int(nbytes) // 4, 1), dtype=torch.float32, device=x.device)
-    loss = torch.zeros(1, dtype=torch.float64, device=x.device) if target is not None else None
+    d = spec.dims(B, T, (_ffi.F_SAVE if save else 0) | _ffi.F_ZERO_LOSS)
+    key = (B, T, bool(save), target is not None)
+    if bufs is not None and bufs.get("key") == key:
+        out, saved, loss = bufs["out"], bufs["saved"], bufs["loss"]
+    else:
+        out = torch.empty_like(x)
+        saved = None
+        if save:
+            nbytes = L.odpd_saved_bytes(ctypes.byref(d))
+            if nbytes < 0:
+                _ffi.check(-1)
+            saved = torch.empty(max(int(nbytes) // 4, 1), dtype=torch.float32, device=x.device)
+        loss = torch.empty(1, dtype=torch.float64, device=x.device) if target is not None else None
+        if bufs is not None:
+            bufs.update(key=key, out=out, saved=saved, loss=loss)
     _ffi.check(L.odpd_backbone_fwd(ctypes.byref(d), _ptr(x), _ptr(target), _ptr(flat), _ptr(out), _ptr(loss),
                                    ctypes.c_double(loss_scale), _ptr(saved), _ptr(stats), _stream()))
     return out, loss, saved
 
 
 def backbone_backward_raw(spec, x, flat, saved, need_dx, need_dw, gout=None, out=None, target=None, gscale=0.0,
-                          gscale_dev=None, gflat=None):
-    """Launch the backward kernel (+ ordered partial reduction). gflat is accumulated into. Returns (gx, gflat)."""
+                          gscale_dev=None, gflat=None, bufs=None):
+    """Launch the backward kernel (+ ordered partial reduction).  A caller-supplied gflat is OVERWRITTEN with the
+    parameter gradient (ODPD_F_OVERWRITE_DW).  Returns (gx, gflat)."""
     L = _ffi.lib()
     B, T = x.shape[0], x.shape[1]
-    flags = (_ffi.F_NEED_DX if need_dx else 0) | (_ffi.F_NEED_DW if need_dw else 0)
+    flags = (_ffi.F_NEED_DX if need_dx else 0) | (_ffi.F_NEED_DW if need_dw else 0) | _ffi.F_OVERWRITE_DW
     d = spec.dims(B, T, flags)
-    gx = torch.empty_like(x) if need_dx else None
-    ws = None
-    if need_dw:
-        if gflat is None:
-            gflat = torch.zeros_like(flat)
-        ws = torch.empty(int(L.odpd_bwd_workspace_bytes(ctypes.byref(d))) // 4, dtype=torch.float32, device=x.device)
+    key = (B, T, bool(need_dx), bool(need_dw))
+    if bufs is not None and bufs.get("key") == key:
+        gx, ws = bufs["gx"], bufs["ws"]
+    else:
+        gx = torch.empty_like(x) if need_dx else None
+        ws = None
+        if need_dw:
+            ws = torch.empty(int(L.odpd_bwd_workspace_bytes(ctypes.byref(d))) // 4, dtype=torch.float32, device=x.device)
+        if bufs is not None:
+            bufs.update(key=key, gx=gx, ws=ws)
+    if need_dw and gflat is None:
+        gflat = torch.empty_like(flat)
     _ffi.check(L.odpd_backbone_bwd(ctypes.byref(d), _ptr(x), _ptr(flat), _ptr(saved), _ptr(gout), _ptr(out), _ptr(target),
                                    ctypes.c_double(gscale), _ptr(gscale_dev), _ptr(gx), _ptr(gflat), _ptr(ws), _stream()))
     return gx, gflat

@@ -1,0 +1,130 @@
+"""Train-step surface: the body of the reference's `net_train` loop (modules/train_funcs.py:28-48) on the native path.
+
+`net_train(...)` keeps the reference signature and semantics (zero_grad -> forward -> MSE -> backward -> clip -> step
+-> loss.item()) and works with any torch optimizer.  `NativeTrainStep` is the fused fast path for the configuration
+every script of record uses (nn.MSELoss + clip_grad_norm_ + AdamW, project.py:262-297): forward kernels with the I/Q
+MSE fused, backward kernels writing one flat gradient, optional data-parallel all-reduce of that flat buffer
+(SURVEY.md §8e), and clip+AdamW in a single launch (odpd_clip_adamw)."""
+import ctypes
+import numpy as np
+import torch
+from torch import nn
+
+from . import _ffi
+from .functional import backbone_forward_raw, backbone_backward_raw, _ptr, _stream
+from .models import CoreModel, CascadedModel
+
+
+def net_train(log, net, dataloader, optimizer, criterion, grad_clip_val, device):
+    """Drop-in for modules/train_funcs.py:16-54 (same arguments, same log side effect)."""
+    net = net.train()
+    losses = []
+    fused = isinstance(criterion, nn.MSELoss) and criterion.reduction == "mean" and hasattr(net, "forward_mse")
+    for features, targets in dataloader:
+        features = features.to(device)
+        targets = targets.to(device)
+        optimizer.zero_grad()
+        if fused:
+            _, loss = net.forward_mse(features, targets)
+        else:
+            loss = criterion(net(features), targets)
+        loss.backward()
+        if grad_clip_val != 0:
+            nn.utils.clip_grad_norm_(net.parameters(), grad_clip_val)
+        optimizer.step()
+        losses.append(loss.item())
+    log["loss"] = np.mean(losses)
+    return net
+
+
+class NativeTrainStep:
+    """One fused train step for a CoreModel (train_pa, steps/train_pa.py:24-29) or a CascadedModel with frozen PA
+    (train_dpd, steps/train_dpd.py:60-63).
+
+    step(features, targets)  -> device float64 loss (no host sync)
+    step_host(features, targets) -> python float; inputs are (pinned) HOST tensors, H2D copies and the loss D2H read
+    happen inside the call (the reference's per-batch `.to(device)` ... `loss.item()`, train_funcs.py:30-48).
+
+    Data parallel: pass `process_group` (torch.distributed); each rank feeds its shard of the global batch, the loss
+    scale uses the GLOBAL element count and one SUM all-reduce runs on [flat_grad, loss] per step."""
+
+    def __init__(self, net, lr=5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, grad_clip_val=200.0,
+                 process_group=None, world_size=1):
+        self.net = net
+        if isinstance(net, CascadedModel):
+            self.dpd, self.pa = net.dpd_model.backbone, net.pa_model.backbone
+            if any(p.requires_grad for p in self.pa.parameters()):
+                raise ValueError("CascadedModel: call freeze_pa_model() first (steps/train_dpd.py:63)")
+            self.train_bb = self.dpd
+        elif isinstance(net, CoreModel):
+            self.dpd, self.pa = None, net.backbone
+            self.train_bb = self.pa
+        else:
+            raise TypeError("NativeTrainStep wants a native CoreModel or CascadedModel")
+        flat, layout = self.train_bb._flat_sync()
+        if self.dpd is not None:
+            self.pa._flat_sync()
+        self.n = sum(n for _, n, _ in layout)
+        dev = flat.device
+        self.device = dev
+        # [flat grad | loss] share one fp32 buffer so data-parallel needs a single all-reduce
+        self.gbuf = torch.zeros(flat.numel() + 4, dtype=torch.float32, device=dev)
+        self.gflat = self.gbuf[:flat.numel()]
+        self.exp_avg = torch.zeros_like(flat)
+        self.exp_avg_sq = torch.zeros_like(flat)
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=dev)
+        self.gnorm = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.betas, self.eps, self.wd, self.clip = betas, eps, weight_decay, float(grad_clip_val)
+        self.pg, self.world = process_group, int(world_size)
+        self._stage = None
+        self._bufs = [dict() for _ in range(4)]
+
+    def set_lr(self, lr):
+        """ReduceLROnPlateau hook (project.py:288-297) — host-side scalar write, no kernel change."""
+        self.lr_dev.fill_(float(lr))
+
+    def step(self, features, targets):
+        L = _ffi.lib()
+        tb = self.train_bb
+        flat, _ = tb._flat_sync()
+        B, T = features.shape[0], features.shape[1]
+        count = float(2 * B * T * self.world)          # nn.MSELoss 'mean' over the GLOBAL batch
+        if self.dpd is None:
+            spec = tb._spec()
+            out, loss, saved = backbone_forward_raw(spec, features, flat, targets, 1.0 / count, True, tb._stats_tensor(self.device),
+                                                    self._bufs[0])
+            backbone_backward_raw(spec, features, flat, saved, False, True, out=out, target=targets, gscale=2.0 / count,
+                                  gflat=self.gflat, bufs=self._bufs[1])
+        else:
+            paflat, _ = self.pa._flat_sync()
+            sd, sp = self.dpd._spec(), self.pa._spec()
+            mid, _, saved_d = backbone_forward_raw(sd, features, flat, None, 0.0, True, self.dpd._stats_tensor(self.device), self._bufs[0])
+            out, loss, saved_p = backbone_forward_raw(sp, mid, paflat, targets, 1.0 / count, True, self.pa._stats_tensor(self.device),
+                                                      self._bufs[2])
+            gmid, _ = backbone_backward_raw(sp, mid, paflat, saved_p, True, False, out=out, target=targets, gscale=2.0 / count,
+                                            bufs=self._bufs[3])
+            backbone_backward_raw(sd, features, flat, saved_d, False, True, gout=gmid, gflat=self.gflat, bufs=self._bufs[1])
+        if self.pg is not None and self.world > 1:
+            self.gbuf[-4] = loss.to(torch.float32)[0]
+            torch.distributed.all_reduce(self.gbuf, group=self.pg)
+            loss = self.gbuf[-4:-3].to(torch.float64)
+        _ffi.check(L.odpd_clip_adamw(_ptr(flat), _ptr(self.gflat), _ptr(self.exp_avg), _ptr(self.exp_avg_sq),
+                                     ctypes.c_int64(self.n), _ptr(self.lr_dev), self.betas[0], self.betas[1], self.eps, self.wd,
+                                     self.clip, _ptr(self.step_dev), _ptr(self.gnorm), 0, _stream()))
+        return loss
+
+    def step_host(self, features_cpu, targets_cpu):
+        if self._stage is None or self._stage[0].shape != features_cpu.shape:
+            self._stage = (torch.empty(features_cpu.shape, dtype=torch.float32, device=self.device),
+                           torch.empty(targets_cpu.shape, dtype=torch.float32, device=self.device))
+        fx, fy = self._stage
+        fx.copy_(features_cpu, non_blocking=True)
+        fy.copy_(targets_cpu, non_blocking=True)
+        return float(self.step(fx, fy).item())
+
+    def grads_as_param_grads(self):
+        """Expose the flat gradient through each parameter's .grad (views), e.g. for inspection or a torch optimizer."""
+        _, layout = self.train_bb._flat_sync()
+        for (_, p), (off, n, shape) in zip(self.train_bb.named_parameters(), layout):
+            p.grad = self.gflat[off:off + n].view(shape)

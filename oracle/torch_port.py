@@ -1,0 +1,180 @@
+"""PyTorch-ATen restatement of the reference backbones (TEST/BENCH INFRASTRUCTURE — never imported by opendpd_b200).
+
+The reference's CPU path *is* a sequence of PyTorch ATen ops: torch.nn.GRU/LSTM (ATen RNN.cpp) for
+gru/lstm/dgru/qgru and one ATen call per Python op for the hand-written cells.  This file restates those op sequences
+functionally over the flat parameter vector of include/odpd.h, so that (a) bench.py can time what the reference's own
+CPU path costs on the GPU box's host cores, where /root/reference does not exist, and (b) tests have a second,
+autograd-derived check of the hand-written backward in odpd_oracle.c.  Pinned against tests/golden/*.npz by
+tests/test_torch_port.py.  Citations: gru.py:45-48, lstm.py:45-48, dgru.py:59-74, qgru.py:59-71, qgru_amp1.py:59-76,
+deltagru.py:60-77/149-266, deltagru_tcnskip.py:89-103/232-304, pgjanet.py:24-77, dvrjanet.py:32-102, gmp.py:18-51."""
+import math
+import torch
+import torch.nn.functional as Fn
+
+
+def split_params(kind, flat, H, K=3):
+    """flat (P,) -> dict of named views, named_parameters() order of the reference module."""
+    shapes = {
+        "gru": [("w_ih", (3 * H, 2)), ("w_hh", (3 * H, H)), ("b_ih", (3 * H,)), ("b_hh", (3 * H,)), ("wo", (2, H)), ("bo", (2,))],
+        "qgru": [("w_ih", (3 * H, 4)), ("w_hh", (3 * H, H)), ("b_ih", (3 * H,)), ("b_hh", (3 * H,)), ("wo", (2, H)), ("bo", (2,))],
+        "lstm": [("w_ih", (4 * H, 2)), ("w_hh", (4 * H, H)), ("b_ih", (4 * H,)), ("b_hh", (4 * H,)), ("wo", (2, H)), ("bo", (2,))],
+        "dgru": [("w_ih", (3 * H, 6)), ("w_hh", (3 * H, H)), ("b_ih", (3 * H,)), ("b_hh", (3 * H,)), ("wo", (2, H + 6)), ("bo", (2,)),
+                 ("wh", (H, H)), ("bh", (H,))],
+        "deltagru": [("w_ih", (3 * H, 6)), ("w_hh", (3 * H, H)), ("b_ih", (3 * H,)), ("b_hh", (3 * H,)), ("wo", (2, H)), ("bo", (2,))],
+        "deltagru_tcnskip": [("w_ih", (3 * H, 6)), ("w_hh", (3 * H, H)), ("wo", (2, H)), ("c0", (3, 2, 3)), ("c2", (2, 3, 1))],
+        "pgjanet": [("wa", (H, H + 1)), ("ba", (H,)), ("wp1", (H, H + 1)), ("bp1", (H,)), ("wp2", (H, H + 1)), ("bp2", (H,)),
+                    ("wf", (H, 2 * H)), ("bf", (H,)), ("wg", (H, 2 * H)), ("bg", (H,)), ("wo", (2, H)), ("bo", (2,))],
+        "dvrjanet": [("cs", (K,)), ("wph", (H, H)), ("wpt", (H, 1)), ("wah", (H, H)), ("wax", (H, 1)), ("wf", (H, H)), ("bf", (H,)),
+                     ("wc", (H, 2 * H)), ("bc", (H,)), ("ws", (H, 2 * H)), ("bs", (H,)), ("wo1", (1, H)), ("bo1", (1,)),
+                     ("wo2", (1, H)), ("bo2", (1,))],
+        "gmp": [("w", (1, 495))],
+    }
+    shapes["qgru_amp1"] = shapes["qgru"]
+    shapes["tres"] = shapes["deltagru_tcnskip"]
+    out, off = {}, 0
+    for name, shp in shapes[kind]:
+        n = math.prod(shp)
+        out[name] = flat[off:off + n].view(shp)
+        off += n
+    assert off == flat.numel(), (kind, off, flat.numel())
+    return out
+
+
+def _feat(kind, x):
+    i, q = x[..., 0:1], x[..., 1:2]
+    if kind in ("gru", "lstm"):
+        return x
+    a2 = torch.pow(i, 2) + torch.pow(q, 2)
+    if kind == "qgru":
+        return torch.cat((i, q, a2, torch.pow(a2, 2)), -1)
+    a = torch.sqrt(a2)
+    a3 = torch.pow(a, 3)
+    if kind == "qgru_amp1":
+        return torch.cat((i, q, a, a3), -1)
+    if kind in ("deltagru_tcnskip", "tres"):
+        nxt = torch.roll(x, shifts=-1, dims=1)
+        return torch.cat((i, q, a, a3, nxt[..., 0:1], nxt[..., 1:2]), -1)
+    return torch.cat((i, q, a, a3, q / a, i / a), -1)
+
+
+def _delta_layer(f, p, H, thx, thh, bias):
+    B, T, _ = f.shape
+    thx_t, thh_t = torch.tensor(thx, dtype=f.dtype), torch.tensor(thh, dtype=f.dtype)
+    xp = f.new_zeros(B, 6); h = f.new_zeros(B, H); hp = f.new_zeros(B, H)
+    M = f.new_zeros(B, 3 * H); Mnh = f.new_zeros(B, H)
+    if bias:
+        M = M + torch.cat((p["b_ih"][:2 * H] + p["b_hh"][:2 * H], p["b_ih"][2 * H:]))
+        Mnh = Mnh + p["b_hh"][2 * H:]
+    hs = []
+    for t in range(T):
+        xt = f[:, t]
+        dx, dh = xt - xp, h - hp
+        ax, ah = dx.abs(), dh.abs()
+        dx = dx.masked_fill(ax < thx_t, 0); dh = dh.masked_fill(ah < thh_t, 0)
+        xp = torch.where(ax >= thx_t, xt, xp); hp = torch.where(ah >= thh_t, h, hp)
+        mx = torch.mm(dx, p["w_ih"].t()) + M
+        mh = torch.mm(dh, p["w_hh"].t())
+        Mr, Mz, Mn = mx[:, :H] + mh[:, :H], mx[:, H:2 * H] + mh[:, H:2 * H], mx[:, 2 * H:]
+        Mnh = mh[:, 2 * H:] + Mnh
+        M = torch.cat((Mr, Mz, Mn), 1)
+        r, z = torch.sigmoid(Mr), torch.sigmoid(Mz)
+        n = torch.tanh(Mn + r * Mnh)
+        h = (1 - z) * n + z * h
+        hs.append(h)
+    return torch.stack(hs, 1)
+
+
+def forward(kind, x, flat, H, K=3, thx=0.0, thh=0.0):
+    """x (B,T,2) -> out (B,T,2), differentiable w.r.t. x and flat."""
+    p = split_params(kind, flat, H, K)
+    B, T, _ = x.shape
+    if kind in ("gru", "qgru", "qgru_amp1", "dgru"):
+        f = _feat(kind, x)
+        h0 = x.new_zeros(1, B, H)
+        hseq, _ = torch._VF.gru(f, h0, [p["w_ih"], p["w_hh"], p["b_ih"], p["b_hh"]], True, 1, 0.0, False, False, True)
+        if kind == "dgru":
+            g = torch.relu(Fn.linear(hseq, p["wh"], p["bh"]))
+            return Fn.linear(torch.cat((g, f), -1), p["wo"], p["bo"])
+        return Fn.linear(hseq, p["wo"], p["bo"])
+    if kind == "lstm":
+        h0 = x.new_zeros(1, B, H)
+        hseq, _, _ = torch._VF.lstm(x, (h0, h0), [p["w_ih"], p["w_hh"], p["b_ih"], p["b_hh"]], True, 1, 0.0, False, False, True)
+        return Fn.linear(hseq, p["wo"], p["bo"])
+    if kind == "deltagru":
+        hseq = _delta_layer(_feat("dgru", x), p, H, thx, thh, True)
+        return Fn.linear(hseq, p["wo"], p["bo"])
+    if kind in ("deltagru_tcnskip", "tres"):
+        xt = x.transpose(1, 2)
+        s = Fn.hardswish(Fn.conv1d(xt, p["c0"], None, 1, 16, 16))
+        s = Fn.hardswish(Fn.conv1d(s, p["c2"])).transpose(1, 2)
+        hseq = _delta_layer(_feat("tres", x), p, H, thx, thh, False)
+        return Fn.linear(hseq, p["wo"]) + s
+    if kind == "pgjanet":
+        h = x.new_zeros(B, H); ys = []
+        for t in range(T):
+            i, q = x[:, t, 0:1], x[:, t, 1:2]
+            a = torch.sqrt(i ** 2 + q ** 2); th = torch.atan2(q, i)
+            an = torch.tanh(Fn.linear(torch.cat((h, a), -1), p["wa"], p["ba"]))
+            p1 = torch.tanh(Fn.linear(torch.cat((h, torch.cos(th)), -1), p["wp1"], p["bp1"]))
+            p2 = torch.tanh(Fn.linear(torch.cat((h, torch.sin(th)), -1), p["wp2"], p["bp2"]))
+            u = an * p1 * p2 * (1 - an) * (1 - p1) * (1 - p2)
+            hu = torch.cat((h, u), -1)
+            f = torch.sigmoid(Fn.linear(hu, p["wf"], p["bf"])); g = torch.tanh(Fn.linear(hu, p["wg"], p["bg"]))
+            h = f * h + (1 - f) * g
+            ys.append(Fn.linear(h, p["wo"], p["bo"]))
+        return torch.stack(ys, 1)
+    if kind == "dvrjanet":
+        hI = x.new_zeros(B, H); hQ = x.new_zeros(B, H); ys = []
+        for t in range(T):
+            i, q = x[:, t, 0:1], x[:, t, 1:2]
+            a = torch.sqrt(i ** 2 + q ** 2); th = torch.atan2(q, i)
+            s = hI + hQ
+            tht = Fn.linear(th, p["wpt"]) + Fn.linear(s, p["wph"])
+            pa = Fn.linear(a, p["wax"]) + Fn.linear(s, p["wah"])
+            at = 0
+            for k in range(1, K + 1):
+                at = at + torch.abs(pa - k / K) * p["cs"][k - 1]
+            f = torch.sigmoid(Fn.linear(s, p["wf"], p["bf"]))
+            gc = torch.tanh(Fn.linear(torch.cat((hI, at * torch.cos(tht)), -1), p["wc"], p["bc"]))
+            gs = torch.tanh(Fn.linear(torch.cat((hQ, at * torch.sin(tht)), -1), p["ws"], p["bs"]))
+            hI = f * hI + (1 - f) * gc; hQ = f * hQ + (1 - f) * gs
+            ys.append(torch.cat((Fn.linear(hI, p["wo1"], p["bo1"]), Fn.linear(hQ, p["wo2"], p["bo2"])), -1))
+        return torch.stack(ys, 1)
+    if kind == "gmp":
+        xc = torch.complex(x[..., 0], x[..., 1])
+        xp = torch.cat((xc.new_zeros(B, 20), xc), 1)              # xp[n] = x[n-20]
+        amp = xp.abs()
+        cols = []
+        for m in range(11):
+            cols.append(xp[:, 10 + m:10 + m + T])                   # x[j+m-10]
+        for pw in range(1, 5):
+            ap = amp ** pw
+            for k in range(11):
+                for m in range(11):
+                    cols.append(xp[:, 10 + m:10 + m + T] * ap[:, k + m:k + m + T])   # x[j+m-10] |x[j+k+m-20]|^pw
+        basis = torch.stack(cols, -1)                               # (B,T,495)
+        y = (basis * p["w"].view(-1)).sum(-1)
+        return torch.stack((y.real, y.imag), -1)
+    raise ValueError(kind)
+
+
+def make_train_step(kind, H, seed=0, K=3, thx=0.0, thh=0.0, lr=5e-4, clip=200.0):
+    """The net_train body (train_funcs.py:33-48) on the PyTorch-CPU restatement: zero_grad, forward, MSELoss, backward,
+    clip_grad_norm_, AdamW step, loss.item()."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from oracle import oracle
+    g = torch.Generator().manual_seed(seed)
+    P = oracle.n_params(kind, H, K)
+    flat = torch.nn.Parameter(0.3 * torch.randn(P, generator=g))
+    opt = torch.optim.AdamW([flat], lr=lr)
+    crit = torch.nn.MSELoss()
+
+    def step(x, y):
+        opt.zero_grad()
+        loss = crit(forward(kind, x, flat, H, K, thx, thh), y)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_([flat], clip)
+        opt.step()
+        return loss.item()
+    return step

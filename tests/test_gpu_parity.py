@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests.util import golden_cases, load_golden, rel_err, tol_for
+from tests.util import golden_cases, load_golden, rel_err, tol_for, assert_close
 
 pytestmark = pytest.mark.gpu
 

@@ -35,3 +35,15 @@ def tol_for(g, key, base=1e-5):
     cos/sin of an unbounded learned phase)."""
     cond = rel_err(g[key], g[key + "64"])
     return max(base, 20.0 * cond)
+
+
+def assert_close(mine, ref, tol, what=""):
+    """Parity criterion for fp32 implementations of piecewise-smooth networks: the 99.99th percentile of
+    |mine-ref|/max|ref| must be below `tol` and the worst element below 100*tol.  The slack on isolated elements
+    exists because ReLU / hardswish / delta-threshold kinks turn a 1-ulp difference of a pre-activation that sits
+    at the kink into a finite jump of one gradient element (observed: 1 element in 262144 at 5.6e-5)."""
+    a = np.asarray(mine, dtype=np.float64); b = np.asarray(ref, dtype=np.float64)
+    e = np.abs(a - b) / (np.max(np.abs(b)) + 1e-300)
+    q = float(np.quantile(e, 0.9999)) if e.size >= 10000 else float(e.max())
+    assert q < tol, f"{what}: p99.99 rel err {q:.3e} >= {tol:.1e}"
+    assert float(e.max()) < 100 * tol, f"{what}: max rel err {float(e.max()):.3e} >= {100 * tol:.1e}"
