@@ -12,12 +12,29 @@ struct GruArgs {
     float *saved;
     float loss_scale, gscale;
     int save, need_dx;
+    // delta cells / DVRJANET
+    float thx, thh;
+    int64_t *stats;
+    int K, cell;
 };
 
 // gru_family.cu : GRU / DGRU / QGRU / QGRU_AMP1
 int64_t gru_family_nparams(int cell, int H);
 int64_t gru_family_saved_floats(int cell, int B, int T, int H);
 int gru_family_run(int cell, const GruArgs &a, int dir, bool dw, cudaStream_t st);
+
+#define ODPD_HAVE_DELTA 1
+// lstm.cu
+int64_t lstm_saved_floats(int B, int T, int H);
+int lstm_run(const GruArgs &a, int dir, bool dw, cudaStream_t st);
+// delta.cu : DELTAGRU / TRES
+int64_t delta_saved_floats(int cell, int B, int T, int H);
+int delta_run(const GruArgs &a, int dir, bool dw, cudaStream_t st);
+// janet.cu : PGJANET / DVRJANET
+int64_t janet_saved_floats(int cell, int B, int T, int H);
+int janet_run(const GruArgs &a, int dir, bool dw, cudaStream_t st);
+// gmp.cu
+int gmp_run(const GruArgs &a, int dir, bool dw, cudaStream_t st);
 
 // remaining families (lstm.cu, delta.cu, janet.cu, gmp.cu) behind one dispatcher in others.cu
 int64_t other_nparams(int cell, int H, int K);

@@ -15,18 +15,74 @@ int64_t other_nparams(int cell, int H, int K) {
     return -1;
 }
 
+static bool implemented(int cell) {
+    switch (cell) {
+    case ODPD_CELL_LSTM: return true;
+#ifdef ODPD_HAVE_DELTA
+    case ODPD_CELL_DELTAGRU: case ODPD_CELL_TRES: return true;
+#endif
+#ifdef ODPD_HAVE_JANET
+    case ODPD_CELL_PGJANET: case ODPD_CELL_DVRJANET: return true;
+#endif
+#ifdef ODPD_HAVE_GMP
+    case ODPD_CELL_GMP: return true;
+#endif
+    }
+    return false;
+}
+
 int64_t other_saved_bytes(const OdpdDims *d) {
-    set_error("cell %d: not implemented yet", d->cell);
-    return -1;
+    int64_t n = -1;
+    switch (d->cell) {
+    case ODPD_CELL_LSTM: n = lstm_saved_floats(d->B, d->T, d->H); break;
+#ifdef ODPD_HAVE_DELTA
+    case ODPD_CELL_DELTAGRU: case ODPD_CELL_TRES: n = delta_saved_floats(d->cell, d->B, d->T, d->H); break;
+#endif
+#ifdef ODPD_HAVE_JANET
+    case ODPD_CELL_PGJANET: case ODPD_CELL_DVRJANET: n = janet_saved_floats(d->cell, d->B, d->T, d->H); break;
+#endif
+#ifdef ODPD_HAVE_GMP
+    case ODPD_CELL_GMP: n = 4; break;
+#endif
+    }
+    if (n < 0) { set_error("cell %d (H=%d): not available in this build", d->cell, d->H); return -1; }
+    return 4 * n;
 }
-int other_fwd(const OdpdDims *d, const float *, const float *, const float *, float *, double *, double, void *, int64_t *, cudaStream_t) {
-    set_error("cell %d: forward not implemented yet", d->cell);
+
+static int run(const OdpdDims *d, const GruArgs &a, int dir, bool dw, cudaStream_t st) {
+    if (!implemented(d->cell)) { set_error("cell %d: not implemented in this build", d->cell); return -3; }
+    switch (d->cell) {
+    case ODPD_CELL_LSTM: return lstm_run(a, dir, dw, st);
+#ifdef ODPD_HAVE_DELTA
+    case ODPD_CELL_DELTAGRU: case ODPD_CELL_TRES: return delta_run(a, dir, dw, st);
+#endif
+#ifdef ODPD_HAVE_JANET
+    case ODPD_CELL_PGJANET: case ODPD_CELL_DVRJANET: return janet_run(a, dir, dw, st);
+#endif
+#ifdef ODPD_HAVE_GMP
+    case ODPD_CELL_GMP: return gmp_run(a, dir, dw, st);
+#endif
+    }
     return -3;
 }
-int other_bwd(const OdpdDims *d, const float *, const float *, const void *, const float *, const float *, const float *, double,
-              const float *, float *, float *, cudaStream_t) {
-    set_error("cell %d: backward not implemented yet", d->cell);
-    return -3;
+
+int other_fwd(const OdpdDims *d, const float *x, const float *target, const float *params, float *out, double *loss, double loss_scale,
+              void *saved, int64_t *stats, cudaStream_t st) {
+    GruArgs a{};
+    a.B = d->B; a.T = d->T; a.H = d->H; a.K = d->K; a.cell = d->cell; a.thx = d->thx; a.thh = d->thh; a.stats = stats;
+    a.x = x; a.target = target; a.params = params; a.out = out; a.loss = loss; a.loss_scale = (float)loss_scale;
+    a.saved = (float *)saved; a.save = (d->flags & ODPD_F_SAVE) != 0;
+    return run(d, a, 0, false, st);
+}
+
+int other_bwd(const OdpdDims *d, const float *x, const float *params, const void *saved, const float *gout, const float *out,
+              const float *target, double gscale, const float *gscale_dev, float *gx, float *partials, cudaStream_t st) {
+    GruArgs a{};
+    a.B = d->B; a.T = d->T; a.H = d->H; a.K = d->K; a.cell = d->cell; a.thx = d->thx; a.thh = d->thh;
+    a.x = x; a.params = params; a.saved = (float *)saved; a.gout = gout; a.out_in = out; a.target = target;
+    a.gscale = (float)gscale; a.gscale_dev = gscale_dev; a.gx = gx; a.partials = partials;
+    a.need_dx = (d->flags & ODPD_F_NEED_DX) != 0;
+    return run(d, a, 1, (d->flags & ODPD_F_NEED_DW) != 0, st);
 }
 
 }  // namespace odpd
