@@ -24,6 +24,8 @@ int64_t gru_family_saved_floats(int cell, int B, int T, int H);
 int gru_family_run(int cell, const GruArgs &a, int dir, bool dw, cudaStream_t st);
 
 #define ODPD_HAVE_DELTA 1
+#define ODPD_HAVE_JANET 1
+#define ODPD_HAVE_GMP 1
 // lstm.cu
 int64_t lstm_saved_floats(int B, int T, int H);
 int lstm_run(const GruArgs &a, int dir, bool dw, cudaStream_t st);

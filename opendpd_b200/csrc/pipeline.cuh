@@ -62,15 +62,17 @@ __device__ __forceinline__ void bcast_dot(const float *line, const float (&w)[HT
 //   rows  : chunk activation rows in shared memory, h_t at rows[tl*ROW + hoff + k]
 //   spo   : scratch [2][CH][33]
 //   skip  : optional per-step additive term (float2 per step, shared memory) or nullptr
-__device__ __forceinline__ void linear_head_chunk(const float *rows, int ROW, int hoff, int HP, int H, int nt, int lane, float wo0, float wo1,
-                                                  float bo0, float bo1, float *spo, const float2 *skip, float2 *out, const float2 *tgt,
-                                                  float &lsum) {
+//   hoff1 : offset of the vector feeding the second output (== hoff for every cell but DVRJANET: y_I from h_I, y_Q from h_Q)
+__device__ __forceinline__ void linear_head_chunk2(const float *rows, int ROW, int hoff, int hoff1, int HP, int H, int nt, int lane, float wo0,
+                                                   float wo1, float bo0, float bo1, float *spo, const float2 *skip, float2 *out,
+                                                   const float2 *tgt, float &lsum) {
     float *spo0 = spo, *spo1 = spo + CH * 33;
 #pragma unroll 4
     for (int tl = 0; tl < nt; ++tl) {
-        const float h = lane < HP ? rows[tl * ROW + hoff + lane] : 0.f;
-        spo0[tl * 33 + lane] = wo0 * h;
-        spo1[tl * 33 + lane] = wo1 * h;
+        const float h0 = lane < HP ? rows[tl * ROW + hoff + lane] : 0.f;
+        const float h1 = lane < HP ? rows[tl * ROW + hoff1 + lane] : 0.f;
+        spo0[tl * 33 + lane] = wo0 * h0;
+        spo1[tl * 33 + lane] = wo1 * h1;
     }
     __syncwarp();
     if (lane < nt) {
@@ -85,6 +87,12 @@ __device__ __forceinline__ void linear_head_chunk(const float *rows, int ROW, in
         }
     }
     __syncwarp();
+}
+
+__device__ __forceinline__ void linear_head_chunk(const float *rows, int ROW, int hoff, int HP, int H, int nt, int lane, float wo0, float wo1,
+                                                  float bo0, float bo1, float *spo, const float2 *skip, float2 *out, const float2 *tgt,
+                                                  float &lsum) {
+    linear_head_chunk2(rows, ROW, hoff, hoff, HP, H, nt, lane, wo0, wo1, bo0, bo1, spo, skip, out, tgt, lsum);
 }
 
 // dLoss/dout for one chunk, one timestep per lane: explicit gout tensor or fused MSE gradient gs*(out-target)

@@ -13,6 +13,7 @@ from torch import nn
 from . import _ffi
 from .functional import backbone_forward_raw, backbone_backward_raw, _ptr, _stream
 from .models import CoreModel, CascadedModel
+from .dp import allreduce_flat_
 
 
 def net_train(log, net, dataloader, optimizer, criterion, grad_clip_val, device):
@@ -84,12 +85,13 @@ class NativeTrainStep:
         """ReduceLROnPlateau hook (project.py:288-297) — host-side scalar write, no kernel change."""
         self.lr_dev.fill_(float(lr))
 
-    def step(self, features, targets):
+    def step(self, features, targets, global_count=None):
+        """global_count: number of scalars of the GLOBAL batch (2*B_global*T); defaults to 2*B*T*world (equal shards)."""
         L = _ffi.lib()
         tb = self.train_bb
         flat, _ = tb._flat_sync()
         B, T = features.shape[0], features.shape[1]
-        count = float(2 * B * T * self.world)          # nn.MSELoss 'mean' over the GLOBAL batch
+        count = float(global_count) if global_count else float(2 * B * T * self.world)   # nn.MSELoss 'mean', GLOBAL batch
         if self.dpd is None:
             spec = tb._spec()
             out, loss, saved = backbone_forward_raw(spec, features, flat, targets, 1.0 / count, True, tb._stats_tensor(self.device),
@@ -107,7 +109,7 @@ class NativeTrainStep:
             backbone_backward_raw(sd, features, flat, saved_d, False, True, gout=gmid, gflat=self.gflat, bufs=self._bufs[1])
         if self.pg is not None and self.world > 1:
             self.gbuf[-4] = loss.to(torch.float32)[0]
-            torch.distributed.all_reduce(self.gbuf, group=self.pg)
+            allreduce_flat_(self.gbuf, self.pg)
             loss = self.gbuf[-4:-3].to(torch.float64)
         _ffi.check(L.odpd_clip_adamw(_ptr(flat), _ptr(self.gflat), _ptr(self.exp_avg), _ptr(self.exp_avg_sq),
                                      ctypes.c_int64(self.n), _ptr(self.lr_dev), self.betas[0], self.betas[1], self.eps, self.wd,

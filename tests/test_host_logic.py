@@ -1,0 +1,72 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol include/odpd.h declares (no compute calls),
+parameter counts / flat layout / state_dict names agree with the reference (via the golden fixtures), loud failure without CUDA."""
+import ctypes
+import os
+import re
+import numpy as np
+import pytest
+import torch
+
+from tests.util import ROOT, golden_cases, load_golden
+from opendpd_b200 import _ffi, models
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "odpd.h")).read()
+    declared = set(re.findall(r"\b(odpd_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(_ffi.SYMBOLS), (declared ^ set(_ffi.SYMBOLS))
+    L = _ffi.lib()
+    for name in declared:
+        assert hasattr(L, name)
+    assert L.odpd_version() >= 100
+
+
+def test_error_reporting_without_gpu_work():
+    L = _ffi.lib()
+    d = _ffi.OdpdDims(99, 1, 1, 8, 0, 0, 0.0, 0.0)
+    assert L.odpd_saved_bytes(ctypes.byref(d)) < 0
+    assert b"unknown cell" in L.odpd_last_error()
+    d = _ffi.OdpdDims(_ffi.CELLS["gru"], 1, 1, 64, 0, 0, 0.0, 0.0)
+    assert L.odpd_saved_bytes(ctypes.byref(d)) < 0 and b"hidden_size" in L.odpd_last_error()
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_param_count_and_flat_layout_match_reference(name):
+    g = load_golden(name)
+    net = models.CoreModel(2, max(g["H"], 1), 1, g["kind"], num_dvr_units=g["K"], thx=g["thx"], thh=g["thh"])
+    names = [n for n, _ in net.backbone.named_parameters()]
+    assert names == [n for n, _ in g["param_index"]]
+    assert [list(p.shape) for _, p in net.backbone.named_parameters()] == [s for _, s in g["param_index"]]
+    n = sum(p.numel() for p in net.backbone.parameters())
+    assert n == g["params"].size == _ffi.n_params(g["kind"], g["H"], g["K"])
+    flat, layout = net.backbone._flat_sync()
+    off = 0
+    for (o, cnt, shape), (_, p) in zip(layout, net.backbone.named_parameters()):
+        assert o == off and p.data_ptr() == flat.data_ptr() + 4 * off
+        off += cnt
+    with torch.no_grad():      # in-place optimiser-style updates go through to the flat buffer
+        for p in net.backbone.parameters():
+            p.add_(1.0)
+    assert torch.equal(flat[:off], torch.cat([p.detach().reshape(-1) for p in net.backbone.parameters()]))
+
+
+def test_reference_checkpoint_names():
+    net = models.CoreModel(2, 15, 1, "deltagru_tcnskip", thx=0.01, thh=0.05)
+    assert list(net.state_dict()) == ["backbone.rnn.x2h.weight", "backbone.rnn.h2h.weight", "backbone.fc_out.weight",
+                                      "backbone.tcn.0.weight", "backbone.tcn.2.weight"]
+    assert sum(p.numel() for p in net.parameters()) == 999          # README's "996" model, SURVEY §4
+    assert sum(p.numel() for p in models.CoreModel(2, 13, 1, "dgru").parameters()) == 1041
+    assert net.backbone.thx == 0.01 and net.backbone.thh == 0.05 and net.backbone.get_temporal_sparsity() == {}
+
+
+def test_cpu_tensor_is_rejected_loudly():
+    net = models.CoreModel(2, 8, 1, "gru")
+    with pytest.raises(_ffi.OdpdError):
+        net(torch.zeros(1, 4, 2))
+
+
+def test_unsupported_configs_raise():
+    with pytest.raises(NotImplementedError):
+        models.CoreModel(2, 8, 2, "gru")            # num_layers=2
+    with pytest.raises(ValueError):
+        models.CoreModel(2, 8, 1, "rvtdcnn")         # out of the hot-path scope
