@@ -101,14 +101,16 @@ __device__ __forceinline__ void features_bwd(float i, float q, const float *gf, 
         return;
     }
     const float a = sqrtf(a2);
-    float ga = gf[2] + 3.0f * a * a * gf[3];
-    if constexpr (FM == FM_DGRU6) {
-        ga -= (q * gf[4] + i * gf[5]) / a2;
-        gi += gf[5] / a;
-        gq += gf[4] / a;
-    }
+    const float ga = gf[2] + 3.0f * a2 * gf[3];
     gi += ga * i / a;
     gq += ga * q / a;
+    if constexpr (FM == FM_DGRU6) {
+        // sin = q/a, cos = i/a.  Autograd's form (g_cos/a - (q g_sin + i g_cos) i / a^3) cancels catastrophically for small a;
+        // the algebraically identical  d/di = q*w, d/dq = -i*w  with  w = (g_cos q - g_sin i)/a^3  does not.
+        const float w = (gf[5] * q - gf[4] * i) / (a2 * a);
+        gi = fmaf(q, w, gi);
+        gq = fmaf(-i, w, gq);
+    }
 }
 
 // ---------------------------------------------------------------- parameter staging: global -> shared via the TMA bulk-copy engine

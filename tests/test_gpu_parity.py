@@ -161,7 +161,7 @@ def test_cpu_tensor_fails_loudly():
         net(torch.zeros(1, 4, 2))
 
 
-@pytest.mark.parametrize("kind,H,B,T,thx,thh", [("deltagru", 15, 8, 200, 0.01, 0.05), ("deltagru_tcnskip", 15, 8, 200, 0.01, 0.05),
+@pytest.mark.parametrize("kind,H,B,T,thx,thh", [("deltagru", 15, 64, 200, 0.01, 0.05), ("deltagru_tcnskip", 15, 64, 200, 0.01, 0.05),
                                                 ("deltagru_tcnskip", 15, 256, 200, 0.01, 0.05), ("deltagru_tcnskip", 15, 64, 2048, 0.01, 0.05),
                                                 ("deltagru", 10, 16, 96, 0.0, 0.0), ("deltagru_tcnskip", 26, 4, 64, 0.02, 0.02)])
 def test_delta_oracle_parity_with_mask_accounting(kind, H, B, T, thx, thh):
