@@ -146,15 +146,22 @@ __global__ void __launch_bounds__(96, 1) gru_fwd_kernel(GruArgs a) {
                 float *ac = sact + (c & 1) * SM::ACT;
                 const float *hrow = (c == 0) ? zero : sact + ((c - 1) & 1) * SM::ACT + (CH - 1) * ROW + 4 * HP;
                 float xr = xp[0], xz = xp[HP], xn = xp[2 * HP];
+                float pr_ = 0.f, pz_ = 0.f, pn_ = 0.f, phg_ = 0.f;   // gate values of the previous step, stored one iteration late
                 for (int tl = 0; tl < nt; ++tl) {
-                    // prefetch next step's input projection (independent of h)
-                    const int tn = (tl + 1 < nt) ? tl + 1 : tl;
-                    const float nxr = xp[tn * 3 * HP], nxz = xp[tn * 3 * HP + HP], nxn = xp[tn * 3 * HP + 2 * HP];
-                    float ar0 = xr, ar1 = 0.f, az0 = xz, az1 = 0.f, an0 = b_hn, an1 = 0.f;
+                    // broadcast h_{t-1}: issue the loads first, everything below that does not need them fills the latency
                     const float4 *hb4 = reinterpret_cast<const float4 *>(hrow);
                     float4 hv[HP / 4];
 #pragma unroll
                     for (int k4 = 0; k4 < HP / 4; ++k4) hv[k4] = hb4[k4];
+                    // prefetch next step's input projection (independent of h)
+                    const int tn = (tl + 1 < nt) ? tl + 1 : tl;
+                    const float nxr = xp[tn * 3 * HP], nxz = xp[tn * 3 * HP + HP], nxn = xp[tn * 3 * HP + 2 * HP];
+                    // deferred activation stores of step tl-1 (off the dependent chain)
+                    if (tl > 0 && lane < HP) {
+                        float *prow = ac + (tl - 1) * ROW;
+                        prow[lane] = pr_; prow[HP + lane] = pz_; prow[2 * HP + lane] = pn_; prow[3 * HP + lane] = phg_;
+                    }
+                    float ar0 = xr, ar1 = 0.f, az0 = xz, az1 = 0.f, an0 = b_hn, an1 = 0.f;
 #pragma unroll
                     for (int k4 = 0; k4 < HP / 4; ++k4) {
                         const float hk[4] = {hv[k4].x, hv[k4].y, hv[k4].z, hv[k4].w};
@@ -162,25 +169,28 @@ __global__ void __launch_bounds__(96, 1) gru_fwd_kernel(GruArgs a) {
                         for (int e = 0; e < 4; ++e) {
                             const int k = k4 * 4 + e;
                             if (k < HT) {
-                                if (k & 1) { ar1 = fmaf(whr[k], hk[e], ar1); az1 = fmaf(whz[k], hk[e], az1); an1 = fmaf(whn[k], hk[e], an1); }
-                                else       { ar0 = fmaf(whr[k], hk[e], ar0); az0 = fmaf(whz[k], hk[e], az0); an0 = fmaf(whn[k], hk[e], an0); }
+                                if (k & 1) { ar1 = fmaf(whr[k], hk[e], ar1); an1 = fmaf(whn[k], hk[e], an1); az1 = fmaf(whz[k], hk[e], az1); }
+                                else       { ar0 = fmaf(whr[k], hk[e], ar0); an0 = fmaf(whn[k], hk[e], an0); az0 = fmaf(whz[k], hk[e], az0); }
                             }
                         }
                     }
                     const float r = sigmoidf_(ar0 + ar1);
-                    const float z = sigmoidf_(az0 + az1);
                     const float hgn = an0 + an1;
+                    const float z = sigmoidf_(az0 + az1);
                     const float n = tanhf_(fmaf(r, hgn, xn));
                     h = fmaf(h - n, z, n);
                     float *row = ac + tl * ROW;
-                    if (lane < HP) {
-                        row[4 * HP + lane] = h;
-                        row[lane] = r; row[HP + lane] = z; row[2 * HP + lane] = n; row[3 * HP + lane] = hgn;
-                    }
+                    if (lane < HP) row[4 * HP + lane] = h;
                     hrow = row + 4 * HP;
+                    pr_ = r; pz_ = z; pn_ = n; phg_ = hgn;
                     xr = nxr; xz = nxz; xn = nxn;
                     __syncwarp();
                 }
+                if (lane < HP) {
+                    float *prow = ac + (nt - 1) * ROW;
+                    prow[lane] = pr_; prow[HP + lane] = pz_; prow[2 * HP + lane] = pn_; prow[3 * HP + lane] = phg_;
+                }
+                __syncwarp();
                 fence_async_smem();   // rows of this chunk are bulk-stored by the post warp next stage
             }
             __syncthreads();
@@ -268,7 +278,7 @@ __global__ void __launch_bounds__(96, 1) gru_fwd_kernel(GruArgs a) {
 // SPLIT: the F "feature lanes" (which turn the gate gradients into dL/dfeatures) do not fit next to the H unit lanes in
 // one warp (H+F>32); lanes 0..F-1 then serve the features.
 template <int HT, int FM, int HEAD, bool DW>
-__global__ void __launch_bounds__(96, 1) gru_bwd_kernel(GruArgs a) {
+__global__ void __launch_bounds__(128, 1) gru_bwd_kernel(GruArgs a) {
     constexpr int F = FeatN<FM>::value, HP = Pad4<HT>::value, ROW = Row<HT, HEAD>::value;
     constexpr bool SPLIT = (HT + F > 32);
     using SM = BwdSmem<HT, HEAD>;
@@ -440,14 +450,17 @@ __global__ void __launch_bounds__(96, 1) gru_bwd_kernel(GruArgs a) {
             __syncthreads();
         }
     } else {
-        // =============================== post: weight gradients (registers) and dL/dx
+        // =============================== post (two warps, the FFMA issue rate of one warp is the limit):
+        //   warp 2 "post-A": dL/dW_hh (3H accumulators per lane)
+        //   warp 3 "post-B": dL/dW_ih, biases, head gradients, dL/dfeatures -> dL/dx, time-parallel tail
+        const bool roleA = (warp == 2);
         const int fl = SPLIT ? lane : lane - H;   // feature column served by this lane (if 0<=fl<F)
         const bool isf = fl >= 0 && fl < F;
-        float wicol[3 * HT];                      // column fl of W_ih (feature lanes)
+        float wicol[3 * HT];                      // column fl of W_ih (feature lanes, post-B)
 #pragma unroll
         for (int g = 0; g < 3; ++g)
 #pragma unroll
-            for (int k = 0; k < HT; ++k) wicol[g * HT + k] = (isf && k < H) ? sp[L.oWih + (g * H + k) * F + fl] : 0.f;
+            for (int k = 0; k < HT; ++k) wicol[g * HT + k] = (!roleA && isf && k < H) ? sp[L.oWih + (g * H + k) * F + fl] : 0.f;
         const float wof0 = (HEAD && isf) ? sp[L.oWo + H + fl] : 0.f, wof1 = (HEAD && isf) ? sp[L.oWo + L.O + H + fl] : 0.f;
         float gwhh[DW ? 3 * HT : 1], gwih[DW ? 3 * F : 1], gwh[(DW && HEAD) ? HT : 1], gwof[(DW && HEAD) ? 2 * F : 1];
         float gb_r = 0.f, gb_z = 0.f, gb_n = 0.f, gb_hn = 0.f, gwo0 = 0.f, gwo1 = 0.f, gbh = 0.f, gbo0 = 0.f, gbo1 = 0.f;
@@ -472,123 +485,149 @@ __global__ void __launch_bounds__(96, 1) gru_bwd_kernel(GruArgs a) {
                 const float *pr = spre + (sc % 3) * SM::PRE;
                 const float *dp = sdp + (sc % 3) * SM::DH;
                 const float *Gb = sG + (sc & 1) * SM::G;
-                for (int tl = 0; tl < nt; ++tl) {
-                    const float *G = Gb + tl * 4 * HP;
-                    const float4 *G4 = reinterpret_cast<const float4 *>(G);
-                    const float *row = ac + (tl + 1) * ROW;
-                    const float hp = row[4 * HP - ROW + lp], ht = row[4 * HP + lp];
-                    const float2 go = *reinterpret_cast<const float2 *>(pr + tl * 12 + 8);
-                    float feat[8];
-                    {
-                        const float4 *fp = reinterpret_cast<const float4 *>(pr + tl * 12);
-                        const float4 f0 = fp[0];
-                        feat[0] = f0.x; feat[1] = f0.y; feat[2] = f0.z; feat[3] = f0.w;
-                        if (F > 4) { const float4 f1 = fp[1]; feat[4] = f1.x; feat[5] = f1.y; feat[6] = f1.z; feat[7] = f1.w; }
-                    }
+                if (roleA) {
                     if constexpr (DW) {
-                        const float ar = G[lp], az = G[HP + lp], anr = G[2 * HP + lp], an = G[3 * HP + lp];
-#pragma unroll
-                        for (int q = 0; q < F; ++q) {
-                            gwih[q] = fmaf(ar, feat[q], gwih[q]);
-                            gwih[F + q] = fmaf(az, feat[q], gwih[F + q]);
-                            gwih[2 * F + q] = fmaf(an, feat[q], gwih[2 * F + q]);
-                        }
-                        gb_r += ar; gb_z += az; gb_n += an; gb_hn += anr;
-                        if constexpr (HEAD) {
-                            const float g = row[5 * HP + lp];
-                            gwo0 = fmaf(go.x, g, gwo0); gwo1 = fmaf(go.y, g, gwo1);
-                            gbh += dp[tl * HP + lp];
-                            const float4 *dp4 = reinterpret_cast<const float4 *>(dp + tl * HP);
+#pragma unroll 2
+                        for (int tl = 0; tl < nt; ++tl) {
+                            const float4 *G4 = reinterpret_cast<const float4 *>(Gb + tl * 4 * HP);
+                            const float hp = ac[tl * ROW + 4 * HP + lp];      // row tl = step t-1
 #pragma unroll
                             for (int k4 = 0; k4 < HP / 4; ++k4) {
-                                const float4 dv = dp4[k4];
-                                const float dk[4] = {dv.x, dv.y, dv.z, dv.w};
+                                const float4 v_r = G4[k4], v_z = G4[HP / 4 + k4], v_nh = G4[2 * (HP / 4) + k4];
+                                const float kr[4] = {v_r.x, v_r.y, v_r.z, v_r.w}, kz[4] = {v_z.x, v_z.y, v_z.z, v_z.w};
+                                const float knh[4] = {v_nh.x, v_nh.y, v_nh.z, v_nh.w};
 #pragma unroll
-                                for (int e = 0; e < 4; ++e) { const int k = k4 * 4 + e; if (k < HT) gwh[k] = fmaf(dk[e], ht, gwh[k]); }
-                            }
-                        } else {
-                            gwo0 = fmaf(go.x, ht, gwo0); gwo1 = fmaf(go.y, ht, gwo1);
-                        }
-                    }
-                    float fa0 = 0.f, fa1 = 0.f;
-#pragma unroll
-                    for (int k4 = 0; k4 < HP / 4; ++k4) {
-                        const float4 v_r = G4[k4], v_z = G4[HP / 4 + k4], v_nh = G4[2 * (HP / 4) + k4], v_nx = G4[3 * (HP / 4) + k4];
-                        const float kr[4] = {v_r.x, v_r.y, v_r.z, v_r.w}, kz[4] = {v_z.x, v_z.y, v_z.z, v_z.w};
-                        const float knh[4] = {v_nh.x, v_nh.y, v_nh.z, v_nh.w}, knx[4] = {v_nx.x, v_nx.y, v_nx.z, v_nx.w};
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int k = k4 * 4 + e;
-                            if (k < HT) {
-                                if (a.need_dx) {
-                                    fa0 = fmaf(wicol[k], kr[e], fa0);
-                                    fa1 = fmaf(wicol[HT + k], kz[e], fa1);
-                                    fa0 = fmaf(wicol[2 * HT + k], knx[e], fa0);
-                                }
-                                if constexpr (DW) {
-                                    gwhh[k] = fmaf(kr[e], hp, gwhh[k]);
-                                    gwhh[HT + k] = fmaf(kz[e], hp, gwhh[HT + k]);
-                                    gwhh[2 * HT + k] = fmaf(knh[e], hp, gwhh[2 * HT + k]);
+                                for (int e = 0; e < 4; ++e) {
+                                    const int k = k4 * 4 + e;
+                                    if (k < HT) {
+                                        gwhh[k] = fmaf(kr[e], hp, gwhh[k]);
+                                        gwhh[HT + k] = fmaf(kz[e], hp, gwhh[HT + k]);
+                                        gwhh[2 * HT + k] = fmaf(knh[e], hp, gwhh[2 * HT + k]);
+                                    }
                                 }
                             }
                         }
                     }
-                    if (a.need_dx && isf) sdf[tl * 8 + fl] = (fa0 + fa1) + (HEAD ? fmaf(wof0, go.x, wof1 * go.y) : 0.f);
-                }
-                __syncwarp();
-                // time-parallel tail of the chunk: one timestep per lane
-                if (lane < nt) {
-                    const float *p = pr + lane * 12;
-                    if constexpr (DW) {
-                        gbo0 += p[8]; gbo1 += p[9];
-                        if constexpr (HEAD) {
+                } else {
+                    for (int tl = 0; tl < nt; ++tl) {
+                        const float *G = Gb + tl * 4 * HP;
+                        const float4 *G4 = reinterpret_cast<const float4 *>(G);
+                        const float *row = ac + (tl + 1) * ROW;
+                        const float ht = row[4 * HP + lp];
+                        const float2 go = *reinterpret_cast<const float2 *>(pr + tl * 12 + 8);
+                        float feat[8];
+                        {
+                            const float4 *fp = reinterpret_cast<const float4 *>(pr + tl * 12);
+                            const float4 f0 = fp[0];
+                            feat[0] = f0.x; feat[1] = f0.y; feat[2] = f0.z; feat[3] = f0.w;
+                            if (F > 4) { const float4 f1 = fp[1]; feat[4] = f1.x; feat[5] = f1.y; feat[6] = f1.z; feat[7] = f1.w; }
+                        }
+                        if constexpr (DW) {
+                            const float ar = G[lp], az = G[HP + lp], anr = G[2 * HP + lp], an = G[3 * HP + lp];
 #pragma unroll
-                            for (int q = 0; q < F; ++q) { gwof[q] = fmaf(p[8], p[q], gwof[q]); gwof[F + q] = fmaf(p[9], p[q], gwof[F + q]); }
+                            for (int q = 0; q < F; ++q) {
+                                gwih[q] = fmaf(ar, feat[q], gwih[q]);
+                                gwih[F + q] = fmaf(az, feat[q], gwih[F + q]);
+                                gwih[2 * F + q] = fmaf(an, feat[q], gwih[2 * F + q]);
+                            }
+                            gb_r += ar; gb_z += az; gb_n += an; gb_hn += anr;
+                            if constexpr (HEAD) {
+                                const float g = row[5 * HP + lp];
+                                gwo0 = fmaf(go.x, g, gwo0); gwo1 = fmaf(go.y, g, gwo1);
+                                gbh += dp[tl * HP + lp];
+                                const float4 *dp4 = reinterpret_cast<const float4 *>(dp + tl * HP);
+#pragma unroll
+                                for (int k4 = 0; k4 < HP / 4; ++k4) {
+                                    const float4 dv = dp4[k4];
+                                    const float dk[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) { const int k = k4 * 4 + e; if (k < HT) gwh[k] = fmaf(dk[e], ht, gwh[k]); }
+                                }
+                            } else {
+                                gwo0 = fmaf(go.x, ht, gwo0); gwo1 = fmaf(go.y, ht, gwo1);
+                            }
+                        }
+                        if (a.need_dx) {
+                            float fa0 = 0.f, fa1 = 0.f;
+#pragma unroll
+                            for (int k4 = 0; k4 < HP / 4; ++k4) {
+                                const float4 v_r = G4[k4], v_z = G4[HP / 4 + k4], v_nx = G4[3 * (HP / 4) + k4];
+                                const float kr[4] = {v_r.x, v_r.y, v_r.z, v_r.w}, kz[4] = {v_z.x, v_z.y, v_z.z, v_z.w};
+                                const float knx[4] = {v_nx.x, v_nx.y, v_nx.z, v_nx.w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const int k = k4 * 4 + e;
+                                    if (k < HT) {
+                                        fa0 = fmaf(wicol[k], kr[e], fa0);
+                                        fa1 = fmaf(wicol[HT + k], kz[e], fa1);
+                                        fa0 = fmaf(wicol[2 * HT + k], knx[e], fa0);
+                                    }
+                                }
+                            }
+                            if (isf) sdf[tl * 8 + fl] = (fa0 + fa1) + (HEAD ? fmaf(wof0, go.x, wof1 * go.y) : 0.f);
                         }
                     }
-                    if (gx2) {
-                        const float2 v = __ldg(x2 + t0 + lane);
-                        float gf[8];
+                    __syncwarp();
+                    // time-parallel tail of the chunk: one timestep per lane
+                    if (lane < nt) {
+                        const float *p = pr + lane * 12;
+                        if constexpr (DW) {
+                            gbo0 += p[8]; gbo1 += p[9];
+                            if constexpr (HEAD) {
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) gf[q] = (q < F) ? sdf[lane * 8 + q] : 0.f;
-                        float gi, gq;
-                        features_bwd<FM>(v.x, v.y, gf, gi, gq);
-                        gx2[t0 + lane] = make_float2(gi, gq);
+                                for (int q = 0; q < F; ++q) { gwof[q] = fmaf(p[8], p[q], gwof[q]); gwof[F + q] = fmaf(p[9], p[q], gwof[F + q]); }
+                            }
+                        }
+                        if (gx2) {
+                            const float2 v = __ldg(x2 + t0 + lane);
+                            float gf[8];
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) gf[q] = (q < F) ? sdf[lane * 8 + q] : 0.f;
+                            float gi, gq;
+                            features_bwd<FM>(v.x, v.y, gf, gi, gq);
+                            gx2[t0 + lane] = make_float2(gi, gq);
+                        }
                     }
+                    __syncwarp();
                 }
-                __syncwarp();
             }
             __syncthreads();
         }
         if constexpr (DW) {
             if (a.partials) {
                 float *prt = a.partials + (size_t)b * L.P;
-                if (act) {
+                if (roleA) {
+                    if (act) {
 #pragma unroll
-                    for (int g = 0; g < 3; ++g) {
+                        for (int g = 0; g < 3; ++g)
 #pragma unroll
-                        for (int q = 0; q < F; ++q) prt[L.oWih + (g * H + lane) * F + q] = gwih[g * F + q];
-#pragma unroll
-                        for (int k = 0; k < HT; ++k)
-                            if (k < H) prt[L.oWhh + (g * H + k) * H + lane] = gwhh[g * HT + k];
+                            for (int k = 0; k < HT; ++k)
+                                if (k < H) prt[L.oWhh + (g * H + k) * H + lane] = gwhh[g * HT + k];
                     }
-                    prt[L.obih + lane] = gb_r; prt[L.obih + H + lane] = gb_z; prt[L.obih + 2 * H + lane] = gb_n;
-                    prt[L.obhh + lane] = gb_r; prt[L.obhh + H + lane] = gb_z; prt[L.obhh + 2 * H + lane] = gb_hn;
-                    prt[L.oWo + lane] = gwo0; prt[L.oWo + L.O + lane] = gwo1;
+                } else {
+                    if (act) {
+#pragma unroll
+                        for (int g = 0; g < 3; ++g)
+#pragma unroll
+                            for (int q = 0; q < F; ++q) prt[L.oWih + (g * H + lane) * F + q] = gwih[g * F + q];
+                        prt[L.obih + lane] = gb_r; prt[L.obih + H + lane] = gb_z; prt[L.obih + 2 * H + lane] = gb_n;
+                        prt[L.obhh + lane] = gb_r; prt[L.obhh + H + lane] = gb_z; prt[L.obhh + 2 * H + lane] = gb_hn;
+                        prt[L.oWo + lane] = gwo0; prt[L.oWo + L.O + lane] = gwo1;
+                        if constexpr (HEAD) {
+#pragma unroll
+                            for (int k = 0; k < HT; ++k)
+                                if (k < H) prt[L.oWh + k * H + lane] = gwh[k];
+                            prt[L.obh + lane] = gbh;
+                        }
+                    }
+                    gbo0 = warp_sum(gbo0); gbo1 = warp_sum(gbo1);
+                    if (lane == 0) { prt[L.obo] = gbo0; prt[L.obo + 1] = gbo1; }
                     if constexpr (HEAD) {
 #pragma unroll
-                        for (int k = 0; k < HT; ++k)
-                            if (k < H) prt[L.oWh + k * H + lane] = gwh[k];
-                        prt[L.obh + lane] = gbh;
-                    }
-                }
-                gbo0 = warp_sum(gbo0); gbo1 = warp_sum(gbo1);
-                if (lane == 0) { prt[L.obo] = gbo0; prt[L.obo + 1] = gbo1; }
-                if constexpr (HEAD) {
-#pragma unroll
-                    for (int q = 0; q < 2 * F; ++q) {
-                        const float sum = warp_sum(gwof[q]);
-                        if (lane == 0) prt[L.oWo + (q / F) * L.O + H + (q % F)] = sum;
+                        for (int q = 0; q < 2 * F; ++q) {
+                            const float sum = warp_sum(gwof[q]);
+                            if (lane == 0) prt[L.oWo + (q / F) * L.O + H + (q % F)] = sum;
+                        }
                     }
                 }
             }
@@ -624,11 +663,11 @@ static int launch_bwd(const GruArgs &a, bool dw, cudaStream_t st) {
     if (dw) {
         auto k = gru_bwd_kernel<HT, FM, HEAD, true>;
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k<<<a.B, 96, smem, st>>>(a);
+        k<<<a.B, 128, smem, st>>>(a);
     } else {
         auto k = gru_bwd_kernel<HT, FM, HEAD, false>;
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k<<<a.B, 96, smem, st>>>(a);
+        k<<<a.B, 128, smem, st>>>(a);
     }
     return check_launch("gru_bwd_kernel");
 }
