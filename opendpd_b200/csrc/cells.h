@@ -35,6 +35,10 @@ int delta_run(const GruArgs &a, int dir, bool dw, cudaStream_t st);
 // janet.cu : PGJANET / DVRJANET
 int64_t janet_saved_floats(int cell, int B, int T, int H);
 int janet_run(const GruArgs &a, int dir, bool dw, cudaStream_t st);
+// qgru_qat.cu : fake-quantised GRU (QAT)
+int64_t qat_nparams(int H);
+int64_t qat_saved_floats(int B, int T, int H);
+int qat_run(const GruArgs &a, int dir, bool dw, cudaStream_t st);
 // gmp.cu
 int gmp_run(const GruArgs &a, int dir, bool dw, cudaStream_t st);
 

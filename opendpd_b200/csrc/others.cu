@@ -11,13 +11,14 @@ int64_t other_nparams(int cell, int H, int K) {
     case ODPD_CELL_PGJANET: return (int64_t)3 * (H * (H + 1) + H) + 2 * (2 * H * H + H) + 2 * H + 2;
     case ODPD_CELL_DVRJANET: return (int64_t)K + 3 * H * H + 2 * H + H + 2 * (2 * H * H + H) + 2 * (H + 1);
     case ODPD_CELL_GMP: return 495;
+    case ODPD_CELL_QGRU_QAT: case ODPD_CELL_QGRU_AMP1_QAT: return qat_nparams(H);
     }
     return -1;
 }
 
 static bool implemented(int cell) {
     switch (cell) {
-    case ODPD_CELL_LSTM: return true;
+    case ODPD_CELL_LSTM: case ODPD_CELL_QGRU_QAT: case ODPD_CELL_QGRU_AMP1_QAT: return true;
 #ifdef ODPD_HAVE_DELTA
     case ODPD_CELL_DELTAGRU: case ODPD_CELL_TRES: return true;
 #endif
@@ -35,6 +36,7 @@ int64_t other_saved_bytes(const OdpdDims *d) {
     int64_t n = -1;
     switch (d->cell) {
     case ODPD_CELL_LSTM: n = lstm_saved_floats(d->B, d->T, d->H); break;
+    case ODPD_CELL_QGRU_QAT: case ODPD_CELL_QGRU_AMP1_QAT: n = qat_saved_floats(d->B, d->T, d->H); break;
 #ifdef ODPD_HAVE_DELTA
     case ODPD_CELL_DELTAGRU: case ODPD_CELL_TRES: n = delta_saved_floats(d->cell, d->B, d->T, d->H); break;
 #endif
@@ -53,6 +55,7 @@ static int run(const OdpdDims *d, const GruArgs &a, int dir, bool dw, cudaStream
     if (!implemented(d->cell)) { set_error("cell %d: not implemented in this build", d->cell); return -3; }
     switch (d->cell) {
     case ODPD_CELL_LSTM: return lstm_run(a, dir, dw, st);
+    case ODPD_CELL_QGRU_QAT: case ODPD_CELL_QGRU_AMP1_QAT: return qat_run(a, dir, dw, st);
 #ifdef ODPD_HAVE_DELTA
     case ODPD_CELL_DELTAGRU: case ODPD_CELL_TRES: return delta_run(a, dir, dw, st);
 #endif

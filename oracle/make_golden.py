@@ -48,6 +48,17 @@ def frames(X, Y, B, T, seed):
 
 def build(kind, H, seed, thx=0.0, thh=0.0, K=3):
     torch.manual_seed(seed)
+    if kind.endswith("_qat"):
+        # config 5: the reference's own QAT environment (quant/__init__.py:20-37 -> quant_envs.py Base_GRUQuantEnv) around the float QGRU
+        from quant import get_quant_model
+        float_net = models.CoreModel(input_size=2, hidden_size=H, num_layers=1, backbone_type=kind[:-4])
+
+        class _Proj:
+            quant, n_bits_w, n_bits_a, pretrained_model, quant_dir_label = True, K & 255, (K >> 8) & 255, "", ""
+        qnet = get_quant_model(_Proj(), float_net)
+        assert type(qnet.backbone.rnn).__name__ == "GRU" and qnet is not float_net, "quant env fell back to the float model"
+        qnet.train()
+        return qnet
     if kind == "pgjanet":
         bb = PGJANET(hidden_size=H, output_size=2, bias=True)
         bb.reset_parameters()
@@ -129,7 +140,8 @@ def _run(net, x, y, dtype, tap_cls=None):
     res["out"] = out.detach().numpy()
     res["loss"] = np.array(loss.item(), dtype=np.float64)
     res["gx"] = xt.grad.numpy()
-    res["gparams"] = np.concatenate([p.grad.numpy().reshape(-1) for _, p in net.backbone.named_parameters()])
+    res["gparams"] = np.concatenate([(p.grad if p.grad is not None else torch.zeros_like(p)).numpy().reshape(-1)
+                                     for _, p in net.backbone.named_parameters()])   # unused quantiser scales: grad None == 0
     return res
 
 
@@ -158,6 +170,10 @@ CASES = [
     ("gmp_b2_t7",            "gmp", 0, 2, 7, 21, 0, 0),
     ("qgru_h10_b4_t50",      "qgru", 10, 4, 50, 22, 0, 0),
     ("qgru_amp1_h10_b4_t50", "qgru_amp1", 10, 4, 50, 23, 0, 0),
+    # QAT (config 5): K packs bits_w | bits_a<<8
+    ("qgruqat_w8a8_h10_b4_t50", "qgru_qat", 10, 4, 50, 24, 0, 0, 8 | (8 << 8)),
+    ("qgruqat_w16a16_h10_b3_t33", "qgru_qat", 10, 3, 33, 25, 0, 0, 16 | (16 << 8)),
+    ("qgruamp1qat_w8a8_h8_b2_t20", "qgru_amp1_qat", 8, 2, 20, 26, 0, 0, 8 | (8 << 8)),
 ]
 
 
@@ -165,9 +181,14 @@ def main():
     X, Y = load_apa()
     os.makedirs(OUT, exist_ok=True)
     manifest = {}
-    for name, kind, H, B, T, seed, thx, thh in CASES:
+    only = set(sys.argv[1:])
+    for case in CASES:
+        name, kind, H, B, T, seed, thx, thh = case[:8]
+        K = case[8] if len(case) > 8 else 3
+        if only and name not in only:
+            continue
         x, y = frames(X, Y, B, T, seed)
-        net = build(kind, max(H, 1), seed, thx, thh)
+        net = build(kind, max(H, 1), seed, thx, thh, K)
         tap_cls = None
         if kind == "deltagru":
             from backbones.deltagru import DeltaGRULayer as tap_cls
@@ -179,7 +200,7 @@ def main():
         net.float()
         rec = dict(x=x, y=y, params=params.astype(np.float32), kind=np.array(kind), H=np.array(H),
                    thx=np.array(thx, dtype=np.float64), thh=np.array(thh, dtype=np.float64),
-                   K=np.array(3), param_index=np.array(json.dumps(param_index(net))))
+                   K=np.array(K), param_index=np.array(json.dumps(param_index(net))))
         for k, v in r32.items():
             rec[k] = v
         for k, v in r64.items():
@@ -189,7 +210,10 @@ def main():
         manifest[name] = dict(kind=kind, H=H, B=B, T=T, n_params=int(params.size), loss=float(r32["loss"]),
                               bytes=os.path.getsize(path))
         print(name, manifest[name], flush=True)
-    with open(os.path.join(OUT, "MANIFEST.json"), "w") as f:
+    mpath = os.path.join(OUT, "MANIFEST.json")
+    if only and os.path.exists(mpath):
+        old = json.load(open(mpath)); old.update(manifest); manifest = old
+    with open(mpath, "w") as f:
         json.dump(manifest, f, indent=1)
 
 

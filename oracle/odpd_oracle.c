@@ -54,7 +54,7 @@
 #endif
 
 enum { CELL_GRU = 0, CELL_LSTM = 1, CELL_DGRU = 2, CELL_DELTAGRU = 3, CELL_TRES = 4, CELL_PGJANET = 5,
-       CELL_DVRJANET = 6, CELL_GMP = 7, CELL_QGRU = 8, CELL_QGRU_AMP1 = 9 };
+       CELL_DVRJANET = 6, CELL_GMP = 7, CELL_QGRU = 8, CELL_QGRU_AMP1 = 9, CELL_QGRU_QAT = 10, CELL_QGRU_AMP1_QAT = 11 };
 
 typedef struct {
     int cell, B, T, H, K;
@@ -79,12 +79,15 @@ static inline REAL dotv(const REAL *w, const REAL *v, int n) {
 static int n_features(int cell) {
     switch (cell) {
     case CELL_GRU: case CELL_LSTM: return 2;
-    case CELL_QGRU: case CELL_QGRU_AMP1: return 4;
+    case CELL_QGRU: case CELL_QGRU_AMP1: case CELL_QGRU_QAT: case CELL_QGRU_AMP1_QAT: return 4;
     default: return 6;
     }
 }
 
+static int base_cell(int cell) { return cell == CELL_QGRU_QAT ? CELL_QGRU : (cell == CELL_QGRU_AMP1_QAT ? CELL_QGRU_AMP1 : cell); }
+
 static void features_fwd(int cell, const REAL *x, int T, int t, REAL *f) {
+    cell = base_cell(cell);
     volatile REAL i = x[2 * t], q = x[2 * t + 1];
     volatile REAL ii = i * i, qq = q * q;
     volatile REAL a2 = ii + qq;
@@ -103,6 +106,7 @@ static void features_fwd(int cell, const REAL *x, int T, int t, REAL *f) {
 
 /* accumulate d(loss)/dx from d(loss)/dfeatures; gx is the whole (T,2) row because TRES rolls. */
 static void features_bwd(int cell, const REAL *x, int T, int t, const REAL *gf, REAL *gx) {
+    cell = base_cell(cell);
     REAL i = x[2 * t], q = x[2 * t + 1];
     REAL gi = gf[0], gq = gf[1];
     if (cell == CELL_GRU || cell == CELL_LSTM) { gx[2 * t] += gi; gx[2 * t + 1] += gq; return; }
@@ -673,6 +677,117 @@ static void seq_gmp(const Ctx *c, const REAL *x, const REAL *gout, REAL *out, RE
     }
 }
 
+
+/* ================================================================ fake-quantised GRU (QAT), config 5
+ * quant/modules/gru.py GRUCell.forward :32-61 with the module swaps of quant/quant_envs.py:132-305:
+ *   nn.Linear -> INT_Linear (quant_layers.py:70-82: weight and input each fake-quantised, float bias, 16-bit out_quantizer only
+ *   for fc_out and only in eval), Sigmoid/Tanh/Add/Mul -> Quant_* (quant_ops.py:14-66).
+ * Fake quantiser (quantizers.py:56-81): s = 2^round(log2|scale|); q(v) = s * rne(clamp(v/s, -2^(b-1), 2^(b-1)-1)); backward = STE
+ * through round, zero outside the clamp (inclusive bounds, torch.clamp).  The 13 scale parameters get zero gradient.
+ * params (named_parameters order): x2h.W(3H,4) x2h.b(3H) s0 s1 s2 | h2h.W(3H,H) h2h.b(3H) s3 s4 s5 | s6(sigmoid) s7(tanh) s8(add) s9(mul)
+ *                                  | fc_out.W(2,H) fc_out.b(2) s10 s11 s12.   K packs the bit widths: bits_w | bits_a<<8 | eval<<16. */
+typedef struct { REAL s, qn, qp; } Quant;
+static Quant mkq(REAL scale, int bits) {
+    Quant q; q.s = (REAL)pow(2.0, nearbyint(log2(fabs((double)scale)))); q.qn = -(REAL)pow(2.0, bits - 1); q.qp = (REAL)pow(2.0, bits - 1) - 1; return q;
+}
+static inline REAL qf(const Quant *q, REAL v, int *inrange) {
+    REAL u = v / q->s;
+    if (inrange) *inrange = (u >= q->qn && u <= q->qp);
+    u = u < q->qn ? q->qn : (u > q->qp ? q->qp : u);
+    return (REAL)nearbyint((double)u) * q->s;
+}
+static void seq_qgru_qat(const Ctx *c, const REAL *x, const REAL *gout, REAL *out, REAL *gx, REAL *gp, int phase) {
+    const int H = c->H, T = c->T, F = 4, bw = c->K & 255, ba = (c->K >> 8) & 255, eval = (c->K >> 16) & 1;
+    const REAL *p = c->params;
+    const REAL *Wx = p, *bx = Wx + 3 * H * F, *sx = bx + 3 * H, *Wh = sx + 3, *bh = Wh + 3 * H * H, *sh = bh + 3 * H, *sop = sh + 3,
+               *Wo = sop + 4, *bo = Wo + 2 * H, *so = bo + 2;
+    const Quant qxw = mkq(sx[0], bw), qxa = mkq(sx[1], ba), qhw = mkq(sh[0], bw), qha = mkq(sh[1], ba), qsig = mkq(sop[0], ba),
+                qtanh = mkq(sop[1], ba), qadd = mkq(sop[2], ba), qmul = mkq(sop[3], ba), qow = mkq(so[0], bw), qoa = mkq(so[1], ba),
+                qoo = mkq(so[2], 16);
+    static __thread REAL *hs = NULL; static __thread size_t hs_n = 0;
+    if (hs_n < (size_t)(T + 1) * H) { free(hs); hs = (REAL *)malloc(sizeof(REAL) * (size_t)(T + 1) * H); hs_n = (size_t)(T + 1) * H; }
+    REAL Wxq[192 * 4], Whq[192 * 64], Woq[128]; int cWx[192 * 4], cWh[192 * 64], cWo[128];
+    for (int i = 0; i < 3 * H * F; ++i) Wxq[i] = qf(&qxw, Wx[i], &cWx[i]);
+    for (int i = 0; i < 3 * H * H; ++i) Whq[i] = qf(&qhw, Wh[i], &cWh[i]);
+    for (int i = 0; i < 2 * H; ++i) Woq[i] = qf(&qow, Wo[i], &cWo[i]);
+    REAL *gWx = gp, *gbx = gp ? gWx + 3 * H * F : NULL, *gWh = gp ? gbx + 3 * H + 3 : NULL, *gbh = gp ? gWh + 3 * H * H : NULL,
+         *gWo = gp ? gbh + 3 * H + 3 + 4 : NULL, *gbo = gp ? gWo + 2 * H : NULL;
+    if (phase == 0) for (int j = 0; j < H; ++j) hs[j] = 0;
+    REAL gH[64] = {0};
+    for (int step = 0; step < T; ++step) {
+        const int t = phase == 0 ? step : T - 1 - step;
+        const REAL *hp = hs + (size_t)t * H;
+        REAL f[8], fq[4]; int cf[4];
+        features_fwd(c->cell, x, T, t, f);
+        for (int k = 0; k < F; ++k) fq[k] = qf(&qxa, f[k], &cf[k]);
+        REAL hq[64]; int chq[64];
+        for (int k = 0; k < H; ++k) hq[k] = qf(&qha, hp[k], &chq[k]);
+        REAL xg[192], hg[192];
+        for (int r = 0; r < 3 * H; ++r) {
+            xg[r] = dotv(Wxq + (size_t)r * F, fq, F) + bx[r];
+            hg[r] = dotv(Whq + (size_t)r * H, hq, H) + bh[r];
+        }
+        REAL sr[64], sz[64], tn[64], rr[64], zz[64], nn[64], m1[64], hn[64];
+        int c_ar[64], c_az[64], c_an[64], c_r[64], c_z[64], c_n[64], c_m1[64], c_m2[64], c_m3[64], c_h[64];
+        for (int j = 0; j < H; ++j) {
+            REAL ar = qf(&qadd, xg[j] + hg[j], &c_ar[j]); sr[j] = sigm(ar); rr[j] = qf(&qsig, sr[j], &c_r[j]);
+            REAL az = qf(&qadd, xg[H + j] + hg[H + j], &c_az[j]); sz[j] = sigm(az); zz[j] = qf(&qsig, sz[j], &c_z[j]);
+            m1[j] = qf(&qmul, rr[j] * hg[2 * H + j], &c_m1[j]);
+            REAL an = qf(&qadd, xg[2 * H + j] + m1[j], &c_an[j]); tn[j] = R_TANH(an); nn[j] = qf(&qtanh, tn[j], &c_n[j]);
+            REAL m2 = qf(&qmul, zz[j] * hp[j], &c_m2[j]);
+            REAL m3 = qf(&qmul, ((REAL)1 - zz[j]) * nn[j], &c_m3[j]);
+            hn[j] = qf(&qadd, m2 + m3, &c_h[j]);
+        }
+        if (phase == 0) {
+            memcpy(hs + (size_t)(t + 1) * H, hn, sizeof(REAL) * H);
+            REAL qo[64];
+            for (int j = 0; j < H; ++j) qo[j] = qf(&qoa, hn[j], NULL);
+            for (int o = 0; o < 2; ++o) {
+                REAL y = dotv(Woq + (size_t)o * H, qo, H) + bo[o];
+                out[2 * t + o] = eval ? qf(&qoo, y, NULL) : y;
+            }
+            continue;
+        }
+        /* ---- backward of step t (everything above was recomputed from the saved h_{t-1}) */
+        const REAL go[2] = {gout[2 * t], gout[2 * t + 1]};
+        for (int j = 0; j < H; ++j) {
+            int cq; REAL qo = qf(&qoa, hn[j], &cq);
+            for (int o = 0; o < 2; ++o) { if (cWo[o * H + j]) gWo[o * H + j] += go[o] * qo; }
+            if (cq) gH[j] += Woq[j] * go[0] + Woq[H + j] * go[1];
+        }
+        gbo[0] += go[0]; gbo[1] += go[1];
+        REAL g_xg[192], g_hg[192], ghp[64];
+        for (int j = 0; j < H; ++j) {
+            REAL gs3 = c_h[j] ? gH[j] : 0;
+            REAL gm2 = c_m2[j] ? gs3 : 0, gm3 = c_m3[j] ? gs3 : 0;
+            REAL gz = gm2 * hp[j] - gm3 * nn[j];
+            ghp[j] = gm2 * zz[j];
+            REAL gn = gm3 * ((REAL)1 - zz[j]);
+            REAL gtn = c_n[j] ? gn : 0;
+            REAL gan = gtn * ((REAL)1 - tn[j] * tn[j]);
+            REAL gsn = c_an[j] ? gan : 0;                       /* d/d(xg_n + m1) */
+            REAL gm1 = c_m1[j] ? gsn : 0;
+            REAL gr = gm1 * hg[2 * H + j];
+            REAL gsr = c_r[j] ? gr : 0;
+            REAL gar = gsr * sr[j] * ((REAL)1 - sr[j]);
+            REAL gsum_r = c_ar[j] ? gar : 0;
+            REAL gsz = c_z[j] ? gz : 0;
+            REAL gaz = gsz * sz[j] * ((REAL)1 - sz[j]);
+            REAL gsum_z = c_az[j] ? gaz : 0;
+            g_xg[j] = gsum_r; g_hg[j] = gsum_r; g_xg[H + j] = gsum_z; g_hg[H + j] = gsum_z;
+            g_xg[2 * H + j] = gsn; g_hg[2 * H + j] = gm1 * rr[j];
+        }
+        REAL gfq[4] = {0, 0, 0, 0}, ghq[64] = {0};
+        for (int r = 0; r < 3 * H; ++r) {
+            gbx[r] += g_xg[r]; gbh[r] += g_hg[r];
+            for (int k = 0; k < F; ++k) { if (cWx[r * F + k]) gWx[r * F + k] += g_xg[r] * fq[k]; gfq[k] += Wxq[r * F + k] * g_xg[r]; }
+            for (int k = 0; k < H; ++k) { if (cWh[r * H + k]) gWh[r * H + k] += g_hg[r] * hq[k]; ghq[k] += Whq[r * H + k] * g_hg[r]; }
+        }
+        for (int k = 0; k < H; ++k) gH[k] = ghp[k] + (chq[k] ? ghq[k] : 0);
+        if (gx) { REAL gf[8] = {0}; for (int k = 0; k < F; ++k) gf[k] = cf[k] ? gfq[k] : 0; features_bwd(c->cell, x, T, t, gf, gx); }
+    }
+}
+
 static size_t n_params(int cell, int H, int K) {
     switch (cell) {
     case CELL_GRU: return (size_t)3 * H * 2 + 3 * H * H + 6 * H + 2 * H + 2;
@@ -684,6 +799,7 @@ static size_t n_params(int cell, int H, int K) {
     case CELL_PGJANET: return (size_t)3 * (H * (H + 1) + H) + 2 * (2 * H * H + H) + 2 * H + 2;
     case CELL_DVRJANET: return (size_t)K + 3 * H * H + 2 * H + H + 2 * (2 * H * H + H) + 2 * (H + 1);
     case CELL_GMP: return 495;
+    case CELL_QGRU_QAT: case CELL_QGRU_AMP1_QAT: return (size_t)3 * H * 4 + 3 * H * H + 6 * H + 2 * H + 2 + 13;
     }
     return 0;
 }
@@ -697,6 +813,7 @@ static void seq_dispatch(const Ctx *c, const REAL *x, const REAL *gout, REAL *ou
     case CELL_PGJANET: seq_pgjanet(c, x, gout, out, gx, gp, phase); break;
     case CELL_DVRJANET: seq_dvrjanet(c, x, gout, out, gx, gp, phase); break;
     case CELL_GMP: seq_gmp(c, x, gout, out, gx, gp, phase); break;
+    case CELL_QGRU_QAT: case CELL_QGRU_AMP1_QAT: seq_qgru_qat(c, x, gout, out, gx, gp, phase); break;
     }
 }
 

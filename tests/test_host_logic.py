@@ -33,7 +33,14 @@ def test_error_reporting_without_gpu_work():
 @pytest.mark.parametrize("name", golden_cases())
 def test_param_count_and_flat_layout_match_reference(name):
     g = load_golden(name)
-    net = models.CoreModel(2, max(g["H"], 1), 1, g["kind"], num_dvr_units=g["K"], thx=g["thx"], thh=g["thh"])
+    if g["kind"].endswith("_qat"):
+        from opendpd_b200.quant import get_quant_model
+
+        class _Proj:
+            quant, n_bits_w, n_bits_a, pretrained_model = True, g["K"] & 255, (g["K"] >> 8) & 255, ""
+        net = get_quant_model(_Proj(), models.CoreModel(2, g["H"], 1, g["kind"][:-4]))
+    else:
+        net = models.CoreModel(2, max(g["H"], 1), 1, g["kind"], num_dvr_units=g["K"], thx=g["thx"], thh=g["thh"])
     names = [n for n, _ in net.backbone.named_parameters()]
     assert names == [n for n, _ in g["param_index"]]
     assert [list(p.shape) for _, p in net.backbone.named_parameters()] == [s for _, s in g["param_index"]]
