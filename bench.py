@@ -28,6 +28,7 @@ WORKLOADS = {
     "c4p": dict(name="C4: PGJANET H=15 (1727 params) DPD step, per-GPU B=128 x T=4096, fp32", kind="pgjanet", H=15, B=128, T=4096),
     "c4d": dict(name="C4: DVRJANET H=15 K=3 (1685 params) DPD step, per-GPU B=128 x T=4096, fp32", kind="dvrjanet", H=15, B=128, T=4096),
     "c5g": dict(name="C5: GMP (495 params) DPD step, per-GPU B=128 x T=50, fp32", kind="gmp", H=1, B=128, T=50),
+    "c5q": dict(name="C5: QGRU H=10 W8A8 QAT (515 params) DPD step, per-GPU B=128 x T=50, fp32 fake-quant", kind="qgru_qat", H=10, B=128, T=50),
     "lstm": dict(name="LSTM H=9 (488 params) train_pa step, B=64 x T=2048, fp32", kind="lstm", H=9, B=64, T=2048),
 }
 WORKLOAD = WORKLOADS["c2a"]
@@ -198,7 +199,14 @@ def main():
         pg = dist.group.WORLD
 
     torch.manual_seed(0)                               # same initial weights on every rank
-    net = models.CoreModel(2, wl["H"], 1, wl["kind"], num_dvr_units=3, thx=0.01, thh=0.05).to(dev)
+    if wl["kind"] == "qgru_qat":
+        from opendpd_b200.quant import get_quant_model
+
+        class _Proj:
+            quant, n_bits_w, n_bits_a, pretrained_model = True, 8, 8, ""
+        net = get_quant_model(_Proj(), models.CoreModel(2, wl["H"], 1, "qgru")).to(dev).train()
+    else:
+        net = models.CoreModel(2, wl["H"], 1, wl["kind"], num_dvr_units=3, thx=0.01, thh=0.05).to(dev)
     if "pa" in wl:                                      # train_dpd: DPD in front of a frozen PA (steps/train_dpd.py:60-63)
         torch.manual_seed(1)
         pa_net = models.CoreModel(2, wl["pa"][1], 1, wl["pa"][0]).to(dev)

@@ -38,6 +38,28 @@ def net_train(log, net, dataloader, optimizer, criterion, grad_clip_val, device)
     return net
 
 
+def net_eval(log, net, dataloader, criterion, device):
+    """Drop-in for modules/train_funcs.py:57-90: forward-only pass over whole segments (B<=256, T=nperseg up to 19 662),
+    returns (net, prediction, ground_truth) as numpy like the reference."""
+    net = net.eval()
+    fused = isinstance(criterion, nn.MSELoss) and criterion.reduction == "mean" and hasattr(net, "forward_mse")
+    with torch.no_grad():
+        losses, prediction, ground_truth = [], [], []
+        for features, targets in dataloader:
+            features = features.to(device)
+            targets = targets.to(device)
+            if fused:
+                outputs, loss = net.forward_mse(features, targets)
+            else:
+                outputs = net(features)
+                loss = criterion(outputs, targets)
+            prediction.append(outputs.cpu())
+            ground_truth.append(targets.cpu())
+            losses.append(loss.item())
+    log["loss"] = np.mean(losses)
+    return net, torch.cat(prediction, dim=0).numpy(), torch.cat(ground_truth, dim=0).numpy()
+
+
 class NativeTrainStep:
     """One fused train step for a CoreModel (train_pa, steps/train_pa.py:24-29) or a CascadedModel with frozen PA
     (train_dpd, steps/train_dpd.py:60-63).

@@ -33,12 +33,20 @@ def _flat(net):
     return torch.cat([p.detach().reshape(-1) for p in net.parameters()]).cpu().numpy()
 
 
-@pytest.mark.parametrize("kind,H", [("dgru", 13), ("gru", 32), ("deltagru_tcnskip", 15), ("pgjanet", 10), ("gmp", 1)])
+@pytest.mark.parametrize("kind,H", [("dgru", 13), ("gru", 32), ("deltagru_tcnskip", 15), ("pgjanet", 10), ("gmp", 1), ("lstm", 9),
+                                    ("dvrjanet", 10), ("qgru_qat", 10)])
 def test_fused_step_equals_stock_loop(kind, H):
     from opendpd_b200 import models
     from opendpd_b200.train import NativeTrainStep
     torch.manual_seed(0)
-    a = models.CoreModel(2, H, 1, kind, num_dvr_units=3, thx=0.01, thh=0.05).cuda()
+    if kind == "qgru_qat":
+        from opendpd_b200.quant import get_quant_model
+
+        class _Proj:
+            quant, n_bits_w, n_bits_a, pretrained_model = True, 16, 16, ""
+        a = get_quant_model(_Proj(), models.CoreModel(2, H, 1, "qgru")).cuda().train()
+    else:
+        a = models.CoreModel(2, H, 1, kind, num_dvr_units=3, thx=0.01, thh=0.05).cuda()
     b = copy.deepcopy(a)
     batches = [_data(6, 70, s) for s in range(4)]
     la = _stock_steps(a, batches)
@@ -130,3 +138,25 @@ def test_state_dict_roundtrip_after_training():
     net2.load_state_dict(sd)
     net2 = net2.cuda()
     assert torch.equal(net2(x), net(x))
+
+
+@pytest.mark.parametrize("kind,H,B,T", [("dgru", 13, 2, 19662), ("deltagru_tcnskip", 15, 1, 19662), ("gru", 32, 3, 2560)])
+def test_eval_path_whole_segments(kind, H, B, T):
+    """net_eval / run_dpd run forward-only over whole segments (T = nperseg up to 19 662, B = 1..6)."""
+    from oracle import oracle
+    from opendpd_b200 import models
+    from opendpd_b200.train import net_eval
+    from tests.util import assert_close
+    torch.manual_seed(6)
+    net = models.CoreModel(2, H, 1, kind, thx=0.0, thh=0.0).cuda()
+    g = torch.Generator().manual_seed(8)
+    x = (0.25 * torch.randn(B, T, 2, generator=g)).clamp(-0.8, 0.8)
+    y = 0.9 * x
+    log = {}
+    _, pred, gt = net_eval(log, net, [(x, y)], nn.MSELoss(), torch.device("cuda"))
+    params = np.concatenate([p.detach().cpu().numpy().ravel() for _, p in net.backbone.named_parameters()])
+    r64 = oracle.run(kind, x.numpy(), params, target=y.numpy(), H=H, dtype=np.float64, want_grads=False, nthreads=4)
+    r32 = oracle.run(kind, x.numpy(), params, target=y.numpy(), H=H, dtype=np.float32, want_grads=False, nthreads=4)
+    tol = max(1e-5, 3 * float(np.quantile(np.abs(r32["out"] - r64["out"]) / np.abs(r64["out"]).max(), 0.9999)))
+    assert_close(pred, r64["out"], tol, "eval out")
+    assert abs(log["loss"] - r64["loss"]) <= 1e-5 * r64["loss"] and np.array_equal(gt, y.numpy())
