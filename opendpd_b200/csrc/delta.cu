@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(96, 1) delta_fwd_kernel(GruArgs a) {
 
 // ================================================================ backward
 template <int HT, bool TRES, bool DW>
-__global__ void __launch_bounds__(96, 1) delta_bwd_kernel(GruArgs a) {
+__global__ void __launch_bounds__(128, 1) delta_bwd_kernel(GruArgs a) {
     constexpr int HP = Pad4<HT>::value, ROW = DRow<HT>::value, F = 6;
     constexpr int FM = TRES ? FM_TRES6 : FM_DGRU6;
     using SM = DBwdSmem<HT, TRES>;
@@ -437,9 +437,11 @@ __global__ void __launch_bounds__(96, 1) delta_bwd_kernel(GruArgs a) {
             }
         }
     } else {
-        // =============================== post: weight gradients, dL/dfeatures with the x_hat routing, dL/dx
+        // =============================== post, two warps (FFMA issue rate of one warp is the limit):
+        //   warp 2 "post-A": dL/dW_hh;   warp 3 "post-B": dL/dW_ih, head, dL/dfeatures with the x_hat routing, dL/dx
+        const bool roleA = (warp == 2);
         const int fl = lane - H;                 // feature lanes H..H+5 (H+6<=32 enforced by the host)
-        const bool isf = fl >= 0 && fl < F;
+        const bool isf = !roleA && fl >= 0 && fl < F;
         float wic[3 * HT];
 #pragma unroll
         for (int g = 0; g < 3; ++g)
@@ -459,10 +461,34 @@ __global__ void __launch_bounds__(96, 1) delta_bwd_kernel(GruArgs a) {
             if (sc >= 0) {
                 const int c = nchunks - 1 - sc, t0 = c * CH, nt = min(CH, T - t0);
                 const float *ac = sact + (sc % 3) * SM::ACT, *pr = spre + (sc % 3) * SM::PRE, *Gb = sG + (sc & 1) * SM::G;
+                if (roleA) {
+                    if constexpr (DW) {
+#pragma unroll 2
+                        for (int tl = 0; tl < nt; ++tl) {
+                            const float4 *G4 = reinterpret_cast<const float4 *>(Gb + tl * 4 * HP);
+                            const float dhm = ac[(tl + 1) * ROW + 5 * HP + lp];
+#pragma unroll
+                            for (int k4 = 0; k4 < HP / 4; ++k4) {
+                                const float4 v_r = G4[k4], v_z = G4[HP / 4 + k4], v_nh = G4[2 * (HP / 4) + k4];
+                                const float kr[4] = {v_r.x, v_r.y, v_r.z, v_r.w}, kz[4] = {v_z.x, v_z.y, v_z.z, v_z.w};
+                                const float knh[4] = {v_nh.x, v_nh.y, v_nh.z, v_nh.w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const int k = k4 * 4 + e;
+                                    if (k < HT) {
+                                        gwhh[k] = fmaf(kr[e], dhm, gwhh[k]);
+                                        gwhh[HT + k] = fmaf(kz[e], dhm, gwhh[HT + k]);
+                                        gwhh[2 * HT + k] = fmaf(knh[e], dhm, gwhh[2 * HT + k]);
+                                    }
+                                }
+                            }
+                        }
+                    }
+                } else {
                 for (int tl = nt - 1; tl >= 0; --tl) {
                     const float *G = Gb + tl * 4 * HP;
                     const float *row = ac + (tl + 1) * ROW;
-                    const float ht = row[4 * HP + lp], dhm = row[5 * HP + lp];
+                    const float ht = row[4 * HP + lp];
                     const float4 dx0 = *reinterpret_cast<const float4 *>(row + 6 * HP), dx1 = *reinterpret_cast<const float4 *>(row + 6 * HP + 4);
                     const float dx[F] = {dx0.x, dx0.y, dx0.z, dx0.w, dx1.x, dx1.y};
                     const unsigned mx = __float_as_uint(dx1.z);
@@ -477,23 +503,20 @@ __global__ void __launch_bounds__(96, 1) delta_bwd_kernel(GruArgs a) {
                         gwo0 = fmaf(pr[tl * 12], ht, gwo0); gwo1 = fmaf(pr[tl * 12 + 1], ht, gwo1);
                     }
                     float fa0 = 0.f, fa1 = 0.f;
-                    const float4 *G4 = reinterpret_cast<const float4 *>(G);
+                    if (gx2) {
+                        const float4 *G4 = reinterpret_cast<const float4 *>(G);
 #pragma unroll
-                    for (int k4 = 0; k4 < HP / 4; ++k4) {
-                        const float4 v_r = G4[k4], v_z = G4[HP / 4 + k4], v_nh = G4[2 * (HP / 4) + k4], v_nx = G4[3 * (HP / 4) + k4];
-                        const float kr[4] = {v_r.x, v_r.y, v_r.z, v_r.w}, kz[4] = {v_z.x, v_z.y, v_z.z, v_z.w};
-                        const float knh[4] = {v_nh.x, v_nh.y, v_nh.z, v_nh.w}, knx[4] = {v_nx.x, v_nx.y, v_nx.z, v_nx.w};
+                        for (int k4 = 0; k4 < HP / 4; ++k4) {
+                            const float4 v_r = G4[k4], v_z = G4[HP / 4 + k4], v_nx = G4[3 * (HP / 4) + k4];
+                            const float kr[4] = {v_r.x, v_r.y, v_r.z, v_r.w}, kz[4] = {v_z.x, v_z.y, v_z.z, v_z.w};
+                            const float knx[4] = {v_nx.x, v_nx.y, v_nx.z, v_nx.w};
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int k = k4 * 4 + e;
-                            if (k < HT) {
-                                fa0 = fmaf(wic[k], kr[e], fa0);
-                                fa1 = fmaf(wic[HT + k], kz[e], fa1);
-                                fa0 = fmaf(wic[2 * HT + k], knx[e], fa0);
-                                if constexpr (DW) {
-                                    gwhh[k] = fmaf(kr[e], dhm, gwhh[k]);
-                                    gwhh[HT + k] = fmaf(kz[e], dhm, gwhh[HT + k]);
-                                    gwhh[2 * HT + k] = fmaf(knh[e], dhm, gwhh[2 * HT + k]);
+                            for (int e = 0; e < 4; ++e) {
+                                const int k = k4 * 4 + e;
+                                if (k < HT) {
+                                    fa0 = fmaf(wic[k], kr[e], fa0);
+                                    fa1 = fmaf(wic[HT + k], kz[e], fa1);
+                                    fa0 = fmaf(wic[2 * HT + k], knx[e], fa0);
                                 }
                             }
                         }
@@ -535,6 +558,7 @@ __global__ void __launch_bounds__(96, 1) delta_bwd_kernel(GruArgs a) {
                     if (lane < nt) gx2[t] = make_float2(gi, gq);
                 }
                 __syncwarp();
+                }   // post-B
             }
             __syncthreads();
         }
@@ -542,15 +566,19 @@ __global__ void __launch_bounds__(96, 1) delta_bwd_kernel(GruArgs a) {
             if (a.partials) {
                 float *prt = a.partials + (size_t)b * L.P;
                 if (act) {
+                    if (roleA) {
 #pragma unroll
-                    for (int g = 0; g < 3; ++g) {
+                        for (int g = 0; g < 3; ++g)
 #pragma unroll
-                        for (int q = 0; q < F; ++q) prt[L.oWih + (g * H + lane) * F + q] = gwih[g * F + q];
+                            for (int k = 0; k < HT; ++k)
+                                if (k < H) prt[L.oWhh + (g * H + k) * H + lane] = gwhh[g * HT + k];
+                    } else {
 #pragma unroll
-                        for (int k = 0; k < HT; ++k)
-                            if (k < H) prt[L.oWhh + (g * H + k) * H + lane] = gwhh[g * HT + k];
+                        for (int g = 0; g < 3; ++g)
+#pragma unroll
+                            for (int q = 0; q < F; ++q) prt[L.oWih + (g * H + lane) * F + q] = gwih[g * F + q];
+                        prt[L.oWo + lane] = gwo0; prt[L.oWo + H + lane] = gwo1;
                     }
-                    prt[L.oWo + lane] = gwo0; prt[L.oWo + H + lane] = gwo1;
                 }
             }
         }
@@ -575,8 +603,8 @@ static int delta_launch(const GruArgs &a, int dir, bool dw, cudaStream_t st) {
         k<<<a.B, 96, smem, st>>>(a);
     } else {
         const size_t smem = (size_t)DBwdSmem<HT, TRES>::total(Ppad) * 4;
-        if (dw) { auto k = delta_bwd_kernel<HT, TRES, true>; cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); k<<<a.B, 96, smem, st>>>(a); }
-        else { auto k = delta_bwd_kernel<HT, TRES, false>; cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); k<<<a.B, 96, smem, st>>>(a); }
+        if (dw) { auto k = delta_bwd_kernel<HT, TRES, true>; cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); k<<<a.B, 128, smem, st>>>(a); }
+        else { auto k = delta_bwd_kernel<HT, TRES, false>; cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); k<<<a.B, 128, smem, st>>>(a); }
     }
     return check_launch("delta kernel");
 }
