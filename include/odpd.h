@@ -132,6 +132,31 @@ int odpd_clip_adamw(float *param, float *grad, float *exp_avg, float *exp_avg_sq
                     float beta1, float beta2, float eps, float weight_decay, float max_norm, int64_t *step_dev,
                     float *gnorm_out, int zero_grad, void *stream);
 
+/*
+ * Data-parallel exchange over NVLink peer memory (ONE exchange per train step, the flat [grad | loss] buffer).
+ * The all-reduce is fused into the optimiser kernel: every rank reads every rank's gradient buffer directly through
+ * NVLink/NVSwitch peer mappings, sums them in rank order (so all replicas compute bit-identical updates), clips and applies AdamW —
+ * no NCCL call, no extra launch.  Buffers are symmetric: rank r allocates `odpd_dp_alloc`, exports `odpd_dp_ipc_handle`, the
+ * 64-byte handles are all-gathered out of band (torch.distributed), peers map them with `odpd_dp_ipc_open`.
+ *   layout of one rank's buffer (floats):  [2][stride]  double-buffered by step parity, element n (< stride) = that rank's loss
+ *                                          followed by 2 x uint64 flags (flag[0] = last step whose gradient is published)
+ * These are the only entry points that allocate device memory (peer-mappable memory must come from cudaMalloc).
+ */
+int64_t odpd_dp_buffer_bytes(int64_t n_params);
+int odpd_dp_alloc(int64_t bytes, void **out_ptr);
+int odpd_dp_free(void *ptr);
+int odpd_dp_ipc_handle(void *ptr, unsigned char handle_out[64]);
+int odpd_dp_ipc_open(const unsigned char handle[64], void **out_peer_ptr);
+int odpd_dp_ipc_close(void *peer_ptr);
+/* bufs: HOST array of `world` device pointers (index = rank; bufs[rank] is the caller's own buffer).  The local gradient of this
+ * step must already be in bufs[rank][parity][0..n) (pass it as `gparams` of odpd_backbone_bwd with ODPD_F_OVERWRITE_DW, parity =
+ * (step_dev+1)&1) and the local loss (double, from odpd_backbone_fwd) in `loss_local`.  On return (stream order) `param` is updated,
+ * loss_out[0] = sum of all ranks' losses, gnorm_out = pre-clip norm of the summed gradient.  status_dev[0] != 0 reports a peer
+ * that did not publish within the spin budget (the kernel never hangs). */
+int odpd_dp_clip_adamw(float *param, void *const *bufs, int world, int rank, int64_t n, const double *loss_local,
+                       float *exp_avg, float *exp_avg_sq, const float *lr_dev, float beta1, float beta2, float eps, float weight_decay,
+                       float max_norm, int64_t *step_dev, float *gnorm_out, float *loss_out, int *status_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -37,6 +37,14 @@ SYMBOLS = {
     "odpd_backbone_bwd": (ctypes.c_int, [_DP, _vp, _vp, _vp, _vp, _vp, _vp, _dbl, _vp, _vp, _vp, _vp, _vp]),
     "odpd_clip_adamw": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _flt, _flt, _flt, _flt, _flt, _vp, _vp,
                                        ctypes.c_int, _vp]),
+    "odpd_dp_buffer_bytes": (_i64, [_i64]),
+    "odpd_dp_alloc": (ctypes.c_int, [_i64, ctypes.POINTER(_vp)]),
+    "odpd_dp_free": (ctypes.c_int, [_vp]),
+    "odpd_dp_ipc_handle": (ctypes.c_int, [_vp, ctypes.c_char_p]),
+    "odpd_dp_ipc_open": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(_vp)]),
+    "odpd_dp_ipc_close": (ctypes.c_int, [_vp]),
+    "odpd_dp_clip_adamw": (ctypes.c_int, [_vp, ctypes.POINTER(_vp), ctypes.c_int, ctypes.c_int, _i64, _vp, _vp, _vp, _vp, _flt, _flt,
+                                          _flt, _flt, _flt, _vp, _vp, _vp, _vp, _vp]),
 }
 
 

@@ -34,3 +34,54 @@ def allreduce_flat_(buf, group=None):
     if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size(group) > 1:
         torch.distributed.all_reduce(buf, op=torch.distributed.ReduceOp.SUM, group=group)
     return buf
+
+
+class PeerExchange:
+    """Symmetric NVLink-mapped gradient buffers for the fused all-reduce + clip + AdamW kernel (include/odpd.h, csrc/dp.cu).
+    Each rank owns one cudaMalloc'ed buffer [2][stride] floats + flags; the 64-byte IPC handles are all-gathered once through
+    torch.distributed and every peer buffer is mapped into this process."""
+
+    def __init__(self, n_params, device, group, world, rank):
+        import ctypes
+        from . import _ffi
+        self.L, self.n, self.world, self.rank, self.device = _ffi.lib(), int(n_params), int(world), int(rank), device
+        self.stride = (self.n + 1 + 3) // 4 * 4
+        nbytes = int(self.L.odpd_dp_buffer_bytes(self.n))
+        own = ctypes.c_void_p()
+        _ffi.check(self.L.odpd_dp_alloc(nbytes, ctypes.byref(own)))
+        self.own = own.value
+        hbuf = ctypes.create_string_buffer(64)
+        _ffi.check(self.L.odpd_dp_ipc_handle(ctypes.c_void_p(self.own), hbuf))
+        mine = torch.tensor(list(hbuf.raw), dtype=torch.uint8, device=device)
+        allh = [torch.empty_like(mine) for _ in range(world)]
+        torch.distributed.all_gather(allh, mine, group=group)
+        self.ptrs = (ctypes.c_void_p * world)()
+        self._opened = []
+        for r in range(world):
+            if r == rank:
+                self.ptrs[r] = self.own
+            else:
+                peer = ctypes.c_void_p()
+                _ffi.check(self.L.odpd_dp_ipc_open(bytes(allh[r].cpu().tolist()), ctypes.byref(peer)))
+                self.ptrs[r] = peer.value
+                self._opened.append(peer.value)
+        torch.distributed.barrier(group=group)
+        self.status = torch.zeros(1, dtype=torch.int32, device=device)
+        self.loss_out = torch.zeros(1, dtype=torch.float32, device=device)
+
+    def grad_view(self, parity):
+        """torch view (n floats) of this rank's gradient slot for the given step parity — handed to the backward as `gparams`."""
+        class _Mem:
+            pass
+        m = _Mem()
+        m.__cuda_array_interface__ = {"shape": (self.n,), "typestr": "<f4", "data": (self.own + 4 * parity * self.stride, False), "version": 3}
+        return torch.as_tensor(m, device=self.device)
+
+    def close(self):
+        import ctypes
+        for p in self._opened:
+            self.L.odpd_dp_ipc_close(ctypes.c_void_p(p))
+        self._opened = []
+        if self.own:
+            self.L.odpd_dp_free(ctypes.c_void_p(self.own))
+            self.own = None

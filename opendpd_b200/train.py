@@ -6,6 +6,7 @@ every script of record uses (nn.MSELoss + clip_grad_norm_ + AdamW, project.py:26
 MSE fused, backward kernels writing one flat gradient, optional data-parallel all-reduce of that flat buffer
 (SURVEY.md §8e), and clip+AdamW in a single launch (odpd_clip_adamw)."""
 import ctypes
+import os
 import numpy as np
 import torch
 from torch import nn
@@ -13,7 +14,7 @@ from torch import nn
 from . import _ffi
 from .functional import backbone_forward_raw, backbone_backward_raw, _ptr, _stream
 from .models import CoreModel, CascadedModel
-from .dp import allreduce_flat_
+from .dp import allreduce_flat_, PeerExchange
 
 
 def net_train(log, net, dataloader, optimizer, criterion, grad_clip_val, device):
@@ -72,7 +73,8 @@ class NativeTrainStep:
     scale uses the GLOBAL element count and one SUM all-reduce runs on [flat_grad, loss] per step."""
 
     def __init__(self, net, lr=5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, grad_clip_val=200.0,
-                 process_group=None, world_size=1):
+                 process_group=None, world_size=1, peer_exchange=None):
+        """peer_exchange: None = auto (fused NVLink exchange when world_size>1 and env ODPD_DP_P2P != 0, else NCCL all-reduce)."""
         self.net = net
         if isinstance(net, CascadedModel):
             self.dpd, self.pa = net.dpd_model.backbone, net.pa_model.backbone
@@ -100,6 +102,12 @@ class NativeTrainStep:
         self.gnorm = torch.zeros(1, dtype=torch.float32, device=dev)
         self.betas, self.eps, self.wd, self.clip = betas, eps, weight_decay, float(grad_clip_val)
         self.pg, self.world = process_group, int(world_size)
+        self.px = None
+        use_p2p = peer_exchange if peer_exchange is not None else (os.environ.get("ODPD_DP_P2P", "1") != "0")
+        if self.world > 1 and self.pg is not None and use_p2p and self.n + 1 <= 4096:
+            self.px = PeerExchange(self.n, dev, self.pg, self.world, torch.distributed.get_rank(self.pg))
+            self._px_views = [self.px.grad_view(0), self.px.grad_view(1)]
+        self._host_step = 0
         self._stage = None
         self._bufs = [dict() for _ in range(4)]
 
@@ -114,12 +122,13 @@ class NativeTrainStep:
         flat, _ = tb._flat_sync()
         B, T = features.shape[0], features.shape[1]
         count = float(global_count) if global_count else float(2 * B * T * self.world)   # nn.MSELoss 'mean', GLOBAL batch
+        gflat = self._px_views[(self._host_step + 1) & 1] if self.px is not None else self.gflat
         if self.dpd is None:
             spec = tb._spec()
             out, loss, saved = backbone_forward_raw(spec, features, flat, targets, 1.0 / count, True, tb._stats_tensor(self.device),
                                                     self._bufs[0])
             backbone_backward_raw(spec, features, flat, saved, False, True, out=out, target=targets, gscale=2.0 / count,
-                                  gflat=self.gflat, bufs=self._bufs[1])
+                                  gflat=gflat, bufs=self._bufs[1])
         else:
             paflat, _ = self.pa._flat_sync()
             sd, sp = self.dpd._spec(), self.pa._spec()
@@ -128,7 +137,20 @@ class NativeTrainStep:
                                                       self._bufs[2])
             gmid, _ = backbone_backward_raw(sp, mid, paflat, saved_p, True, False, out=out, target=targets, gscale=2.0 / count,
                                             bufs=self._bufs[3])
-            backbone_backward_raw(sd, features, flat, saved_d, False, True, gout=gmid, gflat=self.gflat, bufs=self._bufs[1])
+            backbone_backward_raw(sd, features, flat, saved_d, False, True, gout=gmid, gflat=gflat, bufs=self._bufs[1])
+        self._host_step += 1
+        if self.px is not None:
+            # fused: NVLink peer reads + ordered sum + clip + AdamW in ONE kernel (csrc/dp.cu)
+            _ffi.check(L.odpd_dp_clip_adamw(_ptr(flat), self.px.ptrs, self.world, self.px.rank, ctypes.c_int64(self.n), _ptr(loss),
+                                            _ptr(self.exp_avg), _ptr(self.exp_avg_sq), _ptr(self.lr_dev), self.betas[0], self.betas[1],
+                                            self.eps, self.wd, self.clip, _ptr(self.step_dev), _ptr(self.gnorm), _ptr(self.px.loss_out),
+                                            _ptr(self.px.status), _stream()))
+            if self._host_step in (1, 2):      # verify the exchange once at start-up (one sync); fall back to NCCL if a peer never published
+                bad = int(self.px.status.item())
+                if bad:
+                    raise _ffi.OdpdError(f"NVLink peer exchange: rank {bad - 1} did not publish its gradient (step {self._host_step}); "
+                                         "re-run with ODPD_DP_P2P=0 to use the NCCL all-reduce")
+            return self.px.loss_out.to(torch.float64)
         if self.pg is not None and self.world > 1:
             self.gbuf[-4] = loss.to(torch.float32)[0]
             allreduce_flat_(self.gbuf, self.pg)
