@@ -128,12 +128,13 @@ def cpu_port_leg(seconds=10.0, kind="dgru", H=13, B=64, T=2048, threads=None):
         # PyTorch's intra-op pool degrades badly when oversubscribed on these ~1e3-element ops: use all host threads it can
         # USE — scan a few pool sizes (one step each) and keep the fastest; the count is reported in `cores`.
         best = None
-        for nthr_t in sorted({cores, min(cores, 32), min(cores, 16), min(cores, 8), min(cores, 4)}, reverse=True):
+        for nthr_t in sorted({cores, min(cores, 32), min(cores, 16), min(cores, 8), min(cores, 4)}):
             torch.set_num_threads(nthr_t)
-            step(xt, yt)
             t1 = time.perf_counter(); step(xt, yt); d1 = time.perf_counter() - t1
             if best is None or d1 < best[1]:
                 best = (nthr_t, d1)
+            elif d1 > 2.0 * best[1]:
+                break                     # larger pools only get slower from here (measured: 128 threads = 17x slower than 4)
         torch.set_num_threads(best[0])
         t0, n = time.perf_counter(), 0
         while time.perf_counter() - t0 < seconds / 2 or n < 3:
@@ -148,7 +149,26 @@ def cpu_port_leg(seconds=10.0, kind="dgru", H=13, B=64, T=2048, threads=None):
     return res
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """The driver parses stdout for ONE JSON line: route everything else (the reference-style 'Backbone Initialized...' print, NCCL's
+    version banner, ...) to stderr at the file-descriptor level and keep the real stdout for the final line."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=400)
@@ -182,7 +202,7 @@ def main():
                 "e2e": {"value": main_leg["value"], "unit": "IQ samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         if "torch_port_error" in r:
             line["torch_port_error"] = r["torch_port_error"]
-        print(json.dumps(line), flush=True)
+        emit(line)
         return
 
     import torch
@@ -312,7 +332,9 @@ def main():
             "kernel_ms": {"fwd": fwd_ms, "bwd": bwd_ms},
             "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                         "traffic": None,
+                         "traffic": ({"odpd::gru_fwd_kernel": 2126336 + 787712, "odpd::gru_bwd_kernel": 53534720 + 4864}.get(dom[0])
+                                     if args.workload == "c2a" else None),
+                         "traffic_source": "profiles/r1_final_gru_ncu_summary.txt (ncu --set full, dram__bytes_read+write per launch; bwd re-reads the 41 MB of saved rows from DRAM only under ncu's cache-flushed replay)",
                          "latency_view": {"timesteps": T, "ns_per_timestep_fwd": fwd_ms * 1e6 / T, "ns_per_timestep_bwd": bwd_ms * 1e6 / T,
                                           "note": "the path is a T-step serial recurrence per sequence: latency-bound, not bandwidth-bound (SURVEY §8d)"}},
         }
@@ -323,7 +345,7 @@ def main():
             line["cpu_c_port"] = r["c_port"]
             if "torch_port_error" in r:
                 line["torch_port_error"] = r["torch_port_error"]
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
