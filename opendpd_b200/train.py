@@ -169,6 +169,62 @@ class NativeTrainStep:
         fy.copy_(targets_cpu, non_blocking=True)
         return float(self.step(fx, fy).item())
 
+    def run_host_batches(self, batches):
+        """Train on an iterable of HOST (pinned) (features, targets) batches — the reference's `for features, targets in
+        dataloader` loop (train_funcs.py:28-48) as a 2-deep pipeline: batch i+1 is copied host->device on a side stream while step i
+        computes, and the loss of step i is read back (async D2H, pinned) while step i+1 is already queued.  Every step still does
+        its own H2D copy and its own loss read-back; they just no longer serialise with the kernels.  Returns the list of losses."""
+        cur = torch.cuda.current_stream()
+        if not hasattr(self, "_cs"):
+            self._cs = torch.cuda.Stream(device=self.device)
+            self._pipe = None
+        cs = self._cs
+        it = iter(batches)
+        nxt = next(it, None)
+        if nxt is None:
+            return []
+        shp = (tuple(nxt[0].shape), tuple(nxt[1].shape))
+        if self._pipe is None or self._pipe["shape"] != shp:
+            mk = lambda s: torch.empty(s, dtype=torch.float32, device=self.device)
+            self._pipe = dict(shape=shp, stage=[(mk(shp[0]), mk(shp[1])) for _ in range(2)],
+                              loss=[torch.zeros(1, dtype=torch.float64).pin_memory() for _ in range(2)],
+                              ev_copy=[torch.cuda.Event() for _ in range(2)], ev_free=[torch.cuda.Event() for _ in range(2)],
+                              ev_loss=[torch.cuda.Event() for _ in range(2)])
+        P = self._pipe
+        used = [False, False]
+
+        def enqueue_copy(slot, batch):
+            with torch.cuda.stream(cs):
+                if used[slot]:
+                    cs.wait_event(P["ev_free"][slot])
+                else:
+                    cs.wait_stream(cur)
+                P["stage"][slot][0].copy_(batch[0], non_blocking=True)
+                P["stage"][slot][1].copy_(batch[1], non_blocking=True)
+                P["ev_copy"][slot].record(cs)
+
+        enqueue_copy(0, nxt)
+        losses, pending, i = [], None, 0
+        while nxt is not None:
+            slot = i & 1
+            nxt = next(it, None)
+            if nxt is not None:
+                enqueue_copy(slot ^ 1, nxt)
+            cur.wait_event(P["ev_copy"][slot])
+            loss_dev = self.step(*P["stage"][slot])
+            P["ev_free"][slot].record(cur)
+            used[slot] = True
+            P["loss"][slot].copy_(loss_dev, non_blocking=True)
+            P["ev_loss"][slot].record(cur)
+            if pending is not None:
+                P["ev_loss"][pending].synchronize()
+                losses.append(float(P["loss"][pending][0]))
+            pending = slot
+            i += 1
+        P["ev_loss"][pending].synchronize()
+        losses.append(float(P["loss"][pending][0]))
+        return losses
+
     def grads_as_param_grads(self):
         """Expose the flat gradient through each parameter's .grad (views), e.g. for inspection or a torch optimizer."""
         _, layout = self.train_bb._flat_sync()

@@ -160,3 +160,18 @@ def test_eval_path_whole_segments(kind, H, B, T):
     tol = max(1e-5, 3 * float(np.quantile(np.abs(r32["out"] - r64["out"]) / np.abs(r64["out"]).max(), 0.9999)))
     assert_close(pred, r64["out"], tol, "eval out")
     assert abs(log["loss"] - r64["loss"]) <= 1e-5 * r64["loss"] and np.array_equal(gt, y.numpy())
+
+
+def test_pipelined_host_loop_equals_sequential():
+    from opendpd_b200 import models
+    from opendpd_b200.train import NativeTrainStep
+    import copy
+    torch.manual_seed(9)
+    a = models.CoreModel(2, 13, 1, "dgru").cuda()
+    b = copy.deepcopy(a)
+    batches = [tuple(t.cpu().pin_memory() for t in _data(4, 64, s)) for s in range(7)]
+    ta, tb = NativeTrainStep(a), NativeTrainStep(b)
+    la = [ta.step_host(x, y) for x, y in batches]
+    lb = tb.run_host_batches(iter(batches))
+    assert la == lb
+    assert np.array_equal(_flat(a), _flat(b))
