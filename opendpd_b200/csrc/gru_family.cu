@@ -127,73 +127,149 @@ __global__ void __launch_bounds__(96, 1) gru_fwd_kernel(GruArgs a) {
         }
     } else if (warp == 0) {
         // =============================== chain: the serial recurrence
-        float whr[HT], whz[HT], whn[HT];
+        if constexpr (HP <= 16) {
+            // Two half-warps share one timestep: lanes 0..15 carry the r and n rows of unit u, lanes 16..31 the z row of the same
+            // unit, so every lane issues 2H FMAs + one sigmoid instead of 3H + two; z comes down with one shuffle, off the r->n path.
+            const int half = lane >> 4, u = lane & 15;
+            const bool au = u < H;
+            const int ju = au ? u : 0;
+            float wA[HT], wB[HT];
 #pragma unroll
-        for (int k = 0; k < HT; ++k) {
-            const bool ok = act && k < H;
-            whr[k] = ok ? sp[L.oWhh + (0 * H + j) * H + k] : 0.f;
-            whz[k] = ok ? sp[L.oWhh + (1 * H + j) * H + k] : 0.f;
-            whn[k] = ok ? sp[L.oWhh + (2 * H + j) * H + k] : 0.f;
-        }
-        const float b_hn = act ? sp[L.obhh + 2 * H + j] : 0.f;
-        const int lp = lane < HP ? lane : 0;  // clamp: lanes >= HP read lane 0's slot and never write
-        float h = 0.f;
-        for (int s = 0; s < nchunks + 2; ++s) {
-            const int c = s - 1;
-            if (c >= 0 && c < nchunks) {
-                const int t0 = c * CH, nt = min(CH, T - t0);
-                const float *xp = sxp + (c & 1) * SM::XP + lp;
-                float *ac = sact + (c & 1) * SM::ACT;
-                const float *hrow = (c == 0) ? zero : sact + ((c - 1) & 1) * SM::ACT + (CH - 1) * ROW + 4 * HP;
-                float xr = xp[0], xz = xp[HP], xn = xp[2 * HP];
-                float pr_ = 0.f, pz_ = 0.f, pn_ = 0.f, phg_ = 0.f;   // gate values of the previous step, stored one iteration late
-                for (int tl = 0; tl < nt; ++tl) {
-                    // broadcast h_{t-1}: issue the loads first, everything below that does not need them fills the latency
-                    const float4 *hb4 = reinterpret_cast<const float4 *>(hrow);
-                    float4 hv[HP / 4];
+            for (int k = 0; k < HT; ++k) {
+                const bool ok = au && k < H;
+                wA[k] = ok ? sp[L.oWhh + ((half ? 1 : 0) * H + ju) * H + k] : 0.f;      // r row (lower) / z row (upper)
+                wB[k] = (ok && !half) ? sp[L.oWhh + (2 * H + ju) * H + k] : 0.f;        // n row (lower only)
+            }
+            const float b_hn = (au && !half) ? sp[L.obhh + 2 * H + ju] : 0.f;
+            const int up = u < HP ? u : 0;
+            float h = 0.f;
+            for (int s = 0; s < nchunks + 2; ++s) {
+                const int c = s - 1;
+                if (c >= 0 && c < nchunks) {
+                    const int t0 = c * CH, nt = min(CH, T - t0);
+                    const float *xpA = sxp + (c & 1) * SM::XP + (half ? HP : 0) + up;     // xr (lower) / xz (upper)
+                    const float *xpN = sxp + (c & 1) * SM::XP + 2 * HP + up;
+                    float *ac = sact + (c & 1) * SM::ACT;
+                    const float *hrow = (c == 0) ? zero : sact + ((c - 1) & 1) * SM::ACT + (CH - 1) * ROW + 4 * HP;
+                    float xa = xpA[0], xn = xpN[0];
+                    float pr_ = 0.f, pz_ = 0.f, pn_ = 0.f, phg_ = 0.f;
+                    // pointer-increment form: the loop body carries no index arithmetic.  Reading one row past the chunk's
+                    // projections (last step's prefetch) stays inside the shared-memory carve-up and the value is never used.
+                    const bool wr = lane < HP;
+                    float *row = ac + lane;                 // row[k*HP] = slot k of this lane's unit
+                    const float *xa_p = xpA, *xn_p = xpN;
+#pragma unroll 1
+                    for (int tl = 0; tl < nt; ++tl) {
+                        const float4 *hb4 = reinterpret_cast<const float4 *>(hrow);
+                        float4 hv[HP / 4];
 #pragma unroll
-                    for (int k4 = 0; k4 < HP / 4; ++k4) hv[k4] = hb4[k4];
-                    // prefetch next step's input projection (independent of h)
-                    const int tn = (tl + 1 < nt) ? tl + 1 : tl;
-                    const float nxr = xp[tn * 3 * HP], nxz = xp[tn * 3 * HP + HP], nxn = xp[tn * 3 * HP + 2 * HP];
-                    // deferred activation stores of step tl-1 (off the dependent chain)
-                    if (tl > 0 && lane < HP) {
-                        float *prow = ac + (tl - 1) * ROW;
-                        prow[lane] = pr_; prow[HP + lane] = pz_; prow[2 * HP + lane] = pn_; prow[3 * HP + lane] = phg_;
-                    }
-                    float ar0 = xr, ar1 = 0.f, az0 = xz, az1 = 0.f, an0 = b_hn, an1 = 0.f;
+                        for (int k4 = 0; k4 < HP / 4; ++k4) hv[k4] = hb4[k4];
+                        xa_p += 3 * HP; xn_p += 3 * HP;
+                        const float nxa = *xa_p, nxn = *xn_p;
+                        if (wr && tl > 0) { row[-ROW] = pr_; row[HP - ROW] = pz_; row[2 * HP - ROW] = pn_; row[3 * HP - ROW] = phg_; }
+                        float a0 = xa, a1 = 0.f, b0 = b_hn, b1 = 0.f;
 #pragma unroll
-                    for (int k4 = 0; k4 < HP / 4; ++k4) {
-                        const float hk[4] = {hv[k4].x, hv[k4].y, hv[k4].z, hv[k4].w};
+                        for (int k4 = 0; k4 < HP / 4; ++k4) {
+                            const float hk[4] = {hv[k4].x, hv[k4].y, hv[k4].z, hv[k4].w};
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int k = k4 * 4 + e;
-                            if (k < HT) {
-                                if (k & 1) { ar1 = fmaf(whr[k], hk[e], ar1); an1 = fmaf(whn[k], hk[e], an1); az1 = fmaf(whz[k], hk[e], az1); }
-                                else       { ar0 = fmaf(whr[k], hk[e], ar0); an0 = fmaf(whn[k], hk[e], an0); az0 = fmaf(whz[k], hk[e], az0); }
+                            for (int e = 0; e < 4; ++e) {
+                                const int k = k4 * 4 + e;
+                                if (k < HT) {
+                                    if (k & 1) { a1 = fmaf(wA[k], hk[e], a1); b1 = fmaf(wB[k], hk[e], b1); }
+                                    else       { a0 = fmaf(wA[k], hk[e], a0); b0 = fmaf(wB[k], hk[e], b0); }
+                                }
                             }
                         }
+                        const float sA = sigmoidf_(a0 + a1);                       // r in lanes 0..15, z in lanes 16..31
+                        const float hgn = b0 + b1;
+                        const float z = __shfl_down_sync(ODPD_FULL, sA, 16);       // lower lanes: z of their unit
+                        const float n = tanhf_(fmaf(sA, hgn, xn));
+                        h = fmaf(h - n, z, n);
+                        if (wr) row[4 * HP] = h;
+                        hrow = row + 4 * HP - lane;
+                        row += ROW;
+                        pr_ = sA; pz_ = z; pn_ = n; phg_ = hgn;
+                        xa = nxa; xn = nxn;
+                        __syncwarp();
                     }
-                    const float r = sigmoidf_(ar0 + ar1);
-                    const float hgn = an0 + an1;
-                    const float z = sigmoidf_(az0 + az1);
-                    const float n = tanhf_(fmaf(r, hgn, xn));
-                    h = fmaf(h - n, z, n);
-                    float *row = ac + tl * ROW;
-                    if (lane < HP) row[4 * HP + lane] = h;
-                    hrow = row + 4 * HP;
-                    pr_ = r; pz_ = z; pn_ = n; phg_ = hgn;
-                    xr = nxr; xz = nxz; xn = nxn;
+                    if (lane < HP) {
+                        float *prow = ac + (nt - 1) * ROW;
+                        prow[lane] = pr_; prow[HP + lane] = pz_; prow[2 * HP + lane] = pn_; prow[3 * HP + lane] = phg_;
+                    }
                     __syncwarp();
+                    fence_async_smem();
                 }
-                if (lane < HP) {
-                    float *prow = ac + (nt - 1) * ROW;
-                    prow[lane] = pr_; prow[HP + lane] = pz_; prow[2 * HP + lane] = pn_; prow[3 * HP + lane] = phg_;
-                }
-                __syncwarp();
-                fence_async_smem();   // rows of this chunk are bulk-stored by the post warp next stage
+                __syncthreads();
             }
-            __syncthreads();
+        } else {
+        float whr[HT], whz[HT], whn[HT];
+#pragma unroll
+            for (int k = 0; k < HT; ++k) {
+                const bool ok = act && k < H;
+                whr[k] = ok ? sp[L.oWhh + (0 * H + j) * H + k] : 0.f;
+                whz[k] = ok ? sp[L.oWhh + (1 * H + j) * H + k] : 0.f;
+                whn[k] = ok ? sp[L.oWhh + (2 * H + j) * H + k] : 0.f;
+            }
+            const float b_hn = act ? sp[L.obhh + 2 * H + j] : 0.f;
+            const int lp = lane < HP ? lane : 0;  // clamp: lanes >= HP read lane 0's slot and never write
+            float h = 0.f;
+            for (int s = 0; s < nchunks + 2; ++s) {
+                const int c = s - 1;
+                if (c >= 0 && c < nchunks) {
+                    const int t0 = c * CH, nt = min(CH, T - t0);
+                    const float *xp = sxp + (c & 1) * SM::XP + lp;
+                    float *ac = sact + (c & 1) * SM::ACT;
+                    const float *hrow = (c == 0) ? zero : sact + ((c - 1) & 1) * SM::ACT + (CH - 1) * ROW + 4 * HP;
+                    float xr = xp[0], xz = xp[HP], xn = xp[2 * HP];
+                    float pr_ = 0.f, pz_ = 0.f, pn_ = 0.f, phg_ = 0.f;   // gate values of the previous step, stored one iteration late
+                    for (int tl = 0; tl < nt; ++tl) {
+                        // broadcast h_{t-1}: issue the loads first, everything below that does not need them fills the latency
+                        const float4 *hb4 = reinterpret_cast<const float4 *>(hrow);
+                        float4 hv[HP / 4];
+#pragma unroll
+                        for (int k4 = 0; k4 < HP / 4; ++k4) hv[k4] = hb4[k4];
+                        // prefetch next step's input projection (independent of h)
+                        const int tn = (tl + 1 < nt) ? tl + 1 : tl;
+                        const float nxr = xp[tn * 3 * HP], nxz = xp[tn * 3 * HP + HP], nxn = xp[tn * 3 * HP + 2 * HP];
+                        // deferred activation stores of step tl-1 (off the dependent chain)
+                        if (tl > 0 && lane < HP) {
+                            float *prow = ac + (tl - 1) * ROW;
+                            prow[lane] = pr_; prow[HP + lane] = pz_; prow[2 * HP + lane] = pn_; prow[3 * HP + lane] = phg_;
+                        }
+                        float ar0 = xr, ar1 = 0.f, az0 = xz, az1 = 0.f, an0 = b_hn, an1 = 0.f;
+#pragma unroll
+                        for (int k4 = 0; k4 < HP / 4; ++k4) {
+                            const float hk[4] = {hv[k4].x, hv[k4].y, hv[k4].z, hv[k4].w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const int k = k4 * 4 + e;
+                                if (k < HT) {
+                                    if (k & 1) { ar1 = fmaf(whr[k], hk[e], ar1); an1 = fmaf(whn[k], hk[e], an1); az1 = fmaf(whz[k], hk[e], az1); }
+                                    else       { ar0 = fmaf(whr[k], hk[e], ar0); an0 = fmaf(whn[k], hk[e], an0); az0 = fmaf(whz[k], hk[e], az0); }
+                                }
+                            }
+                        }
+                        const float r = sigmoidf_(ar0 + ar1);
+                        const float hgn = an0 + an1;
+                        const float z = sigmoidf_(az0 + az1);
+                        const float n = tanhf_(fmaf(r, hgn, xn));
+                        h = fmaf(h - n, z, n);
+                        float *row = ac + tl * ROW;
+                        if (lane < HP) row[4 * HP + lane] = h;
+                        hrow = row + 4 * HP;
+                        pr_ = r; pz_ = z; pn_ = n; phg_ = hgn;
+                        xr = nxr; xz = nxz; xn = nxn;
+                        __syncwarp();
+                    }
+                    if (lane < HP) {
+                        float *prow = ac + (nt - 1) * ROW;
+                        prow[lane] = pr_; prow[HP + lane] = pz_; prow[2 * HP + lane] = pn_; prow[3 * HP + lane] = phg_;
+                    }
+                    __syncwarp();
+                    fence_async_smem();   // rows of this chunk are bulk-stored by the post warp next stage
+                }
+                __syncthreads();
+            }
         }
     } else {
         // =============================== post: head, output, squared error, activation store
