@@ -154,68 +154,139 @@ __global__ void __launch_bounds__(96, 1) delta_fwd_kernel(GruArgs a) {
         }
     } else if (warp == 0) {
         // =============================== chain
+        if constexpr (HP <= 16) {
+            // half-warp split (see gru_family.cu): lanes 0..15 own the r / n-side rows of unit u, lanes 16..31 the z row
+            const int half = lane >> 4, u = lane & 15;
+            const bool au = u < H, lo = (half == 0);
+            const int ju = au ? u : 0, up = u < HP ? u : 0;
+            float wA[HT], wB[HT];
+#pragma unroll
+            for (int k = 0; k < HT; ++k) {
+                const bool ok = au && k < H;
+                wA[k] = ok ? sp[L.oWhh + ((half ? 1 : 0) * H + ju) * H + k] : 0.f;
+                wB[k] = (ok && lo) ? sp[L.oWhh + (2 * H + ju) * H + k] : 0.f;
+            }
+            float h = 0.f, hh = 0.f, MhA = 0.f;
+            float Mnh = (!TRES && au && lo) ? sp[L.obhh + 2 * H + ju] : 0.f;
+            long long zh = 0;
+            int cur = 0;
+            for (int s = 0; s < nchunks + 2; ++s) {
+                const int c = s - 1;
+                if (c >= 0 && c < nchunks) {
+                    const int t0 = c * CH, nt = min(CH, T - t0);
+                    const float *xa_p = sxp + (c & 1) * SM::XP + (half ? HP : 0) + up;
+                    const float *xn_p = sxp + (c & 1) * SM::XP + 2 * HP + up;
+                    float *row = sact + (c & 1) * SM::ACT + lane;
+                    float *rowm = sact + (c & 1) * SM::ACT + 6 * HP + 7;
+                    const bool wr = lane < HP;
+                    float xa = *xa_p, xn = *xn_p;
+#pragma unroll 1
+                    for (int tl = 0; tl < nt; ++tl) {
+                        xa_p += 3 * HP; xn_p += 3 * HP;
+                        const float nxa = *xa_p, nxn = *xn_p;       // one row past the chunk on the last step: in-bounds, unused
+                        const float d = h - hh, ad = fabsf(d);
+                        const float dh = (ad < thh) ? 0.f : d;
+                        const bool keep = ad >= thh;
+                        if (keep) hh = h;
+                        if (au && lo) zh += (dh == 0.f);
+                        const unsigned mh = __ballot_sync(ODPD_FULL, keep && au && lo);
+                        float *line = sdl + cur * HP;
+                        if (wr) line[lane] = au ? dh : 0.f;
+                        __syncwarp();
+                        float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+                        bcast_dot<HT>(line, wA, a0, a1);
+                        bcast_dot<HT>(line, wB, b0, b1);
+                        MhA += a0 + a1; Mnh += b0 + b1;
+                        const float sA = sigmoidf_(xa + MhA);                     // r (lanes 0..15) / z (lanes 16..31)
+                        const float z = __shfl_down_sync(ODPD_FULL, sA, 16);
+                        const float n = tanhf_(fmaf(sA, Mnh, xn));
+                        h = fmaf(z, h, (1.f - z) * n);
+                        if (wr) {
+                            row[0] = sA; row[HP] = z; row[2 * HP] = n; row[3 * HP] = Mnh; row[4 * HP] = h; row[5 * HP] = au ? dh : 0.f;
+                        }
+                        if (lane == 0) *rowm = __uint_as_float(mh);
+                        row += ROW; rowm += ROW;
+                        cur ^= 1;
+                        xa = nxa; xn = nxn;
+                    }
+                    __syncwarp();
+                    fence_async_smem();
+                }
+                __syncthreads();
+            }
+            if (a.stats) {
+                unsigned long long tot = (unsigned long long)zh;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(ODPD_FULL, tot, o);
+                if (lane == 0) {
+                    atomicAdd(reinterpret_cast<unsigned long long *>(a.stats) + 2, tot);
+                    atomicAdd(reinterpret_cast<unsigned long long *>(a.stats) + 3, (unsigned long long)T * H);
+                }
+            }
+        } else {
         float whr[HT], whz[HT], whn[HT];
 #pragma unroll
-        for (int k = 0; k < HT; ++k) {
-            const bool ok = act && k < H;
-            whr[k] = ok ? sp[L.oWhh + (0 * H + j) * H + k] : 0.f;
-            whz[k] = ok ? sp[L.oWhh + (1 * H + j) * H + k] : 0.f;
-            whn[k] = ok ? sp[L.oWhh + (2 * H + j) * H + k] : 0.f;
-        }
-        float h = 0.f, hh = 0.f, Mhr = 0.f, Mhz = 0.f;
-        float Mnh = (!TRES && act) ? sp[L.obhh + 2 * H + j] : 0.f;
-        long long zh = 0;
-        int cur = 0;
-        for (int s = 0; s < nchunks + 2; ++s) {
-            const int c = s - 1;
-            if (c >= 0 && c < nchunks) {
-                const int t0 = c * CH, nt = min(CH, T - t0);
-                const float *xp = sxp + (c & 1) * SM::XP + lp;
-                float *ac = sact + (c & 1) * SM::ACT;
-                float xr = xp[0], xz = xp[HP], xn = xp[2 * HP];
-                for (int tl = 0; tl < nt; ++tl) {
-                    const int tn = (tl + 1 < nt) ? tl + 1 : tl;
-                    const float nxr = xp[tn * 3 * HP], nxz = xp[tn * 3 * HP + HP], nxn = xp[tn * 3 * HP + 2 * HP];
-                    // h-side delta (compute_deltas / update_states)
-                    const float d = h - hh, ad = fabsf(d);
-                    const float dh = (ad < thh) ? 0.f : d;
-                    const bool keep = ad >= thh;
-                    if (keep) hh = h;
-                    if (act) zh += (dh == 0.f);
-                    const unsigned mh = __ballot_sync(ODPD_FULL, keep && act);
-                    float *line = sdl + cur * HP;
-                    if (lane < HP) line[lane] = act ? dh : 0.f;
-                    __syncwarp();
-                    float r0 = 0.f, r1 = 0.f, z0 = 0.f, z1 = 0.f, n0 = 0.f, n1 = 0.f;
-                    bcast_dot<HT>(line, whr, r0, r1);
-                    bcast_dot<HT>(line, whz, z0, z1);
-                    bcast_dot<HT>(line, whn, n0, n1);
-                    Mhr += r0 + r1; Mhz += z0 + z1; Mnh += n0 + n1;
-                    const float r = sigmoidf_(xr + Mhr);
-                    const float z = sigmoidf_(xz + Mhz);
-                    const float n = tanhf_(fmaf(r, Mnh, xn));
-                    h = fmaf(z, h, (1.f - z) * n);
-                    float *row = ac + tl * ROW;
-                    if (lane < HP) {
-                        row[lane] = r; row[HP + lane] = z; row[2 * HP + lane] = n; row[3 * HP + lane] = Mnh; row[4 * HP + lane] = h;
-                        row[5 * HP + lane] = act ? dh : 0.f;
-                    }
-                    if (lane == 0) row[6 * HP + 7] = __uint_as_float(mh);
-                    cur ^= 1;
-                    xr = nxr; xz = nxz; xn = nxn;
-                }
-                __syncwarp();
-                fence_async_smem();
+            for (int k = 0; k < HT; ++k) {
+                const bool ok = act && k < H;
+                whr[k] = ok ? sp[L.oWhh + (0 * H + j) * H + k] : 0.f;
+                whz[k] = ok ? sp[L.oWhh + (1 * H + j) * H + k] : 0.f;
+                whn[k] = ok ? sp[L.oWhh + (2 * H + j) * H + k] : 0.f;
             }
-            __syncthreads();
-        }
-        if (a.stats) {
-            unsigned long long tot = (unsigned long long)zh;
+            float h = 0.f, hh = 0.f, Mhr = 0.f, Mhz = 0.f;
+            float Mnh = (!TRES && act) ? sp[L.obhh + 2 * H + j] : 0.f;
+            long long zh = 0;
+            int cur = 0;
+            for (int s = 0; s < nchunks + 2; ++s) {
+                const int c = s - 1;
+                if (c >= 0 && c < nchunks) {
+                    const int t0 = c * CH, nt = min(CH, T - t0);
+                    const float *xp = sxp + (c & 1) * SM::XP + lp;
+                    float *ac = sact + (c & 1) * SM::ACT;
+                    float xr = xp[0], xz = xp[HP], xn = xp[2 * HP];
+                    for (int tl = 0; tl < nt; ++tl) {
+                        const int tn = (tl + 1 < nt) ? tl + 1 : tl;
+                        const float nxr = xp[tn * 3 * HP], nxz = xp[tn * 3 * HP + HP], nxn = xp[tn * 3 * HP + 2 * HP];
+                        // h-side delta (compute_deltas / update_states)
+                        const float d = h - hh, ad = fabsf(d);
+                        const float dh = (ad < thh) ? 0.f : d;
+                        const bool keep = ad >= thh;
+                        if (keep) hh = h;
+                        if (act) zh += (dh == 0.f);
+                        const unsigned mh = __ballot_sync(ODPD_FULL, keep && act);
+                        float *line = sdl + cur * HP;
+                        if (lane < HP) line[lane] = act ? dh : 0.f;
+                        __syncwarp();
+                        float r0 = 0.f, r1 = 0.f, z0 = 0.f, z1 = 0.f, n0 = 0.f, n1 = 0.f;
+                        bcast_dot<HT>(line, whr, r0, r1);
+                        bcast_dot<HT>(line, whz, z0, z1);
+                        bcast_dot<HT>(line, whn, n0, n1);
+                        Mhr += r0 + r1; Mhz += z0 + z1; Mnh += n0 + n1;
+                        const float r = sigmoidf_(xr + Mhr);
+                        const float z = sigmoidf_(xz + Mhz);
+                        const float n = tanhf_(fmaf(r, Mnh, xn));
+                        h = fmaf(z, h, (1.f - z) * n);
+                        float *row = ac + tl * ROW;
+                        if (lane < HP) {
+                            row[lane] = r; row[HP + lane] = z; row[2 * HP + lane] = n; row[3 * HP + lane] = Mnh; row[4 * HP + lane] = h;
+                            row[5 * HP + lane] = act ? dh : 0.f;
+                        }
+                        if (lane == 0) row[6 * HP + 7] = __uint_as_float(mh);
+                        cur ^= 1;
+                        xr = nxr; xz = nxz; xn = nxn;
+                    }
+                    __syncwarp();
+                    fence_async_smem();
+                }
+                __syncthreads();
+            }
+            if (a.stats) {
+                unsigned long long tot = (unsigned long long)zh;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(ODPD_FULL, tot, o);
-            if (lane == 0) {
-                atomicAdd(reinterpret_cast<unsigned long long *>(a.stats) + 2, tot);
-                atomicAdd(reinterpret_cast<unsigned long long *>(a.stats) + 3, (unsigned long long)T * H);
+                for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(ODPD_FULL, tot, o);
+                if (lane == 0) {
+                    atomicAdd(reinterpret_cast<unsigned long long *>(a.stats) + 2, tot);
+                    atomicAdd(reinterpret_cast<unsigned long long *>(a.stats) + 3, (unsigned long long)T * H);
+                }
             }
         }
     } else {
