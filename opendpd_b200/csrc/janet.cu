@@ -436,7 +436,10 @@ __global__ void __launch_bounds__(96, 1) dvrjanet_fwd_kernel(GruArgs a) {
             wsh[k] = ok ? sp[L.oWs + j * H2 + k] : 0.f; wsv[k] = ok ? sp[L.oWs + j * H2 + H + k] : 0.f;
         }
         const float bf = act ? sp[L.obf + j] : 0.f, bc = act ? sp[L.obc + j] : 0.f, bs = act ? sp[L.obs + j] : 0.f;
-        const float invK = 1.0f / (float)K;
+        // DVR knots k/K (rounded once from double, as the reference's python float -> tensor dtype conversion) and coefficients
+        float knot[8], ck[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { knot[k] = (float)((double)(k + 1) / (double)K); ck[k] = k < K ? sp[L.ocs + k] : 0.f; }
         float hI = 0.f, hQ = 0.f;
         int cur = 0;
         for (int s = 0; s < nchunks + 2; ++s) {
@@ -461,8 +464,8 @@ __global__ void __launch_bounds__(96, 1) dvrjanet_fwd_kernel(GruArgs a) {
                     bcast_dot<HT>(prow + 8 * HP, wsh, gs0, gs1);
                     const float tht = t0a + t1a, pa = p0 + p1;
                     float at = 0.f;
-                    for (int k = 1; k <= K; ++k) at = fmaf(fabsf(pa - (float)((double)k / (double)K)), sp[L.ocs + k - 1], at);
-                    (void)invK;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) at = fmaf(fabsf(pa - knot[k]), ck[k], at);   // ck = 0 beyond K
                     float st, ct;
                     sincosf(tht, &st, &ct);
                     const float f = sigmoidf_(f0 + f1);
@@ -575,6 +578,9 @@ __global__ void __launch_bounds__(96, 1) dvrjanet_bwd_kernel(GruArgs a) {
             csh[k] = ok ? sp[L.oWs + k * H2 + j] : 0.f; csv[k] = ok ? sp[L.oWs + k * H2 + H + j] : 0.f;
             cph[k] = ok ? sp[L.oWph + k * H + j] : 0.f; cah[k] = ok ? sp[L.oWah + k * H + j] : 0.f; cf[k] = ok ? sp[L.oWf + k * H + j] : 0.f;
         }
+        float knot[8], ck[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { knot[k] = (float)((double)(k + 1) / (double)K); ck[k] = k < K ? sp[L.ocs + k] : 0.f; }
         float gI = 0.f, gQ = 0.f;
         for (int s = 0; s < nchunks + 2; ++s) {
             const int sc = s - 1;
@@ -604,9 +610,10 @@ __global__ void __launch_bounds__(96, 1) dvrjanet_bwd_kernel(GruArgs a) {
                     const float gat = fmaf(gvc, ct, gvs * st);
                     const float gtht = at * fmaf(gvs, ct, -gvc * st);
                     float sg = 0.f;
-                    for (int k = 1; k <= K; ++k) {
-                        const float d = pa - (float)((double)k / (double)K);
-                        sg += sp[L.ocs + k - 1] * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const float d = pa - knot[k];
+                        sg = fmaf(ck[k], d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f), sg);
                     }
                     const float gpa = gat * sg;
                     if (lane < HP) { G[3 * HP + lane] = act ? gtht : 0.f; G[4 * HP + lane] = act ? gpa : 0.f; G[5 * HP + lane] = act ? gat : 0.f; }
@@ -634,6 +641,9 @@ __global__ void __launch_bounds__(96, 1) dvrjanet_bwd_kernel(GruArgs a) {
             for (int k = 0; k < HT; ++k) { gch[k] = gcv[k] = gsh[k] = gsvv[k] = gph[k] = gah[k] = gff[k] = 0.f; }
         }
         float gcs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        float knot[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) knot[k] = (float)((double)(k + 1) / (double)K);
         float gpt = 0.f, gax = 0.f, gbf = 0.f, gbc = 0.f, gbs = 0.f, gwo0 = 0.f, gwo1 = 0.f, gbo0 = 0.f, gbo1 = 0.f;
         float2 *gx2 = (a.need_dx && a.gx) ? reinterpret_cast<float2 *>(a.gx) + (size_t)b * T : nullptr;
         for (int s = 0; s < nchunks + 2; ++s) {
@@ -654,8 +664,7 @@ __global__ void __launch_bounds__(96, 1) dvrjanet_bwd_kernel(GruArgs a) {
                         gpt = fmaf(gtht, p0.w, gpt); gax = fmaf(gpa, p0.z, gax);
                         gwo0 = fmaf(go.x, row[7 * HP + lp], gwo0); gwo1 = fmaf(go.y, row[8 * HP + lp], gwo1);
 #pragma unroll
-                        for (int k = 1; k <= 8; ++k)
-                            if (k <= K) gcs[k - 1] = fmaf(gat, fabsf(pa - (float)((double)k / (double)K)), gcs[k - 1]);
+                        for (int k = 0; k < 8; ++k) gcs[k] = fmaf(gat, fabsf(pa - knot[k]), gcs[k]);   // entries >= K are never written out
                         const float4 *G4 = reinterpret_cast<const float4 *>(G);
 #pragma unroll
                         for (int k4 = 0; k4 < HP / 4; ++k4) {
