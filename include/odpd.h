@@ -76,16 +76,35 @@ typedef struct OdpdDims {
     int32_t K;      /* DVRJANET num_dvr_units (dvrjanet.py:6); QAT cells: bit widths */
     uint32_t flags; /* ODPD_F_*                                            */
     float thx, thh; /* delta thresholds (deltagru.py:216-217)              */
+    int32_t tchunks; /* GRU/DGRU/QGRU: time chunks a sequence is cut into and run concurrently (see below).
+                        0 = the library picks from B, T and the SM count; 1 = plain serial recurrence; n = exactly n (<=32) */
+    int32_t twarm;   /* warm-up steps in front of every chunk (rounded up to 32); 0 = default 128 */
 } OdpdDims;
+
+/*
+ * Time-chunked execution (GRU-family cells).  The reference's frames are T-step serial recurrences (nn.GRU inside
+ * gru.py:46 / dgru.py:70 / qgru.py:69) and its batches hold fewer sequences than a B200 has SMs.  A GRU forgets its initial
+ * state geometrically, so the kernels cut each sequence into `tchunks` chunks that run concurrently, each preceded by `twarm`
+ * warm-up steps started from h = 0 (backward: from dL/dh = 0, in reverse time); a verify pass then compares the state every
+ * chunk was started from with the state its predecessor really ended with (|dh| <= 2^-22 forward, 2^-21 relative backward)
+ * and re-runs, serially, every sequence with a failing boundary.  Results therefore never depend on the forgetting
+ * assumption; only the speed does.  odpd_chunk_plan reports what a call with these dims will do:
+ *   out[0] chunks, out[1] steps per chunk, out[2] warm-up steps, out[3] index (in 4-byte units, or -1) of an int32 counter
+ *   inside `saved` (backward = 0) / `workspace` (backward = 1) that counts sequences the verify pass had to re-run; the
+ *   caller zeroes it when it allocates the buffer.
+ */
+int odpd_chunk_plan(const OdpdDims *d, int32_t backward, int32_t out[4]);
 
 int odpd_version(void);
 const char *odpd_last_error(void);
 
 /* number of fp32 parameters of a backbone == reference count_net_params (utils/util.py) of `backbone` */
 int64_t odpd_n_params(int32_t cell, int32_t H, int32_t K);
-/* bytes of the caller-allocated `saved` buffer a forward with ODPD_F_SAVE fills for the matching backward */
+/* bytes of the caller-allocated `saved` buffer odpd_backbone_fwd needs for these dims: the activations a forward with
+ * ODPD_F_SAVE stores for the matching backward, plus (GRU-family, tchunks != 1) a small chunk scratch that is also needed
+ * without ODPD_F_SAVE (0 = no buffer needed, `saved` may be NULL) */
 int64_t odpd_saved_bytes(const OdpdDims *d);
-/* bytes of the caller-allocated scratch `workspace` odpd_backbone_bwd needs (per-sequence grad partials) */
+/* bytes of the caller-allocated scratch `workspace` odpd_backbone_bwd needs (per-(sequence,chunk) grad partials + chunk scratch) */
 int64_t odpd_bwd_workspace_bytes(const OdpdDims *d);
 
 /*
@@ -111,7 +130,7 @@ int odpd_backbone_fwd(const OdpdDims *d, const float *x, const float *target, co
  *                   gscale_dev is an optional device scalar = the upstream dLoss, NULL == 1)
  *   gx              (B,T,2) out (overwritten) when ODPD_F_NEED_DX, else may be NULL
  *   gparams         flat fp32, ACCUMULATED (+=) when ODPD_F_NEED_DW, else may be NULL
- *   workspace       odpd_bwd_workspace_bytes(d)
+ *   workspace       odpd_bwd_workspace_bytes(d)  (may be NULL for a dX-only backward: it then runs the plain serial recurrence)
  * The reduction of per-sequence gradient partials is ordered (no float atomics): results are bit-reproducible
  * run to run for fixed (B,T).
  */

@@ -15,7 +15,8 @@ F_NEED_DX, F_NEED_DW, F_SAVE, F_OVERWRITE_DW, F_ZERO_LOSS = 1, 2, 4, 8, 16
 
 class OdpdDims(ctypes.Structure):
     _fields_ = [("cell", ctypes.c_int32), ("B", ctypes.c_int32), ("T", ctypes.c_int32), ("H", ctypes.c_int32),
-                ("K", ctypes.c_int32), ("flags", ctypes.c_uint32), ("thx", ctypes.c_float), ("thh", ctypes.c_float)]
+                ("K", ctypes.c_int32), ("flags", ctypes.c_uint32), ("thx", ctypes.c_float), ("thh", ctypes.c_float),
+                ("tchunks", ctypes.c_int32), ("twarm", ctypes.c_int32)]
 
 
 class OdpdError(RuntimeError):
@@ -33,6 +34,7 @@ SYMBOLS = {
     "odpd_n_params": (_i64, [_i32, _i32, _i32]),
     "odpd_saved_bytes": (_i64, [_DP]),
     "odpd_bwd_workspace_bytes": (_i64, [_DP]),
+    "odpd_chunk_plan": (ctypes.c_int, [_DP, _i32, ctypes.POINTER(_i32)]),
     "odpd_backbone_fwd": (ctypes.c_int, [_DP, _vp, _vp, _vp, _vp, _vp, _dbl, _vp, _vp, _vp]),
     "odpd_backbone_bwd": (ctypes.c_int, [_DP, _vp, _vp, _vp, _vp, _vp, _vp, _dbl, _vp, _vp, _vp, _vp, _vp]),
     "odpd_clip_adamw": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _flt, _flt, _flt, _flt, _flt, _vp, _vp,

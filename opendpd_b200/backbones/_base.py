@@ -61,7 +61,8 @@ class NativeBackbone(nn.Module, FlatParams):
 
     def _spec(self):
         return CellSpec(self.cell, getattr(self, "hidden_size", 0), getattr(self, "num_dvr_units", 0),
-                        getattr(self, "thx", 0.0), getattr(self, "thh", 0.0))
+                        getattr(self, "thx", 0.0), getattr(self, "thh", 0.0), getattr(self, "time_chunks", None),
+                        getattr(self, "time_warmup", None))
 
     def _stats_tensor(self, device):
         return None

@@ -121,12 +121,23 @@ int64_t odpd_n_params(int32_t cell, int32_t H, int32_t K) {
 
 int64_t odpd_saved_bytes(const OdpdDims *d) {
     if (check_dims(d)) return -1;
-    if (is_gru_family(d->cell)) return 4 * gru_family_saved_floats(d->cell, d->B, d->T, d->H);
-    return other_saved_bytes(d);
+    const bool save = (d->flags & ODPD_F_SAVE) != 0;
+    if (is_gru_family(d->cell)) {
+        const int64_t n = gru_family_saved_floats(d->cell, d->B, d->T, d->H, save, d->tchunks);
+        if (n < 0) { set_error("GRU-family kernels support hidden_size <= 32 (got %d)", d->H); return -1; }
+        return 4 * n;
+    }
+    const int64_t n = other_saved_bytes(d);
+    return (n < 0 || save) ? n : 0;
 }
 
 int64_t odpd_bwd_workspace_bytes(const OdpdDims *d) {
     if (check_dims(d)) return -1;
+    if (is_gru_family(d->cell)) {
+        const int64_t n = gru_family_workspace_floats(d->cell, d->B, d->H, d->tchunks);
+        if (n < 0) { set_error("GRU-family kernels support hidden_size <= 32 (got %d)", d->H); return -1; }
+        return 4 * n + 64;
+    }
     return 4 * (int64_t)(d->B > 0 ? d->B : 1) * odpd_n_params(d->cell, d->H, d->K) + 64;
 }
 
@@ -148,7 +159,8 @@ int odpd_backbone_fwd(const OdpdDims *d, const float *x, const float *target, co
         GruArgs a{};
         a.B = d->B; a.T = d->T; a.H = d->H; a.x = x; a.target = target; a.params = params; a.out = out; a.loss = loss;
         a.loss_scale = (float)loss_scale; a.saved = (float *)saved; a.save = save;
-        return gru_family_run(d->cell, a, 0, false, st);
+        a.tchunks_req = d->tchunks; a.twarm_req = d->twarm;
+        return gru_family_run(d->cell, a, 0, false, st, nullptr);
     }
     return other_fwd(d, x, target, params, out, loss, loss_scale, saved, stats, st);
 }
@@ -167,18 +179,33 @@ int odpd_backbone_bwd(const OdpdDims *d, const float *x, const float *params, co
     ODPD_CHECK(x && (saved || d->cell == ODPD_CELL_GMP), "x/saved must not be NULL");
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t P = odpd_n_params(d->cell, d->H, d->K);
-    int rc;
+    int rc, rows = d->B;
     if (is_gru_family(d->cell)) {
         GruArgs a{};
         a.B = d->B; a.T = d->T; a.H = d->H; a.x = x; a.params = params; a.saved = (float *)saved; a.gout = gout; a.out_in = out;
         a.target = target; a.gscale = (float)gscale; a.gscale_dev = gscale_dev; a.gx = gx; a.partials = (float *)workspace;
         a.need_dx = dx;
-        rc = gru_family_run(d->cell, a, 1, dw, st);
+        a.tchunks_req = d->tchunks; a.twarm_req = d->twarm;
+        rc = gru_family_run(d->cell, a, 1, dw, st, &rows);
     } else {
         rc = other_bwd(d, x, params, saved, gout, out, target, gscale, gscale_dev, gx, (float *)workspace, st);
     }
     if (rc) return rc;
-    if (dw) return reduce_partials((const float *)workspace, d->B, P, gparams, (d->flags & ODPD_F_OVERWRITE_DW) != 0, st);
+    if (dw) return reduce_partials((const float *)workspace, rows, P, gparams, (d->flags & ODPD_F_OVERWRITE_DW) != 0, st);
+    return 0;
+}
+
+int odpd_chunk_plan(const OdpdDims *d, int32_t backward, int32_t out[4]) {
+    if (check_dims(d)) return -1;
+    ODPD_CHECK(out != nullptr, "out is NULL");
+    out[0] = 1; out[1] = d->T; out[2] = 0; out[3] = -1;
+    if (!is_gru_family(d->cell) || d->B == 0 || d->T == 0) return 0;
+    int info[4];
+    const int rc = gru_family_plan(d->cell, d->B, d->T, d->H, d->tchunks, d->twarm, backward ? 1 : 0, (d->flags & ODPD_F_NEED_DW) != 0,
+                                   (d->flags & ODPD_F_SAVE) != 0, info);
+    if (rc) return rc;
+    for (int i = 0; i < 4; ++i) out[i] = info[i];
+    if (d->tchunks == 1) out[3] = -1;
     return 0;
 }
 

@@ -16,12 +16,28 @@ struct GruArgs {
     float thx, thh;
     int64_t *stats;
     int K, cell;
+    // time-chunked ("speculative") execution of the contractive GRU-family recurrences (gru_family.cu):
+    //   C      chunks per sequence (1 = plain serial), Lc = steps per chunk (multiple of 32), Wu = warm-up steps
+    //   mode   0 = run (serial when C==1, else one CTA per (sequence, chunk)), 2 = verify every chunk boundary and re-run the
+    //          sequences that failed serially
+    //   sc_guess/sc_end [B*C][HP]: state a chunk started from after its warm-up / state it ended with;  sc_loss [B*C]: per-chunk
+    //   squared error;  sc_fail: number of sequences that needed the serial re-run (diagnostic)
+    int C, Lc, Wu, mode;
+    float *sc_guess, *sc_end, *sc_loss;
+    int *sc_fail;
+    float tol;
+    int tchunks_req, twarm_req;
 };
 
 // gru_family.cu : GRU / DGRU / QGRU / QGRU_AMP1
 int64_t gru_family_nparams(int cell, int H);
-int64_t gru_family_saved_floats(int cell, int B, int T, int H);
-int gru_family_run(int cell, const GruArgs &a, int dir, bool dw, cudaStream_t st);
+int64_t gru_family_saved_floats(int cell, int B, int T, int H, bool save, int tchunks_req);
+int64_t gru_family_workspace_floats(int cell, int B, int H, int tchunks_req);
+int gru_family_run(int cell, const GruArgs &a, int dir, bool dw, cudaStream_t st, int *rows_out);
+// rows of the per-(sequence,chunk) scratch / gradient-partial workspace for a call of B sequences
+int64_t gru_family_rows(int B, int tchunks_req);
+int64_t gru_family_scratch_floats(int B, int H, int tchunks_req);       // tail of `saved` (fwd) / of the workspace (bwd)
+int gru_family_plan(int cell, int B, int T, int H, int tchunks_req, int twarm_req, int dir, bool dw, bool save, int out[4]);
 
 #define ODPD_HAVE_DELTA 1
 #define ODPD_HAVE_JANET 1

@@ -72,7 +72,37 @@ __global__ void __launch_bounds__(96, 1) gru_fwd_kernel(GruArgs a) {
     float *sact = sft + 3 * SM::FT;          // [2][CH][ROW]
     float *spo = sact + 2 * SM::ACT;         // [2][CH][33]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.x;
+    // time range of this CTA: warm-up [t_lo, t_emit) from h = 0 (nothing emitted), then the emitted steps [t_emit, t_hi)
+    const bool spec = (a.C > 1 && a.mode == 0);
+    int b = blockIdx.x, cc = 0, t_lo = 0, t_emit = 0, t_hi = T;
+    if (spec) {
+        b = blockIdx.x / a.C; cc = blockIdx.x - b * a.C;
+        t_emit = cc * a.Lc; t_lo = max(0, t_emit - a.Wu); t_hi = min(T, t_emit + a.Lc);
+    }
+    if (a.mode == 2) {
+        // verify pass: the state every chunk was started from (after its warm-up) must equal the state the previous chunk ended
+        // with; sequences that pass are done, the others are recomputed serially by this CTA
+        __shared__ int s_bad;
+        if (threadIdx.x == 0) s_bad = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < (a.C - 1) * HP; i += blockDim.x) {
+            const int c1 = 1 + i / HP, k = i % HP;
+            if (k < H) {
+                const float g = a.sc_guess[((size_t)b * a.C + c1) * HP + k], e = a.sc_end[((size_t)b * a.C + c1 - 1) * HP + k];
+                if (!(fabsf(g - e) <= a.tol)) s_bad = 1;
+            }
+        }
+        __syncthreads();
+        if (!s_bad) {
+            if (threadIdx.x == 0 && a.loss && a.target) {
+                float sl = 0.f;
+                for (int c1 = 0; c1 < a.C; ++c1) sl += a.sc_loss[(size_t)b * a.C + c1];
+                atomicAdd(a.loss, (double)sl * (double)a.loss_scale);
+            }
+            return;
+        }
+        if (threadIdx.x == 0) atomicAdd(a.sc_fail, 1);
+    }
 
     stage_params(sp, a.params, L.P, bars);
     if (threadIdx.x < HP) zero[threadIdx.x] = 0.f;
@@ -80,7 +110,7 @@ __global__ void __launch_bounds__(96, 1) gru_fwd_kernel(GruArgs a) {
 
     const bool act = lane < H;
     const int j = act ? lane : 0;
-    const int nchunks = (T + CH - 1) / CH;
+    const int cb = t_lo / CH, nchunks = (t_hi + CH - 1) / CH - cb;   // pipeline stages q = 0..nchunks-1 cover 32-step blocks cb+q
     const float2 *x2 = reinterpret_cast<const float2 *>(a.x) + (size_t)b * T;
 
     if (warp == 1) {
@@ -97,7 +127,7 @@ __global__ void __launch_bounds__(96, 1) gru_fwd_kernel(GruArgs a) {
         const float b_in = act ? sp[L.obih + 2 * H + j] : 0.f;
         for (int s = 0; s < nchunks + 2; ++s) {
             if (s < nchunks) {
-                const int t0 = s * CH, nt = min(CH, T - t0);
+                const int t0 = (cb + s) * CH, nt = min(CH, t_hi - t0);
                 float *ft = sft + (s % 3) * SM::FT, *xp = sxp + (s & 1) * SM::XP;
                 if (lane < nt) {
                     const float2 v = __ldg(x2 + t0 + lane);
@@ -146,7 +176,8 @@ __global__ void __launch_bounds__(96, 1) gru_fwd_kernel(GruArgs a) {
             for (int s = 0; s < nchunks + 2; ++s) {
                 const int c = s - 1;
                 if (c >= 0 && c < nchunks) {
-                    const int t0 = c * CH, nt = min(CH, T - t0);
+                    const int t0 = (cb + c) * CH, nt = min(CH, t_hi - t0);
+                    if (spec && cc > 0 && t0 == t_emit && lane < HP) a.sc_guess[(size_t)blockIdx.x * HP + lane] = h;
                     const float *xpA = sxp + (c & 1) * SM::XP + (half ? HP : 0) + up;     // xr (lower) / xz (upper)
                     const float *xpN = sxp + (c & 1) * SM::XP + 2 * HP + up;
                     float *ac = sact + (c & 1) * SM::ACT;
@@ -201,6 +232,7 @@ __global__ void __launch_bounds__(96, 1) gru_fwd_kernel(GruArgs a) {
                 }
                 __syncthreads();
             }
+            if (spec && lane < HP) a.sc_end[(size_t)blockIdx.x * HP + lane] = h;
         } else {
         float whr[HT], whz[HT], whn[HT];
 #pragma unroll
@@ -216,7 +248,8 @@ __global__ void __launch_bounds__(96, 1) gru_fwd_kernel(GruArgs a) {
             for (int s = 0; s < nchunks + 2; ++s) {
                 const int c = s - 1;
                 if (c >= 0 && c < nchunks) {
-                    const int t0 = c * CH, nt = min(CH, T - t0);
+                    const int t0 = (cb + c) * CH, nt = min(CH, t_hi - t0);
+                    if (spec && cc > 0 && t0 == t_emit && lane < HP) a.sc_guess[(size_t)blockIdx.x * HP + lane] = h;
                     const float *xp = sxp + (c & 1) * SM::XP + lp;
                     float *ac = sact + (c & 1) * SM::ACT;
                     const float *hrow = (c == 0) ? zero : sact + ((c - 1) & 1) * SM::ACT + (CH - 1) * ROW + 4 * HP;
@@ -270,6 +303,7 @@ __global__ void __launch_bounds__(96, 1) gru_fwd_kernel(GruArgs a) {
                 }
                 __syncthreads();
             }
+            if (spec && lane < HP) a.sc_end[(size_t)blockIdx.x * HP + lane] = h;
         }
     } else {
         // =============================== post: head, output, squared error, activation store
@@ -288,8 +322,8 @@ __global__ void __launch_bounds__(96, 1) gru_fwd_kernel(GruArgs a) {
         float lsum = 0.f;
         for (int s = 0; s < nchunks + 2; ++s) {
             const int c = s - 2;
-            if (c >= 0) {
-                const int t0 = c * CH, nt = min(CH, T - t0);
+            if (c >= 0 && (cb + c) * CH >= t_emit) {       // warm-up blocks emit nothing
+                const int t0 = (cb + c) * CH, nt = min(CH, t_hi - t0);
                 float *ac = sact + (c & 1) * SM::ACT;
                 const float *ft = sft + (c % 3) * SM::FT;
 #pragma unroll 2
@@ -343,9 +377,12 @@ __global__ void __launch_bounds__(96, 1) gru_fwd_kernel(GruArgs a) {
             }
             __syncthreads();
         }
-        if (a.loss && y2) {
+        if (y2) {
             lsum = warp_sum(lsum);
-            if (lane == 0) atomicAdd(a.loss, (double)lsum * (double)a.loss_scale);
+            if (lane == 0) {
+                if (spec) a.sc_loss[blockIdx.x] = lsum;       // summed by the verify pass
+                else if (a.loss) atomicAdd(a.loss, (double)lsum * (double)a.loss_scale);
+            }
         }
     }
 }
@@ -371,7 +408,30 @@ __global__ void __launch_bounds__(128, 1) gru_bwd_kernel(GruArgs a) {
     float *sG = sdp + 3 * SM::DH;            // [2][CH][4*HP]
     float *sdf = sG + 2 * SM::G;             // [CH][8]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.x;
+    // time range of this CTA (reverse time): warm-up steps [t_ehi, t_hi) from dL/dh = 0 (nothing emitted), then [t_elo, t_ehi)
+    const bool spec = (a.C > 1 && a.mode == 0);
+    int b = blockIdx.x, t_elo = 0, t_ehi = T, t_hi = T;
+    if (spec) {
+        b = blockIdx.x / a.C;
+        const int cc = blockIdx.x - b * a.C;
+        t_elo = cc * a.Lc; t_ehi = min(T, t_elo + a.Lc); t_hi = min(T, t_ehi + a.Wu);
+    }
+    if (a.mode == 2) {
+        // verify pass: dL/dh a chunk started from (after its warm-up over the following steps) against what the following chunk
+        // really handed down; relative to the size of that vector.  Failing sequences are recomputed serially by this CTA.
+        __shared__ int s_bad;
+        if (threadIdx.x == 0) s_bad = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < a.C - 1; i += blockDim.x) {
+            const float *g = a.sc_guess + ((size_t)b * a.C + i) * HP, *e = a.sc_end + ((size_t)b * a.C + i + 1) * HP;
+            float m = 0.f, dmax = 0.f;
+            for (int k = 0; k < H; ++k) { m = fmaxf(m, fabsf(e[k])); dmax = fmaxf(dmax, fabsf(g[k] - e[k])); }
+            if (!(dmax <= a.tol * m + 1e-37f) || !(m == m)) s_bad = 1;
+        }
+        __syncthreads();
+        if (!s_bad) return;
+        if (threadIdx.x == 0) atomicAdd(a.sc_fail, 1);
+    }
 
     if (threadIdx.x == 0) { mbar_init(bars + 1, 1); mbar_init(bars + 2, 1); mbar_init(bars + 3, 1); }
     stage_params(sp, a.params, L.P, bars);   // contains the mbarrier-init fence + __syncthreads
@@ -379,7 +439,8 @@ __global__ void __launch_bounds__(128, 1) gru_bwd_kernel(GruArgs a) {
     const bool act = lane < H;
     const int j = act ? lane : 0;
     const int lp = lane < HP ? lane : 0;
-    const int nchunks = (T + CH - 1) / CH;
+    // 32-step blocks [cb, ce) are processed last to first; blocks >= ce_emit are warm-up
+    const int cb = t_elo / CH, ce = (t_hi + CH - 1) / CH, nchunks = ce - cb, ce_emit = (t_ehi + CH - 1) / CH;
     const float2 *x2 = reinterpret_cast<const float2 *>(a.x) + (size_t)b * T;
     const float *svg = a.saved + (size_t)b * T * ROW;
 
@@ -398,7 +459,7 @@ __global__ void __launch_bounds__(128, 1) gru_bwd_kernel(GruArgs a) {
         const float gs = a.gscale * (a.gscale_dev ? __ldg(a.gscale_dev) : 1.0f);
         for (int s = 0; s < nchunks + 2; ++s) {
             if (s < nchunks) {
-                const int c = nchunks - 1 - s, t0 = c * CH, nt = min(CH, T - t0);
+                const int c = ce - 1 - s, t0 = c * CH, nt = min(CH, t_hi - t0);
                 const int slot = s % 3;
                 float *ac = sact + slot * SM::ACT;
                 float *pr = spre + slot * SM::PRE;
@@ -479,7 +540,8 @@ __global__ void __launch_bounds__(128, 1) gru_bwd_kernel(GruArgs a) {
         for (int s = 0; s < nchunks + 2; ++s) {
             const int sc = s - 1;
             if (sc >= 0 && sc < nchunks) {
-                const int c = nchunks - 1 - sc, t0 = c * CH, nt = min(CH, T - t0);
+                const int c = ce - 1 - sc, t0 = c * CH, nt = min(CH, t_hi - t0);
+                if (spec && c == ce_emit - 1 && t_ehi < T && lane < HP) a.sc_guess[(size_t)blockIdx.x * HP + lane] = gH;
                 const float *ac = sact + (sc % 3) * SM::ACT + lp;
                 const float *dh = sdh + (sc & 1) * SM::DH + lp;
                 float *Gb = sG + (sc & 1) * SM::G;
@@ -525,6 +587,7 @@ __global__ void __launch_bounds__(128, 1) gru_bwd_kernel(GruArgs a) {
             }
             __syncthreads();
         }
+        if (spec && lane < HP) a.sc_end[(size_t)blockIdx.x * HP + lane] = gH;
     } else {
         // =============================== post (two warps, the FFMA issue rate of one warp is the limit):
         //   warp 2 "post-A": dL/dW_hh (3H accumulators per lane)
@@ -555,8 +618,8 @@ __global__ void __launch_bounds__(128, 1) gru_bwd_kernel(GruArgs a) {
         float2 *gx2 = (a.need_dx && a.gx) ? reinterpret_cast<float2 *>(a.gx) + (size_t)b * T : nullptr;
         for (int s = 0; s < nchunks + 2; ++s) {
             const int sc = s - 2;
-            if (sc >= 0) {
-                const int c = nchunks - 1 - sc, t0 = c * CH, nt = min(CH, T - t0);
+            if (sc >= 0 && ce - 1 - sc < ce_emit) {          // warm-up blocks emit nothing
+                const int c = ce - 1 - sc, t0 = c * CH, nt = min(CH, t_hi - t0);
                 const float *ac = sact + (sc % 3) * SM::ACT;
                 const float *pr = spre + (sc % 3) * SM::PRE;
                 const float *dp = sdp + (sc % 3) * SM::DH;
@@ -671,7 +734,13 @@ __global__ void __launch_bounds__(128, 1) gru_bwd_kernel(GruArgs a) {
         }
         if constexpr (DW) {
             if (a.partials) {
-                float *prt = a.partials + (size_t)b * L.P;
+                // one partial row per CTA: (sequence, chunk) when chunked, else the sequence's first row (the serial re-run of the
+                // verify pass then clears the sequence's other rows)
+                float *prt = a.partials + (size_t)(spec ? blockIdx.x : b * a.C) * L.P;
+                if (a.mode == 2) {
+                    const int tid = threadIdx.x - 64;   // the two post warps
+                    for (int i = tid; i < (a.C - 1) * L.P; i += 64) prt[L.P + i] = 0.f;
+                }
                 if (roleA) {
                     if (act) {
 #pragma unroll
@@ -723,35 +792,138 @@ static int gru_tier(int H) {
     return -1;
 }
 
+// ---------------------------------------------------------------- time-chunk plan
+// A GRU started from the wrong state forgets it geometrically (contractive gates), so a sequence can be cut into C chunks that
+// run CONCURRENTLY, each preceded by Wu warm-up steps from h = 0; a verify pass then checks every chunk boundary against the
+// state the previous chunk really produced and re-runs failing sequences serially.  The backward is the same
+// trick on the linear dL/dh recurrence in reverse time.
+static constexpr int SPEC_ROWS_AUTO = 2048, SPEC_CMAX = 32, SPEC_WARM_DEFAULT = 128;
+static constexpr float SPEC_TOL_FWD = 2.3841858e-07f;   // 2^-22 absolute on h in (-1,1)
+static constexpr float SPEC_TOL_BWD = 4.7683716e-07f;   // 2^-21 relative to max|dL/dh| at the boundary
+
+int64_t gru_family_rows(int B, int tchunks_req) {
+    if (B <= 0) return 1;
+    if (tchunks_req == 1) return B;
+    if (tchunks_req > 1) return (int64_t)B * (tchunks_req < SPEC_CMAX ? tchunks_req : SPEC_CMAX);
+    return B > SPEC_ROWS_AUTO ? B : SPEC_ROWS_AUTO;
+}
+int64_t gru_family_scratch_floats(int B, int H, int tchunks_req) {
+    const int ht = gru_tier(H);
+    if (ht < 0) return -1;
+    return gru_family_rows(B, tchunks_req) * (2 * ((ht + 3) & ~3) + 1) + 4;
+}
+
+static int num_sms() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
+// fills a.C / a.Lc / a.Wu;  slots = CTAs of this kernel the device holds at once
+static void make_plan(GruArgs &a, int slots, bool have_scratch) {
+    a.C = 1; a.Lc = a.T; a.Wu = 0;
+    const int req = a.tchunks_req;
+    if (req == 1 || !have_scratch || a.T < 2 * CH) return;
+    const int Wu = a.twarm_req > 0 ? ((a.twarm_req + CH - 1) / CH) * CH : SPEC_WARM_DEFAULT;
+    const int nblk = (a.T + CH - 1) / CH;
+    auto lc_of = [&](int C) { return ((nblk + C - 1) / C) * CH; };
+    auto valid = [&](int C) { return (int64_t)(C - 1) * lc_of(C) < a.T; };
+    int C = 1;
+    if (req > 1) {
+        C = req < SPEC_CMAX ? req : SPEC_CMAX;
+        while (C > 1 && !valid(C)) --C;
+    } else {
+        if (slots > SPEC_ROWS_AUTO) slots = SPEC_ROWS_AUTO;
+        while (2 * C <= SPEC_CMAX && (int64_t)a.B * 2 * C <= slots && valid(2 * C) && lc_of(2 * C) >= Wu) C *= 2;
+    }
+    if (C > 1 && (int64_t)a.B * C <= gru_family_rows(a.B, req)) { a.C = C; a.Lc = lc_of(C); a.Wu = Wu; }
+}
+
+// dir: 0 fwd, 1 bwd, 2 fwd plan only, 3 bwd plan only (plan -> info[0..3] = C, Lc, Wu, float offset of the fail counter)
 template <int HT, int FM, int HEAD>
-static int launch_fwd(const GruArgs &a, cudaStream_t st) {
+static int launch_fwd(GruArgs a, cudaStream_t st, bool plan_only, int *info) {
+    constexpr int HP = Pad4<HT>::value, ROW = Row<HT, HEAD>::value;
     const GruLayout<FM, HEAD> L(a.H);
     const size_t smem = (size_t)FwdSmem<HT, HEAD>::total((L.P + 3) & ~3) * sizeof(float);
     auto k = gru_fwd_kernel<HT, FM, HEAD>;
-    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<a.B, 96, smem, st>>>(a);
+    static int occ = 0;
+    if (!occ) {
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, 96, smem) != cudaSuccess || occ <= 0) occ = 1;
+    }
+    const int64_t rows = gru_family_rows(a.B, a.tchunks_req);
+    const size_t soff = a.save ? (size_t)a.B * a.T * ROW : 0;
+    float *scr = a.saved ? a.saved + soff : nullptr;
+    make_plan(a, occ * num_sms(), scr != nullptr || plan_only);
+    if (info) { info[0] = a.C; info[1] = a.Lc; info[2] = a.Wu; info[3] = 0; }
+    if (plan_only) {
+        if (info) { const int64_t off = (int64_t)soff + rows * (2 * HP + 1); info[3] = off > 0x7fffffff ? -1 : (int)off; }
+        return 0;
+    }
+    if (a.C > 1) {
+        a.sc_guess = scr; a.sc_end = scr + rows * HP; a.sc_loss = scr + 2 * rows * HP;
+        a.sc_fail = reinterpret_cast<int *>(scr + rows * (2 * HP + 1));
+        a.tol = SPEC_TOL_FWD;
+        a.mode = 0;
+        k<<<a.B * a.C, 96, smem, st>>>(a);
+        a.mode = 2;
+        k<<<a.B, 96, smem, st>>>(a);
+    } else {
+        a.mode = 0;
+        k<<<a.B, 96, smem, st>>>(a);
+    }
     return check_launch("gru_fwd_kernel");
 }
-template <int HT, int FM, int HEAD>
-static int launch_bwd(const GruArgs &a, bool dw, cudaStream_t st) {
+template <int HT, int FM, int HEAD, bool DW>
+static int launch_bwd_t(GruArgs a, cudaStream_t st, bool plan_only, int *info) {
+    constexpr int HP = Pad4<HT>::value;
     const GruLayout<FM, HEAD> L(a.H);
     const size_t smem = (size_t)BwdSmem<HT, HEAD>::total((L.P + 3) & ~3) * sizeof(float);
-    if (dw) {
-        auto k = gru_bwd_kernel<HT, FM, HEAD, true>;
+    auto k = gru_bwd_kernel<HT, FM, HEAD, DW>;
+    static int occ = 0;
+    if (!occ) {
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, 128, smem) != cudaSuccess || occ <= 0) occ = 1;
+    }
+    // workspace = [rows][P] gradient partials (4-float aligned) | [rows][HP] guess | [rows][HP] end | fail counter
+    const int64_t rows = gru_family_rows(a.B, a.tchunks_req);
+    const size_t woff = (size_t)((rows * L.P + 3) & ~(int64_t)3);
+    float *scr = a.partials ? a.partials + woff : nullptr;
+    make_plan(a, occ * num_sms(), scr != nullptr || plan_only);
+    if (info) { info[0] = a.C; info[1] = a.Lc; info[2] = a.Wu; info[3] = 0; }
+    if (plan_only) {
+        if (info) { const int64_t off = (int64_t)woff + rows * 2 * HP; info[3] = off > 0x7fffffff ? -1 : (int)off; }
+        return 0;
+    }
+    if (a.C > 1) {
+        a.sc_guess = scr; a.sc_end = scr + rows * HP;
+        a.sc_fail = reinterpret_cast<int *>(scr + rows * 2 * HP);
+        a.tol = SPEC_TOL_BWD;
+        a.mode = 0;
+        k<<<a.B * a.C, 128, smem, st>>>(a);
+        a.mode = 2;
         k<<<a.B, 128, smem, st>>>(a);
     } else {
-        auto k = gru_bwd_kernel<HT, FM, HEAD, false>;
-        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        a.mode = 0;
         k<<<a.B, 128, smem, st>>>(a);
     }
+    if (info) info[0] = a.C;
     return check_launch("gru_bwd_kernel");
 }
 
 template <int FM, int HEAD>
-static int dispatch(const GruArgs &a, int dir, bool dw, cudaStream_t st) {
-#define X(HTV, FMV, HEADV)                                                                  \
-    if (a.H <= HTV) return dir == 0 ? launch_fwd<HTV, FMV, HEADV>(a, st) : launch_bwd<HTV, FMV, HEADV>(a, dw, st);
+static int dispatch(const GruArgs &a, int dir, bool dw, cudaStream_t st, int *info) {
+    const bool plan_only = dir >= 2;
+    const int d = dir & 1;
+#define X(HTV, FMV, HEADV)                                                                         \
+    if (a.H <= HTV)                                                                                \
+        return d == 0 ? launch_fwd<HTV, FMV, HEADV>(a, st, plan_only, info)                        \
+                      : (dw ? launch_bwd_t<HTV, FMV, HEADV, true>(a, st, plan_only, info)          \
+                            : launch_bwd_t<HTV, FMV, HEADV, false>(a, st, plan_only, info));
     ODPD_GRU_TIERS(X, FM, HEAD)
 #undef X
     set_error("GRU-family kernels support hidden_size <= 32 (got %d)", a.H);
@@ -765,21 +937,43 @@ int64_t gru_family_nparams(int cell, int H) {
     default: return gru_nparams<FM_QGRU4, 0>(H);
     }
 }
-int64_t gru_family_saved_floats(int cell, int B, int T, int H) {
+// `saved` = [B][T][ROW] activation rows (only when the forward saves) followed by the chunk scratch
+int64_t gru_family_saved_floats(int cell, int B, int T, int H, bool save, int tchunks_req) {
     const int ht = gru_tier(H);
     if (ht < 0) return -1;
-    return (int64_t)B * T * (cell == ODPD_CELL_DGRU ? 6 : 5) * ((ht + 3) & ~3);
+    const int64_t rowsz = save ? (int64_t)B * T * (cell == ODPD_CELL_DGRU ? 6 : 5) * ((ht + 3) & ~3) : 0;
+    return rowsz + (tchunks_req == 1 ? 0 : gru_family_scratch_floats(B, H, tchunks_req));
+}
+int64_t gru_family_workspace_floats(int cell, int B, int H, int tchunks_req) {
+    const int ht = gru_tier(H);
+    if (ht < 0) return -1;
+    const int64_t rows = gru_family_rows(B, tchunks_req);
+    return ((rows * gru_family_nparams(cell, H) + 3) & ~(int64_t)3) + rows * 2 * ((ht + 3) & ~3) + 4;
 }
 
-int gru_family_run(int cell, const GruArgs &a, int dir, bool dw, cudaStream_t st) {
+static int run_or_plan(int cell, const GruArgs &a, int dir, bool dw, cudaStream_t st, int *info) {
     switch (cell) {
-    case ODPD_CELL_GRU: return dispatch<FM_RAW2, 0>(a, dir, dw, st);
-    case ODPD_CELL_DGRU: return dispatch<FM_DGRU6, 1>(a, dir, dw, st);
-    case ODPD_CELL_QGRU: return dispatch<FM_QGRU4, 0>(a, dir, dw, st);
-    case ODPD_CELL_QGRU_AMP1: return dispatch<FM_AMP4, 0>(a, dir, dw, st);
+    case ODPD_CELL_GRU: return dispatch<FM_RAW2, 0>(a, dir, dw, st, info);
+    case ODPD_CELL_DGRU: return dispatch<FM_DGRU6, 1>(a, dir, dw, st, info);
+    case ODPD_CELL_QGRU: return dispatch<FM_QGRU4, 0>(a, dir, dw, st, info);
+    case ODPD_CELL_QGRU_AMP1: return dispatch<FM_AMP4, 0>(a, dir, dw, st, info);
     }
     set_error("gru_family_run: bad cell %d", cell);
     return -1;
+}
+
+// rows_out: number of gradient-partial rows the backward wrote (B * chunks), for the ordered reduction that follows
+int gru_family_run(int cell, const GruArgs &a, int dir, bool dw, cudaStream_t st, int *rows_out) {
+    int info[4] = {1, 0, 0, 0};
+    const int rc = run_or_plan(cell, a, dir, dw, st, info);
+    if (rows_out) *rows_out = a.B * info[0];
+    return rc;
+}
+
+int gru_family_plan(int cell, int B, int T, int H, int tchunks_req, int twarm_req, int dir, bool dw, bool save, int out[4]) {
+    GruArgs a{};
+    a.B = B; a.T = T; a.H = H; a.tchunks_req = tchunks_req; a.twarm_req = twarm_req; a.save = save;
+    return run_or_plan(cell, a, 2 + (dir & 1), dw, nullptr, out);
 }
 
 }  // namespace odpd

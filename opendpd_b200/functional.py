@@ -1,6 +1,7 @@
 """Autograd bridge: one torch.autograd.Function that runs a whole backbone forward (optionally + fused I/Q MSE)
 and its backward through libodpd.so.  PyTorch is plumbing here (allocation, streams, autograd graph edges)."""
 import ctypes
+import os
 import torch
 from . import _ffi
 
@@ -16,13 +17,32 @@ def _stream():
 class CellSpec:
     """Static description of one native backbone call."""
 
-    def __init__(self, cell, H, K=0, thx=0.0, thh=0.0):
+    def __init__(self, cell, H, K=0, thx=0.0, thh=0.0, tchunks=None, twarm=None):
+        """tchunks / twarm: OdpdDims.tchunks / .twarm (include/odpd.h "Time-chunked execution"); None = environment
+        ODPD_TCHUNKS[_FWD|_BWD] / ODPD_TWARM, else 0 = the library picks.  tchunks may be an int or a (forward, backward) pair."""
         self.cell, self.H, self.K, self.thx, self.thh = cell, int(H), int(K or 0), float(thx), float(thh)
         self.cell_id = _ffi.CELLS[cell]
         self.keep_saved = None
+        env = os.environ.get
+        if tchunks is None:
+            both = env("ODPD_TCHUNKS", "0")
+            tchunks = (int(env("ODPD_TCHUNKS_FWD", both)), int(env("ODPD_TCHUNKS_BWD", both)))
+        elif isinstance(tchunks, int):
+            tchunks = (tchunks, tchunks)
+        self.tchunks = tuple(int(v) for v in tchunks)
+        self.twarm = int(env("ODPD_TWARM", "0")) if twarm is None else int(twarm)
 
-    def dims(self, B, T, flags):
-        return _ffi.OdpdDims(self.cell_id, int(B), int(T), self.H, self.K, int(flags), self.thx, self.thh)
+    def dims(self, B, T, flags, backward=False):
+        return _ffi.OdpdDims(self.cell_id, int(B), int(T), self.H, self.K, int(flags), self.thx, self.thh,
+                             self.tchunks[1 if backward else 0], self.twarm)
+
+    def chunk_plan(self, B, T, backward=False, save=True, need_dw=True):
+        """(chunks, steps per chunk, warm-up steps, index of the re-run counter) the library will use for this call shape."""
+        flags = (_ffi.F_NEED_DW if need_dw else 0) if backward else (_ffi.F_SAVE if save else 0)
+        d = self.dims(B, T, flags, backward)
+        out = (ctypes.c_int32 * 4)()
+        _ffi.check(_ffi.lib().odpd_chunk_plan(ctypes.byref(d), 1 if backward else 0, out))
+        return tuple(int(v) for v in out)
 
 
 def _check_x(x):
@@ -45,11 +65,14 @@ def backbone_forward_raw(spec, x, flat, target=None, loss_scale=0.0, save=True, 
     else:
         out = torch.empty_like(x)
         saved = None
-        if save:
-            nbytes = L.odpd_saved_bytes(ctypes.byref(d))
-            if nbytes < 0:
-                _ffi.check(-1)
+        nbytes = L.odpd_saved_bytes(ctypes.byref(d))     # activations (when saving) + chunk scratch
+        if nbytes < 0:
+            _ffi.check(-1)
+        if save or nbytes > 0:
             saved = torch.empty(max(int(nbytes) // 4, 1), dtype=torch.float32, device=x.device)
+            idx = spec.chunk_plan(B, T, False, save)[3]
+            if idx >= 0:
+                saved[idx:idx + 1].zero_()               # re-run counter of the verify pass
         loss = torch.empty(1, dtype=torch.float64, device=x.device) if target is not None else None
         if bufs is not None:
             bufs.update(key=key, out=out, saved=saved, loss=loss)
@@ -65,15 +88,16 @@ def backbone_backward_raw(spec, x, flat, saved, need_dx, need_dw, gout=None, out
     L = _ffi.lib()
     B, T = x.shape[0], x.shape[1]
     flags = (_ffi.F_NEED_DX if need_dx else 0) | (_ffi.F_NEED_DW if need_dw else 0) | _ffi.F_OVERWRITE_DW
-    d = spec.dims(B, T, flags)
+    d = spec.dims(B, T, flags, backward=True)
     key = (B, T, bool(need_dx), bool(need_dw))
     if bufs is not None and bufs.get("key") == key:
         gx, ws = bufs["gx"], bufs["ws"]
     else:
         gx = torch.empty_like(x) if need_dx else None
-        ws = None
-        if need_dw:
-            ws = torch.empty(int(L.odpd_bwd_workspace_bytes(ctypes.byref(d))) // 4, dtype=torch.float32, device=x.device)
+        ws = torch.empty(int(L.odpd_bwd_workspace_bytes(ctypes.byref(d))) // 4, dtype=torch.float32, device=x.device)
+        idx = spec.chunk_plan(B, T, True, True, need_dw)[3]
+        if idx >= 0:
+            ws[idx:idx + 1].zero_()                      # re-run counter of the verify pass
         if bufs is not None:
             bufs.update(key=key, gx=gx, ws=ws)
     if need_dw and gflat is None:
@@ -81,6 +105,14 @@ def backbone_backward_raw(spec, x, flat, saved, need_dx, need_dw, gout=None, out
     _ffi.check(L.odpd_backbone_bwd(ctypes.byref(d), _ptr(x), _ptr(flat), _ptr(saved), _ptr(gout), _ptr(out), _ptr(target),
                                    ctypes.c_double(gscale), _ptr(gscale_dev), _ptr(gx), _ptr(gflat), _ptr(ws), _stream()))
     return gx, gflat
+
+
+def chunk_reruns(spec, buf, B, T, backward=False, save=True, need_dw=True):
+    """Number of sequences the verify pass re-ran serially since `buf` (saved / workspace) was allocated (host sync)."""
+    idx = spec.chunk_plan(B, T, backward, save, need_dw)[3]
+    if idx < 0 or buf is None:
+        return 0
+    return int(buf[idx:idx + 1].view(torch.int32).item())
 
 
 class BackboneFn(torch.autograd.Function):

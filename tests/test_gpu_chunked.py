@@ -1,0 +1,142 @@
+"""Time-chunked execution of the GRU-family kernels (include/odpd.h "Time-chunked execution"): every sequence is cut into
+chunks that run concurrently after a warm-up, a verify pass checks each chunk boundary and re-runs failing sequences serially.
+These tests pin (1) chunked == serial == oracle on the same seeded inputs, (2) the verify pass really catches a warm-up that
+is too short and the serial re-run restores the serial result bit for bit, (3) ragged frame lengths and the forward-only path."""
+import numpy as np
+import pytest
+import torch
+
+from tests.util import rel_err, assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+def _inputs(B, T, seed=7):
+    gen = torch.Generator().manual_seed(seed)
+    xc = (0.2 * torch.randn(B, T, 2, generator=gen)).clamp(-0.7, 0.7)
+    yc = xc * (1 - 0.2 * (xc ** 2).sum(-1, keepdim=True))
+    return xc, yc
+
+
+def _run(net, xc, yc, tchunks, twarm, dx=True):
+    """fwd(+MSE) + bwd through the raw C-ABI wrappers so that the scratch buffers (re-run counters) stay reachable."""
+    from opendpd_b200.functional import CellSpec, backbone_forward_raw, backbone_backward_raw, chunk_reruns
+    bb = net.backbone
+    flat, _ = bb._flat_sync()
+    spec = CellSpec(bb.cell, bb.hidden_size, tchunks=tchunks, twarm=twarm)
+    B, T = xc.shape[0], xc.shape[1]
+    x, y = xc.cuda(), yc.cuda()
+    count = float(2 * B * T)
+    fb, bbuf = {}, {}
+    out, loss, saved = backbone_forward_raw(spec, x, flat, y, 1.0 / count, True, None, fb)
+    gx, gflat = backbone_backward_raw(spec, x, flat, saved, dx, True, out=out, target=y, gscale=2.0 / count, bufs=bbuf)
+    torch.cuda.synchronize()
+    return dict(out=out.cpu().numpy(), loss=float(loss.item()), gx=None if gx is None else gx.cpu().numpy(), gp=gflat.cpu().numpy()[:bb.flat_layout()[1]],
+                plan_f=spec.chunk_plan(B, T, False), plan_b=spec.chunk_plan(B, T, True),
+                reruns_f=chunk_reruns(spec, saved, B, T, False), reruns_b=chunk_reruns(spec, bbuf["ws"], B, T, True))
+
+
+@pytest.mark.parametrize("kind,H,B,T,tchunks,twarm", [
+    ("dgru", 13, 64, 2048, (8, 4), 128),     # BASELINE configs[1] with the plan the library picks on a 148-SM part
+    ("dgru", 13, 64, 2048, (16, 16), 64),
+    ("dgru", 13, 64, 2048, 0, 0),            # auto
+    ("gru", 32, 8, 1024, (8, 8), 128),       # configs[0]
+    ("dgru", 13, 7, 1000, (4, 3), 96),       # ragged: T is not a multiple of 32 * chunks
+    ("dgru", 23, 32, 2048, 0, 0),            # the frozen PA of config 3
+    ("qgru", 10, 16, 512, (4, 2), 128),
+    ("qgru_amp1", 10, 16, 512, (2, 4), 128),
+    ("gru", 8, 3, 4096, (32, 32), 0),
+])
+def test_chunked_matches_serial_and_oracle(kind, H, B, T, tchunks, twarm):
+    from oracle import oracle
+    from opendpd_b200 import models
+    torch.manual_seed(1234)
+    net = models.CoreModel(2, H, 1, kind).cuda()
+    xc, yc = _inputs(B, T)
+    ser = _run(net, xc, yc, 1, 0)
+    chk = _run(net, xc, yc, tchunks, twarm)
+    assert ser["plan_f"][0] == 1 and ser["plan_b"][0] == 1
+    assert chk["plan_f"][0] > 1 and chk["plan_b"][0] > 1, (chk["plan_f"], chk["plan_b"])
+    if tchunks != 0:
+        tc = tchunks if isinstance(tchunks, tuple) else (tchunks, tchunks)
+        assert (chk["plan_f"][0], chk["plan_b"][0]) == tc
+    # freshly initialised GRUs forget within a few dozen steps: no boundary may fail with a warm-up >= 64
+    assert chk["reruns_f"] == 0 and chk["reruns_b"] == 0, (chk["reruns_f"], chk["reruns_b"])
+    # chunked vs serial kernels: same arithmetic, chunk starts differ by <= 2^-22 -> far inside the parity budget
+    assert rel_err(chk["out"], ser["out"]) < 2e-6
+    assert rel_err(chk["gx"], ser["gx"]) < 2e-6
+    assert rel_err(chk["gp"], ser["gp"]) < 2e-6
+    assert abs(chk["loss"] - ser["loss"]) <= 1e-6 * abs(ser["loss"])
+    # and against the CPU oracle (fp64 arbiter), same criterion as test_oracle_parity_seeded
+    params = np.concatenate([p.detach().cpu().numpy().ravel() for _, p in net.backbone.named_parameters()])
+    r64 = oracle.run(kind, xc.numpy(), params, target=yc.numpy(), H=H, dtype=np.float64, nthreads=8)
+    r32 = oracle.run(kind, xc.numpy(), params, target=yc.numpy(), H=H, dtype=np.float32, nthreads=8)
+
+    def q(a, b):
+        e = np.abs(a.astype(np.float64) - b) / (np.abs(b).max() + 1e-300)
+        return float(np.quantile(e, 0.9999)) if e.size >= 10000 else float(e.max())
+    for key, mine in (("out", chk["out"]), ("gx", chk["gx"]), ("gparams", chk["gp"])):
+        assert_close(mine, r64[key], max(1e-5, 3 * q(r32[key], r64[key])), key)
+    assert abs(chk["loss"] - r64["loss"]) <= 1e-5 * abs(r64["loss"])
+
+
+def test_verify_pass_catches_short_warmup_and_reruns_serially():
+    """Slowly forgetting weights (recurrent matrix scaled x2.5) + a 32-step warm-up: chunk boundaries do not meet, the verify pass must
+    flag them and the serial re-run must reproduce the serial kernel bit for bit for the re-run sequences."""
+    from opendpd_b200 import models
+    torch.manual_seed(77)
+    net = models.CoreModel(2, 13, 1, "dgru").cuda()
+    with torch.no_grad():
+        net.backbone.rnn.weight_hh_l0.mul_(2.5)
+    xc, yc = _inputs(16, 1024, seed=3)
+    ser = _run(net, xc, yc, 1, 0)
+    chk = _run(net, xc, yc, (16, 16), 32)
+    assert chk["reruns_f"] > 0, (chk["reruns_f"], chk["reruns_b"])
+    if chk["reruns_f"] == 16:                                   # every sequence re-run: identical to the serial kernel
+        assert np.array_equal(chk["out"], ser["out"])
+    if chk["reruns_f"] == 16 and chk["reruns_b"] == 16:
+        assert np.array_equal(chk["gx"], ser["gx"])
+    assert rel_err(chk["out"], ser["out"]) < 2e-6
+    assert rel_err(chk["gx"], ser["gx"]) < 5e-6
+    assert rel_err(chk["gp"], ser["gp"]) < 5e-6
+    assert abs(chk["loss"] - ser["loss"]) <= 1e-6 * abs(ser["loss"])
+
+
+def test_chunked_dx_only_backward_and_cascade_shapes():
+    """Frozen-PA mode (dX only, no weight gradients) through the chunked backward."""
+    from opendpd_b200 import models
+    from opendpd_b200.functional import CellSpec, backbone_forward_raw, backbone_backward_raw
+    torch.manual_seed(5)
+    net = models.CoreModel(2, 23, 1, "dgru").cuda()
+    bb = net.backbone
+    flat, _ = bb._flat_sync()
+    xc, yc = _inputs(32, 1024, seed=9)
+    x, y = xc.cuda(), yc.cuda()
+    res = []
+    for tch in (1, (4, 4)):
+        spec = CellSpec(bb.cell, bb.hidden_size, tchunks=tch, twarm=128)
+        out, loss, saved = backbone_forward_raw(spec, x, flat, y, 1.0 / x.numel(), True, None)
+        gx, _ = backbone_backward_raw(spec, x, flat, saved, True, False, out=out, target=y, gscale=2.0 / x.numel())
+        res.append((out.cpu().numpy(), gx.cpu().numpy()))
+    assert rel_err(res[1][0], res[0][0]) < 2e-6
+    assert rel_err(res[1][1], res[0][1]) < 2e-6
+
+
+def test_forward_only_long_segment_is_chunked():
+    """net_eval shape (train_funcs.py:57-90): B<=6 whole segments of 19 662 samples, no activations saved."""
+    from opendpd_b200 import models
+    from opendpd_b200.functional import CellSpec, backbone_forward_raw
+    torch.manual_seed(8)
+    net = models.CoreModel(2, 13, 1, "dgru").cuda()
+    bb = net.backbone
+    flat, _ = bb._flat_sync()
+    xc, yc = _inputs(3, 19662, seed=1)
+    x, y = xc.cuda(), yc.cuda()
+    outs = []
+    for tch in (1, 0):
+        spec = CellSpec(bb.cell, bb.hidden_size, tchunks=tch, twarm=0)
+        out, loss, saved = backbone_forward_raw(spec, x, flat, y, 1.0 / x.numel(), False, None)
+        outs.append((out.cpu().numpy(), float(loss.item()), spec.chunk_plan(3, 19662, False, save=False)))
+    assert outs[0][2][0] == 1 and outs[1][2][0] >= 16
+    assert rel_err(outs[1][0], outs[0][0]) < 2e-6
+    assert abs(outs[1][1] - outs[0][1]) <= 1e-6 * abs(outs[0][1])
