@@ -112,8 +112,10 @@ __global__ void __launch_bounds__(96, 1) gru_fwd_kernel(GruArgs a) {
     const int j = act ? lane : 0;
     const int cb = t_lo / CH, nchunks = (t_hi + CH - 1) / CH - cb;   // pipeline stages q = 0..nchunks-1 cover 32-step blocks cb+q
     const float2 *x2 = reinterpret_cast<const float2 *>(a.x) + (size_t)b * T;
+    // fixed roles per warp (measured: rotating the roles of co-resident CTAs over the sub-partitions is 20-50 % slower)
+    const int role = warp;
 
-    if (warp == 1) {
+    if (role == 1) {
         // =============================== pre: features + input projection, one chunk ahead of the chain
         float wir[F], wiz[F], win[F];
 #pragma unroll
@@ -155,7 +157,7 @@ __global__ void __launch_bounds__(96, 1) gru_fwd_kernel(GruArgs a) {
             }
             __syncthreads();
         }
-    } else if (warp == 0) {
+    } else if (role == 0) {
         // =============================== chain: the serial recurrence
         if constexpr (HP <= 16) {
             // Two half-warps share one timestep: lanes 0..15 carry the r and n rows of unit u, lanes 16..31 the z row of the same
@@ -390,6 +392,8 @@ __global__ void __launch_bounds__(96, 1) gru_fwd_kernel(GruArgs a) {
 // ================================================================ backward
 // SPLIT: the F "feature lanes" (which turn the gate gradients into dL/dfeatures) do not fit next to the H unit lanes in
 // one warp (H+F>32); lanes 0..F-1 then serve the features.
+// (capping registers for three CTAs per SM — __launch_bounds__(128, 3) — was measured and does not pay: the chunked backward is
+// bound by per-SM throughput, 6 chunks x 3 CTAs/SM takes as long as 4 chunks x 2 CTAs/SM, and the serial kernel gets 15 % slower)
 template <int HT, int FM, int HEAD, bool DW>
 __global__ void __launch_bounds__(128, 1) gru_bwd_kernel(GruArgs a) {
     constexpr int F = FeatN<FM>::value, HP = Pad4<HT>::value, ROW = Row<HT, HEAD>::value;
@@ -435,6 +439,7 @@ __global__ void __launch_bounds__(128, 1) gru_bwd_kernel(GruArgs a) {
 
     if (threadIdx.x == 0) { mbar_init(bars + 1, 1); mbar_init(bars + 2, 1); mbar_init(bars + 3, 1); }
     stage_params(sp, a.params, L.P, bars);   // contains the mbarrier-init fence + __syncthreads
+    const int role = warp;
 
     const bool act = lane < H;
     const int j = act ? lane : 0;
@@ -445,7 +450,7 @@ __global__ void __launch_bounds__(128, 1) gru_bwd_kernel(GruArgs a) {
     const float *svg = a.saved + (size_t)b * T * ROW;
 
     // stage s: pre -> chunk index (nchunks-1-s), chain -> one stage later, post -> two stages later
-    if (warp == 1) {
+    if (role == 1) {
         // =============================== pre
         float whT[HEAD ? HT : 1];
         if constexpr (HEAD) {
@@ -529,7 +534,7 @@ __global__ void __launch_bounds__(128, 1) gru_bwd_kernel(GruArgs a) {
             }
             __syncthreads();
         }
-    } else if (warp == 0) {
+    } else if (role == 0) {
         // =============================== chain: reverse-time recurrence of dL/dh
         float wcol[3 * HT];   // column j of W_hh
 #pragma unroll
@@ -592,7 +597,7 @@ __global__ void __launch_bounds__(128, 1) gru_bwd_kernel(GruArgs a) {
         // =============================== post (two warps, the FFMA issue rate of one warp is the limit):
         //   warp 2 "post-A": dL/dW_hh (3H accumulators per lane)
         //   warp 3 "post-B": dL/dW_ih, biases, head gradients, dL/dfeatures -> dL/dx, time-parallel tail
-        const bool roleA = (warp == 2);
+        const bool roleA = (role == 2);
         const int fl = SPLIT ? lane : lane - H;   // feature column served by this lane (if 0<=fl<F)
         const bool isf = fl >= 0 && fl < F;
         float wicol[3 * HT];                      // column fl of W_ih (feature lanes, post-B)
@@ -738,7 +743,7 @@ __global__ void __launch_bounds__(128, 1) gru_bwd_kernel(GruArgs a) {
                 // verify pass then clears the sequence's other rows)
                 float *prt = a.partials + (size_t)(spec ? blockIdx.x : b * a.C) * L.P;
                 if (a.mode == 2) {
-                    const int tid = threadIdx.x - 64;   // the two post warps
+                    const int tid = (role - 2) * 32 + lane;   // the two post warps
                     for (int i = tid; i < (a.C - 1) * L.P; i += 64) prt[L.P + i] = 0.f;
                 }
                 if (roleA) {
@@ -837,8 +842,15 @@ static void make_plan(GruArgs &a, int slots, bool have_scratch) {
         C = req < SPEC_CMAX ? req : SPEC_CMAX;
         while (C > 1 && !valid(C)) --C;
     } else {
+        // cost model: every CTA walks Lc + Wu steps; CTAs beyond what the device holds at once wait for a second wave
         if (slots > SPEC_ROWS_AUTO) slots = SPEC_ROWS_AUTO;
-        while (2 * C <= SPEC_CMAX && (int64_t)a.B * 2 * C <= slots && valid(2 * C) && lc_of(2 * C) >= Wu) C *= 2;
+        if (slots < 1) slots = 1;
+        int64_t best = (int64_t)((a.B + slots - 1) / slots) * a.T;
+        for (int c = 2; c <= SPEC_CMAX; ++c) {
+            if (!valid(c) || lc_of(c) < Wu || (int64_t)a.B * c > SPEC_ROWS_AUTO) continue;
+            const int64_t cost = (int64_t)(((int64_t)a.B * c + slots - 1) / slots) * (lc_of(c) + Wu);
+            if (cost < best) { best = cost; C = c; }
+        }
     }
     if (C > 1 && (int64_t)a.B * C <= gru_family_rows(a.B, req)) { a.C = C; a.Lc = lc_of(C); a.Wu = Wu; }
 }
@@ -850,10 +862,11 @@ static int launch_fwd(GruArgs a, cudaStream_t st, bool plan_only, int *info) {
     const GruLayout<FM, HEAD> L(a.H);
     const size_t smem = (size_t)FwdSmem<HT, HEAD>::total((L.P + 3) & ~3) * sizeof(float);
     auto k = gru_fwd_kernel<HT, FM, HEAD>;
+    constexpr int NTH = 96;
     static int occ = 0;
     if (!occ) {
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, 96, smem) != cudaSuccess || occ <= 0) occ = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, NTH, smem) != cudaSuccess || occ <= 0) occ = 1;
     }
     const int64_t rows = gru_family_rows(a.B, a.tchunks_req);
     const size_t soff = a.save ? (size_t)a.B * a.T * ROW : 0;
@@ -864,30 +877,31 @@ static int launch_fwd(GruArgs a, cudaStream_t st, bool plan_only, int *info) {
         if (info) { const int64_t off = (int64_t)soff + rows * (2 * HP + 1); info[3] = off > 0x7fffffff ? -1 : (int)off; }
         return 0;
     }
+
     if (a.C > 1) {
         a.sc_guess = scr; a.sc_end = scr + rows * HP; a.sc_loss = scr + 2 * rows * HP;
         a.sc_fail = reinterpret_cast<int *>(scr + rows * (2 * HP + 1));
         a.tol = SPEC_TOL_FWD;
         a.mode = 0;
-        k<<<a.B * a.C, 96, smem, st>>>(a);
+        k<<<a.B * a.C, NTH, smem, st>>>(a);
         a.mode = 2;
-        k<<<a.B, 96, smem, st>>>(a);
+        k<<<a.B, NTH, smem, st>>>(a);
     } else {
         a.mode = 0;
-        k<<<a.B, 96, smem, st>>>(a);
+        k<<<a.B, NTH, smem, st>>>(a);
     }
     return check_launch("gru_fwd_kernel");
 }
 template <int HT, int FM, int HEAD, bool DW>
 static int launch_bwd_t(GruArgs a, cudaStream_t st, bool plan_only, int *info) {
-    constexpr int HP = Pad4<HT>::value;
+    constexpr int HP = Pad4<HT>::value, NTH = 128;
     const GruLayout<FM, HEAD> L(a.H);
     const size_t smem = (size_t)BwdSmem<HT, HEAD>::total((L.P + 3) & ~3) * sizeof(float);
     auto k = gru_bwd_kernel<HT, FM, HEAD, DW>;
     static int occ = 0;
     if (!occ) {
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, 128, smem) != cudaSuccess || occ <= 0) occ = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, NTH, smem) != cudaSuccess || occ <= 0) occ = 1;
     }
     // workspace = [rows][P] gradient partials (4-float aligned) | [rows][HP] guess | [rows][HP] end | fail counter
     const int64_t rows = gru_family_rows(a.B, a.tchunks_req);
@@ -899,17 +913,18 @@ static int launch_bwd_t(GruArgs a, cudaStream_t st, bool plan_only, int *info) {
         if (info) { const int64_t off = (int64_t)woff + rows * 2 * HP; info[3] = off > 0x7fffffff ? -1 : (int)off; }
         return 0;
     }
+
     if (a.C > 1) {
         a.sc_guess = scr; a.sc_end = scr + rows * HP;
         a.sc_fail = reinterpret_cast<int *>(scr + rows * 2 * HP);
         a.tol = SPEC_TOL_BWD;
         a.mode = 0;
-        k<<<a.B * a.C, 128, smem, st>>>(a);
+        k<<<a.B * a.C, NTH, smem, st>>>(a);
         a.mode = 2;
-        k<<<a.B, 128, smem, st>>>(a);
+        k<<<a.B, NTH, smem, st>>>(a);
     } else {
         a.mode = 0;
-        k<<<a.B, 128, smem, st>>>(a);
+        k<<<a.B, NTH, smem, st>>>(a);
     }
     if (info) info[0] = a.C;
     return check_launch("gru_bwd_kernel");
@@ -942,7 +957,7 @@ int64_t gru_family_saved_floats(int cell, int B, int T, int H, bool save, int tc
     const int ht = gru_tier(H);
     if (ht < 0) return -1;
     const int64_t rowsz = save ? (int64_t)B * T * (cell == ODPD_CELL_DGRU ? 6 : 5) * ((ht + 3) & ~3) : 0;
-    return rowsz + (tchunks_req == 1 ? 0 : gru_family_scratch_floats(B, H, tchunks_req));
+    return rowsz + gru_family_scratch_floats(B, H, tchunks_req);
 }
 int64_t gru_family_workspace_floats(int cell, int B, int H, int tchunks_req) {
     const int ht = gru_tier(H);

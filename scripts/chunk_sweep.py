@@ -19,8 +19,11 @@ def main():
     xs, ys = synth_batches(POOL, B, T, 1000)
     xd, yd = xs.cuda(), ys.cuda()
     count = float(2 * B * T)
-    plans = [((1, 1), 0), ((2, 2), 128), ((4, 4), 128), ((8, 4), 128), ((8, 8), 128), ((16, 8), 128), ((16, 16), 128), ((8, 4), 64), ((8, 8), 64),
-             ((16, 8), 64), ((16, 16), 64), ((32, 16), 64), ((8, 4), 96), ((0, 0), 0)]
+    plans = [((1, 1), 0), ((4, 4), 128), ((8, 4), 128), ((8, 5), 128), ((8, 6), 128), ((8, 8), 128), ((16, 8), 128), ((8, 6), 64), ((8, 6), 96),
+             ((16, 16), 64), ((0, 0), 0)]
+    if os.environ.get("SWEEP_PLANS"):
+        plans = [tuple(p) for p in json.loads(os.environ["SWEEP_PLANS"])]
+        plans = [((p[0], p[1]), p[2]) for p in plans]
     for tch, tw in plans:
         spec = CellSpec(bb.cell, H, tchunks=tch, twarm=tw)
         fb, bbuf = {}, {}
