@@ -311,17 +311,15 @@ def main():
     bwd_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
     # time-chunk plan of every backbone call in the step (include/odpd.h "Time-chunked execution") and how many sequences the
     # verify passes had to re-run serially over the whole run (0 = every chunk boundary met within tolerance on every step)
-    from opendpd_b200.functional import chunk_reruns
+    from opendpd_b200.functional import chunk_reruns, chunk_worst_mismatch
     chunk_info, launches = [], 2                       # reduce_partials + clip_adamw
-    calls = ([(trainer.train_bb, False, 0, True, True), (trainer.train_bb, True, 1, True, True)] if "pa" not in wl else
-             [(trainer.dpd, False, 0, True, True), (trainer.pa, False, 2, True, True), (trainer.pa, True, 3, True, False),
-              (trainer.dpd, True, 1, True, True)])
-    for mod, backward, bi, save, need_dw in calls:
+    for mod, backward, bi, save, need_dw in trainer.chunk_calls():
         sp_ = mod._spec()
         plan = sp_.chunk_plan(B, T, backward, save, need_dw)
         buf = trainer._bufs[bi].get("ws" if backward else "saved")
         chunk_info.append({"cell": mod.cell, "dir": "bwd" if backward else "fwd", "chunks": plan[0], "steps_per_chunk": plan[1],
-                           "warmup_steps": plan[2], "serial_reruns": chunk_reruns(sp_, buf, B, T, backward, save, need_dw)})
+                           "warmup_steps": plan[2], "serial_reruns": chunk_reruns(sp_, buf, B, T, backward, save, need_dw),
+                           "worst_boundary_mismatch_over_tolerance": chunk_worst_mismatch(sp_, buf, B, T, backward, save, need_dw)})
         launches += 2 if plan[0] > 1 else 1
     if wl["kind"] == "gmp":
         launches += 1
@@ -355,7 +353,7 @@ def main():
                                   "reduce_partials_kernel", "clip_adamw_kernel"] if "pa" not in wl else
                                  ["dpd_fwd", "pa_fwd(+MSE)", "pa_bwd<dX>", "dpd_bwd<DW>", "(+1 verify launch per chunked call)", "reduce_partials_kernel",
                                   "clip_adamw_kernel", "(gmp: +1)"]),
-            "time_chunks": chunk_info,
+            "time_chunks": chunk_info, "time_chunk_events": trainer.chunk_events,
             "kernel_ms": {"fwd": fwd_ms, "bwd": bwd_ms},
             "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",

@@ -76,9 +76,9 @@ typedef struct OdpdDims {
     int32_t K;      /* DVRJANET num_dvr_units (dvrjanet.py:6); QAT cells: bit widths */
     uint32_t flags; /* ODPD_F_*                                            */
     float thx, thh; /* delta thresholds (deltagru.py:216-217)              */
-    int32_t tchunks; /* GRU/DGRU/QGRU: time chunks a sequence is cut into and run concurrently (see below).
+    int32_t tchunks; /* GRU/DGRU/QGRU/LSTM/PGJANET/DVRJANET: time chunks a sequence is cut into and run concurrently (see below).
                         0 = the library picks from B, T and the SM count; 1 = plain serial recurrence; n = exactly n (<=32) */
-    int32_t twarm;   /* warm-up steps in front of every chunk (rounded up to 32); 0 = default 128 */
+    int32_t twarm;   /* warm-up steps in front of every chunk (rounded up to 32); 0 = the cell's default (128; JANET cells 256) */
 } OdpdDims;
 
 /*
@@ -86,12 +86,14 @@ typedef struct OdpdDims {
  * gru.py:46 / dgru.py:70 / qgru.py:69) and its batches hold fewer sequences than a B200 has SMs.  A GRU forgets its initial
  * state geometrically, so the kernels cut each sequence into `tchunks` chunks that run concurrently, each preceded by `twarm`
  * warm-up steps started from h = 0 (backward: from dL/dh = 0, in reverse time); a verify pass then compares the state every
- * chunk was started from with the state its predecessor really ended with (|dh| <= 2^-22 forward, 2^-21 relative backward)
+ * chunk was started from with the state its predecessor really ended with (max|diff| <= 2^-18 * max|state| at the boundary)
  * and re-runs, serially, every sequence with a failing boundary.  Results therefore never depend on the forgetting
  * assumption; only the speed does.  odpd_chunk_plan reports what a call with these dims will do:
  *   out[0] chunks, out[1] steps per chunk, out[2] warm-up steps, out[3] index (in 4-byte units, or -1) of an int32 counter
- *   inside `saved` (backward = 0) / `workspace` (backward = 1) that counts sequences the verify pass had to re-run; the
- *   caller zeroes it when it allocates the buffer.
+ *   inside `saved` (backward = 0) / `workspace` (backward = 1) that counts sequences the verify pass had to re-run, followed by
+ *   a float holding the largest boundary mismatch seen so far in units of the tolerance; the caller zeroes both when it
+ *   allocates the buffer.  LSTM, PGJANET and DVRJANET are chunked the same way (JANET default warm-up 256); the delta cells,
+ *   GMP and the QAT cell always run serially.
  */
 int odpd_chunk_plan(const OdpdDims *d, int32_t backward, int32_t out[4]);
 

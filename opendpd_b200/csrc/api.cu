@@ -127,8 +127,7 @@ int64_t odpd_saved_bytes(const OdpdDims *d) {
         if (n < 0) { set_error("GRU-family kernels support hidden_size <= 32 (got %d)", d->H); return -1; }
         return 4 * n;
     }
-    const int64_t n = other_saved_bytes(d);
-    return (n < 0 || save) ? n : 0;
+    return other_saved_bytes(d);
 }
 
 int64_t odpd_bwd_workspace_bytes(const OdpdDims *d) {
@@ -138,7 +137,9 @@ int64_t odpd_bwd_workspace_bytes(const OdpdDims *d) {
         if (n < 0) { set_error("GRU-family kernels support hidden_size <= 32 (got %d)", d->H); return -1; }
         return 4 * n + 64;
     }
-    return 4 * (int64_t)(d->B > 0 ? d->B : 1) * odpd_n_params(d->cell, d->H, d->K) + 64;
+    const int64_t n = other_workspace_floats(d);
+    if (n < 0) { set_error("cell %d: hidden_size %d is not supported", d->cell, d->H); return -1; }
+    return 4 * n + 64;
 }
 
 int odpd_backbone_fwd(const OdpdDims *d, const float *x, const float *target, const float *params, float *out, double *loss,
@@ -188,7 +189,7 @@ int odpd_backbone_bwd(const OdpdDims *d, const float *x, const float *params, co
         a.tchunks_req = d->tchunks; a.twarm_req = d->twarm;
         rc = gru_family_run(d->cell, a, 1, dw, st, &rows);
     } else {
-        rc = other_bwd(d, x, params, saved, gout, out, target, gscale, gscale_dev, gx, (float *)workspace, st);
+        rc = other_bwd(d, x, params, saved, gout, out, target, gscale, gscale_dev, gx, (float *)workspace, st, &rows);
     }
     if (rc) return rc;
     if (dw) return reduce_partials((const float *)workspace, rows, P, gparams, (d->flags & ODPD_F_OVERWRITE_DW) != 0, st);
@@ -199,8 +200,15 @@ int odpd_chunk_plan(const OdpdDims *d, int32_t backward, int32_t out[4]) {
     if (check_dims(d)) return -1;
     ODPD_CHECK(out != nullptr, "out is NULL");
     out[0] = 1; out[1] = d->T; out[2] = 0; out[3] = -1;
-    if (!is_gru_family(d->cell) || d->B == 0 || d->T == 0) return 0;
+    if (d->B == 0 || d->T == 0 || d->cell == ODPD_CELL_GMP) return 0;
     int info[4];
+    if (!is_gru_family(d->cell)) {
+        const int rc = other_plan(d, backward, info);
+        if (rc) return rc;
+        for (int i = 0; i < 4; ++i) out[i] = info[i];
+        if (d->tchunks == 1) out[3] = -1;
+        return 0;
+    }
     const int rc = gru_family_plan(d->cell, d->B, d->T, d->H, d->tchunks, d->twarm, backward ? 1 : 0, (d->flags & ODPD_F_NEED_DW) != 0,
                                    (d->flags & ODPD_F_SAVE) != 0, info);
     if (rc) return rc;

@@ -26,7 +26,7 @@ struct GruArgs {
     float *sc_guess, *sc_end, *sc_loss;
     int *sc_fail;
     float tol;
-    int tchunks_req, twarm_req;
+    int tchunks_req, twarm_req, twarm_default;
 };
 
 // gru_family.cu : GRU / DGRU / QGRU / QGRU_AMP1
@@ -34,23 +34,22 @@ int64_t gru_family_nparams(int cell, int H);
 int64_t gru_family_saved_floats(int cell, int B, int T, int H, bool save, int tchunks_req);
 int64_t gru_family_workspace_floats(int cell, int B, int H, int tchunks_req);
 int gru_family_run(int cell, const GruArgs &a, int dir, bool dw, cudaStream_t st, int *rows_out);
-// rows of the per-(sequence,chunk) scratch / gradient-partial workspace for a call of B sequences
-int64_t gru_family_rows(int B, int tchunks_req);
-int64_t gru_family_scratch_floats(int B, int H, int tchunks_req);       // tail of `saved` (fwd) / of the workspace (bwd)
 int gru_family_plan(int cell, int B, int T, int H, int tchunks_req, int twarm_req, int dir, bool dw, bool save, int out[4]);
 
 #define ODPD_HAVE_DELTA 1
 #define ODPD_HAVE_JANET 1
 #define ODPD_HAVE_GMP 1
 // lstm.cu
-int64_t lstm_saved_floats(int B, int T, int H);
-int lstm_run(const GruArgs &a, int dir, bool dw, cudaStream_t st);
+int64_t lstm_saved_floats(int B, int T, int H, bool save, int tchunks_req);
+int64_t lstm_workspace_floats(int B, int H, int64_t P, int tchunks_req);
+int lstm_run(const GruArgs &a, int dir, bool dw, cudaStream_t st, int *info);   // dir +2 = plan only; info[0..3] see chunking.cuh
 // delta.cu : DELTAGRU / TRES
 int64_t delta_saved_floats(int cell, int B, int T, int H);
 int delta_run(const GruArgs &a, int dir, bool dw, cudaStream_t st);
 // janet.cu : PGJANET / DVRJANET
-int64_t janet_saved_floats(int cell, int B, int T, int H);
-int janet_run(const GruArgs &a, int dir, bool dw, cudaStream_t st);
+int64_t janet_saved_floats(int cell, int B, int T, int H, bool save, int tchunks_req);
+int64_t janet_workspace_floats(int cell, int B, int H, int64_t P, int tchunks_req);
+int janet_run(const GruArgs &a, int dir, bool dw, cudaStream_t st, int *info);
 // qgru_qat.cu : fake-quantised GRU (QAT)
 int64_t qat_nparams(int H);
 int64_t qat_saved_floats(int B, int T, int H);
@@ -61,10 +60,12 @@ int gmp_run(const GruArgs &a, int dir, bool dw, cudaStream_t st);
 // remaining families (lstm.cu, delta.cu, janet.cu, gmp.cu) behind one dispatcher in others.cu
 int64_t other_nparams(int cell, int H, int K);
 int64_t other_saved_bytes(const OdpdDims *d);
+int64_t other_workspace_floats(const OdpdDims *d);
+int other_plan(const OdpdDims *d, int backward, int out[4]);
 int other_fwd(const OdpdDims *d, const float *x, const float *target, const float *params, float *out, double *loss, double loss_scale,
               void *saved, int64_t *stats, cudaStream_t st);
 int other_bwd(const OdpdDims *d, const float *x, const float *params, const void *saved, const float *gout, const float *out,
-              const float *target, double gscale, const float *gscale_dev, float *gx, float *partials, cudaStream_t st);
+              const float *target, double gscale, const float *gscale_dev, float *gx, float *partials, cudaStream_t st, int *rows_out);
 
 int reduce_partials(const float *part, int nrows, int64_t P, float *g, int overwrite, cudaStream_t st);
 

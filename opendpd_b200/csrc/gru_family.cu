@@ -17,6 +17,7 @@
 // The flat parameter block is staged once per CTA into shared memory by a TMA bulk copy.
 #include "cells.h"
 #include "pipeline.cuh"
+#include "chunking.cuh"
 
 namespace odpd {
 
@@ -72,37 +73,10 @@ __global__ void __launch_bounds__(96, 1) gru_fwd_kernel(GruArgs a) {
     float *sact = sft + 3 * SM::FT;          // [2][CH][ROW]
     float *spo = sact + 2 * SM::ACT;         // [2][CH][33]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // time range of this CTA: warm-up [t_lo, t_emit) from h = 0 (nothing emitted), then the emitted steps [t_emit, t_hi)
-    const bool spec = (a.C > 1 && a.mode == 0);
-    int b = blockIdx.x, cc = 0, t_lo = 0, t_emit = 0, t_hi = T;
-    if (spec) {
-        b = blockIdx.x / a.C; cc = blockIdx.x - b * a.C;
-        t_emit = cc * a.Lc; t_lo = max(0, t_emit - a.Wu); t_hi = min(T, t_emit + a.Lc);
-    }
-    if (a.mode == 2) {
-        // verify pass: the state every chunk was started from (after its warm-up) must equal the state the previous chunk ended
-        // with; sequences that pass are done, the others are recomputed serially by this CTA
-        __shared__ int s_bad;
-        if (threadIdx.x == 0) s_bad = 0;
-        __syncthreads();
-        for (int i = threadIdx.x; i < (a.C - 1) * HP; i += blockDim.x) {
-            const int c1 = 1 + i / HP, k = i % HP;
-            if (k < H) {
-                const float g = a.sc_guess[((size_t)b * a.C + c1) * HP + k], e = a.sc_end[((size_t)b * a.C + c1 - 1) * HP + k];
-                if (!(fabsf(g - e) <= a.tol)) s_bad = 1;
-            }
-        }
-        __syncthreads();
-        if (!s_bad) {
-            if (threadIdx.x == 0 && a.loss && a.target) {
-                float sl = 0.f;
-                for (int c1 = 0; c1 < a.C; ++c1) sl += a.sc_loss[(size_t)b * a.C + c1];
-                atomicAdd(a.loss, (double)sl * (double)a.loss_scale);
-            }
-            return;
-        }
-        if (threadIdx.x == 0) atomicAdd(a.sc_fail, 1);
-    }
+    const FwdRange R = fwd_range(a);          // chunking.cuh: warm-up [t_lo, t_emit) from h = 0, emitted steps [t_emit, t_hi)
+    const bool spec = R.spec;
+    const int b = R.b, cc = R.cc, t_lo = R.t_lo, t_emit = R.t_emit, t_hi = R.t_hi;
+    if (a.mode == 2 && fwd_verify_pass(a, b, HP, HP, H)) return;   // every chunk boundary of this sequence holds
 
     stage_params(sp, a.params, L.P, bars);
     if (threadIdx.x < HP) zero[threadIdx.x] = 0.f;
@@ -381,10 +355,7 @@ __global__ void __launch_bounds__(96, 1) gru_fwd_kernel(GruArgs a) {
         }
         if (y2) {
             lsum = warp_sum(lsum);
-            if (lane == 0) {
-                if (spec) a.sc_loss[blockIdx.x] = lsum;       // summed by the verify pass
-                else if (a.loss) atomicAdd(a.loss, (double)lsum * (double)a.loss_scale);
-            }
+            if (lane == 0) chunk_store_loss(a, spec, lsum);
         }
     }
 }
@@ -412,30 +383,10 @@ __global__ void __launch_bounds__(128, 1) gru_bwd_kernel(GruArgs a) {
     float *sG = sdp + 3 * SM::DH;            // [2][CH][4*HP]
     float *sdf = sG + 2 * SM::G;             // [CH][8]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // time range of this CTA (reverse time): warm-up steps [t_ehi, t_hi) from dL/dh = 0 (nothing emitted), then [t_elo, t_ehi)
-    const bool spec = (a.C > 1 && a.mode == 0);
-    int b = blockIdx.x, t_elo = 0, t_ehi = T, t_hi = T;
-    if (spec) {
-        b = blockIdx.x / a.C;
-        const int cc = blockIdx.x - b * a.C;
-        t_elo = cc * a.Lc; t_ehi = min(T, t_elo + a.Lc); t_hi = min(T, t_ehi + a.Wu);
-    }
-    if (a.mode == 2) {
-        // verify pass: dL/dh a chunk started from (after its warm-up over the following steps) against what the following chunk
-        // really handed down; relative to the size of that vector.  Failing sequences are recomputed serially by this CTA.
-        __shared__ int s_bad;
-        if (threadIdx.x == 0) s_bad = 0;
-        __syncthreads();
-        for (int i = threadIdx.x; i < a.C - 1; i += blockDim.x) {
-            const float *g = a.sc_guess + ((size_t)b * a.C + i) * HP, *e = a.sc_end + ((size_t)b * a.C + i + 1) * HP;
-            float m = 0.f, dmax = 0.f;
-            for (int k = 0; k < H; ++k) { m = fmaxf(m, fabsf(e[k])); dmax = fmaxf(dmax, fabsf(g[k] - e[k])); }
-            if (!(dmax <= a.tol * m + 1e-37f) || !(m == m)) s_bad = 1;
-        }
-        __syncthreads();
-        if (!s_bad) return;
-        if (threadIdx.x == 0) atomicAdd(a.sc_fail, 1);
-    }
+    const BwdRange R = bwd_range(a);          // chunking.cuh: warm-up [t_ehi, t_hi) from dL/dh = 0, emitted steps [t_elo, t_ehi)
+    const bool spec = R.spec;
+    const int b = R.b, t_elo = R.t_elo, t_ehi = R.t_ehi, t_hi = R.t_hi;
+    if (a.mode == 2 && bwd_verify_pass(a, b, HP, HP, H)) return;
 
     if (threadIdx.x == 0) { mbar_init(bars + 1, 1); mbar_init(bars + 2, 1); mbar_init(bars + 3, 1); }
     stage_params(sp, a.params, L.P, bars);   // contains the mbarrier-init fence + __syncthreads
@@ -739,13 +690,7 @@ __global__ void __launch_bounds__(128, 1) gru_bwd_kernel(GruArgs a) {
         }
         if constexpr (DW) {
             if (a.partials) {
-                // one partial row per CTA: (sequence, chunk) when chunked, else the sequence's first row (the serial re-run of the
-                // verify pass then clears the sequence's other rows)
-                float *prt = a.partials + (size_t)(spec ? blockIdx.x : b * a.C) * L.P;
-                if (a.mode == 2) {
-                    const int tid = (role - 2) * 32 + lane;   // the two post warps
-                    for (int i = tid; i < (a.C - 1) * L.P; i += 64) prt[L.P + i] = 0.f;
-                }
+                float *prt = chunk_partial_row(a, spec, b, L.P, (role - 2) * 32 + lane, 64);   // both post warps
                 if (roleA) {
                     if (act) {
 #pragma unroll
@@ -797,137 +742,26 @@ static int gru_tier(int H) {
     return -1;
 }
 
-// ---------------------------------------------------------------- time-chunk plan
-// A GRU started from the wrong state forgets it geometrically (contractive gates), so a sequence can be cut into C chunks that
-// run CONCURRENTLY, each preceded by Wu warm-up steps from h = 0; a verify pass then checks every chunk boundary against the
-// state the previous chunk really produced and re-runs failing sequences serially.  The backward is the same
-// trick on the linear dL/dh recurrence in reverse time.
-static constexpr int SPEC_ROWS_AUTO = 2048, SPEC_CMAX = 32, SPEC_WARM_DEFAULT = 128;
-static constexpr float SPEC_TOL_FWD = 2.3841858e-07f;   // 2^-22 absolute on h in (-1,1)
-static constexpr float SPEC_TOL_BWD = 4.7683716e-07f;   // 2^-21 relative to max|dL/dh| at the boundary
-
-int64_t gru_family_rows(int B, int tchunks_req) {
-    if (B <= 0) return 1;
-    if (tchunks_req == 1) return B;
-    if (tchunks_req > 1) return (int64_t)B * (tchunks_req < SPEC_CMAX ? tchunks_req : SPEC_CMAX);
-    return B > SPEC_ROWS_AUTO ? B : SPEC_ROWS_AUTO;
-}
-int64_t gru_family_scratch_floats(int B, int H, int tchunks_req) {
-    const int ht = gru_tier(H);
-    if (ht < 0) return -1;
-    return gru_family_rows(B, tchunks_req) * (2 * ((ht + 3) & ~3) + 1) + 4;
-}
-
-static int num_sms() {
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-    }
-    return n;
-}
-
-// fills a.C / a.Lc / a.Wu;  slots = CTAs of this kernel the device holds at once
-static void make_plan(GruArgs &a, int slots, bool have_scratch) {
-    a.C = 1; a.Lc = a.T; a.Wu = 0;
-    const int req = a.tchunks_req;
-    if (req == 1 || !have_scratch || a.T < 2 * CH) return;
-    const int Wu = a.twarm_req > 0 ? ((a.twarm_req + CH - 1) / CH) * CH : SPEC_WARM_DEFAULT;
-    const int nblk = (a.T + CH - 1) / CH;
-    auto lc_of = [&](int C) { return ((nblk + C - 1) / C) * CH; };
-    auto valid = [&](int C) { return (int64_t)(C - 1) * lc_of(C) < a.T; };
-    int C = 1;
-    if (req > 1) {
-        C = req < SPEC_CMAX ? req : SPEC_CMAX;
-        while (C > 1 && !valid(C)) --C;
-    } else {
-        // cost model: every CTA walks Lc + Wu steps; CTAs beyond what the device holds at once wait for a second wave
-        if (slots > SPEC_ROWS_AUTO) slots = SPEC_ROWS_AUTO;
-        if (slots < 1) slots = 1;
-        int64_t best = (int64_t)((a.B + slots - 1) / slots) * a.T;
-        for (int c = 2; c <= SPEC_CMAX; ++c) {
-            if (!valid(c) || lc_of(c) < Wu || (int64_t)a.B * c > SPEC_ROWS_AUTO) continue;
-            const int64_t cost = (int64_t)(((int64_t)a.B * c + slots - 1) / slots) * (lc_of(c) + Wu);
-            if (cost < best) { best = cost; C = c; }
-        }
-    }
-    if (C > 1 && (int64_t)a.B * C <= gru_family_rows(a.B, req)) { a.C = C; a.Lc = lc_of(C); a.Wu = Wu; }
-}
-
-// dir: 0 fwd, 1 bwd, 2 fwd plan only, 3 bwd plan only (plan -> info[0..3] = C, Lc, Wu, float offset of the fail counter)
+// dir: 0 fwd, 1 bwd, 2 fwd plan only, 3 bwd plan only (plan -> info[0..3] = chunks, steps per chunk, warm-up, index of the re-run counter)
 template <int HT, int FM, int HEAD>
 static int launch_fwd(GruArgs a, cudaStream_t st, bool plan_only, int *info) {
     constexpr int HP = Pad4<HT>::value, ROW = Row<HT, HEAD>::value;
     const GruLayout<FM, HEAD> L(a.H);
     const size_t smem = (size_t)FwdSmem<HT, HEAD>::total((L.P + 3) & ~3) * sizeof(float);
-    auto k = gru_fwd_kernel<HT, FM, HEAD>;
-    constexpr int NTH = 96;
     static int occ = 0;
-    if (!occ) {
-        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, NTH, smem) != cudaSuccess || occ <= 0) occ = 1;
-    }
-    const int64_t rows = gru_family_rows(a.B, a.tchunks_req);
-    const size_t soff = a.save ? (size_t)a.B * a.T * ROW : 0;
-    float *scr = a.saved ? a.saved + soff : nullptr;
-    make_plan(a, occ * num_sms(), scr != nullptr || plan_only);
-    if (info) { info[0] = a.C; info[1] = a.Lc; info[2] = a.Wu; info[3] = 0; }
-    if (plan_only) {
-        if (info) { const int64_t off = (int64_t)soff + rows * (2 * HP + 1); info[3] = off > 0x7fffffff ? -1 : (int)off; }
-        return 0;
-    }
-
-    if (a.C > 1) {
-        a.sc_guess = scr; a.sc_end = scr + rows * HP; a.sc_loss = scr + 2 * rows * HP;
-        a.sc_fail = reinterpret_cast<int *>(scr + rows * (2 * HP + 1));
-        a.tol = SPEC_TOL_FWD;
-        a.mode = 0;
-        k<<<a.B * a.C, NTH, smem, st>>>(a);
-        a.mode = 2;
-        k<<<a.B, NTH, smem, st>>>(a);
-    } else {
-        a.mode = 0;
-        k<<<a.B, NTH, smem, st>>>(a);
-    }
-    return check_launch("gru_fwd_kernel");
+    const int64_t soff = a.save ? (int64_t)a.B * a.T * ROW : 0;     // `saved` = [B][T][ROW] rows (when saving) | chunk scratch
+    return chunk_launch(gru_fwd_kernel<HT, FM, HEAD>, 96, smem, &occ, a, 0, a.saved ? a.saved + soff : nullptr, soff, HP, st, plan_only, info,
+                        "gru_fwd_kernel");
 }
 template <int HT, int FM, int HEAD, bool DW>
 static int launch_bwd_t(GruArgs a, cudaStream_t st, bool plan_only, int *info) {
-    constexpr int HP = Pad4<HT>::value, NTH = 128;
+    constexpr int HP = Pad4<HT>::value;
     const GruLayout<FM, HEAD> L(a.H);
     const size_t smem = (size_t)BwdSmem<HT, HEAD>::total((L.P + 3) & ~3) * sizeof(float);
-    auto k = gru_bwd_kernel<HT, FM, HEAD, DW>;
     static int occ = 0;
-    if (!occ) {
-        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, NTH, smem) != cudaSuccess || occ <= 0) occ = 1;
-    }
-    // workspace = [rows][P] gradient partials (4-float aligned) | [rows][HP] guess | [rows][HP] end | fail counter
-    const int64_t rows = gru_family_rows(a.B, a.tchunks_req);
-    const size_t woff = (size_t)((rows * L.P + 3) & ~(int64_t)3);
-    float *scr = a.partials ? a.partials + woff : nullptr;
-    make_plan(a, occ * num_sms(), scr != nullptr || plan_only);
-    if (info) { info[0] = a.C; info[1] = a.Lc; info[2] = a.Wu; info[3] = 0; }
-    if (plan_only) {
-        if (info) { const int64_t off = (int64_t)woff + rows * 2 * HP; info[3] = off > 0x7fffffff ? -1 : (int)off; }
-        return 0;
-    }
-
-    if (a.C > 1) {
-        a.sc_guess = scr; a.sc_end = scr + rows * HP;
-        a.sc_fail = reinterpret_cast<int *>(scr + rows * 2 * HP);
-        a.tol = SPEC_TOL_BWD;
-        a.mode = 0;
-        k<<<a.B * a.C, NTH, smem, st>>>(a);
-        a.mode = 2;
-        k<<<a.B, NTH, smem, st>>>(a);
-    } else {
-        a.mode = 0;
-        k<<<a.B, NTH, smem, st>>>(a);
-    }
-    if (info) info[0] = a.C;
-    return check_launch("gru_bwd_kernel");
+    const int64_t woff = (chunk_rows(a.B, a.tchunks_req) * L.P + 3) & ~(int64_t)3;   // workspace = [rows][P] partials | chunk scratch
+    return chunk_launch(gru_bwd_kernel<HT, FM, HEAD, DW>, 128, smem, &occ, a, 1, a.partials ? a.partials + woff : nullptr, woff, HP, st,
+                        plan_only, info, "gru_bwd_kernel");
 }
 
 template <int FM, int HEAD>
@@ -956,14 +790,14 @@ int64_t gru_family_nparams(int cell, int H) {
 int64_t gru_family_saved_floats(int cell, int B, int T, int H, bool save, int tchunks_req) {
     const int ht = gru_tier(H);
     if (ht < 0) return -1;
-    const int64_t rowsz = save ? (int64_t)B * T * (cell == ODPD_CELL_DGRU ? 6 : 5) * ((ht + 3) & ~3) : 0;
-    return rowsz + gru_family_scratch_floats(B, H, tchunks_req);
+    const int HP = (ht + 3) & ~3;
+    const int64_t rowsz = save ? (int64_t)B * T * (cell == ODPD_CELL_DGRU ? 6 : 5) * HP : 0;
+    return rowsz + chunk_fwd_scratch_floats(chunk_rows(B, tchunks_req), HP);
 }
 int64_t gru_family_workspace_floats(int cell, int B, int H, int tchunks_req) {
     const int ht = gru_tier(H);
     if (ht < 0) return -1;
-    const int64_t rows = gru_family_rows(B, tchunks_req);
-    return ((rows * gru_family_nparams(cell, H) + 3) & ~(int64_t)3) + rows * 2 * ((ht + 3) & ~3) + 4;
+    return chunk_workspace_floats(chunk_rows(B, tchunks_req), gru_family_nparams(cell, H), (ht + 3) & ~3);
 }
 
 static int run_or_plan(int cell, const GruArgs &a, int dir, bool dw, cudaStream_t st, int *info) {

@@ -11,6 +11,7 @@
 // atan2f / sinf / cosf are the full-range libdevice versions (the learned phase th~ is unbounded, SURVEY §7 hard part 2).
 #include "cells.h"
 #include "pipeline.cuh"
+#include "chunking.cuh"
 
 namespace odpd {
 
@@ -58,13 +59,17 @@ __global__ void __launch_bounds__(96, 1) pgjanet_fwd_kernel(GruArgs a) {
     float *sact = sxp + 2 * SM::XP;          // [2][CH][ROW]
     float *spo = sact + 2 * SM::ACT;
     float *sul = spo + 2 * SM::PO;           // [2][HP] u broadcast line
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, b = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const FwdRange R = fwd_range(a);          // chunking.cuh; recurrent state per chunk = h, HP floats
+    const bool spec = R.spec;
+    const int b = R.b, t_emit = R.t_emit, t_hi = R.t_hi;
+    if (a.mode == 2 && fwd_verify_pass(a, b, HP, HP, H)) return;
     stage_params(sp, a.params, L.P, bars);
     if (threadIdx.x < HP) zero[threadIdx.x] = 0.f;
     __syncthreads();
     const bool act = lane < H;
     const int j = act ? lane : 0, lp = lane < HP ? lane : 0;
-    const int nchunks = (T + CH - 1) / CH;
+    const int cb = R.t_lo / CH, nchunks = (t_hi + CH - 1) / CH - cb;
     const float2 *x2 = reinterpret_cast<const float2 *>(a.x) + (size_t)b * T;
 
     if (warp == 1) {
@@ -72,7 +77,7 @@ __global__ void __launch_bounds__(96, 1) pgjanet_fwd_kernel(GruArgs a) {
         const float ba = act ? sp[L.oba + j] : 0.f, b1 = act ? sp[L.obp1 + j] : 0.f, b2 = act ? sp[L.obp2 + j] : 0.f;
         for (int s = 0; s < nchunks + 2; ++s) {
             if (s < nchunks) {
-                const int t0 = s * CH, nt = min(CH, T - t0);
+                const int t0 = (cb + s) * CH, nt = min(CH, t_hi - t0);
                 float *xp = sxp + (s & 1) * SM::XP;
                 float fa = 0.f, fc = 0.f, fs = 0.f;
                 if (lane < nt) { const float2 v = __ldg(x2 + t0 + lane); pg_features(v.x, v.y, fa, fc, fs); }
@@ -98,7 +103,8 @@ __global__ void __launch_bounds__(96, 1) pgjanet_fwd_kernel(GruArgs a) {
         for (int s = 0; s < nchunks + 2; ++s) {
             const int c = s - 1;
             if (c >= 0 && c < nchunks) {
-                const int t0 = c * CH, nt = min(CH, T - t0);
+                const int t0 = (cb + c) * CH, nt = min(CH, t_hi - t0);
+                if (spec && R.cc > 0 && t0 == t_emit && lane < HP) a.sc_guess[(size_t)blockIdx.x * HP + lane] = h;
                 const float *xp = sxp + (c & 1) * SM::XP + lp;
                 float *ac = sact + (c & 1) * SM::ACT;
                 const float *hrow = (c == 0) ? zero : sact + ((c - 1) & 1) * SM::ACT + (CH - 1) * ROW + 6 * HP;
@@ -135,6 +141,7 @@ __global__ void __launch_bounds__(96, 1) pgjanet_fwd_kernel(GruArgs a) {
             }
             __syncthreads();
         }
+        if (spec && lane < HP) a.sc_end[(size_t)blockIdx.x * HP + lane] = h;
     } else {
         const float wo0 = act ? sp[L.oWo + j] : 0.f, wo1 = act ? sp[L.oWo + H + j] : 0.f;
         const float bo0 = sp[L.obo], bo1 = sp[L.obo + 1];
@@ -144,8 +151,8 @@ __global__ void __launch_bounds__(96, 1) pgjanet_fwd_kernel(GruArgs a) {
         float lsum = 0.f;
         for (int s = 0; s < nchunks + 2; ++s) {
             const int c = s - 2;
-            if (c >= 0) {
-                const int t0 = c * CH, nt = min(CH, T - t0);
+            if (c >= 0 && (cb + c) * CH >= t_emit) {       // warm-up blocks emit nothing
+                const int t0 = (cb + c) * CH, nt = min(CH, t_hi - t0);
                 float *ac = sact + (c & 1) * SM::ACT;
                 if (svg && lane == 0) tma_store_1d(svg + (size_t)t0 * ROW, ac, (uint32_t)(nt * ROW * 4));
                 linear_head_chunk(ac, ROW, 6 * HP, HP, H, nt, lane, wo0, wo1, bo0, bo1, spo, nullptr, o2 + t0, y2 ? y2 + t0 : nullptr, lsum);
@@ -154,9 +161,9 @@ __global__ void __launch_bounds__(96, 1) pgjanet_fwd_kernel(GruArgs a) {
             }
             __syncthreads();
         }
-        if (a.loss && y2) {
+        if (y2) {
             lsum = warp_sum(lsum);
-            if (lane == 0) atomicAdd(a.loss, (double)lsum * (double)a.loss_scale);
+            if (lane == 0) chunk_store_loss(a, spec, lsum);
         }
     }
 }
@@ -177,12 +184,17 @@ __global__ void __launch_bounds__(96, 1) pgjanet_bwd_kernel(GruArgs a) {
     float *sG = sdh + 2 * SM::DH;            // [2][CH][5HP]: af | ag | aa | a1 | a2
     float *sdf = sG + 2 * SM::G;             // [CH][4]: ga gc gs
     float *sl = sdf + SM::DF;                // [2][2HP] chain broadcast lines for (af,ag) — also stored in sG; kept separate for double buffering
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, b = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const BwdRange R = bwd_range(a);          // chunking.cuh; adjoint state per chunk: HP floats
+    const bool spec = R.spec;
+    const int b = R.b, t_ehi = R.t_ehi, t_hi = R.t_hi;
+    if (a.mode == 2 && bwd_verify_pass(a, b, HP, HP, H)) return;
     if (threadIdx.x == 0) { mbar_init(bars + 1, 1); mbar_init(bars + 2, 1); mbar_init(bars + 3, 1); }
     stage_params(sp, a.params, L.P, bars);
     const bool act = lane < H;
     const int j = act ? lane : 0, lp = lane < HP ? lane : 0;
-    const int nchunks = (T + CH - 1) / CH;
+    // 32-step blocks [cb, ce) are processed last to first; blocks >= ce_emit are warm-up
+    const int cb = R.t_elo / CH, ce = (t_hi + CH - 1) / CH, nchunks = ce - cb, ce_emit = (t_ehi + CH - 1) / CH;
     const float2 *x2 = reinterpret_cast<const float2 *>(a.x) + (size_t)b * T;
     const float *svg = a.saved + (size_t)b * T * ROW;
     (void)sl;
@@ -195,7 +207,7 @@ __global__ void __launch_bounds__(96, 1) pgjanet_bwd_kernel(GruArgs a) {
         const float gs = a.gscale * (a.gscale_dev ? __ldg(a.gscale_dev) : 1.0f);
         for (int s = 0; s < nchunks + 2; ++s) {
             if (s < nchunks) {
-                const int c = nchunks - 1 - s, t0 = c * CH, nt = min(CH, T - t0), slot = s % 3;
+                const int c = ce - 1 - s, t0 = c * CH, nt = min(CH, t_hi - t0), slot = s % 3;
                 float *ac = sact + slot * SM::ACT, *pr = spre + slot * SM::PRE, *dh = sdh + (s & 1) * SM::DH;
                 uint64_t *bar = bars + 1 + slot;
                 load_rows_with_prev(ac, svg, ROW, t0, nt, lane, bar);
@@ -229,7 +241,8 @@ __global__ void __launch_bounds__(96, 1) pgjanet_bwd_kernel(GruArgs a) {
         for (int s = 0; s < nchunks + 2; ++s) {
             const int sc = s - 1;
             if (sc >= 0 && sc < nchunks) {
-                const int c = nchunks - 1 - sc, t0 = c * CH, nt = min(CH, T - t0);
+                const int c = ce - 1 - sc, t0 = c * CH, nt = min(CH, t_hi - t0);
+                if (spec && c == ce_emit - 1 && t_ehi < T && lane < HP) a.sc_guess[(size_t)blockIdx.x * HP + lane] = gH;
                 const float *ac = sact + (sc % 3) * SM::ACT + lp;
                 const float *dh = sdh + (sc & 1) * SM::DH + lp;
                 float *Gb = sG + (sc & 1) * SM::G;
@@ -267,6 +280,7 @@ __global__ void __launch_bounds__(96, 1) pgjanet_bwd_kernel(GruArgs a) {
             }
             __syncthreads();
         }
+        if (spec && lane < HP) a.sc_end[(size_t)blockIdx.x * HP + lane] = gH;
     } else {
         const int fl = lane - H;                   // feature lanes H..H+2: d/da, d/dcos, d/dsin
         const bool isf = fl >= 0 && fl < 3;
@@ -286,8 +300,8 @@ __global__ void __launch_bounds__(96, 1) pgjanet_bwd_kernel(GruArgs a) {
         float2 *gx2 = (a.need_dx && a.gx) ? reinterpret_cast<float2 *>(a.gx) + (size_t)b * T : nullptr;
         for (int s = 0; s < nchunks + 2; ++s) {
             const int sc = s - 2;
-            if (sc >= 0) {
-                const int c = nchunks - 1 - sc, t0 = c * CH, nt = min(CH, T - t0);
+            if (sc >= 0 && ce - 1 - sc < ce_emit) {          // warm-up blocks emit nothing
+                const int c = ce - 1 - sc, t0 = c * CH, nt = min(CH, t_hi - t0);
                 const float *ac = sact + (sc % 3) * SM::ACT, *pr = spre + (sc % 3) * SM::PRE, *Gb = sG + (sc & 1) * SM::G;
                 for (int tl = 0; tl < nt; ++tl) {
                     const float *G = Gb + tl * 5 * HP;
@@ -341,7 +355,7 @@ __global__ void __launch_bounds__(96, 1) pgjanet_bwd_kernel(GruArgs a) {
         }
         if constexpr (DW) {
             if (a.partials) {
-                float *prt = a.partials + (size_t)b * L.P;
+                float *prt = chunk_partial_row(a, spec, b, L.P, lane, 32);
                 if (act) {
 #pragma unroll
                     for (int k = 0; k < HT; ++k)
@@ -398,20 +412,24 @@ __global__ void __launch_bounds__(96, 1) dvrjanet_fwd_kernel(GruArgs a) {
     float *sact = sxp + 2 * SM::XP;          // [2][CH][ROW]
     float *spo = sact + 2 * SM::ACT;
     float *sln = spo + 2 * SM::PO;           // [2][3HP]: s | a~cos | a~sin lines
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, b = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const FwdRange R = fwd_range(a);          // chunking.cuh; recurrent state per chunk = (h_I, h_Q), 2*HP floats
+    const bool spec = R.spec;
+    const int b = R.b, t_emit = R.t_emit, t_hi = R.t_hi;
+    if (a.mode == 2 && fwd_verify_pass(a, b, 2 * HP, HP, H)) return;
     stage_params(sp, a.params, L.P, bars);
     for (int i = threadIdx.x; i < ROW; i += blockDim.x) zero[i] = 0.f;
     __syncthreads();
     const bool act = lane < H;
     const int j = act ? lane : 0, lp = lane < HP ? lane : 0;
-    const int nchunks = (T + CH - 1) / CH;
+    const int cb = R.t_lo / CH, nchunks = (t_hi + CH - 1) / CH - cb;
     const float2 *x2 = reinterpret_cast<const float2 *>(a.x) + (size_t)b * T;
 
     if (warp == 1) {
         const float wpt = act ? sp[L.oWpt + j] : 0.f, wax = act ? sp[L.oWax + j] : 0.f;
         for (int s = 0; s < nchunks + 2; ++s) {
             if (s < nchunks) {
-                const int t0 = s * CH, nt = min(CH, T - t0);
+                const int t0 = (cb + s) * CH, nt = min(CH, t_hi - t0);
                 float *xp = sxp + (s & 1) * SM::XP;
                 float fa = 0.f, fth = 0.f;
                 if (lane < nt) {
@@ -445,7 +463,11 @@ __global__ void __launch_bounds__(96, 1) dvrjanet_fwd_kernel(GruArgs a) {
         for (int s = 0; s < nchunks + 2; ++s) {
             const int c = s - 1;
             if (c >= 0 && c < nchunks) {
-                const int t0 = c * CH, nt = min(CH, T - t0);
+                const int t0 = (cb + c) * CH, nt = min(CH, t_hi - t0);
+                if (spec && R.cc > 0 && t0 == t_emit && lane < HP) {
+                    a.sc_guess[(size_t)blockIdx.x * 2 * HP + lane] = hI;
+                    a.sc_guess[(size_t)blockIdx.x * 2 * HP + HP + lane] = hQ;
+                }
                 const float *xp = sxp + (c & 1) * SM::XP + lp;
                 float *ac = sact + (c & 1) * SM::ACT;
                 const float *prow = (c == 0) ? zero : sact + ((c - 1) & 1) * SM::ACT + (CH - 1) * ROW;
@@ -491,6 +513,10 @@ __global__ void __launch_bounds__(96, 1) dvrjanet_fwd_kernel(GruArgs a) {
             }
             __syncthreads();
         }
+        if (spec && lane < HP) {
+            a.sc_end[(size_t)blockIdx.x * 2 * HP + lane] = hI;
+            a.sc_end[(size_t)blockIdx.x * 2 * HP + HP + lane] = hQ;
+        }
     } else {
         const float wo0 = act ? sp[L.oWo1 + j] : 0.f, wo1 = act ? sp[L.oWo2 + j] : 0.f;
         const float bo0 = sp[L.obo1], bo1 = sp[L.obo2];
@@ -500,8 +526,8 @@ __global__ void __launch_bounds__(96, 1) dvrjanet_fwd_kernel(GruArgs a) {
         float lsum = 0.f;
         for (int s = 0; s < nchunks + 2; ++s) {
             const int c = s - 2;
-            if (c >= 0) {
-                const int t0 = c * CH, nt = min(CH, T - t0);
+            if (c >= 0 && (cb + c) * CH >= t_emit) {       // warm-up blocks emit nothing
+                const int t0 = (cb + c) * CH, nt = min(CH, t_hi - t0);
                 float *ac = sact + (c & 1) * SM::ACT;
                 if (svg && lane == 0) tma_store_1d(svg + (size_t)t0 * ROW, ac, (uint32_t)(nt * ROW * 4));
                 linear_head_chunk2(ac, ROW, 7 * HP, 8 * HP, HP, H, nt, lane, wo0, wo1, bo0, bo1, spo, nullptr, o2 + t0, y2 ? y2 + t0 : nullptr, lsum);
@@ -510,9 +536,9 @@ __global__ void __launch_bounds__(96, 1) dvrjanet_fwd_kernel(GruArgs a) {
             }
             __syncthreads();
         }
-        if (a.loss && y2) {
+        if (y2) {
             lsum = warp_sum(lsum);
-            if (lane == 0) atomicAdd(a.loss, (double)lsum * (double)a.loss_scale);
+            if (lane == 0) chunk_store_loss(a, spec, lsum);
         }
     }
 }
@@ -532,12 +558,17 @@ __global__ void __launch_bounds__(96, 1) dvrjanet_bwd_kernel(GruArgs a) {
     float *sdh = spre + 3 * SM::PRE;         // [2][CH][2HP]: dL/dh_I | dL/dh_Q from the head
     float *sG = sdh + 2 * SM::DH;            // [2][CH][6HP]: ac | as | af | gtht | gpa | gat
     float *sdf = sG + 2 * SM::G;             // [CH][2]: gth, ga
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, b = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const BwdRange R = bwd_range(a);          // chunking.cuh; adjoint state per chunk: 2 * HP floats
+    const bool spec = R.spec;
+    const int b = R.b, t_ehi = R.t_ehi, t_hi = R.t_hi;
+    if (a.mode == 2 && bwd_verify_pass(a, b, 2 * HP, HP, H)) return;
     if (threadIdx.x == 0) { mbar_init(bars + 1, 1); mbar_init(bars + 2, 1); mbar_init(bars + 3, 1); }
     stage_params(sp, a.params, L.P, bars);
     const bool act = lane < H;
     const int j = act ? lane : 0, lp = lane < HP ? lane : 0;
-    const int nchunks = (T + CH - 1) / CH;
+    // 32-step blocks [cb, ce) are processed last to first; blocks >= ce_emit are warm-up
+    const int cb = R.t_elo / CH, ce = (t_hi + CH - 1) / CH, nchunks = ce - cb, ce_emit = (t_ehi + CH - 1) / CH;
     const float2 *x2 = reinterpret_cast<const float2 *>(a.x) + (size_t)b * T;
     const float *svg = a.saved + (size_t)b * T * ROW;
 
@@ -549,7 +580,7 @@ __global__ void __launch_bounds__(96, 1) dvrjanet_bwd_kernel(GruArgs a) {
         const float gs = a.gscale * (a.gscale_dev ? __ldg(a.gscale_dev) : 1.0f);
         for (int s = 0; s < nchunks + 2; ++s) {
             if (s < nchunks) {
-                const int c = nchunks - 1 - s, t0 = c * CH, nt = min(CH, T - t0), slot = s % 3;
+                const int c = ce - 1 - s, t0 = c * CH, nt = min(CH, t_hi - t0), slot = s % 3;
                 float *ac = sact + slot * SM::ACT, *pr = spre + slot * SM::PRE, *dh = sdh + (s & 1) * SM::DH;
                 uint64_t *bar = bars + 1 + slot;
                 load_rows_with_prev(ac, svg, ROW, t0, nt, lane, bar);
@@ -585,7 +616,11 @@ __global__ void __launch_bounds__(96, 1) dvrjanet_bwd_kernel(GruArgs a) {
         for (int s = 0; s < nchunks + 2; ++s) {
             const int sc = s - 1;
             if (sc >= 0 && sc < nchunks) {
-                const int c = nchunks - 1 - sc, t0 = c * CH, nt = min(CH, T - t0);
+                const int c = ce - 1 - sc, t0 = c * CH, nt = min(CH, t_hi - t0);
+                if (spec && c == ce_emit - 1 && t_ehi < T && lane < HP) {
+                    a.sc_guess[(size_t)blockIdx.x * 2 * HP + lane] = gI;
+                    a.sc_guess[(size_t)blockIdx.x * 2 * HP + HP + lane] = gQ;
+                }
                 const float *ac = sact + (sc % 3) * SM::ACT + lp;
                 const float *dh = sdh + (sc & 1) * SM::DH + lp;
                 float *Gb = sG + (sc & 1) * SM::G;
@@ -629,6 +664,10 @@ __global__ void __launch_bounds__(96, 1) dvrjanet_bwd_kernel(GruArgs a) {
             }
             __syncthreads();
         }
+        if (spec && lane < HP) {
+            a.sc_end[(size_t)blockIdx.x * 2 * HP + lane] = gI;
+            a.sc_end[(size_t)blockIdx.x * 2 * HP + HP + lane] = gQ;
+        }
     } else {
         const int fl = lane - H;                   // feature lanes H (d/dtheta), H+1 (d/da)
         const bool isf = fl >= 0 && fl < 2;
@@ -648,8 +687,8 @@ __global__ void __launch_bounds__(96, 1) dvrjanet_bwd_kernel(GruArgs a) {
         float2 *gx2 = (a.need_dx && a.gx) ? reinterpret_cast<float2 *>(a.gx) + (size_t)b * T : nullptr;
         for (int s = 0; s < nchunks + 2; ++s) {
             const int sc = s - 2;
-            if (sc >= 0) {
-                const int c = nchunks - 1 - sc, t0 = c * CH, nt = min(CH, T - t0);
+            if (sc >= 0 && ce - 1 - sc < ce_emit) {          // warm-up blocks emit nothing
+                const int c = ce - 1 - sc, t0 = c * CH, nt = min(CH, t_hi - t0);
                 const float *ac = sact + (sc % 3) * SM::ACT, *pr = spre + (sc % 3) * SM::PRE, *Gb = sG + (sc & 1) * SM::G;
                 for (int tl = 0; tl < nt; ++tl) {
                     const float *G = Gb + tl * 6 * HP;
@@ -705,7 +744,7 @@ __global__ void __launch_bounds__(96, 1) dvrjanet_bwd_kernel(GruArgs a) {
         }
         if constexpr (DW) {
             if (a.partials) {
-                float *prt = a.partials + (size_t)b * L.P;
+                float *prt = chunk_partial_row(a, spec, b, L.P, lane, 32);
                 if (act) {
 #pragma unroll
                     for (int k = 0; k < HT; ++k)
@@ -737,36 +776,52 @@ static int janet_tier(int H) {
 #undef X
     return -1;
 }
+// The JANET cells forget slowly (gate products; measured on PGJANET at init: the adjoint loses ~0.94x per step, 2e-4 left after
+// 128 steps, 4e-8 after 256), so their default warm-up is 256 steps.
+static constexpr int JANET_WARM = 256;
+// dir: 0 fwd, 1 bwd, +2 = plan only
 template <int HT>
-static int janet_launch(const GruArgs &a, int dir, bool dw, cudaStream_t st) {
+static int janet_launch(const GruArgs &a, int dir, bool dw, cudaStream_t st, int *info) {
+    constexpr int HP = Pad4<HT>::value;
     const bool pg = a.cell == ODPD_CELL_PGJANET;
     const int P = pg ? PgLayout(a.H).P : DvLayout(a.H, a.K).P;
     const int Ppad = (P + 3) & ~3;
-#define LAUNCH(KERN, SMEMT)                                                                   \
-    {                                                                                         \
-        const size_t smem = (size_t)SMEMT::total(Ppad) * 4;                                   \
-        auto k = KERN;                                                                        \
-        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
-        k<<<a.B, 96, smem, st>>>(a);                                                          \
+    const bool plan_only = dir >= 2, fwd = (dir & 1) == 0;
+    const int ss = pg ? HP : 2 * HP, ROW = pg ? PgRow<HT>::value : DvRow<HT>::value;
+    const int64_t off = fwd ? (a.save ? (int64_t)a.B * a.T * ROW : 0) : ((chunk_rows(a.B, a.tchunks_req) * P + 3) & ~(int64_t)3);
+    float *base = fwd ? a.saved : a.partials;
+    float *scr = base ? base + off : nullptr;
+#define LAUNCH(KERN, SMEMT, NAME)                                                                                             \
+    {                                                                                                                         \
+        static int occ = 0;                                                                                                   \
+        return chunk_launch(KERN, 96, (size_t)SMEMT::total(Ppad) * 4, &occ, a, fwd ? 0 : 1, scr, off, ss, st, plan_only, info, NAME, JANET_WARM); \
     }
     if (pg) {
-        if (dir == 0) LAUNCH(pgjanet_fwd_kernel<HT>, PgFwdSmem<HT>)
-        else if (dw) LAUNCH((pgjanet_bwd_kernel<HT, true>), PgBwdSmem<HT>)
-        else LAUNCH((pgjanet_bwd_kernel<HT, false>), PgBwdSmem<HT>)
+        if (fwd) LAUNCH(pgjanet_fwd_kernel<HT>, PgFwdSmem<HT>, "pgjanet_fwd_kernel")
+        else if (dw) LAUNCH((pgjanet_bwd_kernel<HT, true>), PgBwdSmem<HT>, "pgjanet_bwd_kernel")
+        else LAUNCH((pgjanet_bwd_kernel<HT, false>), PgBwdSmem<HT>, "pgjanet_bwd_kernel")
     } else {
-        if (dir == 0) LAUNCH(dvrjanet_fwd_kernel<HT>, DvFwdSmem<HT>)
-        else if (dw) LAUNCH((dvrjanet_bwd_kernel<HT, true>), DvBwdSmem<HT>)
-        else LAUNCH((dvrjanet_bwd_kernel<HT, false>), DvBwdSmem<HT>)
+        if (fwd) LAUNCH(dvrjanet_fwd_kernel<HT>, DvFwdSmem<HT>, "dvrjanet_fwd_kernel")
+        else if (dw) LAUNCH((dvrjanet_bwd_kernel<HT, true>), DvBwdSmem<HT>, "dvrjanet_bwd_kernel")
+        else LAUNCH((dvrjanet_bwd_kernel<HT, false>), DvBwdSmem<HT>, "dvrjanet_bwd_kernel")
     }
 #undef LAUNCH
-    return check_launch("janet kernel");
 }
-int64_t janet_saved_floats(int cell, int B, int T, int H) {
+int64_t janet_saved_floats(int cell, int B, int T, int H, bool save, int tchunks_req) {
     const int ht = janet_tier(H);
-    return ht < 0 ? -1 : (int64_t)B * T * (cell == ODPD_CELL_PGJANET ? 7 : 9) * ((ht + 3) & ~3);
+    if (ht < 0) return -1;
+    const int HP = (ht + 3) & ~3;
+    const bool pg = cell == ODPD_CELL_PGJANET;
+    return (save ? (int64_t)B * T * (pg ? 7 : 9) * HP : 0) + chunk_fwd_scratch_floats(chunk_rows(B, tchunks_req), pg ? HP : 2 * HP);
 }
-int janet_run(const GruArgs &a, int dir, bool dw, cudaStream_t st) {
-#define X(HTV) if (a.H <= HTV) return janet_launch<HTV>(a, dir, dw, st);
+int64_t janet_workspace_floats(int cell, int B, int H, int64_t P, int tchunks_req) {
+    const int ht = janet_tier(H);
+    if (ht < 0) return -1;
+    const int HP = (ht + 3) & ~3;
+    return chunk_workspace_floats(chunk_rows(B, tchunks_req), P, cell == ODPD_CELL_PGJANET ? HP : 2 * HP);
+}
+int janet_run(const GruArgs &a, int dir, bool dw, cudaStream_t st, int *info) {
+#define X(HTV) if (a.H <= HTV) return janet_launch<HTV>(a, dir, dw, st, info);
     ODPD_JANET_TIERS(X)
 #undef X
     set_error("JANET kernels support hidden_size <= 24 (got %d)", a.H);

@@ -3,6 +3,7 @@
 // (gate order i,f,g,o; c' = f*c + i*g; h' = o*tanh(c')), plus nn.MSELoss.  Same 3-warp chunk pipeline as gru_family.cu.
 #include "cells.h"
 #include "pipeline.cuh"
+#include "chunking.cuh"
 
 namespace odpd {
 
@@ -42,13 +43,17 @@ __global__ void __launch_bounds__(96, 1) lstm_fwd_kernel(GruArgs a) {
     float *sxp = zero + ROW;                 // [2][CH][4*HP]
     float *sact = sxp + 2 * SM::XP;          // [2][CH][ROW]
     float *spo = sact + 2 * SM::ACT;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, b = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const FwdRange R = fwd_range(a);          // chunking.cuh; recurrent state per chunk = (c, h), 2*HP floats
+    const bool spec = R.spec;
+    const int b = R.b, t_emit = R.t_emit, t_hi = R.t_hi;
+    if (a.mode == 2 && fwd_verify_pass(a, b, 2 * HP, HP, H)) return;
     stage_params(sp, a.params, L.P, bars);
     for (int i = threadIdx.x; i < ROW; i += blockDim.x) zero[i] = 0.f;
     __syncthreads();
     const bool act = lane < H;
     const int j = act ? lane : 0, lp = lane < HP ? lane : 0;
-    const int nchunks = (T + CH - 1) / CH;
+    const int cb = R.t_lo / CH, nchunks = (t_hi + CH - 1) / CH - cb;
     const float2 *x2 = reinterpret_cast<const float2 *>(a.x) + (size_t)b * T;
 
     if (warp == 1) {
@@ -61,7 +66,7 @@ __global__ void __launch_bounds__(96, 1) lstm_fwd_kernel(GruArgs a) {
         }
         for (int s = 0; s < nchunks + 2; ++s) {
             if (s < nchunks) {
-                const int t0 = s * CH, nt = min(CH, T - t0);
+                const int t0 = (cb + s) * CH, nt = min(CH, t_hi - t0);
                 float *xp = sxp + (s & 1) * SM::XP;
                 float2 v = make_float2(0.f, 0.f);
                 if (lane < nt) v = __ldg(x2 + t0 + lane);
@@ -85,11 +90,15 @@ __global__ void __launch_bounds__(96, 1) lstm_fwd_kernel(GruArgs a) {
             wg[k] = ok ? sp[L.oWhh + (2 * H + j) * H + k] : 0.f;
             wo[k] = ok ? sp[L.oWhh + (3 * H + j) * H + k] : 0.f;
         }
-        float c = 0.f;
+        float c = 0.f, hl = 0.f;
         for (int s = 0; s < nchunks + 2; ++s) {
             const int ck = s - 1;
             if (ck >= 0 && ck < nchunks) {
-                const int t0 = ck * CH, nt = min(CH, T - t0);
+                const int t0 = (cb + ck) * CH, nt = min(CH, t_hi - t0);
+                if (spec && R.cc > 0 && t0 == t_emit && lane < HP) {
+                    a.sc_guess[(size_t)blockIdx.x * 2 * HP + lane] = c;
+                    a.sc_guess[(size_t)blockIdx.x * 2 * HP + HP + lane] = hl;
+                }
                 const float *xp = sxp + (ck & 1) * SM::XP + lp;
                 float *ac = sact + (ck & 1) * SM::ACT;
                 const float *hrow = (ck == 0) ? zero : sact + ((ck - 1) & 1) * SM::ACT + (CH - 1) * ROW + 5 * HP;
@@ -106,6 +115,7 @@ __global__ void __launch_bounds__(96, 1) lstm_fwd_kernel(GruArgs a) {
                     c = fmaf(fg, c, ig * gg);
                     const float tc = tanhf_(c);
                     const float h = og * tc;
+                    hl = h;
                     float *row = ac + tl * ROW;
                     if (lane < HP) {
                         row[5 * HP + lane] = h;
@@ -120,6 +130,10 @@ __global__ void __launch_bounds__(96, 1) lstm_fwd_kernel(GruArgs a) {
             }
             __syncthreads();
         }
+        if (spec && lane < HP) {
+            a.sc_end[(size_t)blockIdx.x * 2 * HP + lane] = c;
+            a.sc_end[(size_t)blockIdx.x * 2 * HP + HP + lane] = hl;
+        }
     } else {
         const float wo0 = act ? sp[L.oWo + j] : 0.f, wo1 = act ? sp[L.oWo + H + j] : 0.f;
         const float bo0 = sp[L.obo], bo1 = sp[L.obo + 1];
@@ -129,8 +143,8 @@ __global__ void __launch_bounds__(96, 1) lstm_fwd_kernel(GruArgs a) {
         float lsum = 0.f;
         for (int s = 0; s < nchunks + 2; ++s) {
             const int ck = s - 2;
-            if (ck >= 0) {
-                const int t0 = ck * CH, nt = min(CH, T - t0);
+            if (ck >= 0 && (cb + ck) * CH >= t_emit) {     // warm-up blocks emit nothing
+                const int t0 = (cb + ck) * CH, nt = min(CH, t_hi - t0);
                 float *ac = sact + (ck & 1) * SM::ACT;
                 if (svg && lane == 0) tma_store_1d(svg + (size_t)t0 * ROW, ac, (uint32_t)(nt * ROW * 4));
                 linear_head_chunk(ac, ROW, 5 * HP, HP, H, nt, lane, wo0, wo1, bo0, bo1, spo, nullptr, o2 + t0, y2 ? y2 + t0 : nullptr, lsum);
@@ -139,9 +153,9 @@ __global__ void __launch_bounds__(96, 1) lstm_fwd_kernel(GruArgs a) {
             }
             __syncthreads();
         }
-        if (a.loss && y2) {
+        if (y2) {
             lsum = warp_sum(lsum);
-            if (lane == 0) atomicAdd(a.loss, (double)lsum * (double)a.loss_scale);
+            if (lane == 0) chunk_store_loss(a, spec, lsum);
         }
     }
 }
@@ -161,12 +175,17 @@ __global__ void __launch_bounds__(96, 1) lstm_bwd_kernel(GruArgs a) {
     float *sdh = spre + 3 * SM::PRE;         // [2][CH][HP]
     float *sG = sdh + 2 * SM::DH;            // [2][CH][4HP]: di df dg do
     float *sdf = sG + 2 * SM::G;             // [CH][2]
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, b = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const BwdRange R = bwd_range(a);          // chunking.cuh; adjoint state per chunk = (dL/dh, dL/dc), 2*HP floats
+    const bool spec = R.spec;
+    const int b = R.b, t_ehi = R.t_ehi, t_hi = R.t_hi;
+    if (a.mode == 2 && bwd_verify_pass(a, b, 2 * HP, HP, H)) return;
     if (threadIdx.x == 0) { mbar_init(bars + 1, 1); mbar_init(bars + 2, 1); mbar_init(bars + 3, 1); }
     stage_params(sp, a.params, L.P, bars);
     const bool act = lane < H;
     const int j = act ? lane : 0, lp = lane < HP ? lane : 0;
-    const int nchunks = (T + CH - 1) / CH;
+    // 32-step blocks [cb, ce) are processed last to first; blocks >= ce_emit are warm-up
+    const int cb = R.t_elo / CH, ce = (t_hi + CH - 1) / CH, nchunks = ce - cb, ce_emit = (t_ehi + CH - 1) / CH;
     const float2 *x2 = reinterpret_cast<const float2 *>(a.x) + (size_t)b * T;
     const float *svg = a.saved + (size_t)b * T * ROW;
 
@@ -178,7 +197,7 @@ __global__ void __launch_bounds__(96, 1) lstm_bwd_kernel(GruArgs a) {
         const float gs = a.gscale * (a.gscale_dev ? __ldg(a.gscale_dev) : 1.0f);
         for (int s = 0; s < nchunks + 2; ++s) {
             if (s < nchunks) {
-                const int c = nchunks - 1 - s, t0 = c * CH, nt = min(CH, T - t0), slot = s % 3;
+                const int c = ce - 1 - s, t0 = c * CH, nt = min(CH, t_hi - t0), slot = s % 3;
                 float *ac = sact + slot * SM::ACT, *pr = spre + slot * SM::PRE, *dh = sdh + (s & 1) * SM::DH;
                 uint64_t *bar = bars + 1 + slot;
                 load_rows_with_prev(ac, svg, ROW, t0, nt, lane, bar);
@@ -208,7 +227,11 @@ __global__ void __launch_bounds__(96, 1) lstm_bwd_kernel(GruArgs a) {
         for (int s = 0; s < nchunks + 2; ++s) {
             const int sc = s - 1;
             if (sc >= 0 && sc < nchunks) {
-                const int c = nchunks - 1 - sc, t0 = c * CH, nt = min(CH, T - t0);
+                const int c = ce - 1 - sc, t0 = c * CH, nt = min(CH, t_hi - t0);
+                if (spec && c == ce_emit - 1 && t_ehi < T && lane < HP) {
+                    a.sc_guess[(size_t)blockIdx.x * 2 * HP + lane] = gH;
+                    a.sc_guess[(size_t)blockIdx.x * 2 * HP + HP + lane] = gC;
+                }
                 const float *ac = sact + (sc % 3) * SM::ACT + lp;
                 const float *dh = sdh + (sc & 1) * SM::DH + lp;
                 float *Gb = sG + (sc & 1) * SM::G;
@@ -241,6 +264,10 @@ __global__ void __launch_bounds__(96, 1) lstm_bwd_kernel(GruArgs a) {
             }
             __syncthreads();
         }
+        if (spec && lane < HP) {
+            a.sc_end[(size_t)blockIdx.x * 2 * HP + lane] = gH;
+            a.sc_end[(size_t)blockIdx.x * 2 * HP + HP + lane] = gC;
+        }
     } else {
         const int fl = lane - H;                       // lanes H, H+1 serve dL/dI, dL/dQ   (H<=30; H=31,32 use lanes 0,1 below)
         const bool split = (H + 2 > 32);
@@ -263,8 +290,8 @@ __global__ void __launch_bounds__(96, 1) lstm_bwd_kernel(GruArgs a) {
         float2 *gx2 = (a.need_dx && a.gx) ? reinterpret_cast<float2 *>(a.gx) + (size_t)b * T : nullptr;
         for (int s = 0; s < nchunks + 2; ++s) {
             const int sc = s - 2;
-            if (sc >= 0) {
-                const int c = nchunks - 1 - sc, t0 = c * CH, nt = min(CH, T - t0);
+            if (sc >= 0 && ce - 1 - sc < ce_emit) {          // warm-up blocks emit nothing
+                const int c = ce - 1 - sc, t0 = c * CH, nt = min(CH, t_hi - t0);
                 const float *ac = sact + (sc % 3) * SM::ACT, *pr = spre + (sc % 3) * SM::PRE, *Gb = sG + (sc & 1) * SM::G;
                 for (int tl = 0; tl < nt; ++tl) {
                     const float *G = Gb + tl * 4 * HP;
@@ -311,7 +338,7 @@ __global__ void __launch_bounds__(96, 1) lstm_bwd_kernel(GruArgs a) {
         }
         if constexpr (DW) {
             if (a.partials) {
-                float *prt = a.partials + (size_t)b * L.P;
+                float *prt = chunk_partial_row(a, spec, b, L.P, lane, 32);
                 if (act) {
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
@@ -339,27 +366,42 @@ static int lstm_tier(int H) {
 #undef X
     return -1;
 }
-template <int HT> static int lstm_launch(const GruArgs &a, int dir, bool dw, cudaStream_t st) {
+// dir: 0 fwd, 1 bwd, +2 = plan only
+template <int HT> static int lstm_launch(const GruArgs &a, int dir, bool dw, cudaStream_t st, int *info) {
+    constexpr int HP = Pad4<HT>::value, ROW = LRow<HT>::value;
     const LstmLayout L(a.H);
     const int Ppad = (L.P + 3) & ~3;
-    if (dir == 0) {
+    const bool plan_only = dir >= 2;
+    if ((dir & 1) == 0) {
         const size_t smem = (size_t)LFwdSmem<HT>::total(Ppad) * 4;
-        auto k = lstm_fwd_kernel<HT>;
-        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k<<<a.B, 96, smem, st>>>(a);
-    } else {
-        const size_t smem = (size_t)LBwdSmem<HT>::total(Ppad) * 4;
-        if (dw) { auto k = lstm_bwd_kernel<HT, true>; cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); k<<<a.B, 96, smem, st>>>(a); }
-        else { auto k = lstm_bwd_kernel<HT, false>; cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); k<<<a.B, 96, smem, st>>>(a); }
+        static int occ = 0;
+        const int64_t soff = a.save ? (int64_t)a.B * a.T * ROW : 0;
+        return chunk_launch(lstm_fwd_kernel<HT>, 96, smem, &occ, a, 0, a.saved ? a.saved + soff : nullptr, soff, 2 * HP, st, plan_only, info,
+                            "lstm_fwd_kernel");
     }
-    return check_launch("lstm kernel");
+    const size_t smem = (size_t)LBwdSmem<HT>::total(Ppad) * 4;
+    const int64_t woff = (chunk_rows(a.B, a.tchunks_req) * L.P + 3) & ~(int64_t)3;
+    float *scr = a.partials ? a.partials + woff : nullptr;
+    if (dw) {
+        static int occ = 0;
+        return chunk_launch(lstm_bwd_kernel<HT, true>, 96, smem, &occ, a, 1, scr, woff, 2 * HP, st, plan_only, info, "lstm_bwd_kernel");
+    }
+    static int occ0 = 0;
+    return chunk_launch(lstm_bwd_kernel<HT, false>, 96, smem, &occ0, a, 1, scr, woff, 2 * HP, st, plan_only, info, "lstm_bwd_kernel");
 }
-int64_t lstm_saved_floats(int B, int T, int H) {
+int64_t lstm_saved_floats(int B, int T, int H, bool save, int tchunks_req) {
     const int ht = lstm_tier(H);
-    return ht < 0 ? -1 : (int64_t)B * T * 7 * ((ht + 3) & ~3);
+    if (ht < 0) return -1;
+    const int HP = (ht + 3) & ~3;
+    return (save ? (int64_t)B * T * 7 * HP : 0) + chunk_fwd_scratch_floats(chunk_rows(B, tchunks_req), 2 * HP);
 }
-int lstm_run(const GruArgs &a, int dir, bool dw, cudaStream_t st) {
-#define X(HTV) if (a.H <= HTV) return lstm_launch<HTV>(a, dir, dw, st);
+int64_t lstm_workspace_floats(int B, int H, int64_t P, int tchunks_req) {
+    const int ht = lstm_tier(H);
+    if (ht < 0) return -1;
+    return chunk_workspace_floats(chunk_rows(B, tchunks_req), P, 2 * ((ht + 3) & ~3));
+}
+int lstm_run(const GruArgs &a, int dir, bool dw, cudaStream_t st, int *info) {
+#define X(HTV) if (a.H <= HTV) return lstm_launch<HTV>(a, dir, dw, st, info);
     ODPD_LSTM_TIERS(X)
 #undef X
     set_error("LSTM kernels support hidden_size <= 32 (got %d)", a.H);

@@ -59,7 +59,7 @@ def backbone_forward_raw(spec, x, flat, target=None, loss_scale=0.0, save=True, 
     L = _ffi.lib()
     B, T = x.shape[0], x.shape[1]
     d = spec.dims(B, T, (_ffi.F_SAVE if save else 0) | _ffi.F_ZERO_LOSS)
-    key = (B, T, bool(save), target is not None)
+    key = (B, T, bool(save), target is not None, spec.tchunks[0])
     if bufs is not None and bufs.get("key") == key:
         out, saved, loss = bufs["out"], bufs["saved"], bufs["loss"]
     else:
@@ -72,7 +72,7 @@ def backbone_forward_raw(spec, x, flat, target=None, loss_scale=0.0, save=True, 
             saved = torch.empty(max(int(nbytes) // 4, 1), dtype=torch.float32, device=x.device)
             idx = spec.chunk_plan(B, T, False, save)[3]
             if idx >= 0:
-                saved[idx:idx + 1].zero_()               # re-run counter of the verify pass
+                saved[idx:idx + 2].zero_()               # re-run counter + worst boundary mismatch of the verify pass
         loss = torch.empty(1, dtype=torch.float64, device=x.device) if target is not None else None
         if bufs is not None:
             bufs.update(key=key, out=out, saved=saved, loss=loss)
@@ -89,7 +89,7 @@ def backbone_backward_raw(spec, x, flat, saved, need_dx, need_dw, gout=None, out
     B, T = x.shape[0], x.shape[1]
     flags = (_ffi.F_NEED_DX if need_dx else 0) | (_ffi.F_NEED_DW if need_dw else 0) | _ffi.F_OVERWRITE_DW
     d = spec.dims(B, T, flags, backward=True)
-    key = (B, T, bool(need_dx), bool(need_dw))
+    key = (B, T, bool(need_dx), bool(need_dw), spec.tchunks[1])
     if bufs is not None and bufs.get("key") == key:
         gx, ws = bufs["gx"], bufs["ws"]
     else:
@@ -97,7 +97,7 @@ def backbone_backward_raw(spec, x, flat, saved, need_dx, need_dw, gout=None, out
         ws = torch.empty(int(L.odpd_bwd_workspace_bytes(ctypes.byref(d))) // 4, dtype=torch.float32, device=x.device)
         idx = spec.chunk_plan(B, T, True, True, need_dw)[3]
         if idx >= 0:
-            ws[idx:idx + 1].zero_()                      # re-run counter of the verify pass
+            ws[idx:idx + 2].zero_()                      # re-run counter + worst boundary mismatch of the verify pass
         if bufs is not None:
             bufs.update(key=key, gx=gx, ws=ws)
     if need_dw and gflat is None:
@@ -113,6 +113,15 @@ def chunk_reruns(spec, buf, B, T, backward=False, save=True, need_dw=True):
     if idx < 0 or buf is None:
         return 0
     return int(buf[idx:idx + 1].view(torch.int32).item())
+
+
+def chunk_worst_mismatch(spec, buf, B, T, backward=False, save=True, need_dw=True):
+    """Largest chunk-boundary mismatch the verify pass has seen since `buf` was allocated, in units of its tolerance
+    (<= 1 passes; host sync)."""
+    idx = spec.chunk_plan(B, T, backward, save, need_dw)[3]
+    if idx < 0 or buf is None:
+        return 0.0
+    return float(buf[idx + 1:idx + 2].item())
 
 
 class BackboneFn(torch.autograd.Function):

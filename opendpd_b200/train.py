@@ -110,6 +110,13 @@ class NativeTrainStep:
         self._host_step = 0
         self._stage = None
         self._bufs = [dict() for _ in range(4)]
+        # self-tuning of the time-chunked kernels (include/odpd.h "Time-chunked execution"): every `chunk_check_every` steps the
+        # re-run counters of the verify passes are read back (asynchronously, one check late); a backbone whose chunk boundaries
+        # stopped meeting — its weights moved towards a longer memory — gets its warm-up doubled, and past 1024 steps falls back
+        # to the plain serial kernels.  Correctness never depends on this: failing sequences are always re-run serially.
+        self.chunk_check_every = int(os.environ.get("ODPD_CHUNK_CHECK_EVERY", "32"))
+        self.chunk_events = []          # [(step, cell, 'fwd'|'bwd', action)]
+        self._ctl = {}
 
     def set_lr(self, lr):
         """ReduceLROnPlateau hook (project.py:288-297) — host-side scalar write, no kernel change."""
@@ -139,6 +146,8 @@ class NativeTrainStep:
                                             bufs=self._bufs[3])
             backbone_backward_raw(sd, features, flat, saved_d, False, True, gout=gmid, gflat=gflat, bufs=self._bufs[1])
         self._host_step += 1
+        if self.chunk_check_every > 0 and self._host_step % self.chunk_check_every == 0:
+            self._chunk_control(B, T)
         if self.px is not None:
             # fused: NVLink peer reads + ordered sum + clip + AdamW in ONE kernel (csrc/dp.cu)
             _ffi.check(L.odpd_dp_clip_adamw(_ptr(flat), self.px.ptrs, self.world, self.px.rank, ctypes.c_int64(self.n), _ptr(loss),
@@ -159,6 +168,43 @@ class NativeTrainStep:
                                      ctypes.c_int64(self.n), _ptr(self.lr_dev), self.betas[0], self.betas[1], self.eps, self.wd,
                                      self.clip, _ptr(self.step_dev), _ptr(self.gnorm), 0, _stream()))
         return loss
+
+    def chunk_calls(self):
+        """The backbone launches of one step: (module, backward?, index into self._bufs, forward saves?, backward needs dW?)."""
+        if self.dpd is None:
+            return [(self.train_bb, False, 0, True, True), (self.train_bb, True, 1, True, True)]
+        return [(self.dpd, False, 0, True, True), (self.pa, False, 2, True, True), (self.pa, True, 3, True, False), (self.dpd, True, 1, True, True)]
+
+    def _chunk_control(self, B, T):
+        for mod, backward, bi, save, need_dw in self.chunk_calls():
+            buf = self._bufs[bi].get("ws" if backward else "saved")
+            if buf is None:
+                continue
+            spec = mod._spec()
+            plan = spec.chunk_plan(B, T, backward, save, need_dw)
+            if plan[0] <= 1 or plan[3] < 0:
+                continue
+            st = self._ctl.setdefault((id(mod), backward), dict(pin=torch.zeros(2, dtype=torch.int32).pin_memory(), ev=None, seen=0, ptr=0))
+            if st["ptr"] != buf.data_ptr():                       # buffer re-allocated (shape or plan changed): counters restart
+                st.update(ptr=buf.data_ptr(), ev=None, seen=0)
+            if st["ev"] is not None:
+                st["ev"].synchronize()                            # copy enqueued a whole check interval ago
+                cnt = int(st["pin"][0])
+                if cnt > st["seen"]:
+                    st["seen"] = cnt
+                    wu = 2 * plan[2]
+                    if wu <= 1024 and wu <= T // 2:
+                        mod.time_warmup = wu
+                        self.chunk_events.append((self._host_step, mod.cell, "bwd" if backward else "fwd", f"warm-up -> {wu}"))
+                    else:
+                        tc = list(spec.tchunks)
+                        tc[1 if backward else 0] = 1
+                        mod.time_chunks = tuple(tc)
+                        self.chunk_events.append((self._host_step, mod.cell, "bwd" if backward else "fwd", "serial"))
+                    continue
+            st["pin"].copy_(buf[plan[3]:plan[3] + 2].view(torch.int32), non_blocking=True)
+            st["ev"] = torch.cuda.Event()
+            st["ev"].record()
 
     def step_host(self, features_cpu, targets_cpu):
         if self._stage is None or self._stage[0].shape != features_cpu.shape:

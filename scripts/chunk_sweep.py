@@ -6,13 +6,13 @@ import numpy as np
 import torch
 from bench import synth_batches
 from opendpd_b200 import models
-from opendpd_b200.functional import CellSpec, backbone_forward_raw, backbone_backward_raw, chunk_reruns
+from opendpd_b200.functional import CellSpec, backbone_forward_raw, backbone_backward_raw, chunk_reruns, chunk_worst_mismatch
 
 
 def main():
     kind, H, B, T = (sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])) if len(sys.argv) > 4 else ("dgru", 13, 64, 2048)
     torch.manual_seed(0)
-    net = models.CoreModel(2, H, 1, kind).cuda()
+    net = models.CoreModel(2, H, 1, kind, num_dvr_units=3).cuda()
     bb = net.backbone
     flat, _ = bb._flat_sync()
     POOL = 40
@@ -25,7 +25,8 @@ def main():
         plans = [tuple(p) for p in json.loads(os.environ["SWEEP_PLANS"])]
         plans = [((p[0], p[1]), p[2]) for p in plans]
     for tch, tw in plans:
-        spec = CellSpec(bb.cell, H, tchunks=tch, twarm=tw)
+        spec = bb._spec()
+        spec.tchunks, spec.twarm = tuple(tch), tw
         fb, bbuf = {}, {}
         n = 60
         ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(n)]
@@ -42,7 +43,9 @@ def main():
         f = float(np.median([e[0].elapsed_time(e[1]) for e in ev])); b = float(np.median([e[1].elapsed_time(e[2]) for e in ev]))
         print(json.dumps({"tchunks": tch, "twarm": tw, "plan_f": spec.chunk_plan(B, T, False), "plan_b": spec.chunk_plan(B, T, True),
                           "fwd_ms": round(f, 4), "bwd_ms": round(b, 4), "reruns_f": chunk_reruns(spec, saved, B, T, False),
-                          "reruns_b": chunk_reruns(spec, bbuf["ws"], B, T, True), "loss": float(loss.item())}), flush=True)
+                          "reruns_b": chunk_reruns(spec, bbuf["ws"], B, T, True),
+                          "worst_f": chunk_worst_mismatch(spec, saved, B, T, False), "worst_b": chunk_worst_mismatch(spec, bbuf["ws"], B, T, True),
+                          "loss": float(loss.item())}), flush=True)
 
 
 if __name__ == "__main__":
