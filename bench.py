@@ -247,6 +247,11 @@ def main():
         torch.cuda.synchronize()
 
     sampler = ClockSampler(local)
+    # ---- setup (untimed): the trainer replays one captured CUDA graph per (features, targets) buffer pair; capture them for every
+    # batch of the pool now so that neither the warm-up nor the timed steps contain a capture
+    if getattr(trainer, "use_graphs", False):
+        for i in range(POOL + 1):
+            trainer.step(xd[i % POOL], yd[i % POOL])
     # ---- warm-up
     for i in range(W):
         trainer.step(xd[i % POOL], yd[i % POOL])
@@ -287,28 +292,37 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
 
-    # ---- per-kernel durations (CUDA events between launches on the launching stream) for the roofline of the dominant kernel
+    # ---- per-kernel durations for the roofline of the dominant kernel: CUDA events around a CUDA-graph replay of NK back-to-back
+    # launches of the forward (distinct cold batches of the pool) and of the backward (on the batch the last forward saved, as in a
+    # real step) — a replay keeps the device fed; issuing each launch from Python (~0.1 ms of host time) would time the host instead
     from opendpd_b200.functional import backbone_forward_raw, backbone_backward_raw
     bb = trainer.train_bb if "pa" not in wl else trainer.pa
     flat, _ = bb._flat_sync()
     spec = bb._spec()
-    nk = min(K, 50)
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(nk)]
+    NK = min(POOL, 64)
     count = float(2 * B * T)
     gflat = torch.empty_like(flat)
     kb0, kb1 = {}, {}
-    for i in range(-2, nk):
-        xb, yb = xd[(i * 7 + 3) % POOL], yd[(i * 7 + 3) % POOL]
-        e = ev[max(i, 0)]
-        e[0].record()
-        out, _, saved = backbone_forward_raw(spec, xb, flat, yb, 1.0 / count, True, None, kb0)
-        e[1].record()
-        backbone_backward_raw(spec, xb, flat, saved, False, True, out=out, target=yb, gscale=2.0 / count, gflat=gflat, bufs=kb1)
-        e[2].record()
+    out, _, saved = backbone_forward_raw(spec, xd[0], flat, yd[0], 1.0 / count, True, None, kb0)       # eager: allocates the buffers
+    backbone_backward_raw(spec, xd[0], flat, saved, False, True, out=out, target=yd[0], gscale=2.0 / count, gflat=gflat, bufs=kb1)
     torch.cuda.synchronize()
+
+    def replay_ms(fn):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
+            for i in range(NK):
+                fn(i)
+        g.replay()
+        torch.cuda.synchronize()
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); g.replay(); b_.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b_) / NK
+    fwd_ms = replay_ms(lambda i: backbone_forward_raw(spec, xd[(i * 7 + 3) % POOL], flat, yd[(i * 7 + 3) % POOL], 1.0 / count, True, None, kb0))
+    last = ((NK - 1) * 7 + 3) % POOL
+    bwd_ms = replay_ms(lambda i: backbone_backward_raw(spec, xd[last], flat, saved, False, True, out=out, target=yd[last], gscale=2.0 / count,
+                                                       gflat=gflat, bufs=kb1))
     clocks = sampler.stop()
-    fwd_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
-    bwd_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
     # time-chunk plan of every backbone call in the step (include/odpd.h "Time-chunked execution") and how many sequences the
     # verify passes had to re-run serially over the whole run (0 = every chunk boundary met within tolerance on every step)
     from opendpd_b200.functional import chunk_reruns, chunk_worst_mismatch
@@ -340,7 +354,8 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["name"], "global_batch": B * world, "per_gpu_batch": B, "frame_len": T,
                        "parallelism": f"dp{world}", "optimizer": "clip_grad_norm_(200)+AdamW(lr=5e-4) fused on the flat buffer",
-                       "l2": f"inputs larger than L2: pool of {POOL} distinct 2x1MiB batches, L2 flushed (256 MiB write) after warm-up",
+                       "l2": f"inputs larger than L2: pool of {POOL} distinct 2x{2 * B * T * 4 / 2**20:.3g}MiB batches, L2 flushed (256 MiB write) after warm-up",
+                       "cuda_graphs": bool(getattr(trainer, "use_graphs", False)),
                        "final_loss": final_loss},
             "clocks": clocks,
             "e2e": {"value": world * B * T * K / e2e_s, "unit": "IQ samples/s", "ms_per_step": e2e_s / K * 1e3,

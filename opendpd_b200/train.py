@@ -110,20 +110,53 @@ class NativeTrainStep:
         self._host_step = 0
         self._stage = None
         self._bufs = [dict() for _ in range(4)]
-        # self-tuning of the time-chunked kernels (include/odpd.h "Time-chunked execution"): every `chunk_check_every` steps the
+        # self-tuning of the time-chunked kernels (include/odpd.h "Time-chunked execution"): every `chunk_check_every` steps (8) the
         # re-run counters of the verify passes are read back (asynchronously, one check late); a backbone whose chunk boundaries
         # stopped meeting — its weights moved towards a longer memory — gets its warm-up doubled, and past 1024 steps falls back
         # to the plain serial kernels.  Correctness never depends on this: failing sequences are always re-run serially.
-        self.chunk_check_every = int(os.environ.get("ODPD_CHUNK_CHECK_EVERY", "32"))
+        self.chunk_check_every = int(os.environ.get("ODPD_CHUNK_CHECK_EVERY", "8"))
         self.chunk_events = []          # [(step, cell, 'fwd'|'bwd', action)]
         self._ctl = {}
+        # CUDA graphs: one step is 6-10 small launches issued through ctypes, which costs more host time (~0.2 ms) than the kernels
+        # take on the device.  Single-GPU steps are therefore captured once per (features, targets) buffer pair and replayed: every
+        # device-side scalar the step needs (step counter, learning rate, loss) already lives in device memory, so a replay is exact.
+        self.use_graphs = os.environ.get("ODPD_GRAPHS", "1") != "0" and self.world == 1
+        self._graphs, self._graph_warm = {}, set()
 
     def set_lr(self, lr):
         """ReduceLROnPlateau hook (project.py:288-297) — host-side scalar write, no kernel change."""
         self.lr_dev.fill_(float(lr))
 
     def step(self, features, targets, global_count=None):
-        """global_count: number of scalars of the GLOBAL batch (2*B_global*T); defaults to 2*B*T*world (equal shards)."""
+        """One train step; returns the device float64 loss (no host sync).
+        global_count: number of scalars of the GLOBAL batch (2*B_global*T); defaults to 2*B*T*world (equal shards)."""
+        B, T = features.shape[0], features.shape[1]
+        if not self.use_graphs:
+            loss = self._step_impl(features, targets, global_count)
+        else:
+            shape_key = (tuple(features.shape), tuple(targets.shape), global_count)
+            key = (features.data_ptr(), targets.data_ptr()) + shape_key
+            g = self._graphs.get(key)
+            if g is None and shape_key not in self._graph_warm:
+                # first step of a shape runs eagerly: allocates the cached buffers, sets kernel attributes
+                self._graph_warm.add(shape_key)
+                loss = self._step_impl(features, targets, global_count)
+            else:
+                if g is None:
+                    if len(self._graphs) >= 256:
+                        self._graphs.pop(next(iter(self._graphs)))
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                        gl = self._step_impl(features, targets, global_count)
+                    g = self._graphs[key] = (graph, gl, features, targets)      # keeps the captured buffers alive
+                g[0].replay()
+                loss = g[1]
+        self._host_step += 1
+        if self.chunk_check_every > 0 and self._host_step % self.chunk_check_every == 0:
+            self._chunk_control(B, T)
+        return loss
+
+    def _step_impl(self, features, targets, global_count=None):
         L = _ffi.lib()
         tb = self.train_bb
         flat, _ = tb._flat_sync()
@@ -145,16 +178,13 @@ class NativeTrainStep:
             gmid, _ = backbone_backward_raw(sp, mid, paflat, saved_p, True, False, out=out, target=targets, gscale=2.0 / count,
                                             bufs=self._bufs[3])
             backbone_backward_raw(sd, features, flat, saved_d, False, True, gout=gmid, gflat=gflat, bufs=self._bufs[1])
-        self._host_step += 1
-        if self.chunk_check_every > 0 and self._host_step % self.chunk_check_every == 0:
-            self._chunk_control(B, T)
         if self.px is not None:
             # fused: NVLink peer reads + ordered sum + clip + AdamW in ONE kernel (csrc/dp.cu)
             _ffi.check(L.odpd_dp_clip_adamw(_ptr(flat), self.px.ptrs, self.world, self.px.rank, ctypes.c_int64(self.n), _ptr(loss),
                                             _ptr(self.exp_avg), _ptr(self.exp_avg_sq), _ptr(self.lr_dev), self.betas[0], self.betas[1],
                                             self.eps, self.wd, self.clip, _ptr(self.step_dev), _ptr(self.gnorm), _ptr(self.px.loss_out),
                                             _ptr(self.px.status), _stream()))
-            if self._host_step in (1, 2):      # verify the exchange once at start-up (one sync); fall back to NCCL if a peer never published
+            if self._host_step in (0, 1):      # verify the exchange once at start-up (one sync); fall back to NCCL if a peer never published
                 bad = int(self.px.status.item())
                 if bad:
                     raise _ffi.OdpdError(f"NVLink peer exchange: rank {bad - 1} did not publish its gradient (step {self._host_step}); "
@@ -193,6 +223,7 @@ class NativeTrainStep:
                 if cnt > st["seen"]:
                     st["seen"] = cnt
                     wu = 2 * plan[2]
+                    self._graphs.clear()                          # captured launches carry the old plan
                     if wu <= 1024 and wu <= T // 2:
                         mod.time_warmup = wu
                         self.chunk_events.append((self._host_step, mod.cell, "bwd" if backward else "fwd", f"warm-up -> {wu}"))

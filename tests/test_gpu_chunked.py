@@ -148,3 +148,31 @@ def test_forward_only_long_segment_is_chunked():
     assert outs[0][2][0] == 1 and outs[1][2][0] >= 16
     assert rel_err(outs[1][0], outs[0][0]) < 5e-6
     assert abs(outs[1][1] - outs[0][1]) <= 1e-6 * abs(outs[0][1])
+
+
+def test_trainer_grows_warmup_when_boundaries_stop_meeting():
+    """NativeTrainStep reads the re-run counters back every few steps and doubles the warm-up of a backbone whose chunk
+    boundaries fail (here: slowly forgetting weights + a deliberately short 32-step warm-up).  Training results are unaffected:
+    every step equals the all-serial trainer's step within the chunk tolerance."""
+    from opendpd_b200 import models
+    from opendpd_b200.train import NativeTrainStep
+    import copy
+    torch.manual_seed(21)
+    net = models.CoreModel(2, 13, 1, "dgru").cuda()
+    with torch.no_grad():
+        net.backbone.rnn.weight_hh_l0.mul_(2.5)
+    ref = copy.deepcopy(net)
+    net.backbone.time_chunks, net.backbone.time_warmup = (8, 8), 32
+    ref.backbone.time_chunks = (1, 1)
+    tr, trr = NativeTrainStep(net), NativeTrainStep(ref)
+    tr.chunk_check_every = 2
+    xc, yc = _inputs(16, 1024, seed=4)
+    x, y = xc.cuda(), yc.cuda()
+    for i in range(16):
+        la, lb = tr.step(x, y), trr.step(x, y)
+        assert abs(la.item() - lb.item()) <= 2e-6 * abs(lb.item()), (i, la.item(), lb.item())
+    assert any("warm-up" in e[3] for e in tr.chunk_events), tr.chunk_events
+    assert net.backbone.time_warmup >= 64
+    pa = torch.cat([p.detach().reshape(-1) for p in net.parameters()])
+    pb = torch.cat([p.detach().reshape(-1) for p in ref.parameters()])
+    assert (pa - pb).abs().max().item() < 1e-5
