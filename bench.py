@@ -247,11 +247,17 @@ def main():
         torch.cuda.synchronize()
 
     sampler = ClockSampler(local)
-    # ---- setup (untimed): the trainer replays one captured CUDA graph per (features, targets) buffer pair; capture them for every
-    # batch of the pool now so that neither the warm-up nor the timed steps contain a capture
+    # ---- setup (untimed): the trainer replays one captured CUDA graph per (features, targets) buffer pair and tunes the warm-up of
+    # its time-chunked kernels while it trains; run passes over the pool until a whole pass neither captured a graph for a new
+    # plan nor changed a plan, so that the warm-up and the timed steps below are steady-state replays
+    settle_steps = 0
     if getattr(trainer, "use_graphs", False):
-        for i in range(POOL + 1):
-            trainer.step(xd[i % POOL], yd[i % POOL])
+        n_ev = -1
+        while (n_ev != len(trainer.chunk_events) or settle_steps < 160) and settle_steps < 12 * (POOL + 8) + 160:
+            n_ev = len(trainer.chunk_events)
+            for i in range(POOL + 8):
+                trainer.step(xd[i % POOL], yd[i % POOL])
+            settle_steps += POOL + 8
     # ---- warm-up
     for i in range(W):
         trainer.step(xd[i % POOL], yd[i % POOL])
@@ -355,7 +361,7 @@ def main():
             "config": {"workload": wl["name"], "global_batch": B * world, "per_gpu_batch": B, "frame_len": T,
                        "parallelism": f"dp{world}", "optimizer": "clip_grad_norm_(200)+AdamW(lr=5e-4) fused on the flat buffer",
                        "l2": f"inputs larger than L2: pool of {POOL} distinct 2x{2 * B * T * 4 / 2**20:.3g}MiB batches, L2 flushed (256 MiB write) after warm-up",
-                       "cuda_graphs": bool(getattr(trainer, "use_graphs", False)),
+                       "cuda_graphs": bool(getattr(trainer, "use_graphs", False)), "untimed_settle_steps": settle_steps,
                        "final_loss": final_loss},
             "clocks": clocks,
             "e2e": {"value": world * B * T * K / e2e_s, "unit": "IQ samples/s", "ms_per_step": e2e_s / K * 1e3,

@@ -169,12 +169,13 @@ int odpd_dp_free(void *ptr);
 int odpd_dp_ipc_handle(void *ptr, unsigned char handle_out[64]);
 int odpd_dp_ipc_open(const unsigned char handle[64], void **out_peer_ptr);
 int odpd_dp_ipc_close(void *peer_ptr);
-/* bufs: HOST array of `world` device pointers (index = rank; bufs[rank] is the caller's own buffer).  The local gradient of this
- * step must already be in bufs[rank][parity][0..n) (pass it as `gparams` of odpd_backbone_bwd with ODPD_F_OVERWRITE_DW, parity =
- * (step_dev+1)&1) and the local loss (double, from odpd_backbone_fwd) in `loss_local`.  On return (stream order) `param` is updated,
+/* bufs: HOST array of `world` device pointers (index = rank; bufs[rank] is the caller's own buffer).  grad_local: this rank's flat
+ * gradient of the step (the kernel publishes it into bufs[rank][parity], parity = (step_dev+1)&1 read on the device, so the launch
+ * is identical every step and can be replayed from a CUDA graph); NULL = the caller already wrote it there (`gparams` of
+ * odpd_backbone_bwd with ODPD_F_OVERWRITE_DW).  The local loss (double, from odpd_backbone_fwd) is passed in `loss_local`.  On return (stream order) `param` is updated,
  * loss_out[0] = sum of all ranks' losses, gnorm_out = pre-clip norm of the summed gradient.  status_dev[0] != 0 reports a peer
  * that did not publish within the spin budget (the kernel never hangs). */
-int odpd_dp_clip_adamw(float *param, void *const *bufs, int world, int rank, int64_t n, const double *loss_local,
+int odpd_dp_clip_adamw(float *param, void *const *bufs, int world, int rank, int64_t n, const float *grad_local, const double *loss_local,
                        float *exp_avg, float *exp_avg_sq, const float *lr_dev, float beta1, float beta2, float eps, float weight_decay,
                        float max_norm, int64_t *step_dev, float *gnorm_out, float *loss_out, int *status_dev, void *stream);
 

@@ -20,7 +20,8 @@ __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned l
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-__global__ void __launch_bounds__(1024) dp_clip_adamw_kernel(float *__restrict__ p, DpPtrs bufs, int world, int rank, int64_t n, const double *loss_local,
+__global__ void __launch_bounds__(1024) dp_clip_adamw_kernel(float *__restrict__ p, DpPtrs bufs, int world, int rank, int64_t n,
+                                                             const float *__restrict__ grad_local, const double *loss_local,
                                                              float *__restrict__ m, float *__restrict__ v, const float *__restrict__ lr_dev, float b1,
                                                              float b2, float eps, float wd, float max_norm, int64_t *step_dev, float *gnorm_out,
                                                              float *loss_out, int *status_dev) {
@@ -31,6 +32,11 @@ __global__ void __launch_bounds__(1024) dp_clip_adamw_kernel(float *__restrict__
     const int64_t stride = dp_stride(n);
     const int par = (int)(step & 1);
     float *own = bufs.buf[rank] + par * stride;
+    if (grad_local) {   // publish: copy this rank's gradient into the slot of this step's parity (chosen on the device: graph-replayable)
+        for (int64_t i = threadIdx.x; i < n; i += blockDim.x) own[i] = grad_local[i];
+        __threadfence_system();
+        __syncthreads();
+    }
     if (threadIdx.x == 0) {
         s_bad = 0;
         own[n] = loss_local ? (float)(*loss_local) : 0.f;
@@ -141,7 +147,7 @@ int odpd_dp_ipc_close(void *peer_ptr) {
     ODPD_CHECK(e == cudaSuccess, "cudaIpcCloseMemHandle: %s", cudaGetErrorString(e));
     return 0;
 }
-int odpd_dp_clip_adamw(float *param, void *const *bufs, int world, int rank, int64_t n, const double *loss_local, float *exp_avg,
+int odpd_dp_clip_adamw(float *param, void *const *bufs, int world, int rank, int64_t n, const float *grad_local, const double *loss_local, float *exp_avg,
                        float *exp_avg_sq, const float *lr_dev, float beta1, float beta2, float eps, float weight_decay, float max_norm,
                        int64_t *step_dev, float *gnorm_out, float *loss_out, int *status_dev, void *stream) {
     ODPD_CHECK(param && bufs && exp_avg && exp_avg_sq && lr_dev && step_dev, "odpd_dp_clip_adamw: NULL buffer");
@@ -149,7 +155,7 @@ int odpd_dp_clip_adamw(float *param, void *const *bufs, int world, int rank, int
     ODPD_CHECK(n >= 1 && n + 1 <= 4096, "odpd_dp_clip_adamw: n=%lld outside 1..4095", (long long)n);
     DpPtrs p{};
     for (int r = 0; r < world; ++r) { ODPD_CHECK(bufs[r] != nullptr, "odpd_dp_clip_adamw: bufs[%d] is NULL", r); p.buf[r] = (float *)bufs[r]; }
-    dp_clip_adamw_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(param, p, world, rank, n, loss_local, exp_avg, exp_avg_sq, lr_dev, beta1, beta2,
+    dp_clip_adamw_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(param, p, world, rank, n, grad_local, loss_local, exp_avg, exp_avg_sq, lr_dev, beta1, beta2,
                                                               eps, weight_decay, max_norm, step_dev, gnorm_out, loss_out, status_dev);
     return check_launch("dp_clip_adamw_kernel");
 }

@@ -19,7 +19,7 @@ class CellSpec:
 
     def __init__(self, cell, H, K=0, thx=0.0, thh=0.0, tchunks=None, twarm=None):
         """tchunks / twarm: OdpdDims.tchunks / .twarm (include/odpd.h "Time-chunked execution"); None = environment
-        ODPD_TCHUNKS[_FWD|_BWD] / ODPD_TWARM, else 0 = the library picks.  tchunks may be an int or a (forward, backward) pair."""
+        ODPD_TCHUNKS[_FWD|_BWD] / ODPD_TWARM, else 0 = the library picks.  Both may be an int or a (forward, backward) pair."""
         self.cell, self.H, self.K, self.thx, self.thh = cell, int(H), int(K or 0), float(thx), float(thh)
         self.cell_id = _ffi.CELLS[cell]
         self.keep_saved = None
@@ -30,11 +30,14 @@ class CellSpec:
         elif isinstance(tchunks, int):
             tchunks = (tchunks, tchunks)
         self.tchunks = tuple(int(v) for v in tchunks)
-        self.twarm = int(env("ODPD_TWARM", "0")) if twarm is None else int(twarm)
+        if twarm is None:
+            twarm = int(env("ODPD_TWARM", "0"))
+        self.twarm = (int(twarm), int(twarm)) if isinstance(twarm, int) else tuple(int(v) for v in twarm)   # (forward, backward)
 
     def dims(self, B, T, flags, backward=False):
-        return _ffi.OdpdDims(self.cell_id, int(B), int(T), self.H, self.K, int(flags), self.thx, self.thh,
-                             self.tchunks[1 if backward else 0], self.twarm)
+        k = 1 if backward else 0
+        twarm = self.twarm if isinstance(self.twarm, int) else self.twarm[k]
+        return _ffi.OdpdDims(self.cell_id, int(B), int(T), self.H, self.K, int(flags), self.thx, self.thh, self.tchunks[k], twarm)
 
     def chunk_plan(self, B, T, backward=False, save=True, need_dw=True):
         """(chunks, steps per chunk, warm-up steps, index of the re-run counter) the library will use for this call shape."""

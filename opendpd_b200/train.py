@@ -118,9 +118,10 @@ class NativeTrainStep:
         self.chunk_events = []          # [(step, cell, 'fwd'|'bwd', action)]
         self._ctl = {}
         # CUDA graphs: one step is 6-10 small launches issued through ctypes, which costs more host time (~0.2 ms) than the kernels
-        # take on the device.  Single-GPU steps are therefore captured once per (features, targets) buffer pair and replayed: every
-        # device-side scalar the step needs (step counter, learning rate, loss) already lives in device memory, so a replay is exact.
-        self.use_graphs = os.environ.get("ODPD_GRAPHS", "1") != "0" and self.world == 1
+        # take on the device.  Steps are therefore captured once per (features, targets) buffer pair and replayed: every scalar the
+        # step needs (step counter, learning rate, loss, the parity of the peer-exchange slot) lives in device memory, so a replay is
+        # exact.  (The NCCL fallback of the data-parallel exchange, ODPD_DP_P2P=0, stays un-captured.)
+        self.use_graphs = os.environ.get("ODPD_GRAPHS", "1") != "0" and (self.world == 1 or self.px is not None)
         self._graphs, self._graph_warm = {}, set()
 
     def set_lr(self, lr):
@@ -162,7 +163,7 @@ class NativeTrainStep:
         flat, _ = tb._flat_sync()
         B, T = features.shape[0], features.shape[1]
         count = float(global_count) if global_count else float(2 * B * T * self.world)   # nn.MSELoss 'mean', GLOBAL batch
-        gflat = self._px_views[(self._host_step + 1) & 1] if self.px is not None else self.gflat
+        gflat = self.gflat
         if self.dpd is None:
             spec = tb._spec()
             out, loss, saved = backbone_forward_raw(spec, features, flat, targets, 1.0 / count, True, tb._stats_tensor(self.device),
@@ -180,11 +181,11 @@ class NativeTrainStep:
             backbone_backward_raw(sd, features, flat, saved_d, False, True, gout=gmid, gflat=gflat, bufs=self._bufs[1])
         if self.px is not None:
             # fused: NVLink peer reads + ordered sum + clip + AdamW in ONE kernel (csrc/dp.cu)
-            _ffi.check(L.odpd_dp_clip_adamw(_ptr(flat), self.px.ptrs, self.world, self.px.rank, ctypes.c_int64(self.n), _ptr(loss),
+            _ffi.check(L.odpd_dp_clip_adamw(_ptr(flat), self.px.ptrs, self.world, self.px.rank, ctypes.c_int64(self.n), _ptr(self.gflat), _ptr(loss),
                                             _ptr(self.exp_avg), _ptr(self.exp_avg_sq), _ptr(self.lr_dev), self.betas[0], self.betas[1],
                                             self.eps, self.wd, self.clip, _ptr(self.step_dev), _ptr(self.gnorm), _ptr(self.px.loss_out),
                                             _ptr(self.px.status), _stream()))
-            if self._host_step in (0, 1):      # verify the exchange once at start-up (one sync); fall back to NCCL if a peer never published
+            if self._host_step < 2 and not torch.cuda.is_current_stream_capturing():      # verify the exchange once at start-up (one sync); fall back to NCCL if a peer never published
                 bad = int(self.px.status.item())
                 if bad:
                     raise _ffi.OdpdError(f"NVLink peer exchange: rank {bad - 1} did not publish its gradient (step {self._host_step}); "
@@ -206,6 +207,12 @@ class NativeTrainStep:
         return [(self.dpd, False, 0, True, True), (self.pa, False, 2, True, True), (self.pa, True, 3, True, False), (self.dpd, True, 1, True, True)]
 
     def _chunk_control(self, B, T):
+        """Self-tuning of the warm-up of the time-chunked kernels, per backbone and direction:
+          grow   x2 when the verify pass had to re-run sequences, or — below the cell's default — when the worst boundary mismatch
+                 exceeds half the tolerance; past 1024 steps that direction falls back to the plain serial kernel
+          shrink /2 (not below 64, never below a length that once failed) after three consecutive checks whose worst mismatch
+                 stayed under a quarter of the tolerance
+        Telemetry is read back asynchronously one check late; results never depend on it (failing sequences are re-run serially)."""
         for mod, backward, bi, save, need_dw in self.chunk_calls():
             buf = self._bufs[bi].get("ws" if backward else "saved")
             if buf is None:
@@ -214,25 +221,43 @@ class NativeTrainStep:
             plan = spec.chunk_plan(B, T, backward, save, need_dw)
             if plan[0] <= 1 or plan[3] < 0:
                 continue
-            st = self._ctl.setdefault((id(mod), backward), dict(pin=torch.zeros(2, dtype=torch.int32).pin_memory(), ev=None, seen=0, ptr=0))
-            if st["ptr"] != buf.data_ptr():                       # buffer re-allocated (shape or plan changed): counters restart
-                st.update(ptr=buf.data_ptr(), ev=None, seen=0)
+            k, name = (1, "bwd") if backward else (0, "fwd")
+            st = self._ctl.setdefault((id(mod), backward), dict(pin=torch.zeros(2, dtype=torch.int32).pin_memory(), ev=None, seen=0, ptr=0,
+                                                                  clean=0, floor=64, base=plan[2], rebase=False))
+            if st["ptr"] != buf.data_ptr():                       # buffer re-allocated (shape or chunk count changed): counters restart
+                st.update(ptr=buf.data_ptr(), ev=None, seen=0, rebase=False)
+            new = None
             if st["ev"] is not None:
                 st["ev"].synchronize()                            # copy enqueued a whole check interval ago
-                cnt = int(st["pin"][0])
-                if cnt > st["seen"]:
-                    st["seen"] = cnt
-                    wu = 2 * plan[2]
-                    self._graphs.clear()                          # captured launches carry the old plan
-                    if wu <= 1024 and wu <= T // 2:
-                        mod.time_warmup = wu
-                        self.chunk_events.append((self._host_step, mod.cell, "bwd" if backward else "fwd", f"warm-up -> {wu}"))
-                    else:
-                        tc = list(spec.tchunks)
-                        tc[1 if backward else 0] = 1
-                        mod.time_chunks = tuple(tc)
-                        self.chunk_events.append((self._host_step, mod.cell, "bwd" if backward else "fwd", "serial"))
-                    continue
+                cnt, ratio = int(st["pin"][0]), float(st["pin"][1:2].view(torch.float32)[0])
+                failed = cnt > st["seen"] and not st["rebase"]    # re-runs counted before the last plan change do not count
+                st["seen"], st["rebase"] = cnt, False
+                wu = plan[2]
+                if failed or (ratio > 0.5 and wu < st["base"]):
+                    new = 2 * wu
+                    st["floor"] = max(st["floor"], new)
+                elif ratio < 0.25:
+                    st["clean"] += 1
+                    if st["clean"] >= 3 and wu // 2 >= st["floor"]:
+                        new = wu // 2
+                else:
+                    st["clean"] = 0
+            if new is not None:
+                st["clean"] = 0
+                self._graphs.clear()                              # captured launches carry the old plan
+                if new <= 1024 and new <= T // 2:
+                    tw = list(spec.twarm)
+                    tw[k] = new
+                    mod.time_warmup = tuple(tw)
+                    self.chunk_events.append((self._host_step, mod.cell, name, f"warm-up {plan[2]} -> {new}" + (" (boundary failed)" if failed else "")))
+                else:
+                    tc = list(spec.tchunks)
+                    tc[k] = 1
+                    mod.time_chunks = tuple(tc)
+                    self.chunk_events.append((self._host_step, mod.cell, name, "serial"))
+                buf[plan[3] + 1:plan[3] + 2].zero_()              # restart the worst-mismatch telemetry under the new plan
+                st.update(ev=None, rebase=True)
+                continue
             st["pin"].copy_(buf[plan[3]:plan[3] + 2].view(torch.int32), non_blocking=True)
             st["ev"] = torch.cuda.Event()
             st["ev"].record()
