@@ -246,21 +246,34 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # Device-resident feed: every step gathers its batch from the pool (cold: the pool is larger than L2) into one fixed staging pair
+    # with two device-to-device copies INSIDE the timed region, then runs the step on the staging buffers.  A fixed address lets the
+    # trainer replay one captured CUDA graph (a new plan of the self-tuning chunk controller then costs one re-capture, not POOL).
+    sx, sy = torch.empty_like(xd[0]), torch.empty_like(yd[0])
+
+    def dev_step(i):
+        sx.copy_(xd[i % POOL])
+        sy.copy_(yd[i % POOL])
+        return trainer.step(sx, sy)
+
     sampler = ClockSampler(local)
     # ---- setup (untimed): the trainer replays one captured CUDA graph per (features, targets) buffer pair and tunes the warm-up of
     # its time-chunked kernels while it trains; run passes over the pool until a whole pass neither captured a graph for a new
     # plan nor changed a plan, so that the warm-up and the timed steps below are steady-state replays
     settle_steps = 0
-    if getattr(trainer, "use_graphs", False):
-        n_ev = -1
-        while (n_ev != len(trainer.chunk_events) or settle_steps < 160) and settle_steps < 12 * (POOL + 8) + 160:
-            n_ev = len(trainer.chunk_events)
-            for i in range(POOL + 8):
-                trainer.step(xd[i % POOL], yd[i % POOL])
-            settle_steps += POOL + 8
+    while settle_steps < 12 * (POOL + 8) + 160:
+        n_ev = len(trainer.chunk_events)
+        for i in range(POOL + 8):
+            dev_step(i)
+        settle_steps += POOL + 8
+        changed = torch.tensor([float(n_ev != len(trainer.chunk_events))], device=dev)
+        if world > 1:
+            dist.all_reduce(changed, op=dist.ReduceOp.MAX)      # every rank must run the same number of (collective) steps
+        if settle_steps >= 160 and changed.item() == 0.0:
+            break
     # ---- warm-up
     for i in range(W):
-        trainer.step(xd[i % POOL], yd[i % POOL])
+        dev_step(i)
     flush.zero_()                                       # evict the pool from L2: every timed step reads a cold batch
     barrier()
     sampler.start()
@@ -268,7 +281,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(K):
-        loss = trainer.step(xd[(W + i) % POOL], yd[(W + i) % POOL])
+        loss = dev_step(W + i)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -360,7 +373,8 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["name"], "global_batch": B * world, "per_gpu_batch": B, "frame_len": T,
                        "parallelism": f"dp{world}", "optimizer": "clip_grad_norm_(200)+AdamW(lr=5e-4) fused on the flat buffer",
-                       "l2": f"inputs larger than L2: pool of {POOL} distinct 2x{2 * B * T * 4 / 2**20:.3g}MiB batches, L2 flushed (256 MiB write) after warm-up",
+                       "l2": f"inputs larger than L2: pool of {POOL} distinct 2x{2 * B * T * 4 / 2**20:.3g}MiB batches, each step's batch copied device-to-device "
+                             f"into a fixed staging pair inside the timed region; L2 flushed (256 MiB write) after warm-up",
                        "cuda_graphs": bool(getattr(trainer, "use_graphs", False)), "untimed_settle_steps": settle_steps,
                        "final_loss": final_loss},
             "clocks": clocks,
