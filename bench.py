@@ -356,6 +356,8 @@ def main():
         launches += 2 if plan[0] > 1 else 1
     if wl["kind"] == "gmp":
         launches += 1
+    # entries of chunk_info that describe the timed (fwd, bwd) kernels of the roofline section (the PA of a cascade, else the backbone)
+    plan_i = (0, 1) if "pa" not in wl else (1, 2)
 
     if rank == 0:
         peaks = {}
@@ -392,11 +394,17 @@ def main():
             "kernel_ms": {"fwd": fwd_ms, "bwd": bwd_ms},
             "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                         "traffic": ({"odpd::gru_fwd_kernel": 2126336 + 787712, "odpd::gru_bwd_kernel": 53534720 + 4864}.get(dom[0])
+                         "traffic": ({"odpd::gru_fwd_kernel": 2132224 + 1246464, "odpd::gru_bwd_kernel": 53540864 + 61184}.get(dom[0])
                                      if args.workload == "c2a" else None),
-                         "traffic_source": "profiles/r1_final_gru_ncu_summary.txt (ncu --set full, dram__bytes_read+write per launch; bwd re-reads the 41 MB of saved rows from DRAM only under ncu's cache-flushed replay)",
-                         "latency_view": {"timesteps": T, "ns_per_timestep_fwd": fwd_ms * 1e6 / T, "ns_per_timestep_bwd": bwd_ms * 1e6 / T,
-                                          "note": "the path is a T-step serial recurrence per sequence: latency-bound, not bandwidth-bound (SURVEY §8d)"}},
+                         "traffic_source": "profiles/r1_chunked_gru_ncu_summary.txt (ncu --set full of the chunked kernels, dram__bytes_read+write per launch; the "
+                                           "backward re-reads the saved activation rows from DRAM only under ncu's cache-flushed replay: live they sit in the 126 MB L2)",
+                         "latency_view": {"timesteps": T,
+                                          "chain_steps_per_cta_fwd": chunk_info[plan_i[0]]["steps_per_chunk"] + chunk_info[plan_i[0]]["warmup_steps"],
+                                          "chain_steps_per_cta_bwd": chunk_info[plan_i[1]]["steps_per_chunk"] + chunk_info[plan_i[1]]["warmup_steps"],
+                                          "ns_per_chain_step_fwd": fwd_ms * 1e6 / max(1, chunk_info[plan_i[0]]["steps_per_chunk"] + chunk_info[plan_i[0]]["warmup_steps"]),
+                                          "ns_per_chain_step_bwd": bwd_ms * 1e6 / max(1, chunk_info[plan_i[1]]["steps_per_chunk"] + chunk_info[plan_i[1]]["warmup_steps"]),
+                                          "note": "a T-step serial recurrence per sequence, cut into concurrently running chunks (DESIGN.md §4.1): bound by the latency of "
+                                                  "one dependent step x the steps one CTA walks, not by bandwidth (SURVEY §8d)"}},
         }
         if world == 1 and not args.no_cpu:
             r = cpu_port_leg(seconds=args.cpu_seconds, kind=wl["kind"], H=wl["H"], B=B, T=T)
