@@ -34,8 +34,7 @@ __global__ void __launch_bounds__(1024) dp_clip_adamw_kernel(float *__restrict__
     float *own = bufs.buf[rank] + par * stride;
     if (grad_local) {   // publish: copy this rank's gradient into the slot of this step's parity (chosen on the device: graph-replayable)
         for (int64_t i = threadIdx.x; i < n; i += blockDim.x) own[i] = grad_local[i];
-        __threadfence_system();
-        __syncthreads();
+        __syncthreads();   // CTA-scope ordering; thread 0's system-scope fence + release below is cumulative over these writes
     }
     if (threadIdx.x == 0) {
         s_bad = 0;
@@ -51,8 +50,8 @@ __global__ void __launch_bounds__(1024) dp_clip_adamw_kernel(float *__restrict__
             const unsigned long long *flag = reinterpret_cast<const unsigned long long *>(bufs.buf[peer] + 2 * stride);
             long long spins = 0;
             while (ld_acquire_sys(flag) < (unsigned long long)step) {
-                if (++spins > (1ll << 26)) { atomicExch(&s_bad, peer + 1); break; }
-                __nanosleep(64);
+                if (++spins > (1ll << 27)) { atomicExch(&s_bad, peer + 1); break; }
+                __nanosleep(20);
             }
         }
     }
@@ -66,7 +65,12 @@ __global__ void __launch_bounds__(1024) dp_clip_adamw_kernel(float *__restrict__
         const int64_t i = threadIdx.x + (int64_t)e * blockDim.x;
         float acc = 0.f;
         if (i <= n) {
-            for (int r = 0; r < world; ++r) acc += __ldcv(bufs.buf[r] + par * stride + i);
+            // issue every peer read before the first add (independent NVLink loads in flight together), then sum in rank order
+            float pv[DP_MAX_WORLD];
+#pragma unroll
+            for (int r = 0; r < DP_MAX_WORLD; ++r) pv[r] = r < world ? __ldcv(bufs.buf[r] + par * stride + i) : 0.f;
+#pragma unroll
+            for (int r = 0; r < DP_MAX_WORLD; ++r) if (r < world) acc += pv[r];
         }
         g[e] = acc;
         if (i < n) ss = fmaf(acc, acc, ss);
