@@ -24,27 +24,40 @@ int check_launch(const char *what) {
     return 0;
 }
 
-// g[p] += sum_{b=0..nrows-1} part[b][p], summed in row order (bit-reproducible)
-__global__ void reduce_partials_kernel(const float *__restrict__ part, int nrows, int64_t P, float *__restrict__ g, int overwrite) {
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= P) return;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int b = 0;
-    for (; b + 3 < nrows; b += 4) {
-        s0 += part[(int64_t)b * P + p];
-        s1 += part[(int64_t)(b + 1) * P + p];
-        s2 += part[(int64_t)(b + 2) * P + p];
-        s3 += part[(int64_t)(b + 3) * P + p];
+// g[p] (+)= sum_{b=0..nrows-1} part[b][p].  Block = 32 parameters x RED_TY row groups: thread (tx,ty) sums rows ty, ty+RED_TY, ... in
+// row order (8 independent loads in flight), the RED_TY group sums are then added in group order — a fixed summation tree, so the result
+// is bit-reproducible run to run; no float atomics.
+static constexpr int RED_TY = 16;
+__global__ void __launch_bounds__(32 * RED_TY) reduce_partials_kernel(const float *__restrict__ part, int nrows, int64_t P, float *__restrict__ g,
+                                                                      int overwrite) {
+    __shared__ float red[RED_TY][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t p = (int64_t)blockIdx.x * 32 + tx;
+    float acc = 0.f;
+    if (p < P) {
+        int b = ty;
+        for (; b + 7 * RED_TY < nrows; b += 8 * RED_TY) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = part[(int64_t)(b + u * RED_TY) * P + p];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc += v[u];
+        }
+        for (; b < nrows; b += RED_TY) acc += part[(int64_t)b * P + p];
     }
-    for (; b < nrows; ++b) s0 += part[(int64_t)b * P + p];
-    const float s = (s0 + s1) + (s2 + s3);
-    g[p] = overwrite ? s : g[p] + s;
+    red[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && p < P) {
+        float s = red[0][tx];
+#pragma unroll
+        for (int k = 1; k < RED_TY; ++k) s += red[k][tx];
+        g[p] = overwrite ? s : g[p] + s;
+    }
 }
 
 int reduce_partials(const float *part, int nrows, int64_t P, float *g, int overwrite, cudaStream_t st) {
     if (P <= 0) return 0;
-    const int threads = 128;
-    reduce_partials_kernel<<<(unsigned)((P + threads - 1) / threads), threads, 0, st>>>(part, nrows, P, g, overwrite);
+    reduce_partials_kernel<<<(unsigned)((P + 31) / 32), 32 * RED_TY, 0, st>>>(part, nrows, P, g, overwrite);
     return check_launch("reduce_partials_kernel");
 }
 
