@@ -67,6 +67,8 @@ enum {
 #define ODPD_F_SAVE 4u       /* forward stores activations for a later odpd_backbone_bwd */
 #define ODPD_F_OVERWRITE_DW 8u /* backward: gparams = sum instead of gparams += sum (saves the caller a memset) */
 #define ODPD_F_ZERO_LOSS 16u /* forward: the library clears *loss (cudaMemsetAsync on `stream`) before accumulating */
+#define ODPD_F_X_BF16 32u      /* `x` holds bf16 pairs instead of fp32 pairs (storage only: widened exactly, arithmetic stays fp32) */
+#define ODPD_F_TARGET_BF16 64u /* same for `target` */
 
 typedef struct OdpdDims {
     int32_t cell;   /* ODPD_CELL_* */
@@ -79,6 +81,12 @@ typedef struct OdpdDims {
     int32_t tchunks; /* GRU/DGRU/QGRU/LSTM/PGJANET/DVRJANET: time chunks a sequence is cut into and run concurrently (see below).
                         0 = the library picks from B, T and the SM count; 1 = plain serial recurrence; n = exactly n (<=32) */
     int32_t twarm;   /* warm-up steps in front of every chunk (rounded up to 32); 0 = the cell's default (128; JANET cells 256) */
+    /* On-device framing (replaces IQFrameDataset's materialised stride-1 frames, modules/data_collector.py:233-252, and the
+     * per-step H2D copy of them, train_funcs.py:30-31): when x_starts != NULL, `x` is the raw (N,2) IQ stream and sequence b
+     * reads samples x_starts[b] .. x_starts[b]+T-1 of it (device int32[B]); same for target_starts / `target`.  NULL = `x` /
+     * `target` are framed (B,T,2) tensors.  out, gout, gx and the saved activations are always framed. */
+    const int32_t *x_starts;
+    const int32_t *target_starts;
 } OdpdDims;
 
 /*

@@ -10,13 +10,13 @@ LIB_PATH = os.path.join(_HERE, "libodpd.so")
 
 CELLS = {"gru": 0, "lstm": 1, "dgru": 2, "deltagru": 3, "deltagru_tcnskip": 4, "pgjanet": 5, "dvrjanet": 6, "gmp": 7,
          "qgru": 8, "qgru_amp1": 9, "qgru_qat": 10, "qgru_amp1_qat": 11}
-F_NEED_DX, F_NEED_DW, F_SAVE, F_OVERWRITE_DW, F_ZERO_LOSS = 1, 2, 4, 8, 16
+F_NEED_DX, F_NEED_DW, F_SAVE, F_OVERWRITE_DW, F_ZERO_LOSS, F_X_BF16, F_TARGET_BF16 = 1, 2, 4, 8, 16, 32, 64
 
 
 class OdpdDims(ctypes.Structure):
     _fields_ = [("cell", ctypes.c_int32), ("B", ctypes.c_int32), ("T", ctypes.c_int32), ("H", ctypes.c_int32),
                 ("K", ctypes.c_int32), ("flags", ctypes.c_uint32), ("thx", ctypes.c_float), ("thh", ctypes.c_float),
-                ("tchunks", ctypes.c_int32), ("twarm", ctypes.c_int32)]
+                ("tchunks", ctypes.c_int32), ("twarm", ctypes.c_int32), ("x_starts", ctypes.c_void_p), ("target_starts", ctypes.c_void_p)]
 
 
 class OdpdError(RuntimeError):

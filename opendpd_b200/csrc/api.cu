@@ -174,6 +174,8 @@ int odpd_backbone_fwd(const OdpdDims *d, const float *x, const float *target, co
         a.B = d->B; a.T = d->T; a.H = d->H; a.x = x; a.target = target; a.params = params; a.out = out; a.loss = loss;
         a.loss_scale = (float)loss_scale; a.saved = (float *)saved; a.save = save;
         a.tchunks_req = d->tchunks; a.twarm_req = d->twarm;
+        a.x_bf16 = (d->flags & ODPD_F_X_BF16) != 0; a.target_bf16 = (d->flags & ODPD_F_TARGET_BF16) != 0;
+        a.x_starts = d->x_starts; a.target_starts = d->target_starts;
         return gru_family_run(d->cell, a, 0, false, st, nullptr);
     }
     return other_fwd(d, x, target, params, out, loss, loss_scale, saved, stats, st);
@@ -200,6 +202,8 @@ int odpd_backbone_bwd(const OdpdDims *d, const float *x, const float *params, co
         a.target = target; a.gscale = (float)gscale; a.gscale_dev = gscale_dev; a.gx = gx; a.partials = (float *)workspace;
         a.need_dx = dx;
         a.tchunks_req = d->tchunks; a.twarm_req = d->twarm;
+        a.x_bf16 = (d->flags & ODPD_F_X_BF16) != 0; a.target_bf16 = (d->flags & ODPD_F_TARGET_BF16) != 0;
+        a.x_starts = d->x_starts; a.target_starts = d->target_starts;
         rc = gru_family_run(d->cell, a, 1, dw, st, &rows);
     } else {
         rc = other_bwd(d, x, params, saved, gout, out, target, gscale, gscale_dev, gx, (float *)workspace, st, &rows);

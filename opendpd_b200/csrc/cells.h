@@ -22,6 +22,9 @@ struct GruArgs {
     //          sequences that failed serially
     //   sc_guess/sc_end [B*C][HP]: state a chunk started from after its warm-up / state it ended with;  sc_loss [B*C]: per-chunk
     //   squared error;  sc_fail: number of sequences that needed the serial re-run (diagnostic)
+    // storage of the IQ tensors: bf16 pairs instead of fp32 pairs; frame starts into a raw (N,2) stream instead of (B,T,2) frames
+    int x_bf16, target_bf16;
+    const int *x_starts, *target_starts;
     int C, Lc, Wu, mode;
     float *sc_guess, *sc_end, *sc_loss;
     int *sc_fail;

@@ -113,6 +113,43 @@ __device__ __forceinline__ void features_bwd(float i, float q, const float *gf, 
     }
 }
 
+// ---------------------------------------------------------------- IQ sample rows
+// One sequence's (T,2) IQ samples as the kernels see them: fp32 pairs, or bf16 pairs (ODPD_F_X_BF16 / ODPD_F_TARGET_BF16: storage only,
+// every value is widened exactly to fp32), starting either at frame b of a framed (B,T,2) tensor or at sample starts[b] of a raw
+// (N,2) stream (OdpdDims.x_starts / .target_starts: the framing of data_collector.py:233-252 done by address arithmetic).
+// Pointer-like on purpose: `row + t` and `__ldg(row + t)` keep the kernels' load sites unchanged.
+struct IqRow {
+    const void *p;
+    int bf16;
+    __device__ __forceinline__ float2 ld(int t) const {
+        if (bf16) {
+            const unsigned v = ::__ldg(reinterpret_cast<const unsigned *>(p) + t);        // [I | Q] as two bf16: I in the low half
+            return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+        }
+        return ::__ldg(reinterpret_cast<const float2 *>(p) + t);
+    }
+    __device__ __forceinline__ IqRow operator+(int t) const {
+        IqRow r;
+        r.bf16 = bf16;
+        r.p = bf16 ? static_cast<const void *>(reinterpret_cast<const unsigned *>(p) + t) : static_cast<const void *>(reinterpret_cast<const float2 *>(p) + t);
+        return r;
+    }
+    __device__ __forceinline__ explicit operator bool() const { return p != nullptr; }
+};
+using ::__ldg;   // keep the built-in overloads visible next to the IqRow one
+__device__ __forceinline__ float2 __ldg(const IqRow &r) { return r.ld(0); }
+__device__ __forceinline__ IqRow iq_row(const void *base, int bf16, const int *starts, int b, int T) {
+    IqRow r;
+    r.bf16 = bf16;
+    r.p = nullptr;
+    if (base) {
+        const size_t off = starts ? (size_t)::__ldg(starts + b) : (size_t)b * T;
+        r.p = bf16 ? static_cast<const void *>(reinterpret_cast<const unsigned *>(base) + off) : static_cast<const void *>(reinterpret_cast<const float2 *>(base) + off);
+    }
+    return r;
+}
+__device__ __forceinline__ IqRow iq_none() { IqRow r; r.p = nullptr; r.bf16 = 0; return r; }
+
 // ---------------------------------------------------------------- parameter staging: global -> shared via the TMA bulk-copy engine
 // One elected thread issues cp.async.bulk (SASS: UBLKCP) on an mbarrier; everybody waits on the barrier phase.
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }

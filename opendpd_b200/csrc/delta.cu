@@ -32,7 +32,7 @@ __device__ __forceinline__ float hswish(float v) { return v * fminf(fmaxf(v + 3.
 __device__ __forceinline__ float hswish_grad(float v) { return v < -3.f ? 0.f : (v <= 3.f ? v / 3.f + 0.5f : 1.f); }
 
 // TCN skip at one timestep (deltagru_tcnskip.py:32-49): Conv1d(2->3,k3,dil16,pad16) -> Hardswish -> Conv1d(3->2,k1) -> Hardswish
-__device__ __forceinline__ void tcn_point(const float2 *x2, int T, int t, const float *w0, const float *w2, float *c1, float *c2) {
+__device__ __forceinline__ void tcn_point(IqRow x2, int T, int t, const float *w0, const float *w2, float *c1, float *c2) {
     float2 xs[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(96, 1) delta_fwd_kernel(GruArgs a) {
     const bool act = lane < H;
     const int j = act ? lane : 0, lp = lane < HP ? lane : 0;
     const int nchunks = (T + CH - 1) / CH;
-    const float2 *x2 = reinterpret_cast<const float2 *>(a.x) + (size_t)b * T;
+    const IqRow x2 = iq_row(a.x, a.x_bf16, a.x_starts, b, T);
     const float thx = a.thx, thh = a.thh;
 
     if (warp == 1) {
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(96, 1) delta_fwd_kernel(GruArgs a) {
         // =============================== post: head (+skip), loss, activation store
         const float wo0 = act ? sp[L.oWo + j] : 0.f, wo1 = act ? sp[L.oWo + H + j] : 0.f;
         const float bo0 = TRES ? 0.f : sp[L.obo], bo1 = TRES ? 0.f : sp[L.obo + 1];
-        const float2 *y2 = a.target ? reinterpret_cast<const float2 *>(a.target) + (size_t)b * T : nullptr;
+        const IqRow y2 = iq_row(a.target, a.target_bf16, a.target_starts, b, T);
         float2 *o2 = reinterpret_cast<float2 *>(a.out) + (size_t)b * T;
         float *svg = a.save ? a.saved + (size_t)b * T * ROW : nullptr;
         float lsum = 0.f;
@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(96, 1) delta_fwd_kernel(GruArgs a) {
                 __syncwarp();
                 if (svg && lane == 0) tma_store_1d(svg + (size_t)t0 * ROW, ac, (uint32_t)(nt * ROW * 4));
                 linear_head_chunk(ac, ROW, 4 * HP, HP, H, nt, lane, wo0, wo1, bo0, bo1, spo,
-                                  TRES ? reinterpret_cast<const float2 *>(ssk + (c % 3) * SM::SK) : nullptr, o2 + t0, y2 ? y2 + t0 : nullptr, lsum);
+                                  TRES ? reinterpret_cast<const float2 *>(ssk + (c % 3) * SM::SK) : nullptr, o2 + t0, y2 ? y2 + t0 : iq_none(), lsum);
                 if (svg && lane == 0) tma_store_wait_read();
                 __syncwarp();
             }
@@ -351,11 +351,11 @@ __global__ void __launch_bounds__(128, 1) delta_bwd_kernel(GruArgs a) {
     const bool act = lane < H;
     const int j = act ? lane : 0, lp = lane < HP ? lane : 0;
     const int nchunks = (T + CH - 1) / CH;
-    const float2 *x2 = reinterpret_cast<const float2 *>(a.x) + (size_t)b * T;
+    const IqRow x2 = iq_row(a.x, a.x_bf16, a.x_starts, b, T);
     const float *svg = a.saved + (size_t)b * T * ROW;
     const float2 *go2 = a.gout ? reinterpret_cast<const float2 *>(a.gout) + (size_t)b * T : nullptr;
     const float2 *oi2 = a.out_in ? reinterpret_cast<const float2 *>(a.out_in) + (size_t)b * T : nullptr;
-    const float2 *y2 = a.target ? reinterpret_cast<const float2 *>(a.target) + (size_t)b * T : nullptr;
+    const IqRow y2 = iq_row(a.target, a.target_bf16, a.target_starts, b, T);
     const float gs = a.gscale * (a.gscale_dev ? __ldg(a.gscale_dev) : 1.0f);
 
     if (warp == 1) {

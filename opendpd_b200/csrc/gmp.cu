@@ -11,7 +11,7 @@ namespace odpd {
 
 static constexpr int GMP_M = 11, GMP_P = 495;
 
-__device__ __forceinline__ float2 ldx(const float2 *x2, int n, int T) { return (n >= 0 && n < T) ? __ldg(x2 + n) : make_float2(0.f, 0.f); }
+__device__ __forceinline__ float2 ldx(IqRow x2, int n, int T) { return (n >= 0 && n < T) ? __ldg(x2 + n) : make_float2(0.f, 0.f); }
 
 // sum_p w[p] A^(p+1)  for the (k,m) slot
 __device__ __forceinline__ float gmp_poly(const float *w, int k, int m, float A) {
@@ -29,8 +29,8 @@ __global__ void __launch_bounds__(128, 2) gmp_fwd_kernel(GruArgs a) {
     for (int i = threadIdx.x; i < GMP_P; i += blockDim.x) w[i] = a.params[i];
     __syncthreads();
     const int b = blockIdx.y, T = a.T;
-    const float2 *x2 = reinterpret_cast<const float2 *>(a.x) + (size_t)b * T;
-    const float2 *y2 = a.target ? reinterpret_cast<const float2 *>(a.target) + (size_t)b * T : nullptr;
+    const IqRow x2 = iq_row(a.x, a.x_bf16, a.x_starts, b, T);
+    const IqRow y2 = iq_row(a.target, a.target_bf16, a.target_starts, b, T);
     float2 *o2 = reinterpret_cast<float2 *>(a.out) + (size_t)b * T;
     float lsum = 0.f;
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < T; j += gridDim.x * blockDim.x) {
@@ -62,10 +62,10 @@ __global__ void __launch_bounds__(128, 2) gmp_bwd_dx_kernel(GruArgs a) {
     for (int i = threadIdx.x; i < GMP_P; i += blockDim.x) w[i] = a.params[i];
     __syncthreads();
     const int b = blockIdx.y, T = a.T;
-    const float2 *x2 = reinterpret_cast<const float2 *>(a.x) + (size_t)b * T;
+    const IqRow x2 = iq_row(a.x, a.x_bf16, a.x_starts, b, T);
     const float2 *go2 = a.gout ? reinterpret_cast<const float2 *>(a.gout) + (size_t)b * T : nullptr;
     const float2 *oi2 = a.out_in ? reinterpret_cast<const float2 *>(a.out_in) + (size_t)b * T : nullptr;
-    const float2 *y2 = a.target ? reinterpret_cast<const float2 *>(a.target) + (size_t)b * T : nullptr;
+    const IqRow y2 = iq_row(a.target, a.target_bf16, a.target_starts, b, T);
     float2 *gx2 = reinterpret_cast<float2 *>(a.gx) + (size_t)b * T;
     const float gs = a.gscale * (a.gscale_dev ? __ldg(a.gscale_dev) : 1.0f);
     for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < T; n += gridDim.x * blockDim.x) {
@@ -115,10 +115,10 @@ __global__ void __launch_bounds__(128) gmp_bwd_dw_kernel(GruArgs a) {
     for (int i = lane; i < GMP_P; i += 32) acc[warp][i] = 0.f;
     __syncwarp();
     const int b = blockIdx.x, T = a.T;
-    const float2 *x2 = reinterpret_cast<const float2 *>(a.x) + (size_t)b * T;
+    const IqRow x2 = iq_row(a.x, a.x_bf16, a.x_starts, b, T);
     const float2 *go2 = a.gout ? reinterpret_cast<const float2 *>(a.gout) + (size_t)b * T : nullptr;
     const float2 *oi2 = a.out_in ? reinterpret_cast<const float2 *>(a.out_in) + (size_t)b * T : nullptr;
-    const float2 *y2 = a.target ? reinterpret_cast<const float2 *>(a.target) + (size_t)b * T : nullptr;
+    const IqRow y2 = iq_row(a.target, a.target_bf16, a.target_starts, b, T);
     const float gs = a.gscale * (a.gscale_dev ? __ldg(a.gscale_dev) : 1.0f);
     for (int j0 = warp * 32; j0 < T; j0 += 128) {
         const int j = j0 + lane;

@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(96, 1) gru_fwd_kernel(GruArgs a) {
     const bool act = lane < H;
     const int j = act ? lane : 0;
     const int cb = t_lo / CH, nchunks = (t_hi + CH - 1) / CH - cb;   // pipeline stages q = 0..nchunks-1 cover 32-step blocks cb+q
-    const float2 *x2 = reinterpret_cast<const float2 *>(a.x) + (size_t)b * T;
+    const IqRow x2 = iq_row(a.x, a.x_bf16, a.x_starts, b, T);
     // fixed roles per warp (measured: rotating the roles of co-resident CTAs over the sub-partitions is 20-50 % slower)
     const int role = warp;
 
@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(96, 1) gru_fwd_kernel(GruArgs a) {
         const float wo0 = act ? sp[L.oWo + j] : 0.f, wo1 = act ? sp[L.oWo + L.O + j] : 0.f;
         const float bh = (HEAD && act) ? sp[L.obh + j] : 0.f;
         const float bo0 = sp[L.obo], bo1 = sp[L.obo + 1];
-        const float2 *y2 = a.target ? reinterpret_cast<const float2 *>(a.target) + (size_t)b * T : nullptr;
+        const IqRow y2 = iq_row(a.target, a.target_bf16, a.target_starts, b, T);
         float2 *o2 = reinterpret_cast<float2 *>(a.out) + (size_t)b * T;
         float *svg = a.save ? a.saved + (size_t)b * T * ROW : nullptr;
         float *spo0 = spo, *spo1 = spo + SM::PO;
@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(128, 1) gru_bwd_kernel(GruArgs a) {
     const int lp = lane < HP ? lane : 0;
     // 32-step blocks [cb, ce) are processed last to first; blocks >= ce_emit are warm-up
     const int cb = t_elo / CH, ce = (t_hi + CH - 1) / CH, nchunks = ce - cb, ce_emit = (t_ehi + CH - 1) / CH;
-    const float2 *x2 = reinterpret_cast<const float2 *>(a.x) + (size_t)b * T;
+    const IqRow x2 = iq_row(a.x, a.x_bf16, a.x_starts, b, T);
     const float *svg = a.saved + (size_t)b * T * ROW;
 
     // stage s: pre -> chunk index (nchunks-1-s), chain -> one stage later, post -> two stages later
@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(128, 1) gru_bwd_kernel(GruArgs a) {
         const float wo0 = act ? sp[L.oWo + j] : 0.f, wo1 = act ? sp[L.oWo + L.O + j] : 0.f;
         const float2 *go2 = a.gout ? reinterpret_cast<const float2 *>(a.gout) + (size_t)b * T : nullptr;
         const float2 *oi2 = a.out_in ? reinterpret_cast<const float2 *>(a.out_in) + (size_t)b * T : nullptr;
-        const float2 *y2 = a.target ? reinterpret_cast<const float2 *>(a.target) + (size_t)b * T : nullptr;
+        const IqRow y2 = iq_row(a.target, a.target_bf16, a.target_starts, b, T);
         const float gs = a.gscale * (a.gscale_dev ? __ldg(a.gscale_dev) : 1.0f);
         for (int s = 0; s < nchunks + 2; ++s) {
             if (s < nchunks) {

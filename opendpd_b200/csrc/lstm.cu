@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(96, 1) lstm_fwd_kernel(GruArgs a) {
     const bool act = lane < H;
     const int j = act ? lane : 0, lp = lane < HP ? lane : 0;
     const int cb = R.t_lo / CH, nchunks = (t_hi + CH - 1) / CH - cb;
-    const float2 *x2 = reinterpret_cast<const float2 *>(a.x) + (size_t)b * T;
+    const IqRow x2 = iq_row(a.x, a.x_bf16, a.x_starts, b, T);
 
     if (warp == 1) {
         float w0[4], w1[4], bb[4];
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(96, 1) lstm_fwd_kernel(GruArgs a) {
     } else {
         const float wo0 = act ? sp[L.oWo + j] : 0.f, wo1 = act ? sp[L.oWo + H + j] : 0.f;
         const float bo0 = sp[L.obo], bo1 = sp[L.obo + 1];
-        const float2 *y2 = a.target ? reinterpret_cast<const float2 *>(a.target) + (size_t)b * T : nullptr;
+        const IqRow y2 = iq_row(a.target, a.target_bf16, a.target_starts, b, T);
         float2 *o2 = reinterpret_cast<float2 *>(a.out) + (size_t)b * T;
         float *svg = a.save ? a.saved + (size_t)b * T * ROW : nullptr;
         float lsum = 0.f;
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(96, 1) lstm_fwd_kernel(GruArgs a) {
                 const int t0 = (cb + ck) * CH, nt = min(CH, t_hi - t0);
                 float *ac = sact + (ck & 1) * SM::ACT;
                 if (svg && lane == 0) tma_store_1d(svg + (size_t)t0 * ROW, ac, (uint32_t)(nt * ROW * 4));
-                linear_head_chunk(ac, ROW, 5 * HP, HP, H, nt, lane, wo0, wo1, bo0, bo1, spo, nullptr, o2 + t0, y2 ? y2 + t0 : nullptr, lsum);
+                linear_head_chunk(ac, ROW, 5 * HP, HP, H, nt, lane, wo0, wo1, bo0, bo1, spo, nullptr, o2 + t0, y2 ? y2 + t0 : iq_none(), lsum);
                 if (svg && lane == 0) tma_store_wait_read();
                 __syncwarp();
             }
@@ -191,14 +191,14 @@ __global__ void __launch_bounds__(96, 1) lstm_bwd_kernel(GruArgs a) {
     const int j = act ? lane : 0, lp = lane < HP ? lane : 0;
     // 32-step blocks [cb, ce) are processed last to first; blocks >= ce_emit are warm-up
     const int cb = R.t_elo / CH, ce = (t_hi + CH - 1) / CH, nchunks = ce - cb, ce_emit = (t_ehi + CH - 1) / CH;
-    const float2 *x2 = reinterpret_cast<const float2 *>(a.x) + (size_t)b * T;
+    const IqRow x2 = iq_row(a.x, a.x_bf16, a.x_starts, b, T);
     const float *svg = a.saved + (size_t)b * T * ROW;
 
     if (warp == 1) {
         const float wo0 = act ? sp[L.oWo + j] : 0.f, wo1 = act ? sp[L.oWo + H + j] : 0.f;
         const float2 *go2 = a.gout ? reinterpret_cast<const float2 *>(a.gout) + (size_t)b * T : nullptr;
         const float2 *oi2 = a.out_in ? reinterpret_cast<const float2 *>(a.out_in) + (size_t)b * T : nullptr;
-        const float2 *y2 = a.target ? reinterpret_cast<const float2 *>(a.target) + (size_t)b * T : nullptr;
+        const IqRow y2 = iq_row(a.target, a.target_bf16, a.target_starts, b, T);
         const float gs = a.gscale * (a.gscale_dev ? __ldg(a.gscale_dev) : 1.0f);
         for (int s = 0; s < nchunks + 2; ++s) {
             if (s < nchunks) {

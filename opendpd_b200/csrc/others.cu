@@ -94,6 +94,8 @@ int other_fwd(const OdpdDims *d, const float *x, const float *target, const floa
     a.x = x; a.target = target; a.params = params; a.out = out; a.loss = loss; a.loss_scale = (float)loss_scale;
     a.saved = (float *)saved; a.save = (d->flags & ODPD_F_SAVE) != 0;
     a.tchunks_req = d->tchunks; a.twarm_req = d->twarm;
+    a.x_bf16 = (d->flags & ODPD_F_X_BF16) != 0; a.target_bf16 = (d->flags & ODPD_F_TARGET_BF16) != 0;
+    a.x_starts = d->x_starts; a.target_starts = d->target_starts;
     return run(d, a, 0, false, st, nullptr);
 }
 
@@ -105,6 +107,8 @@ int other_bwd(const OdpdDims *d, const float *x, const float *params, const void
     a.gscale = (float)gscale; a.gscale_dev = gscale_dev; a.gx = gx; a.partials = partials;
     a.need_dx = (d->flags & ODPD_F_NEED_DX) != 0;
     a.tchunks_req = d->tchunks; a.twarm_req = d->twarm;
+    a.x_bf16 = (d->flags & ODPD_F_X_BF16) != 0; a.target_bf16 = (d->flags & ODPD_F_TARGET_BF16) != 0;
+    a.x_starts = d->x_starts; a.target_starts = d->target_starts;
     int info[4] = {1, 0, 0, -1};
     const int rc = run(d, a, 1, (d->flags & ODPD_F_NEED_DW) != 0, st, info);
     if (rows_out) *rows_out = d->B * info[0];

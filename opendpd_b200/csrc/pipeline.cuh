@@ -65,7 +65,7 @@ __device__ __forceinline__ void bcast_dot(const float *line, const float (&w)[HT
 //   hoff1 : offset of the vector feeding the second output (== hoff for every cell but DVRJANET: y_I from h_I, y_Q from h_Q)
 __device__ __forceinline__ void linear_head_chunk2(const float *rows, int ROW, int hoff, int hoff1, int HP, int H, int nt, int lane, float wo0,
                                                    float wo1, float bo0, float bo1, float *spo, const float2 *skip, float2 *out,
-                                                   const float2 *tgt, float &lsum) {
+                                                   IqRow tgt, float &lsum) {
     float *spo0 = spo, *spo1 = spo + CH * 33;
 #pragma unroll 4
     for (int tl = 0; tl < nt; ++tl) {
@@ -90,13 +90,13 @@ __device__ __forceinline__ void linear_head_chunk2(const float *rows, int ROW, i
 }
 
 __device__ __forceinline__ void linear_head_chunk(const float *rows, int ROW, int hoff, int HP, int H, int nt, int lane, float wo0, float wo1,
-                                                  float bo0, float bo1, float *spo, const float2 *skip, float2 *out, const float2 *tgt,
+                                                  float bo0, float bo1, float *spo, const float2 *skip, float2 *out, IqRow tgt,
                                                   float &lsum) {
     linear_head_chunk2(rows, ROW, hoff, hoff, HP, H, nt, lane, wo0, wo1, bo0, bo1, spo, skip, out, tgt, lsum);
 }
 
 // dLoss/dout for one chunk, one timestep per lane: explicit gout tensor or fused MSE gradient gs*(out-target)
-__device__ __forceinline__ float2 load_gout(const float2 *go2, const float2 *oi2, const float2 *y2, int t, float gs) {
+__device__ __forceinline__ float2 load_gout(const float2 *go2, const float2 *oi2, IqRow y2, int t, float gs) {
     if (go2) return __ldg(go2 + t);
     const float2 o = __ldg(oi2 + t), y = __ldg(y2 + t);
     return make_float2(gs * (o.x - y.x), gs * (o.y - y.y));

@@ -119,7 +119,7 @@ __device__ __forceinline__ void qctx_init(QCtx<HT, FM> &c, const float *sp, cons
 }
 
 template <int FM>
-__device__ __forceinline__ void q_features(const float2 *x2, int t, float *f) {
+__device__ __forceinline__ void q_features(IqRow x2, int t, float *f) {
     const float2 v = __ldg(x2 + t);
     float ff[8];
     features_fwd<FM>(v.x, v.y, 0.f, 0.f, ff);
@@ -148,8 +148,8 @@ __global__ void __launch_bounds__(128) qgru_qat_fwd_kernel(GruArgs a) {
     const Quant qow = mkq(sp[L.oso], bw), qoa = mkq(sp[L.oso + 1], ba), qoo = mkq(sp[L.oso + 2], 16);
     const float wo0 = act ? qf(qow, sp[L.oWo + (act ? lane : 0)]) : 0.f, wo1 = act ? qf(qow, sp[L.oWo + H + (act ? lane : 0)]) : 0.f;
     const float bo0 = sp[L.obo], bo1 = sp[L.obo + 1];
-    const float2 *x2 = reinterpret_cast<const float2 *>(a.x) + (size_t)b * T;
-    const float2 *y2 = a.target ? reinterpret_cast<const float2 *>(a.target) + (size_t)b * T : nullptr;
+    const IqRow x2 = iq_row(a.x, a.x_bf16, a.x_starts, b, T);
+    const IqRow y2 = iq_row(a.target, a.target_bf16, a.target_starts, b, T);
     float2 *o2 = reinterpret_cast<float2 *>(a.out) + (size_t)b * T;
     float *sv = a.save ? a.saved + (size_t)b * T * HP : nullptr;
     float h = 0.f, lsum = 0.f;
@@ -210,10 +210,10 @@ __global__ void __launch_bounds__(128) qgru_qat_bwd_kernel(GruArgs a) {
     }
 #pragma unroll
     for (int k = 0; k < 12; ++k) gwx[k] = 0.f;
-    const float2 *x2 = reinterpret_cast<const float2 *>(a.x) + (size_t)b * T;
+    const IqRow x2 = iq_row(a.x, a.x_bf16, a.x_starts, b, T);
     const float2 *go2 = a.gout ? reinterpret_cast<const float2 *>(a.gout) + (size_t)b * T : nullptr;
     const float2 *oi2 = a.out_in ? reinterpret_cast<const float2 *>(a.out_in) + (size_t)b * T : nullptr;
-    const float2 *y2 = a.target ? reinterpret_cast<const float2 *>(a.target) + (size_t)b * T : nullptr;
+    const IqRow y2 = iq_row(a.target, a.target_bf16, a.target_starts, b, T);
     float2 *gx2 = (a.need_dx && a.gx) ? reinterpret_cast<float2 *>(a.gx) + (size_t)b * T : nullptr;
     const float *sv = a.saved + (size_t)b * T * HP;
     const float gs = a.gscale * (a.gscale_dev ? __ldg(a.gscale_dev) : 1.0f);

@@ -34,10 +34,11 @@ class CellSpec:
             twarm = int(env("ODPD_TWARM", "0"))
         self.twarm = (int(twarm), int(twarm)) if isinstance(twarm, int) else tuple(int(v) for v in twarm)   # (forward, backward)
 
-    def dims(self, B, T, flags, backward=False):
+    def dims(self, B, T, flags, backward=False, x_starts=None, target_starts=None):
         k = 1 if backward else 0
         twarm = self.twarm if isinstance(self.twarm, int) else self.twarm[k]
-        return _ffi.OdpdDims(self.cell_id, int(B), int(T), self.H, self.K, int(flags), self.thx, self.thh, self.tchunks[k], twarm)
+        return _ffi.OdpdDims(self.cell_id, int(B), int(T), self.H, self.K, int(flags), self.thx, self.thh, self.tchunks[k], twarm,
+                             None if x_starts is None else x_starts.data_ptr(), None if target_starts is None else target_starts.data_ptr())
 
     def chunk_plan(self, B, T, backward=False, save=True, need_dw=True):
         """(chunks, steps per chunk, warm-up steps, index of the re-run counter) the library will use for this call shape."""
@@ -48,11 +49,45 @@ class CellSpec:
         return tuple(int(v) for v in out)
 
 
+class IqStream:
+    """On-device framing (OdpdDims.x_starts / .target_starts): instead of a framed (B,T,2) tensor, hand the kernels the raw (N,2) IQ
+    stream (fp32 or bf16) plus the B frame start indices (device int32) — the reference's IQFrameDataset materialises every stride-1
+    frame (data_collector.py:233-252) and copies B*T*2 floats per step; this copies B indices."""
+
+    def __init__(self, stream, starts, T):
+        if stream.dim() != 2 or stream.size(-1) != 2 or not stream.is_contiguous():
+            raise _ffi.OdpdError("IqStream wants a contiguous (N,2) stream")
+        if starts.dtype != torch.int32 or starts.dim() != 1 or not starts.is_contiguous() or starts.device != stream.device:
+            raise _ffi.OdpdError("IqStream wants contiguous int32 frame starts on the stream's device")
+        self.stream, self.starts, self.T = stream, starts, int(T)
+        self.shape = (starts.numel(), self.T, 2)
+        self.device, self.dtype, self.is_cuda = stream.device, stream.dtype, stream.is_cuda
+
+    def data_ptr(self):
+        return self.stream.data_ptr()
+
+    def frames(self):
+        """Materialised (B,T,2) frames (tests / fallbacks)."""
+        idx = self.starts.long()[:, None] + torch.arange(self.T, device=self.device)[None, :]
+        return self.stream[idx]
+
+
+def _iq(t):
+    """(tensor whose data_ptr the kernel reads, bf16 flag, starts tensor or None) for a framed tensor or an IqStream."""
+    if t is None:
+        return None, False, None
+    if isinstance(t, IqStream):
+        return t.stream, t.stream.dtype == torch.bfloat16, t.starts
+    return t, t.dtype == torch.bfloat16, None
+
+
 def _check_x(x):
     if not x.is_cuda:
         raise _ffi.OdpdError("native backbones run on CUDA tensors only (no CPU fallback); got a CPU tensor")
-    if x.dtype != torch.float32 or x.dim() != 3 or x.size(-1) != 2:
-        raise _ffi.OdpdError(f"expected a float32 (B,T,2) tensor, got {tuple(x.shape)} {x.dtype}")
+    if isinstance(x, IqStream):
+        return x
+    if x.dtype not in (torch.float32, torch.bfloat16) or x.dim() != 3 or x.size(-1) != 2:
+        raise _ffi.OdpdError(f"expected a float32 / bfloat16 (B,T,2) tensor, got {tuple(x.shape)} {x.dtype}")
     return x.contiguous()
 
 
@@ -61,12 +96,15 @@ def backbone_forward_raw(spec, x, flat, target=None, loss_scale=0.0, save=True, 
     `bufs` (dict) caches out/saved/loss allocations across calls of identical shape (NativeTrainStep)."""
     L = _ffi.lib()
     B, T = x.shape[0], x.shape[1]
-    d = spec.dims(B, T, (_ffi.F_SAVE if save else 0) | _ffi.F_ZERO_LOSS)
+    xt, xbf, xst = _iq(x)
+    tt, tbf, tst = _iq(target)
+    d = spec.dims(B, T, (_ffi.F_SAVE if save else 0) | _ffi.F_ZERO_LOSS | (_ffi.F_X_BF16 if xbf else 0) | (_ffi.F_TARGET_BF16 if tbf else 0),
+                  x_starts=xst, target_starts=tst)
     key = (B, T, bool(save), target is not None, spec.tchunks[0])
     if bufs is not None and bufs.get("key") == key:
         out, saved, loss = bufs["out"], bufs["saved"], bufs["loss"]
     else:
-        out = torch.empty_like(x)
+        out = torch.empty((B, T, 2), dtype=torch.float32, device=x.device)
         saved = None
         nbytes = L.odpd_saved_bytes(ctypes.byref(d))     # activations (when saving) + chunk scratch
         if nbytes < 0:
@@ -79,7 +117,7 @@ def backbone_forward_raw(spec, x, flat, target=None, loss_scale=0.0, save=True, 
         loss = torch.empty(1, dtype=torch.float64, device=x.device) if target is not None else None
         if bufs is not None:
             bufs.update(key=key, out=out, saved=saved, loss=loss)
-    _ffi.check(L.odpd_backbone_fwd(ctypes.byref(d), _ptr(x), _ptr(target), _ptr(flat), _ptr(out), _ptr(loss),
+    _ffi.check(L.odpd_backbone_fwd(ctypes.byref(d), _ptr(xt), _ptr(tt), _ptr(flat), _ptr(out), _ptr(loss),
                                    ctypes.c_double(loss_scale), _ptr(saved), _ptr(stats), _stream()))
     return out, loss, saved
 
@@ -90,13 +128,16 @@ def backbone_backward_raw(spec, x, flat, saved, need_dx, need_dw, gout=None, out
     parameter gradient (ODPD_F_OVERWRITE_DW).  Returns (gx, gflat)."""
     L = _ffi.lib()
     B, T = x.shape[0], x.shape[1]
-    flags = (_ffi.F_NEED_DX if need_dx else 0) | (_ffi.F_NEED_DW if need_dw else 0) | _ffi.F_OVERWRITE_DW
-    d = spec.dims(B, T, flags, backward=True)
+    xt, xbf, xst = _iq(x)
+    tt, tbf, tst = _iq(target)
+    flags = ((_ffi.F_NEED_DX if need_dx else 0) | (_ffi.F_NEED_DW if need_dw else 0) | _ffi.F_OVERWRITE_DW |
+             (_ffi.F_X_BF16 if xbf else 0) | (_ffi.F_TARGET_BF16 if tbf else 0))
+    d = spec.dims(B, T, flags, backward=True, x_starts=xst, target_starts=tst)
     key = (B, T, bool(need_dx), bool(need_dw), spec.tchunks[1])
     if bufs is not None and bufs.get("key") == key:
         gx, ws = bufs["gx"], bufs["ws"]
     else:
-        gx = torch.empty_like(x) if need_dx else None
+        gx = torch.empty((B, T, 2), dtype=torch.float32, device=x.device) if need_dx else None
         ws = torch.empty(int(L.odpd_bwd_workspace_bytes(ctypes.byref(d))) // 4, dtype=torch.float32, device=x.device)
         idx = spec.chunk_plan(B, T, True, True, need_dw)[3]
         if idx >= 0:
@@ -105,7 +146,7 @@ def backbone_backward_raw(spec, x, flat, saved, need_dx, need_dw, gout=None, out
             bufs.update(key=key, gx=gx, ws=ws)
     if need_dw and gflat is None:
         gflat = torch.empty_like(flat)
-    _ffi.check(L.odpd_backbone_bwd(ctypes.byref(d), _ptr(x), _ptr(flat), _ptr(saved), _ptr(gout), _ptr(out), _ptr(target),
+    _ffi.check(L.odpd_backbone_bwd(ctypes.byref(d), _ptr(xt), _ptr(flat), _ptr(saved), _ptr(gout), _ptr(out), _ptr(tt),
                                    ctypes.c_double(gscale), _ptr(gscale_dev), _ptr(gx), _ptr(gflat), _ptr(ws), _stream()))
     return gx, gflat
 
@@ -139,6 +180,8 @@ class BackboneFn(torch.autograd.Function):
         x = _check_x(x)
         if target is not None:
             target = _check_x(target)
+        if isinstance(x, IqStream) or isinstance(target, IqStream):
+            raise _ffi.OdpdError("IqStream inputs go through NativeTrainStep.step / the raw wrappers, not through autograd")
         nig = ctx.needs_input_grad  # (spec, layout, flat, stats, target, loss_count, x, *params)
         need_dx = bool(nig[6])
         need_dw = any(nig[7:])
@@ -174,6 +217,8 @@ class BackboneFn(torch.autograd.Function):
         gx, gflat = backbone_backward_raw(ctx.spec, x, ctx.flat, ctx.saved, need_dx, need_dw, gout=gout,
                                           out=out if gout is None else None, target=target if gout is None else None,
                                           gscale=gscale, gscale_dev=gscale_dev)
+        if gx is not None and gx.dtype != x.dtype:
+            gx = gx.to(x.dtype)
         gparams = [None] * len(pmask)
         if need_dw:
             for i, (off, n, shape) in enumerate(ctx.layout):

@@ -12,7 +12,7 @@ import torch
 from torch import nn
 
 from . import _ffi
-from .functional import backbone_forward_raw, backbone_backward_raw, _ptr, _stream
+from .functional import backbone_forward_raw, backbone_backward_raw, IqStream, _ptr, _stream
 from .models import CoreModel, CascadedModel
 from .dp import allreduce_flat_, PeerExchange
 
@@ -135,8 +135,9 @@ class NativeTrainStep:
         if not self.use_graphs:
             loss = self._step_impl(features, targets, global_count)
         else:
-            shape_key = (tuple(features.shape), tuple(targets.shape), global_count)
-            key = (features.data_ptr(), targets.data_ptr()) + shape_key
+            sid = lambda t: t.starts.data_ptr() if isinstance(t, IqStream) else 0
+            shape_key = (tuple(features.shape), tuple(targets.shape), features.dtype, targets.dtype, global_count)
+            key = (features.data_ptr(), targets.data_ptr(), sid(features), sid(targets)) + shape_key
             g = self._graphs.get(key)
             if g is None and shape_key not in self._graph_warm:
                 # first step of a shape runs eagerly: allocates the cached buffers, sets kernel attributes
@@ -156,6 +157,13 @@ class NativeTrainStep:
         if self.chunk_check_every > 0 and self._host_step % self.chunk_check_every == 0:
             self._chunk_control(B, T)
         return loss
+
+    def step_indexed(self, stream_x, stream_y, starts, T, global_count=None):
+        """One train step on frames addressed inside device-resident raw streams (SURVEY f-2: on-device framing inside the kernels):
+        stream_x / stream_y are (N,2) fp32 or bf16 tensors, starts the B frame start indices (device int32) — frame b is
+        stream[starts[b] : starts[b]+T], exactly IQFrameDataset's stride-1 window (data_collector.py:233-252).  Nothing is
+        gathered or copied: the kernels read the stream in place."""
+        return self.step(IqStream(stream_x, starts, T), IqStream(stream_y, starts, T), global_count)
 
     def _step_impl(self, features, targets, global_count=None):
         L = _ffi.lib()
