@@ -23,6 +23,8 @@ WORKLOADS = {
                 pa=("dgru", 13)),
     "c3": dict(name="C3: TRes-DeltaGRU H=15 (999 params, thx .01 thh .05) DPD -> frozen DGRU H=23 PA, B=256 x T=2048, fp32",
                kind="deltagru_tcnskip", H=15, B=256, T=2048, pa=("dgru", 23)),
+    "c3b": dict(name="C3 with bf16 IQ storage (BASELINE configs[2]): TRes-DeltaGRU H=15 DPD -> frozen DGRU H=23 PA, B=256 x T=2048, bf16 in HBM / fp32 arithmetic",
+                kind="deltagru_tcnskip", H=15, B=256, T=2048, pa=("dgru", 23), io="bf16"),
     "c3s": dict(name="C3 (script frame length): TRes-DeltaGRU H=15 DPD -> frozen DGRU H=23 PA, B=256 x T=200, fp32",
                 kind="deltagru_tcnskip", H=15, B=256, T=200, pa=("dgru", 23)),
     "c4p": dict(name="C4: PGJANET H=15 (1727 params) DPD step, per-GPU B=128 x T=4096, fp32", kind="pgjanet", H=15, B=128, T=4096),
@@ -237,6 +239,8 @@ def main():
     # input pool larger than L2 (126 MB): POOL distinct batches, each 2 x 1 MiB
     POOL = max(8, min(80, (160 << 20) // (2 * B * T * 8) + 1))     # >= 160 MB of distinct inputs when the batch is small
     xs, ys = synth_batches(POOL, B, T, 1000 + rank)
+    if wl.get("io") == "bf16":                          # storage only: the kernels widen every sample exactly to fp32
+        xs, ys = xs.bfloat16(), ys.bfloat16()
     xs_pin, ys_pin = xs.pin_memory(), ys.pin_memory()
     xd, yd = xs.to(dev), ys.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -306,6 +310,39 @@ def main():
         trainer.step_host(xs_pin[(W + i) % POOL], ys_pin[(W + i) % POOL])
     torch.cuda.synchronize()
     e2e_seq_ms = (time.perf_counter() - t1) / min(K, 100) * 1e3
+    # on-device framing (SURVEY f-2): the whole pool viewed as one raw (N,2) stream resident in HBM; per step the host sends only the B
+    # frame start indices (pinned -> H2D), the kernels read the stride-1 windows in place, the loss comes back as before
+    NS = POOL * B * T
+    stream_x, stream_y = xd.view(NS, 2), yd.view(NS, 2)
+    gsi = torch.Generator().manual_seed(4242 + rank)
+    starts_pin = torch.randint(0, NS - T, (K + 3, B), generator=gsi).to(torch.int32).pin_memory()
+    starts_dev = [torch.empty(B, dtype=torch.int32, device=dev) for _ in range(2)]
+    loss_pin = [torch.zeros(1, dtype=torch.float64).pin_memory() for _ in range(2)]
+    ev_l = [torch.cuda.Event() for _ in range(2)]
+
+    def indexed_steps(n, off):
+        pending = None
+        for i in range(n):
+            sl = i & 1
+            starts_dev[sl].copy_(starts_pin[off + i], non_blocking=True)
+            ldev = trainer.step_indexed(stream_x, stream_y, starts_dev[sl], T)
+            loss_pin[sl].copy_(ldev, non_blocking=True)
+            ev_l[sl].record()
+            if pending is not None:
+                ev_l[pending].synchronize()
+                assert np.isfinite(float(loss_pin[pending][0]))
+            pending = sl
+        ev_l[pending].synchronize()
+    indexed_steps(3, 0)
+    barrier()
+    t2 = time.perf_counter()
+    indexed_steps(K, 3)
+    torch.cuda.synchronize()
+    e2e_idx_s = time.perf_counter() - t2
+    if world > 1:
+        t = torch.tensor([e2e_idx_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_idx_s = float(t.item())
     if world > 1:
         t = torch.tensor([e2e_s], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -373,7 +410,7 @@ def main():
             "metric": "IQ samples/sec/train-step", "value": world * B * T * K / (ms * 1e-3), "unit": "IQ samples/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["name"], "global_batch": B * world, "per_gpu_batch": B, "frame_len": T,
+            "config": {"workload": wl["name"], "iq_storage": wl.get("io", "f32"), "global_batch": B * world, "per_gpu_batch": B, "frame_len": T,
                        "parallelism": f"dp{world}", "optimizer": "clip_grad_norm_(200)+AdamW(lr=5e-4) fused on the flat buffer",
                        "l2": f"inputs larger than L2: pool of {POOL} distinct 2x{2 * B * T * 4 / 2**20:.3g}MiB batches, each step's batch copied device-to-device "
                              f"into a fixed staging pair inside the timed region; L2 flushed (256 MiB write) after warm-up",
@@ -381,10 +418,15 @@ def main():
                        "final_loss": final_loss},
             "clocks": clocks,
             "e2e": {"value": world * B * T * K / e2e_s, "unit": "IQ samples/s", "ms_per_step": e2e_s / K * 1e3,
-                    "h2d_bytes_per_step": 2 * B * T * 2 * 4, "d2h_bytes_per_step": 8,
+                    "h2d_bytes_per_step": 2 * B * T * 2 * xs.element_size(), "d2h_bytes_per_step": 8,
                     "path": "NativeTrainStep.run_host_batches: per step pinned host (B,T,2) features+targets -> cudaMemcpyAsync (side stream, "
                             "overlapping the previous step) -> fwd/bwd/optimizer kernels -> async D2H of the loss, read one step later",
                     "ms_per_step_sequential": e2e_seq_ms},
+            "e2e_indexed": {"value": world * B * T * K / e2e_idx_s, "unit": "IQ samples/s", "ms_per_step": e2e_idx_s / K * 1e3,
+                            "h2d_bytes_per_step": 4 * B, "d2h_bytes_per_step": 8,
+                            "path": "NativeTrainStep.step_indexed: raw (N,2) streams resident in HBM (the pool viewed flat, > L2); per step the B frame "
+                                    "start indices go pinned host -> device, the kernels read the stride-1 windows in place (OdpdDims.x_starts), "
+                                    "the loss is read back one step later"},
             "gpu_launches": launches * K,
             "kernels_per_step": (["<cell>_fwd_kernel (chunk CTAs; the last CTA of a sequence verifies its boundaries)", "<cell>_bwd_kernel<DW> (same)",
                                   "reduce_partials_kernel", "clip_adamw_kernel"] if "pa" not in wl else

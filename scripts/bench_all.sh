@@ -2,7 +2,7 @@
 # secondary workloads, 1 GPU, no CPU leg; one JSON line each -> gpurun_out/bench_all.jsonl
 mkdir -p gpurun_out
 : > gpurun_out/bench_all.jsonl
-for w in c1 c2a c2b c3 c3s c4p c4d c5g c5q lstm; do
+for w in c1 c2a c2b c3 c3b c3s c4p c4d c5g c5q lstm; do
   timeout 300 python bench.py --workload $w --steps ${STEPS:-100} --warmup 5 --no-cpu 2>>gpurun_out/bench_all.err | tail -1 >> gpurun_out/bench_all.jsonl
 done
 python - <<'PY'
