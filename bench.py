@@ -390,7 +390,7 @@ def main():
         chunk_info.append({"cell": mod.cell, "dir": "bwd" if backward else "fwd", "chunks": plan[0], "steps_per_chunk": plan[1],
                            "warmup_steps": plan[2], "serial_reruns": chunk_reruns(sp_, buf, B, T, backward, save, need_dw),
                            "worst_boundary_mismatch_over_tolerance": chunk_worst_mismatch(sp_, buf, B, T, backward, save, need_dw)})
-        launches += 1
+        launches += 2 if plan[0] > 1 else 1
     if wl["kind"] == "gmp":
         launches += 1
     # entries of chunk_info that describe the timed (fwd, bwd) kernels of the roofline section (the PA of a cascade, else the backbone)
@@ -428,9 +428,10 @@ def main():
                                     "start indices go pinned host -> device, the kernels read the stride-1 windows in place (OdpdDims.x_starts), "
                                     "the loss is read back one step later"},
             "gpu_launches": launches * K,
-            "kernels_per_step": (["<cell>_fwd_kernel (chunk CTAs; the last CTA of a sequence verifies its boundaries)", "<cell>_bwd_kernel<DW> (same)",
+            "kernels_per_step": (["<cell>_fwd_kernel (chunks)", "<cell>_fwd_kernel (verify)", "<cell>_bwd_kernel<DW> (chunks)", "<cell>_bwd_kernel<DW> (verify)",
                                   "reduce_partials_kernel", "clip_adamw_kernel"] if "pa" not in wl else
-                                 ["dpd_fwd", "pa_fwd(+MSE)", "pa_bwd<dX>", "dpd_bwd<DW>", "reduce_partials_kernel", "clip_adamw_kernel", "(gmp: +1)"]),
+                                 ["dpd_fwd", "pa_fwd(+MSE)", "pa_bwd<dX>", "dpd_bwd<DW>", "(+1 verify launch per chunked call)", "reduce_partials_kernel",
+                                  "clip_adamw_kernel", "(gmp: +1)"]),
             "time_chunks": chunk_info, "time_chunk_events": trainer.chunk_events,
             "kernel_ms": {"fwd": fwd_ms, "bwd": bwd_ms},
             "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -93,14 +93,14 @@ typedef struct OdpdDims {
  * Time-chunked execution (GRU-family cells).  The reference's frames are T-step serial recurrences (nn.GRU inside
  * gru.py:46 / dgru.py:70 / qgru.py:69) and its batches hold fewer sequences than a B200 has SMs.  A GRU forgets its initial
  * state geometrically, so the kernels cut each sequence into `tchunks` chunks that run concurrently, each preceded by `twarm`
- * warm-up steps started from h = 0 (backward: from dL/dh = 0, in reverse time); the last chunk of a sequence to finish then
- * compares the state every chunk was started from with the state its predecessor really ended with (max|diff| <= 2^-18 *
- * max|state| at the boundary) and re-runs the sequence serially, in the same launch, if a boundary fails.  Results therefore never depend on the forgetting
+ * warm-up steps started from h = 0 (backward: from dL/dh = 0, in reverse time); a verify pass then compares the state every
+ * chunk was started from with the state its predecessor really ended with (max|diff| <= 2^-18 * max|state| at the boundary)
+ * and re-runs, serially, every sequence with a failing boundary.  Results therefore never depend on the forgetting
  * assumption; only the speed does.  odpd_chunk_plan reports what a call with these dims will do:
  *   out[0] chunks, out[1] steps per chunk, out[2] warm-up steps, out[3] index (in 4-byte units, or -1) of an int32 counter
  *   inside `saved` (backward = 0) / `workspace` (backward = 1) that counts sequences the verify pass had to re-run, followed by
- *   a float holding the largest boundary mismatch seen so far in units of the tolerance and by per-sequence arrival counters; the
- *   caller zeroes the buffer from that index to its end when it allocates it.  LSTM, PGJANET and DVRJANET are chunked the same way (JANET default warm-up 256); the delta cells,
+ *   a float holding the largest boundary mismatch seen so far in units of the tolerance; the caller zeroes both when it
+ *   allocates the buffer.  LSTM, PGJANET and DVRJANET are chunked the same way (JANET default warm-up 256); the delta cells,
  *   GMP and the QAT cell always run serially.
  */
 int odpd_chunk_plan(const OdpdDims *d, int32_t backward, int32_t out[4]);

@@ -28,7 +28,6 @@ struct GruArgs {
     int C, Lc, Wu, mode;
     float *sc_guess, *sc_end, *sc_loss;
     int *sc_fail;
-    int *sc_count;     // [B] chunk CTAs of a sequence that have finished (chunk_is_last_arrival)
     float tol;
     int tchunks_req, twarm_req, twarm_default;
 };

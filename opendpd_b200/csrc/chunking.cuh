@@ -29,10 +29,10 @@ inline int64_t chunk_rows(int B, int tchunks_req) {
     return B > SPEC_ROWS_AUTO ? B : SPEC_ROWS_AUTO;
 }
 // forward scratch (tail of `saved`):  guess[rows][ss] | end[rows][ss] | loss[rows] | int32 re-run counter | float worst boundary
-// mismatch seen so far in units of the tolerance (<= 1 passes) | 2 pad | int32 arrivals[rows] (chunk CTAs of a sequence that finished)
-inline int64_t chunk_fwd_scratch_floats(int64_t rows, int ss) { return rows * (2 * ss + 1) + 4 + rows; }
-// backward scratch (tail of the workspace, after the 4-float-aligned [rows][P] partials):  guess | end | counter | mismatch | pad | arrivals
-inline int64_t chunk_bwd_scratch_floats(int64_t rows, int ss) { return rows * 2 * ss + 4 + rows; }
+// mismatch seen so far in units of the tolerance (<= 1 passes) | pad
+inline int64_t chunk_fwd_scratch_floats(int64_t rows, int ss) { return rows * (2 * ss + 1) + 4; }
+// backward scratch (tail of the workspace, after the 4-float-aligned [rows][P] partials):  guess | end | re-run counter (+pad)
+inline int64_t chunk_bwd_scratch_floats(int64_t rows, int ss) { return rows * 2 * ss + 4; }
 inline int64_t chunk_workspace_floats(int64_t rows, int64_t P, int ss) { return ((rows * P + 3) & ~(int64_t)3) + chunk_bwd_scratch_floats(rows, ss); }
 
 inline int num_sms() {
@@ -73,8 +73,7 @@ inline void chunk_make_plan(GruArgs &a, int slots, bool have_scratch) {
     if (C > 1 && (int64_t)a.B * C <= chunk_rows(a.B, req)) { a.C = C; a.Lc = lc_of(C); a.Wu = Wu; }
 }
 
-// Plan, bind the scratch and launch B*C chunk CTAs (the last CTA of every sequence to finish verifies the sequence's chunk
-// boundaries and, if one fails, re-runs the sequence serially itself) or, with one chunk, B serial CTAs.
+// Plan, bind the scratch and launch:  [B*C chunk CTAs] + [B verify CTAs]  or, with one chunk,  [B serial CTAs].
 //   scr      start of the scratch inside the caller's buffer (nullptr -> serial), scr_off its float offset (for info[3])
 //   ss       floats of recurrent state per (sequence, chunk)
 //   info     optional out: chunks, steps per chunk, warm-up steps, float index of the re-run counter
@@ -98,10 +97,11 @@ inline int chunk_launch(K k, int nthreads, size_t smem, int *occ_cache, GruArgs 
         a.sc_guess = scr; a.sc_end = scr + rows * ss;
         a.sc_loss = dir == 0 ? scr + 2 * rows * ss : nullptr;
         a.sc_fail = reinterpret_cast<int *>(scr + (dir == 0 ? rows * (2 * ss + 1) : rows * 2 * ss));
-        a.sc_count = a.sc_fail + 4;
         a.tol = dir == 0 ? SPEC_TOL_FWD : SPEC_TOL_BWD;
         a.mode = 0;
         k<<<a.B * a.C, nthreads, smem, st>>>(a);
+        a.mode = 2;
+        k<<<a.B, nthreads, smem, st>>>(a);
     } else {
         a.mode = 0;
         k<<<a.B, nthreads, smem, st>>>(a);
@@ -114,11 +114,10 @@ struct FwdRange {   // warm-up [t_lo, t_emit) from the zero state (nothing emitt
     int b, cc, t_lo, t_emit, t_hi;
     bool spec;
 };
-// mode 0: this CTA's chunk (or the whole sequence blockIdx.x when the launch is not chunked); mode 2: the whole sequence bseq
-__device__ __forceinline__ FwdRange fwd_range(const GruArgs &a, int mode, int bseq) {
+__device__ __forceinline__ FwdRange fwd_range(const GruArgs &a) {
     FwdRange r;
-    r.spec = (a.C > 1 && mode == 0);
-    r.b = mode == 2 ? bseq : blockIdx.x; r.cc = 0; r.t_lo = 0; r.t_emit = 0; r.t_hi = a.T;
+    r.spec = (a.C > 1 && a.mode == 0);
+    r.b = blockIdx.x; r.cc = 0; r.t_lo = 0; r.t_emit = 0; r.t_hi = a.T;
     if (r.spec) {
         r.b = blockIdx.x / a.C; r.cc = blockIdx.x - r.b * a.C;
         r.t_emit = r.cc * a.Lc; r.t_lo = max(0, r.t_emit - a.Wu); r.t_hi = min(a.T, r.t_emit + a.Lc);
@@ -129,10 +128,10 @@ struct BwdRange {   // reverse time: warm-up steps [t_ehi, t_hi) from a zero adj
     int b, cc, t_elo, t_ehi, t_hi;
     bool spec;
 };
-__device__ __forceinline__ BwdRange bwd_range(const GruArgs &a, int mode, int bseq) {
+__device__ __forceinline__ BwdRange bwd_range(const GruArgs &a) {
     BwdRange r;
-    r.spec = (a.C > 1 && mode == 0);
-    r.b = mode == 2 ? bseq : blockIdx.x; r.cc = 0; r.t_elo = 0; r.t_ehi = a.T; r.t_hi = a.T;
+    r.spec = (a.C > 1 && a.mode == 0);
+    r.b = blockIdx.x; r.cc = 0; r.t_elo = 0; r.t_ehi = a.T; r.t_hi = a.T;
     if (r.spec) {
         r.b = blockIdx.x / a.C; r.cc = blockIdx.x - r.b * a.C;
         r.t_elo = r.cc * a.Lc; r.t_ehi = min(a.T, r.t_elo + a.Lc); r.t_hi = min(a.T, r.t_ehi + a.Wu);
@@ -140,7 +139,7 @@ __device__ __forceinline__ BwdRange bwd_range(const GruArgs &a, int mode, int bs
     return r;
 }
 
-// Verify pass of the forward (run by the last chunk CTA of a sequence): the state chunk c was started from (after its warm-up) against the
+// Verify pass of the forward (mode 2, one CTA per sequence): the state chunk c was started from (after its warm-up) against the
 // state chunk c-1 ended with.  Returns true when every boundary of sequence b holds — the CTA then adds the sequence's squared
 // error to the loss and exits; false -> the caller recomputes the sequence serially.   State layout: ns vectors of HP floats
 // (stride ss), components >= H are padding.
@@ -153,7 +152,7 @@ __device__ __forceinline__ void chunk_note_ratio(const GruArgs &a, float ratio) 
 __device__ __forceinline__ bool chunk_boundary_ok(const GruArgs &a, const float *g, const float *e, int ss, int HP, int H) {
     float m = 0.f, dmax = 0.f;
     for (int k = 0; k < ss; ++k)
-        if (k % HP < H) { const float ev = __ldcg(e + k), gv = __ldcg(g + k); m = fmaxf(m, fabsf(ev)); dmax = fmaxf(dmax, fabsf(gv - ev)); }
+        if (k % HP < H) { m = fmaxf(m, fabsf(e[k])); dmax = fmaxf(dmax, fabsf(g[k] - e[k])); }
     const float lim = a.tol * m + 1e-37f;
     const bool ok = (dmax <= lim) && (m == m) && (dmax == dmax);
     chunk_note_ratio(a, dmax / lim);
@@ -172,7 +171,7 @@ __device__ __forceinline__ bool fwd_verify_pass(const GruArgs &a, int b, int ss,
     }
     if (threadIdx.x == 0 && a.loss && a.target) {
         float sl = 0.f;
-        for (int c1 = 0; c1 < a.C; ++c1) sl += __ldcg(a.sc_loss + (size_t)b * a.C + c1);
+        for (int c1 = 0; c1 < a.C; ++c1) sl += a.sc_loss[(size_t)b * a.C + c1];
         atomicAdd(a.loss, (double)sl * (double)a.loss_scale);
     }
     return true;
@@ -193,34 +192,6 @@ __device__ __forceinline__ bool bwd_verify_pass(const GruArgs &a, int b, int ss,
     return true;
 }
 
-// Tail of a chunk CTA.  Every chunk CTA of sequence b counts itself in arrivals[b] once all its global writes (and TMA bulk stores)
-// are complete; the CTA that completes the count owns the sequence's verify pass.  Returns true when this CTA must now re-run
-// sequence b serially (a chunk boundary failed); false when the CTA is done.
-__device__ __forceinline__ bool chunk_is_last_arrival(const GruArgs &a, int b) {
-    __shared__ int s_last;
-    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // this thread's bulk stores have been written, not just read
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const int old = atomicAdd(a.sc_count + b, 1);
-        s_last = (old == a.C - 1);
-        if (s_last) a.sc_count[b] = 0;                            // self-cleaning: the next launch starts from zero
-        __threadfence();
-    }
-    __syncthreads();
-    return s_last != 0;
-}
-__device__ __forceinline__ bool chunk_tail_fwd(const GruArgs &a, const FwdRange &R, int ss, int HP, int H) {
-    if (!R.spec) return false;
-    if (!chunk_is_last_arrival(a, R.b)) return false;
-    return !fwd_verify_pass(a, R.b, ss, HP, H);
-}
-__device__ __forceinline__ bool chunk_tail_bwd(const GruArgs &a, const BwdRange &R, int ss, int HP, int H) {
-    if (!R.spec) return false;
-    if (!chunk_is_last_arrival(a, R.b)) return false;
-    return !bwd_verify_pass(a, R.b, ss, HP, H);
-}
-
 // loss of one forward CTA: chunk CTAs park it for the verify pass, serial CTAs add it to the caller's accumulator
 __device__ __forceinline__ void chunk_store_loss(const GruArgs &a, bool spec, float lsum_warp_total) {
     if (spec) a.sc_loss[blockIdx.x] = lsum_warp_total;
@@ -229,9 +200,9 @@ __device__ __forceinline__ void chunk_store_loss(const GruArgs &a, bool spec, fl
 
 // gradient-partial row of one backward CTA: (sequence, chunk) when chunked, else the sequence's first row; the serial re-run of
 // the verify pass clears the sequence's other rows (call from the `nthr` threads that write partials, tid = 0..nthr-1)
-__device__ __forceinline__ float *chunk_partial_row(const GruArgs &a, bool spec, int mode, int b, int64_t P, int tid, int nthr) {
+__device__ __forceinline__ float *chunk_partial_row(const GruArgs &a, bool spec, int b, int64_t P, int tid, int nthr) {
     float *prt = a.partials + (size_t)(spec ? blockIdx.x : b * a.C) * P;
-    if (mode == 2)
+    if (a.mode == 2)
         for (int64_t i = tid; i < (int64_t)(a.C - 1) * P; i += nthr) prt[P + i] = 0.f;
     return prt;
 }

@@ -73,11 +73,10 @@ __global__ void __launch_bounds__(96, 1) gru_fwd_kernel(GruArgs a) {
     float *sact = sft + 3 * SM::FT;          // [2][CH][ROW]
     float *spo = sact + 2 * SM::ACT;         // [2][CH][33]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int mode = 0, bseq = blockIdx.x;
-    for (;;) {
-    const FwdRange R = fwd_range(a, mode, bseq);          // chunking.cuh: warm-up [t_lo, t_emit) from h = 0, emitted steps [t_emit, t_hi)
+    const FwdRange R = fwd_range(a);          // chunking.cuh: warm-up [t_lo, t_emit) from h = 0, emitted steps [t_emit, t_hi)
     const bool spec = R.spec;
     const int b = R.b, cc = R.cc, t_lo = R.t_lo, t_emit = R.t_emit, t_hi = R.t_hi;
+    if (a.mode == 2 && fwd_verify_pass(a, b, HP, HP, H)) return;   // every chunk boundary of this sequence holds
 
     stage_params(sp, a.params, L.P, bars);
     if (threadIdx.x < HP) zero[threadIdx.x] = 0.f;
@@ -359,9 +358,6 @@ __global__ void __launch_bounds__(96, 1) gru_fwd_kernel(GruArgs a) {
             if (lane == 0) chunk_store_loss(a, spec, lsum);
         }
     }
-    if (!chunk_tail_fwd(a, R, HP, HP, H)) break;   // done, unless this CTA is the sequence's last chunk and a boundary failed
-    mode = 2; bseq = R.b;                                   // ... then it re-runs the sequence serially
-    }
 }
 
 // ================================================================ backward
@@ -387,11 +383,10 @@ __global__ void __launch_bounds__(128, 1) gru_bwd_kernel(GruArgs a) {
     float *sG = sdp + 3 * SM::DH;            // [2][CH][4*HP]
     float *sdf = sG + 2 * SM::G;             // [CH][8]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int mode = 0, bseq = blockIdx.x;
-    for (;;) {
-    const BwdRange R = bwd_range(a, mode, bseq);          // chunking.cuh: warm-up [t_ehi, t_hi) from dL/dh = 0, emitted steps [t_elo, t_ehi)
+    const BwdRange R = bwd_range(a);          // chunking.cuh: warm-up [t_ehi, t_hi) from dL/dh = 0, emitted steps [t_elo, t_ehi)
     const bool spec = R.spec;
     const int b = R.b, t_elo = R.t_elo, t_ehi = R.t_ehi, t_hi = R.t_hi;
+    if (a.mode == 2 && bwd_verify_pass(a, b, HP, HP, H)) return;
 
     if (threadIdx.x == 0) { mbar_init(bars + 1, 1); mbar_init(bars + 2, 1); mbar_init(bars + 3, 1); }
     stage_params(sp, a.params, L.P, bars);   // contains the mbarrier-init fence + __syncthreads
@@ -695,7 +690,7 @@ __global__ void __launch_bounds__(128, 1) gru_bwd_kernel(GruArgs a) {
         }
         if constexpr (DW) {
             if (a.partials) {
-                float *prt = chunk_partial_row(a, spec, mode, b, L.P, (role - 2) * 32 + lane, 64);   // both post warps
+                float *prt = chunk_partial_row(a, spec, b, L.P, (role - 2) * 32 + lane, 64);   // both post warps
                 if (roleA) {
                     if (act) {
 #pragma unroll
@@ -732,9 +727,6 @@ __global__ void __launch_bounds__(128, 1) gru_bwd_kernel(GruArgs a) {
                 }
             }
         }
-    }
-    if (!chunk_tail_bwd(a, R, HP, HP, H)) break;   // done, unless this CTA is the sequence's last chunk and a boundary failed
-    mode = 2; bseq = R.b;                                   // ... then it re-runs the sequence serially
     }
 }
 

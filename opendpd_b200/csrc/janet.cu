@@ -60,11 +60,10 @@ __global__ void __launch_bounds__(96, 1) pgjanet_fwd_kernel(GruArgs a) {
     float *spo = sact + 2 * SM::ACT;
     float *sul = spo + 2 * SM::PO;           // [2][HP] u broadcast line
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int mode = 0, bseq = blockIdx.x;
-    for (;;) {
-    const FwdRange R = fwd_range(a, mode, bseq);          // chunking.cuh; recurrent state per chunk = h, HP floats
+    const FwdRange R = fwd_range(a);          // chunking.cuh; recurrent state per chunk = h, HP floats
     const bool spec = R.spec;
     const int b = R.b, t_emit = R.t_emit, t_hi = R.t_hi;
+    if (a.mode == 2 && fwd_verify_pass(a, b, HP, HP, H)) return;
     stage_params(sp, a.params, L.P, bars);
     if (threadIdx.x < HP) zero[threadIdx.x] = 0.f;
     __syncthreads();
@@ -167,9 +166,6 @@ __global__ void __launch_bounds__(96, 1) pgjanet_fwd_kernel(GruArgs a) {
             if (lane == 0) chunk_store_loss(a, spec, lsum);
         }
     }
-    if (!chunk_tail_fwd(a, R, HP, HP, H)) break;   // done, unless this CTA is the sequence's last chunk and a boundary failed
-    mode = 2; bseq = R.b;                                   // ... then it re-runs the sequence serially
-    }
 }
 
 template <int HT, bool DW>
@@ -189,11 +185,10 @@ __global__ void __launch_bounds__(96, 1) pgjanet_bwd_kernel(GruArgs a) {
     float *sdf = sG + 2 * SM::G;             // [CH][4]: ga gc gs
     float *sl = sdf + SM::DF;                // [2][2HP] chain broadcast lines for (af,ag) — also stored in sG; kept separate for double buffering
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int mode = 0, bseq = blockIdx.x;
-    for (;;) {
-    const BwdRange R = bwd_range(a, mode, bseq);          // chunking.cuh; adjoint state per chunk: HP floats
+    const BwdRange R = bwd_range(a);          // chunking.cuh; adjoint state per chunk: HP floats
     const bool spec = R.spec;
     const int b = R.b, t_ehi = R.t_ehi, t_hi = R.t_hi;
+    if (a.mode == 2 && bwd_verify_pass(a, b, HP, HP, H)) return;
     if (threadIdx.x == 0) { mbar_init(bars + 1, 1); mbar_init(bars + 2, 1); mbar_init(bars + 3, 1); }
     stage_params(sp, a.params, L.P, bars);
     const bool act = lane < H;
@@ -360,7 +355,7 @@ __global__ void __launch_bounds__(96, 1) pgjanet_bwd_kernel(GruArgs a) {
         }
         if constexpr (DW) {
             if (a.partials) {
-                float *prt = chunk_partial_row(a, spec, mode, b, L.P, lane, 32);
+                float *prt = chunk_partial_row(a, spec, b, L.P, lane, 32);
                 if (act) {
 #pragma unroll
                     for (int k = 0; k < HT; ++k)
@@ -377,9 +372,6 @@ __global__ void __launch_bounds__(96, 1) pgjanet_bwd_kernel(GruArgs a) {
                 if (lane == 0) { prt[L.obo] = gbo0; prt[L.obo + 1] = gbo1; }
             }
         }
-    }
-    if (!chunk_tail_bwd(a, R, HP, HP, H)) break;   // done, unless this CTA is the sequence's last chunk and a boundary failed
-    mode = 2; bseq = R.b;                                   // ... then it re-runs the sequence serially
     }
 }
 
@@ -421,11 +413,10 @@ __global__ void __launch_bounds__(96, 1) dvrjanet_fwd_kernel(GruArgs a) {
     float *spo = sact + 2 * SM::ACT;
     float *sln = spo + 2 * SM::PO;           // [2][3HP]: s | a~cos | a~sin lines
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int mode = 0, bseq = blockIdx.x;
-    for (;;) {
-    const FwdRange R = fwd_range(a, mode, bseq);          // chunking.cuh; recurrent state per chunk = (h_I, h_Q), 2*HP floats
+    const FwdRange R = fwd_range(a);          // chunking.cuh; recurrent state per chunk = (h_I, h_Q), 2*HP floats
     const bool spec = R.spec;
     const int b = R.b, t_emit = R.t_emit, t_hi = R.t_hi;
+    if (a.mode == 2 && fwd_verify_pass(a, b, 2 * HP, HP, H)) return;
     stage_params(sp, a.params, L.P, bars);
     for (int i = threadIdx.x; i < ROW; i += blockDim.x) zero[i] = 0.f;
     __syncthreads();
@@ -550,9 +541,6 @@ __global__ void __launch_bounds__(96, 1) dvrjanet_fwd_kernel(GruArgs a) {
             if (lane == 0) chunk_store_loss(a, spec, lsum);
         }
     }
-    if (!chunk_tail_fwd(a, R, 2 * HP, HP, H)) break;   // done, unless this CTA is the sequence's last chunk and a boundary failed
-    mode = 2; bseq = R.b;                                   // ... then it re-runs the sequence serially
-    }
 }
 
 template <int HT, bool DW>
@@ -571,11 +559,10 @@ __global__ void __launch_bounds__(96, 1) dvrjanet_bwd_kernel(GruArgs a) {
     float *sG = sdh + 2 * SM::DH;            // [2][CH][6HP]: ac | as | af | gtht | gpa | gat
     float *sdf = sG + 2 * SM::G;             // [CH][2]: gth, ga
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int mode = 0, bseq = blockIdx.x;
-    for (;;) {
-    const BwdRange R = bwd_range(a, mode, bseq);          // chunking.cuh; adjoint state per chunk: 2 * HP floats
+    const BwdRange R = bwd_range(a);          // chunking.cuh; adjoint state per chunk: 2 * HP floats
     const bool spec = R.spec;
     const int b = R.b, t_ehi = R.t_ehi, t_hi = R.t_hi;
+    if (a.mode == 2 && bwd_verify_pass(a, b, 2 * HP, HP, H)) return;
     if (threadIdx.x == 0) { mbar_init(bars + 1, 1); mbar_init(bars + 2, 1); mbar_init(bars + 3, 1); }
     stage_params(sp, a.params, L.P, bars);
     const bool act = lane < H;
@@ -757,7 +744,7 @@ __global__ void __launch_bounds__(96, 1) dvrjanet_bwd_kernel(GruArgs a) {
         }
         if constexpr (DW) {
             if (a.partials) {
-                float *prt = chunk_partial_row(a, spec, mode, b, L.P, lane, 32);
+                float *prt = chunk_partial_row(a, spec, b, L.P, lane, 32);
                 if (act) {
 #pragma unroll
                     for (int k = 0; k < HT; ++k)
@@ -778,9 +765,6 @@ __global__ void __launch_bounds__(96, 1) dvrjanet_bwd_kernel(GruArgs a) {
                 if (lane == 0) { prt[L.obo1] = gbo0; prt[L.obo2] = gbo1; }
             }
         }
-    }
-    if (!chunk_tail_bwd(a, R, 2 * HP, HP, H)) break;   // done, unless this CTA is the sequence's last chunk and a boundary failed
-    mode = 2; bseq = R.b;                                   // ... then it re-runs the sequence serially
     }
 }
 

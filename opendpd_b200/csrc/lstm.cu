@@ -44,11 +44,10 @@ __global__ void __launch_bounds__(96, 1) lstm_fwd_kernel(GruArgs a) {
     float *sact = sxp + 2 * SM::XP;          // [2][CH][ROW]
     float *spo = sact + 2 * SM::ACT;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int mode = 0, bseq = blockIdx.x;
-    for (;;) {
-    const FwdRange R = fwd_range(a, mode, bseq);          // chunking.cuh; recurrent state per chunk = (c, h), 2*HP floats
+    const FwdRange R = fwd_range(a);          // chunking.cuh; recurrent state per chunk = (c, h), 2*HP floats
     const bool spec = R.spec;
     const int b = R.b, t_emit = R.t_emit, t_hi = R.t_hi;
+    if (a.mode == 2 && fwd_verify_pass(a, b, 2 * HP, HP, H)) return;
     stage_params(sp, a.params, L.P, bars);
     for (int i = threadIdx.x; i < ROW; i += blockDim.x) zero[i] = 0.f;
     __syncthreads();
@@ -159,9 +158,6 @@ __global__ void __launch_bounds__(96, 1) lstm_fwd_kernel(GruArgs a) {
             if (lane == 0) chunk_store_loss(a, spec, lsum);
         }
     }
-    if (!chunk_tail_fwd(a, R, 2 * HP, HP, H)) break;   // done, unless this CTA is the sequence's last chunk and a boundary failed
-    mode = 2; bseq = R.b;                                   // ... then it re-runs the sequence serially
-    }
 }
 
 template <int HT, bool DW>
@@ -180,11 +176,10 @@ __global__ void __launch_bounds__(96, 1) lstm_bwd_kernel(GruArgs a) {
     float *sG = sdh + 2 * SM::DH;            // [2][CH][4HP]: di df dg do
     float *sdf = sG + 2 * SM::G;             // [CH][2]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int mode = 0, bseq = blockIdx.x;
-    for (;;) {
-    const BwdRange R = bwd_range(a, mode, bseq);          // chunking.cuh; adjoint state per chunk = (dL/dh, dL/dc), 2*HP floats
+    const BwdRange R = bwd_range(a);          // chunking.cuh; adjoint state per chunk = (dL/dh, dL/dc), 2*HP floats
     const bool spec = R.spec;
     const int b = R.b, t_ehi = R.t_ehi, t_hi = R.t_hi;
+    if (a.mode == 2 && bwd_verify_pass(a, b, 2 * HP, HP, H)) return;
     if (threadIdx.x == 0) { mbar_init(bars + 1, 1); mbar_init(bars + 2, 1); mbar_init(bars + 3, 1); }
     stage_params(sp, a.params, L.P, bars);
     const bool act = lane < H;
@@ -343,7 +338,7 @@ __global__ void __launch_bounds__(96, 1) lstm_bwd_kernel(GruArgs a) {
         }
         if constexpr (DW) {
             if (a.partials) {
-                float *prt = chunk_partial_row(a, spec, mode, b, L.P, lane, 32);
+                float *prt = chunk_partial_row(a, spec, b, L.P, lane, 32);
                 if (act) {
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
@@ -361,9 +356,6 @@ __global__ void __launch_bounds__(96, 1) lstm_bwd_kernel(GruArgs a) {
                 if (lane == 0) { prt[L.obo] = gbo0; prt[L.obo + 1] = gbo1; }
             }
         }
-    }
-    if (!chunk_tail_bwd(a, R, 2 * HP, HP, H)) break;   // done, unless this CTA is the sequence's last chunk and a boundary failed
-    mode = 2; bseq = R.b;                                   // ... then it re-runs the sequence serially
     }
 }
 

@@ -113,7 +113,7 @@ def backbone_forward_raw(spec, x, flat, target=None, loss_scale=0.0, save=True, 
             saved = torch.empty(max(int(nbytes) // 4, 1), dtype=torch.float32, device=x.device)
             idx = spec.chunk_plan(B, T, False, save)[3]
             if idx >= 0:
-                saved[idx:].zero_()                      # re-run counter, worst boundary mismatch, per-sequence arrival counters
+                saved[idx:idx + 2].zero_()               # re-run counter + worst boundary mismatch of the verify pass
         loss = torch.empty(1, dtype=torch.float64, device=x.device) if target is not None else None
         if bufs is not None:
             bufs.update(key=key, out=out, saved=saved, loss=loss)
@@ -141,7 +141,7 @@ def backbone_backward_raw(spec, x, flat, saved, need_dx, need_dw, gout=None, out
         ws = torch.empty(int(L.odpd_bwd_workspace_bytes(ctypes.byref(d))) // 4, dtype=torch.float32, device=x.device)
         idx = spec.chunk_plan(B, T, True, True, need_dw)[3]
         if idx >= 0:
-            ws[idx:].zero_()                             # re-run counter, worst boundary mismatch, per-sequence arrival counters
+            ws[idx:idx + 2].zero_()                      # re-run counter + worst boundary mismatch of the verify pass
         if bufs is not None:
             bufs.update(key=key, gx=gx, ws=ws)
     if need_dw and gflat is None:
