@@ -436,7 +436,7 @@ def main():
             "kernel_ms": {"fwd": fwd_ms, "bwd": bwd_ms},
             "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                         "traffic": ({"odpd::gru_fwd_kernel": 2134016 + 1209088, "odpd::gru_bwd_kernel": 53543680 + 28928}.get(dom[0])
+                         "traffic": ({"odpd::gru_fwd_kernel": 2132992 + 974592, "odpd::gru_bwd_kernel": 53541632 + 50688}.get(dom[0])
                                      if args.workload == "c2a" else None),
                          "traffic_source": "profiles/r1_chunked_gru_ncu_summary.txt (ncu --set full of the chunked kernels, dram__bytes_read+write per launch; the "
                                            "backward re-reads the saved activation rows from DRAM only under ncu's cache-flushed replay: live they sit in the 126 MB L2)",
