@@ -4,7 +4,7 @@
  * This is the drop-in boundary for ONE hot path of lab-emi/OpenDPD: the backbone forward/backward (+ I/Q MSE)
  * that `net_train` executes per step (reference: modules/train_funcs.py:28-48 -> models.py:150-176 ->
  * backbones/<name>.py forward).  The reference has no FFI of its own (it is pure PyTorch); the entry points
- * below are what a ctypes/cffi binding added to the reference's backbones/*.py would call — one call replaces
+ * below are what a ctypes/cffi binding added to the reference's backbones/<name>.py would call — one call replaces
  * one `Backbone.forward` (or its autograd backward).  INTEGRATION.md shows that binding.
  *
  * Conventions
@@ -56,7 +56,7 @@ enum {
     ODPD_CELL_GMP = 7,       /* backbones/gmp.py:18-51 */
     ODPD_CELL_QGRU = 8,      /* backbones/qgru.py:59-71 */
     ODPD_CELL_QGRU_AMP1 = 9, /* backbones/qgru_amp1.py:59-76 */
-    ODPD_CELL_QGRU_QAT = 10, /* qgru.py under --quant: quant/modules/gru.py:32-124 + quant/qmodules/* (fake-quant QAT) */
+    ODPD_CELL_QGRU_QAT = 10, /* qgru.py under --quant: quant/modules/gru.py:32-124 + quant/qmodules (fake-quant QAT) */
     ODPD_CELL_QGRU_AMP1_QAT = 11, /* qgru_amp1.py under --quant */
     ODPD_CELL_COUNT = 12
 };

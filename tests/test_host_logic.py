@@ -77,3 +77,51 @@ def test_unsupported_configs_raise():
         models.CoreModel(2, 8, 2, "gru")            # num_layers=2
     with pytest.raises(ValueError):
         models.CoreModel(2, 8, 1, "rvtdcnn")         # out of the hot-path scope
+
+
+def test_dims_struct_matches_the_header_layout():
+    """ctypes mirror of `OdpdDims` (include/odpd.h): ten 4-byte fields then two 8-byte device pointers, and a C compiler agrees."""
+    import subprocess, tempfile
+    assert ctypes.sizeof(_ffi.OdpdDims) == 56
+    assert _ffi.OdpdDims.x_starts.offset == 40 and _ffi.OdpdDims.target_starts.offset == 48
+    src = ('#include <stdio.h>\n#include <stddef.h>\n#include "odpd.h"\nint main(void){printf("%zu %zu %zu %zu\\n", sizeof(OdpdDims), '
+           'offsetof(OdpdDims, tchunks), offsetof(OdpdDims, x_starts), offsetof(OdpdDims, target_starts)); return 0;}\n')
+    with tempfile.TemporaryDirectory() as td:
+        c = os.path.join(td, "t.c")
+        open(c, "w").write(src)
+        exe = os.path.join(td, "t")
+        subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), c, "-o", exe])   # the header is plain C
+        out = subprocess.check_output([exe]).decode().split()
+    assert out == ["56", "32", "40", "48"], out
+
+
+def test_iq_stream_is_the_reference_framing():
+    """functional.IqStream(stream, starts, T).frames() == the stride-1 windows IQFrameDataset materialises
+    (modules/data_collector.py:233-252: frame k = rows [k, k+T) of the stream)."""
+    from opendpd_b200.functional import IqStream
+    g = torch.Generator().manual_seed(0)
+    stream = torch.randn(500, 2, generator=g)
+    T = 37
+    ref = torch.stack([stream[k:k + T] for k in range(500 - T + 1)])      # IQFrameDataset.__init__ (stride 1)
+    starts = torch.tensor([0, 5, 463, 17, 17], dtype=torch.int32)
+    v = IqStream(stream, starts, T)
+    assert v.shape == (5, T, 2) and torch.equal(v.frames(), ref[starts.long()])
+    with pytest.raises(_ffi.OdpdError):
+        IqStream(stream, starts.long(), T)                                # indices must be int32
+    with pytest.raises(_ffi.OdpdError):
+        IqStream(stream.t(), starts, T)                                   # (N,2) contiguous
+
+
+def test_cell_spec_chunk_policy_from_arguments_and_environment(monkeypatch):
+    from opendpd_b200.functional import CellSpec
+    monkeypatch.delenv("ODPD_TCHUNKS", raising=False); monkeypatch.delenv("ODPD_TWARM", raising=False)
+    s = CellSpec("dgru", 13)
+    assert s.tchunks == (0, 0) and s.twarm == (0, 0)
+    d = s.dims(64, 2048, 0, backward=True)
+    assert (d.tchunks, d.twarm, d.x_starts, d.target_starts) == (0, 0, None, None)
+    s = CellSpec("dgru", 13, tchunks=(8, 4), twarm=(64, 128))
+    assert s.dims(64, 2048, 0).tchunks == 8 and s.dims(64, 2048, 0, backward=True).tchunks == 4
+    assert s.dims(64, 2048, 0).twarm == 64 and s.dims(64, 2048, 0, backward=True).twarm == 128
+    monkeypatch.setenv("ODPD_TCHUNKS", "1"); monkeypatch.setenv("ODPD_TCHUNKS_BWD", "2"); monkeypatch.setenv("ODPD_TWARM", "96")
+    s = CellSpec("lstm", 9)
+    assert s.tchunks == (1, 2) and s.twarm == (96, 96)
