@@ -187,6 +187,19 @@ int odpd_dp_clip_adamw(float *param, void *const *bufs, int world, int rank, int
                        float *exp_avg, float *exp_avg_sq, const float *lr_dev, float beta1, float beta2, float eps, float weight_decay,
                        float max_norm, int64_t *step_dev, float *gnorm_out, float *loss_out, int *status_dev, void *stream);
 
+/*
+ * Evaluation metrics (reference: utils/metrics.py, driven by modules/train_funcs.py:93-105).
+ *   odpd_nmse_sums      out[2*s] = sum_n |truth - pred|^2, out[2*s+1] = sum_n |truth|^2 over row s of the (S,N,2) tensors
+ *                       (NMSE = mean_s 10 log10(out[2s]/out[2s+1]), utils/metrics.py:42-53).
+ *   odpd_dft_magnitude  out[s][g][i] (double, fftshift-ed bin order) = |DFT_nfft of segment g of row s of (a - b)|, b may be NULL;
+ *                       segment g = samples g*hop .. g*hop+nfft-1 (zero beyond N: np.fft.fft(x, n) semantics, utils/metrics.py:30),
+ *                       optionally with the segment mean removed (`detrend`) and a periodic Hann window (`hann`) — the pieces of
+ *                       scipy.signal.welch the reference's power_spectrum uses (utils/metrics.py:158-190).  nfft <= 6144.
+ */
+int odpd_nmse_sums(const float *pred, const float *truth, int32_t S, int32_t N, double *out, void *stream);
+int odpd_dft_magnitude(const float *a, const float *b, int32_t S, int32_t N, int32_t nfft, int32_t nseg, int32_t hop, int32_t hann,
+                       int32_t detrend, double *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

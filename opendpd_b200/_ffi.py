@@ -39,6 +39,8 @@ SYMBOLS = {
     "odpd_backbone_bwd": (ctypes.c_int, [_DP, _vp, _vp, _vp, _vp, _vp, _vp, _dbl, _vp, _vp, _vp, _vp, _vp]),
     "odpd_clip_adamw": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _flt, _flt, _flt, _flt, _flt, _vp, _vp,
                                        ctypes.c_int, _vp]),
+    "odpd_nmse_sums": (ctypes.c_int, [_vp, _vp, _i32, _i32, _vp, _vp]),
+    "odpd_dft_magnitude": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "odpd_dp_buffer_bytes": (_i64, [_i64]),
     "odpd_dp_alloc": (ctypes.c_int, [_i64, ctypes.POINTER(_vp)]),
     "odpd_dp_free": (ctypes.c_int, [_vp]),
