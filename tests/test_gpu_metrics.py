@@ -5,7 +5,7 @@ import torch
 
 from tests.test_metrics_oracle import CASES, load
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.filterwarnings("ignore:Mean of empty slice"), pytest.mark.filterwarnings("ignore:invalid value encountered")]
 TOL_DB = 1e-4          # dB; the reference itself works in float32 / complex64
 
 
