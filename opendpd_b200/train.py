@@ -61,6 +61,27 @@ def net_eval(log, net, dataloader, criterion, device):
     return net, torch.cat(prediction, dim=0).numpy(), torch.cat(ground_truth, dim=0).numpy()
 
 
+def warmup_policy(st, wu, failed, ratio):
+    """One decision of the chunk controller for one (backbone, direction).  `st` carries `clean` (consecutive clean checks), `floor`
+    (shortest warm-up still allowed) and `base` (the cell's default); `wu` is the warm-up in use, `failed` whether the verify pass had
+    to re-run sequences since the last check, `ratio` the worst boundary mismatch in units of the tolerance.  Returns the new
+    warm-up, or None to keep the current one.  (Pure: tests/test_host_logic.py drives it without a GPU.)
+      grow   x2 after a failure, or — below the default — when the mismatch exceeds half the tolerance (and never shrink below it again)
+      shrink /2 after three consecutive checks under a quarter of the tolerance, not below `floor`"""
+    if failed or (ratio > 0.5 and wu < st["base"]):
+        st["clean"] = 0
+        st["floor"] = max(st["floor"], 2 * wu)
+        return 2 * wu
+    if ratio < 0.25:
+        st["clean"] += 1
+        if st["clean"] >= 3 and wu // 2 >= st["floor"]:
+            st["clean"] = 0
+            return wu // 2
+        return None
+    st["clean"] = 0
+    return None
+
+
 class NativeTrainStep:
     """One fused train step for a CoreModel (train_pa, steps/train_pa.py:24-29) or a CascadedModel with frozen PA
     (train_dpd, steps/train_dpd.py:60-63).
@@ -234,22 +255,13 @@ class NativeTrainStep:
                                                                   clean=0, floor=64, base=plan[2], rebase=False))
             if st["ptr"] != buf.data_ptr():                       # buffer re-allocated (shape or chunk count changed): counters restart
                 st.update(ptr=buf.data_ptr(), ev=None, seen=0, rebase=False)
-            new = None
+            new, failed = None, False
             if st["ev"] is not None:
                 st["ev"].synchronize()                            # copy enqueued a whole check interval ago
                 cnt, ratio = int(st["pin"][0]), float(st["pin"][1:2].view(torch.float32)[0])
                 failed = cnt > st["seen"] and not st["rebase"]    # re-runs counted before the last plan change do not count
                 st["seen"], st["rebase"] = cnt, False
-                wu = plan[2]
-                if failed or (ratio > 0.5 and wu < st["base"]):
-                    new = 2 * wu
-                    st["floor"] = max(st["floor"], new)
-                elif ratio < 0.25:
-                    st["clean"] += 1
-                    if st["clean"] >= 3 and wu // 2 >= st["floor"]:
-                        new = wu // 2
-                else:
-                    st["clean"] = 0
+                new = warmup_policy(st, plan[2], failed, ratio)
             if new is not None:
                 st["clean"] = 0
                 self._graphs.clear()                              # captured launches carry the old plan
@@ -271,9 +283,9 @@ class NativeTrainStep:
             st["ev"].record()
 
     def step_host(self, features_cpu, targets_cpu):
-        if self._stage is None or self._stage[0].shape != features_cpu.shape:
-            self._stage = (torch.empty(features_cpu.shape, dtype=torch.float32, device=self.device),
-                           torch.empty(targets_cpu.shape, dtype=torch.float32, device=self.device))
+        if self._stage is None or self._stage[0].shape != features_cpu.shape or self._stage[0].dtype != features_cpu.dtype:
+            self._stage = (torch.empty(features_cpu.shape, dtype=features_cpu.dtype, device=self.device),     # fp32 or bf16 storage
+                           torch.empty(targets_cpu.shape, dtype=targets_cpu.dtype, device=self.device))
         fx, fy = self._stage
         fx.copy_(features_cpu, non_blocking=True)
         fy.copy_(targets_cpu, non_blocking=True)
@@ -293,10 +305,10 @@ class NativeTrainStep:
         nxt = next(it, None)
         if nxt is None:
             return []
-        shp = (tuple(nxt[0].shape), tuple(nxt[1].shape))
+        shp = (tuple(nxt[0].shape), tuple(nxt[1].shape), nxt[0].dtype, nxt[1].dtype)
         if self._pipe is None or self._pipe["shape"] != shp:
-            mk = lambda s: torch.empty(s, dtype=torch.float32, device=self.device)
-            self._pipe = dict(shape=shp, stage=[(mk(shp[0]), mk(shp[1])) for _ in range(2)],
+            mk = lambda s, dt: torch.empty(s, dtype=dt, device=self.device)
+            self._pipe = dict(shape=shp, stage=[(mk(shp[0], shp[2]), mk(shp[1], shp[3])) for _ in range(2)],
                               loss=[torch.zeros(1, dtype=torch.float64).pin_memory() for _ in range(2)],
                               ev_copy=[torch.cuda.Event() for _ in range(2)], ev_free=[torch.cuda.Event() for _ in range(2)],
                               ev_loss=[torch.cuda.Event() for _ in range(2)])

@@ -125,3 +125,23 @@ def test_cell_spec_chunk_policy_from_arguments_and_environment(monkeypatch):
     monkeypatch.setenv("ODPD_TCHUNKS", "1"); monkeypatch.setenv("ODPD_TCHUNKS_BWD", "2"); monkeypatch.setenv("ODPD_TWARM", "96")
     s = CellSpec("lstm", 9)
     assert s.tchunks == (1, 2) and s.twarm == (96, 96)
+
+
+def test_warmup_policy_of_the_chunk_controller():
+    """train.warmup_policy: shrink after three clean checks (never below the floor), grow on failures / near-failures, remember
+    a length that failed."""
+    from opendpd_b200.train import warmup_policy
+    st = dict(clean=0, floor=64, base=128)
+    assert warmup_policy(st, 128, False, 0.1) is None and warmup_policy(st, 128, False, 0.2) is None
+    assert warmup_policy(st, 128, False, 0.1) == 64 and st["clean"] == 0          # third clean check: halve
+    for _ in range(5):
+        assert warmup_policy(st, 64, False, 0.05) is None                          # 32 < floor 64: stays
+    assert warmup_policy(st, 64, False, 0.3) is None and st["clean"] == 0          # between the thresholds: no change, streak reset
+    assert warmup_policy(st, 64, False, 0.6) == 128 and st["floor"] == 128         # below the default and > tol/2: grow proactively
+    st = dict(clean=2, floor=64, base=128)
+    assert warmup_policy(st, 128, True, 0.1) == 256 and st["floor"] == 256 and st["clean"] == 0      # a failed boundary: double, remember
+    assert warmup_policy(st, 256, False, 0.9) is None                              # at/above the default only real failures grow it
+    st = dict(clean=0, floor=64, base=256)
+    for _ in range(2):
+        assert warmup_policy(st, 256, False, 0.0) is None
+    assert warmup_policy(st, 256, False, 0.0) == 128
