@@ -91,14 +91,14 @@ def forward(kind, x, flat, H, K=3, thx=0.0, thh=0.0):
     if kind in ("gru", "qgru", "qgru_amp1", "dgru"):
         f = _feat(kind, x)
         h0 = x.new_zeros(1, B, H)
-        hseq, _ = torch._VF.gru(f, h0, [p["w_ih"], p["w_hh"], p["b_ih"], p["b_hh"]], True, 1, 0.0, False, False, True)
+        hseq, _ = torch._VF.gru(f, h0, [p["w_ih"], p["w_hh"], p["b_ih"], p["b_hh"]], True, 1, 0.0, x.is_cuda, False, True)   # train flag: cuDNN's backward needs it (dropout is 0: same arithmetic)
         if kind == "dgru":
             g = torch.relu(Fn.linear(hseq, p["wh"], p["bh"]))
             return Fn.linear(torch.cat((g, f), -1), p["wo"], p["bo"])
         return Fn.linear(hseq, p["wo"], p["bo"])
     if kind == "lstm":
         h0 = x.new_zeros(1, B, H)
-        hseq, _, _ = torch._VF.lstm(x, (h0, h0), [p["w_ih"], p["w_hh"], p["b_ih"], p["b_hh"]], True, 1, 0.0, False, False, True)
+        hseq, _, _ = torch._VF.lstm(x, (h0, h0), [p["w_ih"], p["w_hh"], p["b_ih"], p["b_hh"]], True, 1, 0.0, x.is_cuda, False, True)
         return Fn.linear(hseq, p["wo"], p["bo"])
     if kind == "deltagru":
         hseq = _delta_layer(_feat("dgru", x), p, H, thx, thh, True)
