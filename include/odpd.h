@@ -104,6 +104,10 @@ typedef struct OdpdDims {
  *   GMP and the QAT cell always run serially.
  */
 int odpd_chunk_plan(const OdpdDims *d, int32_t backward, int32_t out[4]);
+/* The planner behind odpd_chunk_plan as a pure host function (no CUDA call; unit-testable without a GPU): the plan for B sequences
+ * of T steps when the device holds `slots` CTAs of the kernel at once, tchunks / twarm as in OdpdDims, default_warm = the cell's
+ * default warm-up.  out[0] chunks, out[1] steps per chunk, out[2] warm-up steps. */
+int odpd_chunk_plan_model(int32_t B, int32_t T, int32_t tchunks, int32_t twarm, int32_t slots, int32_t default_warm, int32_t out[3]);
 
 int odpd_version(void);
 const char *odpd_last_error(void);

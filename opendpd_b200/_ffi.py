@@ -35,6 +35,7 @@ SYMBOLS = {
     "odpd_saved_bytes": (_i64, [_DP]),
     "odpd_bwd_workspace_bytes": (_i64, [_DP]),
     "odpd_chunk_plan": (ctypes.c_int, [_DP, _i32, ctypes.POINTER(_i32)]),
+    "odpd_chunk_plan_model": (ctypes.c_int, [_i32, _i32, _i32, _i32, _i32, _i32, ctypes.POINTER(_i32)]),
     "odpd_backbone_fwd": (ctypes.c_int, [_DP, _vp, _vp, _vp, _vp, _vp, _dbl, _vp, _vp, _vp]),
     "odpd_backbone_bwd": (ctypes.c_int, [_DP, _vp, _vp, _vp, _vp, _vp, _vp, _dbl, _vp, _vp, _vp, _vp, _vp]),
     "odpd_clip_adamw": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _flt, _flt, _flt, _flt, _flt, _vp, _vp,

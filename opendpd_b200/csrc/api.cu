@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include "cells.h"
+#include "chunking.cuh"
 
 namespace odpd {
 
@@ -210,6 +211,15 @@ int odpd_backbone_bwd(const OdpdDims *d, const float *x, const float *params, co
     }
     if (rc) return rc;
     if (dw) return reduce_partials((const float *)workspace, rows, P, gparams, (d->flags & ODPD_F_OVERWRITE_DW) != 0, st);
+    return 0;
+}
+
+int odpd_chunk_plan_model(int32_t B, int32_t T, int32_t tchunks, int32_t twarm, int32_t slots, int32_t default_warm, int32_t out[3]) {
+    ODPD_CHECK(out != nullptr && B >= 0 && T >= 0, "odpd_chunk_plan_model: bad arguments");
+    GruArgs a{};
+    a.B = B; a.T = T; a.tchunks_req = tchunks; a.twarm_req = twarm; a.twarm_default = default_warm;
+    chunk_make_plan(a, slots, true);
+    out[0] = a.C; out[1] = a.Lc; out[2] = a.Wu;
     return 0;
 }
 

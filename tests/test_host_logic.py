@@ -145,3 +145,44 @@ def test_warmup_policy_of_the_chunk_controller():
     for _ in range(2):
         assert warmup_policy(st, 256, False, 0.0) is None
     assert warmup_policy(st, 256, False, 0.0) == 128
+
+
+def _plan(B, T, tchunks=0, twarm=0, slots=592, default_warm=128):
+    out = (ctypes.c_int32 * 3)()
+    assert _ffi.lib().odpd_chunk_plan_model(B, T, tchunks, twarm, slots, default_warm, out) == 0
+    return tuple(out)
+
+
+def test_chunk_planner_headline_plans():
+    """csrc/chunking.cuh chunk_make_plan through its host-only entry point (no GPU needed)."""
+    assert _plan(64, 2048, slots=592) == (8, 256, 128)              # C2a forward: 4 CTAs/SM x 148
+    assert _plan(64, 2048, slots=296) == (4, 512, 128)              # C2a backward: 2 CTAs/SM
+    assert _plan(64, 2048, twarm=64, slots=296) == (4, 512, 64)
+    assert _plan(64, 2048, tchunks=1) == (1, 2048, 0)               # serial on request
+    assert _plan(256, 2048, slots=296) == (1, 2048, 0)              # C3's PA: the sequences alone fill the device
+    assert _plan(8, 1024, slots=592) == (8, 128, 128)               # C1
+    assert _plan(128, 4096, slots=592, default_warm=256) == (4, 1024, 256)
+    assert _plan(3, 19662, slots=592)[0] >= 16                      # net_eval's long segments
+    assert _plan(64, 40) == (1, 40, 0)                              # too short to cut
+    assert _plan(4, 512, tchunks=4, twarm=64) == (4, 128, 64)
+
+
+def test_chunk_planner_invariants():
+    """Every plan: chunks of whole 32-step blocks that tile [0,T) with no empty chunk, warm-up a multiple of 32, and (auto mode) never
+    more CTAs than 2048 rows of scratch, never a warm-up longer than the chunk, never slower than serial under the planner's own cost model."""
+    rng = np.random.default_rng(0)
+    for _ in range(400):
+        B = int(rng.integers(1, 600)); T = int(rng.integers(1, 20000)); slots = int(rng.integers(1, 1300))
+        req = int(rng.choice([0, 0, 0, 1, 2, 3, 5, 8, 16, 32, 40])); tw = int(rng.choice([0, 0, 32, 50, 64, 128, 256]))
+        C, Lc, Wu = _plan(B, T, req, tw, slots)
+        assert C >= 1
+        if C == 1:
+            assert (Lc, Wu) == (T, 0)
+            continue
+        assert Lc % 32 == 0 and Wu % 32 == 0 and Wu > 0 and (C - 1) * Lc < T <= C * Lc
+        if req > 1:
+            assert C <= min(req, 32)
+        if req == 0:
+            assert Lc >= Wu and B * C <= 2048
+            waves = -(-B * C // min(slots, 2048))
+            assert waves * (Lc + Wu) < -(-B // min(slots, 2048)) * T
