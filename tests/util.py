@@ -9,7 +9,7 @@ def golden_cases(kinds=None):
     out = []
     for f in sorted(glob.glob(os.path.join(GOLDEN, "*.npz"))):
         name = os.path.basename(f)[:-4]
-        if name.startswith("metrics_"):          # evaluation-metric goldens: tests/test_metrics_oracle.py
+        if name.startswith(("metrics_", "next_")):   # evaluation-metric goldens (tests/test_metrics_oracle.py); cells without a CUDA path yet
             continue
         if kinds is None or any(name.startswith(k) for k in kinds):
             out.append(name)
