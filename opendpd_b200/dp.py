@@ -29,6 +29,13 @@ def gather_frames(stream, starts, frame_length):
     return stream[idx]
 
 
+def frame_starts(indices, device):
+    """This rank's frame indices (shard_batch_indices) as the device int32 vector `NativeTrainStep.step_indexed` /
+    `OdpdDims.x_starts` take: with stride-1 framing (data_collector.py:240-247) frame k starts at sample k, so the indices ARE the
+    start offsets into the raw stream that every rank keeps resident — only these B/N integers differ between ranks and steps."""
+    return torch.as_tensor(indices, dtype=torch.int32).to(device).contiguous()
+
+
 def allreduce_flat_(buf, group=None):
     """SUM all-reduce of the flat [grad | loss] buffer (2-14 KB) — NCCL over NVLink on GPUs, gloo in the CPU tests."""
     if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size(group) > 1:

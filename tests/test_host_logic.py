@@ -186,3 +186,21 @@ def test_chunk_planner_invariants():
             assert Lc >= Wu and B * C <= 2048
             waves = -(-B * C // min(slots, 2048))
             assert waves * (Lc + Wu) < -(-B // min(slots, 2048)) * T
+
+
+def test_sharded_frame_starts_tile_the_reference_batch():
+    """dp.shard_batch_indices + dp.frame_starts: the ranks' start vectors concatenate to the single-process batch of the same seeded
+    permutation, and IqStream on them reproduces IQFrameDataset's frames (CPU tensors: framing logic only)."""
+    from opendpd_b200 import dp
+    from opendpd_b200.functional import IqStream
+    g = torch.Generator().manual_seed(1)
+    stream = torch.randn(700, 2, generator=g)
+    T, B, world = 64, 10, 3
+    perm = dp.epoch_permutation(700 - T + 1, seed=0)
+    for step in (0, 1, 63):
+        parts = [dp.frame_starts(dp.shard_batch_indices(perm, step, B, r, world)[0], "cpu") for r in range(world)]
+        full = perm[step * B:(step + 1) * B]
+        assert torch.equal(torch.cat(parts).long(), full) and all(p.dtype == torch.int32 for p in parts)
+        for p in parts:
+            if p.numel():
+                assert torch.equal(IqStream(stream, p, T).frames(), torch.stack([stream[k:k + T] for k in p.tolist()]))
