@@ -167,12 +167,14 @@ int odpd_clip_adamw(float *param, float *grad, float *exp_avg, float *exp_avg_sq
 
 /*
  * Data-parallel exchange over NVLink peer memory (ONE exchange per train step, the flat [grad | loss] buffer).
- * The all-reduce is fused into the optimiser kernel: every rank reads every rank's gradient buffer directly through
- * NVLink/NVSwitch peer mappings, sums them in rank order (so all replicas compute bit-identical updates), clips and applies AdamW —
- * no NCCL call, no extra launch.  Buffers are symmetric: rank r allocates `odpd_dp_alloc`, exports `odpd_dp_ipc_handle`, the
- * 64-byte handles are all-gathered out of band (torch.distributed), peers map them with `odpd_dp_ipc_open`.
- *   layout of one rank's buffer (floats):  [2][stride]  double-buffered by step parity, element n (< stride) = that rank's loss
- *                                          followed by 2 x uint64 flags (flag[0] = last step whose gradient is published)
+ * The all-reduce is fused into the optimiser kernel and is PUSH based: every rank stores its gradient as 8-byte words
+ * {fp32 bits, step tag} straight into a slot of every peer's receive buffer through the NVLink/NVSwitch peer mappings (data and
+ * flag travel in one store: no fence, no flag round trip, nothing is read across the link), polls its own LOCAL buffer until every
+ * source's words carry this step's tag, sums the sources in rank order (so all replicas compute bit-identical updates), clips
+ * and applies AdamW — no NCCL call, no extra launch.  Buffers are symmetric: rank r allocates `odpd_dp_alloc`, exports
+ * `odpd_dp_ipc_handle`, the 64-byte handles are all-gathered out of band (torch.distributed), peers map them with `odpd_dp_ipc_open`.
+ *   layout of one rank's buffer:  uint2 [2 step parities][world sources][stride]   (stride = n_params + 1 rounded up to 4; element
+ *                                 n_params of a source = that rank's loss), zero-initialised by odpd_dp_alloc; world <= 8
  * These are the only entry points that allocate device memory (peer-mappable memory must come from cudaMalloc).
  */
 int64_t odpd_dp_buffer_bytes(int64_t n_params);
@@ -182,11 +184,11 @@ int odpd_dp_ipc_handle(void *ptr, unsigned char handle_out[64]);
 int odpd_dp_ipc_open(const unsigned char handle[64], void **out_peer_ptr);
 int odpd_dp_ipc_close(void *peer_ptr);
 /* bufs: HOST array of `world` device pointers (index = rank; bufs[rank] is the caller's own buffer).  grad_local: this rank's flat
- * gradient of the step (the kernel publishes it into bufs[rank][parity], parity = (step_dev+1)&1 read on the device, so the launch
- * is identical every step and can be replayed from a CUDA graph); NULL = the caller already wrote it there (`gparams` of
- * odpd_backbone_bwd with ODPD_F_OVERWRITE_DW).  The local loss (double, from odpd_backbone_fwd) is passed in `loss_local`.  On return (stream order) `param` is updated,
- * loss_out[0] = sum of all ranks' losses, gnorm_out = pre-clip norm of the summed gradient.  status_dev[0] != 0 reports a peer
- * that did not publish within the spin budget (the kernel never hangs). */
+ * gradient of the step (`gparams` of odpd_backbone_bwd), loss_local its loss (double, from odpd_backbone_fwd).  The slot parity is
+ * (step_dev+1)&1, read on the device, so the launch is identical every step and can be replayed from a CUDA graph.  On return
+ * (stream order) `param` is updated, loss_out[0] = sum of all ranks' losses, gnorm_out = pre-clip norm of the summed gradient.
+ * status_dev[0] != 0 (= 1 + rank of a peer) reports a peer that did not publish within 2 s: the kernel then leaves the parameters
+ * and the step counter untouched instead of hanging; the caller must poll status_dev and stop (NativeTrainStep does, and raises). */
 int odpd_dp_clip_adamw(float *param, void *const *bufs, int world, int rank, int64_t n, const float *grad_local, const double *loss_local,
                        float *exp_avg, float *exp_avg_sq, const float *lr_dev, float beta1, float beta2, float eps, float weight_decay,
                        float max_norm, int64_t *step_dev, float *gnorm_out, float *loss_out, int *status_dev, void *stream);

@@ -192,10 +192,19 @@ int odpd_backbone_bwd(const OdpdDims *d, const float *x, const float *params, co
     ODPD_CHECK(!dx || gx, "ODPD_F_NEED_DX set but gx==NULL");
     ODPD_CHECK(!dw || (gparams && workspace), "ODPD_F_NEED_DW set but gparams/workspace==NULL");
     ODPD_CHECK(gout || (out && target), "need gout, or out+target for the fused MSE gradient");
-    if (d->B == 0 || d->T == 0 || (!dx && !dw)) return 0;
-    ODPD_CHECK(x && (saved || d->cell == ODPD_CELL_GMP), "x/saved must not be NULL");
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t P = odpd_n_params(d->cell, d->H, d->K);
+    if (d->B == 0 || d->T == 0) {
+        // an empty shard (data-parallel rank whose share of the last partial batch is empty) contributes a ZERO gradient: with
+        // OVERWRITE_DW the caller's buffer must not keep the previous step's values
+        if (dw && (d->flags & ODPD_F_OVERWRITE_DW) && P > 0) {
+            cudaError_t e = cudaMemsetAsync(gparams, 0, (size_t)P * sizeof(float), st);
+            ODPD_CHECK(e == cudaSuccess, "cudaMemsetAsync(gparams): %s", cudaGetErrorString(e));
+        }
+        return 0;
+    }
+    if (!dx && !dw) return 0;
+    ODPD_CHECK(x && (saved || d->cell == ODPD_CELL_GMP), "x/saved must not be NULL");
     int rc, rows = d->B;
     if (is_gru_family(d->cell)) {
         GruArgs a{};

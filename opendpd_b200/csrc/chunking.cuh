@@ -35,14 +35,24 @@ inline int64_t chunk_fwd_scratch_floats(int64_t rows, int ss) { return rows * (2
 inline int64_t chunk_bwd_scratch_floats(int64_t rows, int ss) { return rows * 2 * ss + 4; }
 inline int64_t chunk_workspace_floats(int64_t rows, int64_t P, int ss) { return ((rows * P + 3) & ~(int64_t)3) + chunk_bwd_scratch_floats(rows, ss); }
 
+// Per-process caches are keyed by the CURRENT device: cudaFuncSetAttribute and occupancy are per device, and one process may
+// touch several GPUs (tests do).
+static constexpr int ODPD_MAX_DEV = 32;
+struct OccCache { int v[ODPD_MAX_DEV]; };
+inline int cur_dev_slot() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= ODPD_MAX_DEV) dev = 0;
+    return dev;
+}
 inline int num_sms() {
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    static int n[ODPD_MAX_DEV] = {0};
+    const int dev = cur_dev_slot();
+    if (!n[dev]) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        n[dev] = v;
     }
-    return n;
+    return n[dev];
 }
 
 // fills a.C / a.Lc / a.Wu;  slots = CTAs of this kernel the device holds at once
@@ -79,9 +89,10 @@ inline void chunk_make_plan(GruArgs &a, int slots, bool have_scratch) {
 //   info     optional out: chunks, steps per chunk, warm-up steps, float index of the re-run counter
 //   warm     default warm-up of the cell (steps; the caller's OdpdDims.twarm overrides it)
 template <typename K>
-inline int chunk_launch(K k, int nthreads, size_t smem, int *occ_cache, GruArgs a, int dir, float *scr, int64_t scr_off, int ss,
+inline int chunk_launch(K k, int nthreads, size_t smem, OccCache *occ_all, GruArgs a, int dir, float *scr, int64_t scr_off, int ss,
                         cudaStream_t st, bool plan_only, int *info, const char *what, int warm = SPEC_WARM_DEFAULT) {
     a.twarm_default = warm;
+    int *occ_cache = &occ_all->v[cur_dev_slot()];
     if (!*occ_cache) {
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int occ = 0;

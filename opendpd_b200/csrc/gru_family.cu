@@ -748,7 +748,7 @@ static int launch_fwd(GruArgs a, cudaStream_t st, bool plan_only, int *info) {
     constexpr int HP = Pad4<HT>::value, ROW = Row<HT, HEAD>::value;
     const GruLayout<FM, HEAD> L(a.H);
     const size_t smem = (size_t)FwdSmem<HT, HEAD>::total((L.P + 3) & ~3) * sizeof(float);
-    static int occ = 0;
+    static OccCache occ{};
     const int64_t soff = a.save ? (int64_t)a.B * a.T * ROW : 0;     // `saved` = [B][T][ROW] rows (when saving) | chunk scratch
     return chunk_launch(gru_fwd_kernel<HT, FM, HEAD>, 96, smem, &occ, a, 0, a.saved ? a.saved + soff : nullptr, soff, HP, st, plan_only, info,
                         "gru_fwd_kernel");
@@ -758,7 +758,7 @@ static int launch_bwd_t(GruArgs a, cudaStream_t st, bool plan_only, int *info) {
     constexpr int HP = Pad4<HT>::value;
     const GruLayout<FM, HEAD> L(a.H);
     const size_t smem = (size_t)BwdSmem<HT, HEAD>::total((L.P + 3) & ~3) * sizeof(float);
-    static int occ = 0;
+    static OccCache occ{};
     const int64_t woff = (chunk_rows(a.B, a.tchunks_req) * L.P + 3) & ~(int64_t)3;   // workspace = [rows][P] partials | chunk scratch
     return chunk_launch(gru_bwd_kernel<HT, FM, HEAD, DW>, 128, smem, &occ, a, 1, a.partials ? a.partials + woff : nullptr, woff, HP, st,
                         plan_only, info, "gru_bwd_kernel");

@@ -793,7 +793,7 @@ static int janet_launch(const GruArgs &a, int dir, bool dw, cudaStream_t st, int
     float *scr = base ? base + off : nullptr;
 #define LAUNCH(KERN, SMEMT, NAME)                                                                                             \
     {                                                                                                                         \
-        static int occ = 0;                                                                                                   \
+        static OccCache occ{};                                                                                                   \
         return chunk_launch(KERN, 96, (size_t)SMEMT::total(Ppad) * 4, &occ, a, fwd ? 0 : 1, scr, off, ss, st, plan_only, info, NAME, JANET_WARM); \
     }
     if (pg) {

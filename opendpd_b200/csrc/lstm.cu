@@ -374,7 +374,7 @@ template <int HT> static int lstm_launch(const GruArgs &a, int dir, bool dw, cud
     const bool plan_only = dir >= 2;
     if ((dir & 1) == 0) {
         const size_t smem = (size_t)LFwdSmem<HT>::total(Ppad) * 4;
-        static int occ = 0;
+        static OccCache occ{};
         const int64_t soff = a.save ? (int64_t)a.B * a.T * ROW : 0;
         return chunk_launch(lstm_fwd_kernel<HT>, 96, smem, &occ, a, 0, a.saved ? a.saved + soff : nullptr, soff, 2 * HP, st, plan_only, info,
                             "lstm_fwd_kernel");
@@ -383,10 +383,10 @@ template <int HT> static int lstm_launch(const GruArgs &a, int dir, bool dw, cud
     const int64_t woff = (chunk_rows(a.B, a.tchunks_req) * L.P + 3) & ~(int64_t)3;
     float *scr = a.partials ? a.partials + woff : nullptr;
     if (dw) {
-        static int occ = 0;
+        static OccCache occ{};
         return chunk_launch(lstm_bwd_kernel<HT, true>, 96, smem, &occ, a, 1, scr, woff, 2 * HP, st, plan_only, info, "lstm_bwd_kernel");
     }
-    static int occ0 = 0;
+    static OccCache occ0{};
     return chunk_launch(lstm_bwd_kernel<HT, false>, 96, smem, &occ0, a, 1, scr, woff, 2 * HP, st, plan_only, info, "lstm_bwd_kernel");
 }
 int64_t lstm_saved_floats(int B, int T, int H, bool save, int tchunks_req) {

@@ -119,8 +119,10 @@ int odpd_dft_magnitude(const float *a, const float *b, int32_t S, int32_t N, int
                S, N, nfft, nseg, hop);
     if (S == 0) return 0;
     const size_t smem = (size_t)2 * nfft * sizeof(double2);
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(dft_mag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 6144 * 2 * (int)sizeof(double2)); attr = true; }
+    static bool attr[32] = {false};        // cudaFuncSetAttribute is per device
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 32) dev = 0;
+    if (!attr[dev]) { cudaFuncSetAttribute(dft_mag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 6144 * 2 * (int)sizeof(double2)); attr[dev] = true; }
     dim3 grid((unsigned)((nfft + 255) / 256), (unsigned)nseg, (unsigned)S);
     dft_mag_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(reinterpret_cast<const float2 *>(a), reinterpret_cast<const float2 *>(b), N, nfft, nseg, hop,
                                                              hann, detrend, out);

@@ -29,11 +29,17 @@ def gather_frames(stream, starts, frame_length):
     return stream[idx]
 
 
-def frame_starts(indices, device):
-    """This rank's frame indices (shard_batch_indices) as the device int32 vector `NativeTrainStep.step_indexed` /
-    `OdpdDims.x_starts` take: with stride-1 framing (data_collector.py:240-247) frame k starts at sample k, so the indices ARE the
-    start offsets into the raw stream that every rank keeps resident — only these B/N integers differ between ranks and steps."""
-    return torch.as_tensor(indices, dtype=torch.int32).to(device).contiguous()
+def frame_starts(indices, device=None, out=None):
+    """This rank's frame indices (shard_batch_indices) as the int32 vector `NativeTrainStep.step_indexed` / `OdpdDims.x_starts`
+    take: with stride-1 framing (data_collector.py:240-247) frame k starts at sample k, so the indices ARE the start offsets into
+    the raw stream that every rank keeps resident — only these B/N integers differ between ranks and steps.
+    `out` (int32, pinned host or device) is filled in place and returned; without it a new tensor is made on `device` (None = host).
+    Either way `step_indexed` copies the starts into its own persistent device buffer, so no CUDA graph is keyed on this tensor."""
+    idx = torch.as_tensor(indices, dtype=torch.int32)
+    if out is not None:
+        out.copy_(idx, non_blocking=True)
+        return out
+    return idx.contiguous() if device is None else idx.to(device).contiguous()
 
 
 def allreduce_flat_(buf, group=None):
@@ -44,15 +50,16 @@ def allreduce_flat_(buf, group=None):
 
 
 class PeerExchange:
-    """Symmetric NVLink-mapped gradient buffers for the fused all-reduce + clip + AdamW kernel (include/odpd.h, csrc/dp.cu).
-    Each rank owns one cudaMalloc'ed buffer [2][stride] floats + flags; the 64-byte IPC handles are all-gathered once through
-    torch.distributed and every peer buffer is mapped into this process."""
+    """Symmetric NVLink-mapped receive buffers for the fused push all-reduce + clip + AdamW kernel (include/odpd.h, csrc/dp.cu).
+    Each rank owns one cudaMalloc'ed buffer of {value, step tag} words [2 parities][world sources][stride]; the 64-byte IPC handles
+    are all-gathered once through torch.distributed and every peer buffer is mapped into this process."""
 
     def __init__(self, n_params, device, group, world, rank):
         import ctypes
         from . import _ffi
         self.L, self.n, self.world, self.rank, self.device = _ffi.lib(), int(n_params), int(world), int(rank), device
-        self.stride = (self.n + 1 + 3) // 4 * 4
+        if world > 8:
+            raise _ffi.OdpdError("the fused peer exchange covers one NVSwitch node (world <= 8); use ODPD_DP_P2P=0 (NCCL) beyond that")
         nbytes = int(self.L.odpd_dp_buffer_bytes(self.n))
         own = ctypes.c_void_p()
         _ffi.check(self.L.odpd_dp_alloc(nbytes, ctypes.byref(own)))
@@ -75,14 +82,6 @@ class PeerExchange:
         torch.distributed.barrier(group=group)
         self.status = torch.zeros(1, dtype=torch.int32, device=device)
         self.loss_out = torch.zeros(1, dtype=torch.float32, device=device)
-
-    def grad_view(self, parity):
-        """torch view (n floats) of this rank's gradient slot for the given step parity — handed to the backward as `gparams`."""
-        class _Mem:
-            pass
-        m = _Mem()
-        m.__cuda_array_interface__ = {"shape": (self.n,), "typestr": "<f4", "data": (self.own + 4 * parity * self.stride, False), "version": 3}
-        return torch.as_tensor(m, device=self.device)
 
     def close(self):
         import ctypes

@@ -86,7 +86,7 @@ class NativeTrainStep:
     """One fused train step for a CoreModel (train_pa, steps/train_pa.py:24-29) or a CascadedModel with frozen PA
     (train_dpd, steps/train_dpd.py:60-63).
 
-    step(features, targets)  -> device float64 loss (no host sync)
+    step(features, targets)  -> device float64 loss (no host sync); a fresh tensor every call (safe to collect and read later)
     step_host(features, targets) -> python float; inputs are (pinned) HOST tensors, H2D copies and the loss D2H read
     happen inside the call (the reference's per-batch `.to(device)` ... `loss.item()`, train_funcs.py:30-48).
 
@@ -127,7 +127,7 @@ class NativeTrainStep:
         use_p2p = peer_exchange if peer_exchange is not None else (os.environ.get("ODPD_DP_P2P", "1") != "0")
         if self.world > 1 and self.pg is not None and use_p2p and self.n + 1 <= 4096:
             self.px = PeerExchange(self.n, dev, self.pg, self.world, torch.distributed.get_rank(self.pg))
-            self._px_views = [self.px.grad_view(0), self.px.grad_view(1)]
+            self._px_pin, self._px_ev = torch.zeros(1, dtype=torch.int32).pin_memory(), None
         self._host_step = 0
         self._stage = None
         self._bufs = [dict() for _ in range(4)]
@@ -144,14 +144,18 @@ class NativeTrainStep:
         # exact.  (The NCCL fallback of the data-parallel exchange, ODPD_DP_P2P=0, stays un-captured.)
         self.use_graphs = os.environ.get("ODPD_GRAPHS", "1") != "0" and (self.world == 1 or self.px is not None)
         self._graphs, self._graph_warm = {}, set()
+        self._starts_stage = {}
 
     def set_lr(self, lr):
         """ReduceLROnPlateau hook (project.py:288-297) — host-side scalar write, no kernel change."""
         self.lr_dev.fill_(float(lr))
 
-    def step(self, features, targets, global_count=None):
+    def step(self, features, targets, global_count=None, loss_out=None):
         """One train step; returns the device float64 loss (no host sync).
-        global_count: number of scalars of the GLOBAL batch (2*B_global*T); defaults to 2*B*T*world (equal shards)."""
+        global_count: number of scalars of the GLOBAL batch (2*B_global*T); defaults to 2*B*T*world (equal shards).
+        loss_out: optional 1-element float64 tensor (device or pinned host) the loss is copied into (stream-ordered, non-blocking)
+        and which is then returned; without it the step returns a fresh device tensor.  (The kernels accumulate the loss in a
+        buffer that the next step — or the next replay of the captured graph — overwrites, so it is never handed out itself.)"""
         B, T = features.shape[0], features.shape[1]
         if not self.use_graphs:
             loss = self._step_impl(features, targets, global_count)
@@ -174,17 +178,32 @@ class NativeTrainStep:
                     g = self._graphs[key] = (graph, gl, features, targets)      # keeps the captured buffers alive
                 g[0].replay()
                 loss = g[1]
+        if loss_out is not None:
+            loss_out.copy_(loss, non_blocking=True)
+            loss = loss_out
+        else:
+            loss = loss.clone()
         self._host_step += 1
         if self.chunk_check_every > 0 and self._host_step % self.chunk_check_every == 0:
             self._chunk_control(B, T)
+            self._check_exchange()
         return loss
 
-    def step_indexed(self, stream_x, stream_y, starts, T, global_count=None):
+    def step_indexed(self, stream_x, stream_y, starts, T, global_count=None, loss_out=None):
         """One train step on frames addressed inside device-resident raw streams (SURVEY f-2: on-device framing inside the kernels):
-        stream_x / stream_y are (N,2) fp32 or bf16 tensors, starts the B frame start indices (device int32) — frame b is
-        stream[starts[b] : starts[b]+T], exactly IQFrameDataset's stride-1 window (data_collector.py:233-252).  Nothing is
-        gathered or copied: the kernels read the stream in place."""
-        return self.step(IqStream(stream_x, starts, T), IqStream(stream_y, starts, T), global_count)
+        stream_x / stream_y are (N,2) fp32 or bf16 tensors, starts the B frame start indices (int32; device, or pinned host) —
+        frame b is stream[starts[b] : starts[b]+T], exactly IQFrameDataset's stride-1 window (data_collector.py:233-252).  No frame
+        is gathered or copied: the kernels read the stream in place.  The B indices are copied (stream-ordered) into a persistent
+        device buffer owned by the trainer, so every step of a given batch size replays the SAME captured graph whatever tensor
+        `starts` lives in."""
+        B = int(starts.numel())
+        st = self._starts_stage.get(B)
+        if st is None:
+            st = self._starts_stage[B] = torch.empty(B, dtype=torch.int32, device=self.device)
+        if starts.dtype != torch.int32:
+            raise _ffi.OdpdError("step_indexed wants int32 frame starts")
+        st.copy_(starts.reshape(-1), non_blocking=True)
+        return self.step(IqStream(stream_x, st, T), IqStream(stream_y, st, T), global_count, loss_out)
 
     def _step_impl(self, features, targets, global_count=None):
         L = _ffi.lib()
@@ -214,11 +233,6 @@ class NativeTrainStep:
                                             _ptr(self.exp_avg), _ptr(self.exp_avg_sq), _ptr(self.lr_dev), self.betas[0], self.betas[1],
                                             self.eps, self.wd, self.clip, _ptr(self.step_dev), _ptr(self.gnorm), _ptr(self.px.loss_out),
                                             _ptr(self.px.status), _stream()))
-            if self._host_step < 2 and not torch.cuda.is_current_stream_capturing():      # verify the exchange once at start-up (one sync); fall back to NCCL if a peer never published
-                bad = int(self.px.status.item())
-                if bad:
-                    raise _ffi.OdpdError(f"NVLink peer exchange: rank {bad - 1} did not publish its gradient (step {self._host_step}); "
-                                         "re-run with ODPD_DP_P2P=0 to use the NCCL all-reduce")
             return self.px.loss_out.to(torch.float64)
         if self.pg is not None and self.world > 1:
             self.gbuf[-4] = loss.to(torch.float32)[0]
@@ -228,6 +242,27 @@ class NativeTrainStep:
                                      ctypes.c_int64(self.n), _ptr(self.lr_dev), self.betas[0], self.betas[1], self.eps, self.wd,
                                      self.clip, _ptr(self.step_dev), _ptr(self.gnorm), 0, _stream()))
         return loss
+
+    def _check_exchange(self, wait=False):
+        """The fused peer exchange reports a peer that never published through a device status word and skips that step's update
+        (the kernel does not hang).  Read it back asynchronously on the chunk-controller cadence (pinned copy + event, one check
+        late) and fail loudly: a silent skip would leave the replicas diverged.  wait=True synchronises (end of a run)."""
+        if self.px is None or torch.cuda.is_current_stream_capturing():
+            return
+        for _ in range(2 if wait else 1):
+            if self._px_ev is None:
+                self._px_pin.copy_(self.px.status, non_blocking=True)
+                self._px_ev = torch.cuda.Event()
+                self._px_ev.record()
+                if not wait:
+                    return
+            if wait or self._px_ev.query():
+                self._px_ev.synchronize()
+                bad, self._px_ev = int(self._px_pin[0]), None
+                if bad:
+                    raise _ffi.OdpdError(f"NVLink peer exchange: rank {bad - 1} did not publish its gradient within 2 s (around step "
+                                         f"{self._host_step}); this rank skipped the update - replicas are no longer in sync. "
+                                         "Re-run with ODPD_DP_P2P=0 to use the NCCL all-reduce")
 
     def chunk_calls(self):
         """The backbone launches of one step: (module, backward?, index into self._bufs, forward saves?, backward needs dW?)."""
@@ -333,10 +368,9 @@ class NativeTrainStep:
             if nxt is not None:
                 enqueue_copy(slot ^ 1, nxt)
             cur.wait_event(P["ev_copy"][slot])
-            loss_dev = self.step(*P["stage"][slot])
+            self.step(*P["stage"][slot], loss_out=P["loss"][slot])      # async D2H of the loss into the slot's pinned scalar
             P["ev_free"][slot].record(cur)
             used[slot] = True
-            P["loss"][slot].copy_(loss_dev, non_blocking=True)
             P["ev_loss"][slot].record(cur)
             if pending is not None:
                 P["ev_loss"][pending].synchronize()

@@ -207,7 +207,7 @@ def main():
             rec[k + "64"] = v
         path = os.path.join(OUT, name + ".npz")
         np.savez_compressed(path, **rec)
-        manifest[name] = dict(kind=kind, H=H, B=B, T=T, n_params=int(params.size), loss=float(r32["loss"]),
+        manifest[name] = dict(kind=kind, H=H, B=B, T=T, seed=seed, n_params=int(params.size), loss=float(r32["loss"]),
                               bytes=os.path.getsize(path))
         print(name, manifest[name], flush=True)
     mpath = os.path.join(OUT, "MANIFEST.json")

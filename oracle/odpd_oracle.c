@@ -298,6 +298,13 @@ static inline REAL hardswish_grad(REAL v) { /* ATen hardswish_backward */
     return v < (REAL)-3 ? 0 : (v <= (REAL)3 ? v / (REAL)3 + (REAL)0.5 : (REAL)1);
 }
 
+/* Optional diagnostic for the guard-band test of the delta-h mask (SURVEY.md §7 hard part 1): when set, the forward also stores
+ * |delta_h| - thh (signed distance of the compare `abs(delta) >= th`, deltagru.py:176-183) for every (b,t,unit) into a caller
+ * buffer (B,T,H); addressed through the sequence's mask_h row, so it needs want_masks. */
+static REAL *SUF(g_dh_margin) = NULL;
+static const uint64_t *SUF(g_dh_margin_mask_base) = NULL;
+void SUF(odpd_oracle_set_dh_margin)(REAL *buf, const uint64_t *mask_h_base) { SUF(g_dh_margin) = buf; SUF(g_dh_margin_mask_base) = mask_h_base; }
+
 static void seq_delta(const Ctx *c, const REAL *x, const REAL *gout, REAL *out, REAL *gx, REAL *gp, int phase,
                       uint64_t *mask_x, uint64_t *mask_h, int64_t *stats) {
     const int H = c->H, T = c->T, F = 6, tres = (c->cell == CELL_TRES);
@@ -333,6 +340,8 @@ static void seq_delta(const Ctx *c, const REAL *x, const REAL *gout, REAL *out, 
             }
             for (int j = 0; j < H; ++j) {
                 REAL d = h[j] - hp[j], a = R_FABS(d);
+                if (mask_h && SUF(g_dh_margin))
+                    SUF(g_dh_margin)[((size_t)(mask_h - SUF(g_dh_margin_mask_base)) + t) * H + j] = a - c->thh;
                 if (a < c->thh) d = 0;
                 if (a >= c->thh) { hp[j] = h[j]; mh |= (uint64_t)1 << j; }
                 dh[j] = d; zh += (d == 0);

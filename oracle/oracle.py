@@ -21,6 +21,8 @@ def lib():
         _lib = ctypes.CDLL(so)
         for f in (_lib.odpd_oracle_run_f32, _lib.odpd_oracle_run_f64):
             f.restype = ctypes.c_int
+        for f in (_lib.odpd_oracle_set_dh_margin_f32, _lib.odpd_oracle_set_dh_margin_f64):
+            f.restype, f.argtypes = None, [ctypes.c_void_p, ctypes.c_void_p]
         _lib.odpd_oracle_n_params.restype = ctypes.c_size_t
         _lib.odpd_oracle_n_params.argtypes = [ctypes.c_int] * 3
     return _lib
@@ -31,8 +33,10 @@ def n_params(cell, H, K=3):
 
 
 def run(cell, x, params, target=None, gout=None, H=0, K=3, thx=0.0, thh=0.0, want_grads=True, dtype=np.float32,
-        loss_count=None, nthreads=1, want_masks=False):
-    """Forward (+MSE) (+backward) of one (B,T,2) batch on the CPU oracle. Returns a dict of numpy arrays."""
+        loss_count=None, nthreads=1, want_masks=False, want_dh_margin=False):
+    """Forward (+MSE) (+backward) of one (B,T,2) batch on the CPU oracle. Returns a dict of numpy arrays.
+    want_dh_margin (delta cells, implies want_masks): also `dh_margin` (B,T,H) = |delta_h| - thh before masking."""
+    want_masks = want_masks or want_dh_margin
     L = lib()
     dt = np.dtype(dtype)
     fn = L.odpd_oracle_run_f32 if dt == np.float32 else L.odpd_oracle_run_f64
@@ -55,11 +59,18 @@ def run(cell, x, params, target=None, gout=None, H=0, K=3, thx=0.0, thh=0.0, wan
 
     def p(a):
         return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+    margin = None
+    setm = L.odpd_oracle_set_dh_margin_f32 if dt == np.float32 else L.odpd_oracle_set_dh_margin_f64
+    if want_dh_margin:
+        margin = np.zeros((B, T, int(H)), dtype=dt)
+        setm(p(margin), p(mh))
     rc = fn(ctypes.c_int(CELLS[cell]), ctypes.c_int(B), ctypes.c_int(T), ctypes.c_int(int(H)), ctypes.c_int(int(K)),
             ctypes.c_double(float(thx)), ctypes.c_double(float(thh)), p(x), p(tgt), p(go), p(params), p(out),
             ctypes.byref(loss), ctypes.c_double(loss_count), p(gx), p(gp), p(mx), p(mh), p(stats),
             ctypes.c_int(int(nthreads)))
+    if want_dh_margin:
+        setm(None, None)
     if rc != 0:
         raise RuntimeError("oracle rejected the arguments")
-    return dict(out=out, loss=loss.value if tgt is not None else None, gx=gx, gparams=gp, mask_x=mx, mask_h=mh,
+    return dict(dh_margin=margin, out=out, loss=loss.value if tgt is not None else None, gx=gx, gparams=gp, mask_x=mx, mask_h=mh,
                 stats=stats)

@@ -100,10 +100,21 @@ def test_verify_pass_catches_short_warmup_and_reruns_serially():
     ser = _run(net, xc, yc, 1, 0)
     chk = _run(net, xc, yc, (16, 16), 32)
     assert chk["reruns_f"] > 0, (chk["reruns_f"], chk["reruns_b"])
-    if chk["reruns_f"] == 16:                                   # every sequence re-run: identical to the serial kernel
-        assert np.array_equal(chk["out"], ser["out"])
-    if chk["reruns_f"] == 16 and chk["reruns_b"] == 16:
-        assert np.array_equal(chk["gx"], ser["gx"])
+    # per sequence, unconditionally: a re-run sequence IS the serial kernel's result (bit for bit); a sequence whose boundaries all
+    # held keeps its chunked result, which must sit within the chunk tolerance of the serial one.  So at least `reruns` sequences
+    # are bit-equal and every other one is close.
+    B = chk["out"].shape[0]
+    eq_f = [bool(np.array_equal(chk["out"][b], ser["out"][b])) for b in range(B)]
+    assert sum(eq_f) >= chk["reruns_f"], (sum(eq_f), chk["reruns_f"])
+    for b in range(B):
+        if not eq_f[b]:
+            assert rel_err(chk["out"][b], ser["out"][b]) < 5e-6, b
+    # dL/dx of a sequence is bit-equal to the serial kernel's when both its forward and its backward were re-run
+    eq_b = [bool(np.array_equal(chk["gx"][b], ser["gx"][b])) for b in range(B)]
+    assert sum(eq_b) >= chk["reruns_f"] + chk["reruns_b"] - B, (sum(eq_b), chk["reruns_f"], chk["reruns_b"])
+    for b in range(B):
+        if not eq_b[b]:
+            assert rel_err(chk["gx"][b], ser["gx"][b]) < 5e-6, b
     assert rel_err(chk["out"], ser["out"]) < 5e-6
     assert rel_err(chk["gx"], ser["gx"]) < 5e-6
     assert rel_err(chk["gp"], ser["gp"]) < 5e-6

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests.util import golden_cases, load_golden, rel_err, tol_for, assert_close
+from tests.util import GOLDEN, golden_cases, load_golden, rel_err, tol_for, assert_close, note_achieved
 
 pytestmark = pytest.mark.gpu
 
@@ -88,10 +88,13 @@ def test_golden_parity(name, fused):
         loss = torch.nn.MSELoss()(out, y)
     loss.backward()
     torch.cuda.synchronize()
-    assert rel_err(out.detach().cpu().numpy(), g["out"]) < tol_for(g, "out")
-    assert abs(loss.item() - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
-    assert rel_err(x.grad.cpu().numpy(), g["gx"]) < tol_for(g, "gx")
-    assert rel_err(grads_flat(net), g["gparams"]) < tol_for(g, "gparams")
+    errs = dict(out=rel_err(out.detach().cpu().numpy(), g["out"]), gx=rel_err(x.grad.cpu().numpy(), g["gx"]),
+                gparams=rel_err(grads_flat(net), g["gparams"]), loss=abs(loss.item() - float(g["loss"])) / abs(float(g["loss"])))
+    note_achieved(name, **errs, tol_out=tol_for(g, "out"), tol_gx=tol_for(g, "gx"), tol_gparams=tol_for(g, "gparams"))
+    assert errs["out"] < tol_for(g, "out"), errs
+    assert errs["loss"] <= 1e-5, errs
+    assert errs["gx"] < tol_for(g, "gx"), errs
+    assert errs["gparams"] < tol_for(g, "gparams"), errs
     if "mask_x" in g and hasattr(net.backbone, "last_masks"):
         mx, mh = net.backbone.last_masks()
         assert np.array_equal(mx, g["mask_x"])       # delta-x keep mask: bit exact
@@ -171,6 +174,38 @@ def test_cpu_tensor_fails_loudly():
         net(torch.zeros(1, 4, 2))
 
 
+# Guard band of the delta-h compare `abs(h - h_hat) >= thh` (deltagru.py:176-183).  The compared quantity is a difference of two
+# hidden states that each carry the accumulated fp32 rounding of the recurrence (matvec summation order, sigmoid/tanh
+# implementation): a few ulp of |h| <= 1, i.e. a few times 2^-24 ABSOLUTE - not ulps of thh.  A mask bit may therefore differ from
+# the reference's only where the fp64 oracle's | |delta_h| - thh | is below GUARD; everything else must match exactly.
+DH_GUARD = 64 * 2.0 ** -24          # 3.8e-6 absolute; achieved distances are logged to gpurun_out/parity_achieved.jsonl
+
+
+def _check_dh_flips_in_guard_band(mh_gpu, mh_ref32, r64, H, thh, B, what=""):
+    """Every sequence whose delta-h mask differs from the fp32 reference's must have its FIRST differing (t, unit) inside the guard
+    band of the fp64 oracle (after the first flip the trajectories legitimately differ by ~thh until the next keep, so later
+    differences are consequences, not causes).  The same rule is applied to the fp32 reference itself vs fp64 (it flips too).
+    Returns the indices of the sequences with any flip (to be excluded from the tight value comparison)."""
+    margin = np.abs(r64["dh_margin"])                      # (B,T,H): | |delta_h| - thh | in fp64
+    bad, dists = [], []
+    flipped = set()
+    for name, m in (("gpu", mh_gpu), ("ref32", mh_ref32)):
+        diff = m.astype(np.uint64) ^ r64["mask_h"].astype(np.uint64)
+        for b in np.nonzero(diff.any(axis=1))[0]:
+            t = int(np.nonzero(diff[b])[0][0])
+            units = [j for j in range(H) if (int(diff[b, t]) >> j) & 1]
+            d = float(max(margin[b, t, j] for j in units))
+            dists.append(d)
+            flipped.add(int(b))
+            if d > DH_GUARD:
+                bad.append((name, int(b), t, units, d))
+    note_achieved("dh_flip_guard_band " + what, sequences_flipped=len(flipped), of=int(B), worst_first_flip_distance=max(dists, default=0.0),
+                  guard=DH_GUARD, thh=float(thh))
+    assert not bad, f"delta-h mask flips OUTSIDE the guard band {DH_GUARD:.2e}: {bad[:5]}"
+    # sequences where gpu and ref32 agree with each other but both differ from fp64 are also 'flipped' for the value comparison
+    return np.array(sorted(flipped), dtype=int)
+
+
 @pytest.mark.parametrize("kind,H,B,T,thx,thh", [("deltagru", 15, 64, 200, 0.01, 0.05), ("deltagru_tcnskip", 15, 64, 200, 0.01, 0.05),
                                                 ("deltagru_tcnskip", 15, 256, 200, 0.01, 0.05), ("deltagru_tcnskip", 15, 64, 2048, 0.01, 0.05),
                                                 ("deltagru", 10, 16, 96, 0.0, 0.0), ("deltagru_tcnskip", 26, 4, 64, 0.02, 0.02)])
@@ -194,11 +229,10 @@ def test_delta_oracle_parity_with_mask_accounting(kind, H, B, T, thx, thh):
     torch.cuda.synchronize()
     params = np.concatenate([p.detach().cpu().numpy().ravel() for _, p in net.backbone.named_parameters()])
     r32 = oracle.run(kind, xc.numpy(), params, target=yc.numpy(), H=H, thx=thx, thh=thh, dtype=np.float32, nthreads=8, want_masks=True)
-    r64 = oracle.run(kind, xc.numpy(), params, target=yc.numpy(), H=H, thx=thx, thh=thh, dtype=np.float64, nthreads=8, want_masks=True)
+    r64 = oracle.run(kind, xc.numpy(), params, target=yc.numpy(), H=H, thx=thx, thh=thh, dtype=np.float64, nthreads=8, want_dh_margin=True)
     mx, mh = net.backbone.last_masks()
     assert np.array_equal(mx, r32["mask_x"]), "delta-x mask must be bit exact"
-    flipped = np.unique(np.concatenate([np.nonzero(mh != r32["mask_h"])[0], np.nonzero(r64["mask_h"] != r32["mask_h"])[0]]))
-    assert len(flipped) <= max(1, B // 20), f"{len(flipped)} of {B} sequences have a flipped delta-h bit"
+    flipped = _check_dh_flips_in_guard_band(mh, r32["mask_h"], r64, H, thh, B, what=f"{kind} H{H} B{B} T{T}")
     st = net.backbone.raw_statistics()
     assert st[0] == int(r32["stats"][0]) and st[1] == int(r32["stats"][1]) and st[3] == int(r32["stats"][3])
     assert abs(st[2] - int(r32["stats"][2])) <= 4 * H * max(len(flipped), 0) + (0 if len(flipped) == 0 else T)
@@ -270,3 +304,98 @@ def test_qat_oracle_parity_with_flip_accounting(bits):
     else:
         bad_e = np.nonzero(np.abs(oe - re["out"]).reshape(B, -1).max(1) > 0.1 * quantum)[0]
         assert len(bad_e) <= B // 16
+
+
+def _load_full(name):
+    """Full-size reference-generated fixture (oracle/make_full_golden.py) + its inputs rebuilt from the committed IQ streams."""
+    import json, os
+    d = np.load(os.path.join(GOLDEN, name + ".npz"))
+    g = {k: d[k] for k in d.files}
+    for k in ("kind", "target_key"):
+        g[k] = str(g[k])
+    g["H"], g["K"], g["thx"], g["thh"] = int(g["H"]), int(g["K"]), float(g["thx"]), float(g["thh"])
+    g["param_index"] = json.loads(str(g["param_index"]))
+    z = np.load(os.path.join(GOLDEN, "iq_streams.npz"))
+    T = g["out"].shape[1]
+    X, Y = z["APA_200MHz.x"], z[g["target_key"]]
+    g["x"] = np.stack([X[k:k + T] for k in g["starts"]])
+    g["y"] = np.stack([Y[k:k + T] for k in g["starts"]])
+    return g
+
+
+@pytest.mark.parametrize("chunked", [False, True])
+def test_full_size_c2a_against_the_reference(chunked):
+    """BASELINE.json configs[1] at full size on real data: DGRU H=13, 64 x 2048 APA_200MHz frames, outputs of the UNMODIFIED
+    reference (fp32 run for every element, fp64 arbiter for the first 32 sequences / all parameter gradients)."""
+    g = _load_full("full_c2a")
+    net = build_native(g)
+    if not chunked:
+        net.backbone.time_chunks = (1, 1)
+    x = torch.from_numpy(g["x"]).cuda().requires_grad_(True)
+    out, loss = net.forward_mse(x, torch.from_numpy(g["y"]).cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    o, gx, gp = out.detach().cpu().numpy(), x.grad.cpu().numpy(), grads_flat(net)
+    n64 = g["out64"].shape[0]
+    # vs the fp64 arbiter: tolerance = north-star 1e-5, widened only by the fp32 conditioning the reference itself shows
+    for key, mine, r32, r64 in (("out", o[:n64], g["out"][:n64], g["out64"]), ("gx", gx[:n64], g["gx"][:n64], g["gx64"]),
+                                ("gparams", gp, g["gparams"], g["gparams64"])):
+        assert_close(mine, r64, max(1e-5, 3 * _q_err(r32, r64)), f"full_c2a {key} vs fp64 reference")
+    # vs the fp32 reference, whole batch
+    assert_close(o, g["out"], 1e-5, "full_c2a out vs fp32 reference")
+    assert_close(gx, g["gx"], max(1e-5, 3 * _q_err(g["gx"][:n64], g["gx64"])), "full_c2a gx vs fp32 reference")
+    assert abs(loss.item() - float(g["loss64"])) <= 1e-5 * abs(float(g["loss64"]))
+
+
+def test_full_size_c3_against_the_reference():
+    """BASELINE.json configs[2] at full size on real data: TRes-DeltaGRU H=15 (thx .01, thh .05), 256 x 2048 APA_200MHz frames,
+    target gain*x.  delta-x masks and counters bit exact; delta-h flips only inside the guard band (fp64 oracle margins)."""
+    from oracle import oracle
+    g = _load_full("full_c3")
+    net = build_native(g)
+    net.backbone.keep_masks = True
+    x = torch.from_numpy(g["x"]).cuda().requires_grad_(True)
+    out, loss = net.forward_mse(x, torch.from_numpy(g["y"]).cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    B, T, H = g["x"].shape[0], g["x"].shape[1], g["H"]
+    mx, mh = net.backbone.last_masks()
+    assert np.array_equal(mx, g["mask_x"].astype(np.uint64)), "delta-x mask must equal the reference's bit for bit"
+    # margins of the compare come from the fp64 oracle (pinned to the reference: its masks must equal the fp64 reference's)
+    r64 = oracle.run(g["kind"], g["x"], g["params"], target=g["y"], H=H, thx=g["thx"], thh=g["thh"], dtype=np.float64, nthreads=16,
+                     want_dh_margin=True)
+    assert np.array_equal(r64["mask_h"], g["mask_h64"].astype(np.uint64)) and np.array_equal(r64["mask_x"], g["mask_x64"].astype(np.uint64))
+    flipped = _check_dh_flips_in_guard_band(mh, g["mask_h"].astype(np.uint64), r64, H, g["thh"], B, what="full_c3")
+    st = net.backbone.raw_statistics()
+    assert st[0] == int(g["stats"][0]) and st[1] == int(g["stats"][1]) and st[3] == int(g["stats"][3])
+    good = np.setdiff1d(np.arange(B), flipped)
+    assert len(good) >= B // 2, f"only {len(good)} of {B} sequences are flip-free"
+    o, gx = out.detach().cpu().numpy(), x.grad.cpu().numpy()
+    n64 = g["out64"].shape[0]
+    cond_o = _q_err(g["out"][:n64], g["out64"]); cond_g = _q_err(g["gx"][:n64], g["gx64"])
+    note_achieved("full_c3 conditioning", cond_out=cond_o, cond_gx=cond_g, flip_free=int(len(good)))
+    assert_close(o[good], r64["out"][good], max(1e-5, 3 * cond_o), "full_c3 out vs fp64 oracle (flip-free sequences)")
+    assert_close(gx[good], r64["gx"][good], max(1e-5, 5 * cond_g), "full_c3 gx vs fp64 oracle (flip-free sequences)")
+    # loss over the whole batch: a flip moves one sequence's output by O(thh * |W|) for a few steps - bounded, not exact
+    assert abs(loss.item() - float(g["loss64"])) <= 1e-4 * abs(float(g["loss64"]))
+
+
+def test_integration_snippet_runs():
+    """INTEGRATION.md §2's reference-side ctypes binding, executed verbatim, must produce the native forward."""
+    import re, os
+    from opendpd_b200 import models, _ffi
+    from tests.util import ROOT
+    _ffi.lib()
+    md = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    code = [b for b in re.findall(r"```python\n(.*?)```", md, flags=re.S) if "class OdpdDims(ctypes.Structure)" in b][0]
+    ns = {}
+    exec(compile(code, "INTEGRATION.md", "exec"), ns)
+    torch.manual_seed(0)
+    net = models.CoreModel(2, 13, 1, "dgru").cuda()
+    flat, _ = net.backbone._flat_sync()
+    x = (0.25 * torch.randn(5, 300, 2)).cuda()
+    mine = ns["dgru_forward"](x, flat, 13)
+    with torch.no_grad():
+        ref = net(x)
+    torch.cuda.synchronize()
+    assert torch.equal(mine, ref)

@@ -9,7 +9,7 @@ def golden_cases(kinds=None):
     out = []
     for f in sorted(glob.glob(os.path.join(GOLDEN, "*.npz"))):
         name = os.path.basename(f)[:-4]
-        if name.startswith(("metrics_", "next_")):   # evaluation-metric goldens (tests/test_metrics_oracle.py); cells without a CUDA path yet
+        if name.startswith(("metrics_", "next_", "iq_streams", "full_")):   # evaluation-metric goldens (tests/test_metrics_oracle.py); cells without a CUDA path yet
             continue
         if kinds is None or any(name.startswith(k) for k in kinds):
             out.append(name)
@@ -31,21 +31,37 @@ def rel_err(a, b):
     return float(np.max(np.abs(a - b)) / (np.max(np.abs(b)) + 1e-300))
 
 
+ACHIEVED = os.path.join(ROOT, "gpurun_out", "parity_achieved.jsonl")
+
+
+def note_achieved(what, **kw):
+    """Append the error figures a parity assertion actually saw to gpurun_out/parity_achieved.jsonl (when that directory exists:
+    GPU box runs), so tolerances can be judged against what is achieved, not only against what is allowed."""
+    try:
+        if os.path.isdir(os.path.dirname(ACHIEVED)):
+            with open(ACHIEVED, "a") as f:
+                f.write(json.dumps(dict(test=os.environ.get("PYTEST_CURRENT_TEST", "").split(" ")[0], what=what, **kw)) + "\n")
+    except OSError:
+        pass
+
+
 def tol_for(g, key, base=1e-5):
     """Tolerance for comparing an fp32 implementation with the fp32 reference: the north-star 1e-5, widened only
     where the reference's own fp32-vs-fp64 disagreement shows the case is ill-conditioned (e.g. DVRJANET's
-    cos/sin of an unbounded learned phase)."""
+    cos/sin of an unbounded learned phase): 5x that disagreement."""
     cond = rel_err(g[key], g[key + "64"])
-    return max(base, 20.0 * cond)
+    return max(base, 5.0 * cond)
 
 
 def assert_close(mine, ref, tol, what=""):
     """Parity criterion for fp32 implementations of piecewise-smooth networks: the 99.99th percentile of
-    |mine-ref|/max|ref| must be below `tol` and the worst element below 100*tol.  The slack on isolated elements
-    exists because ReLU / hardswish / delta-threshold kinks turn a 1-ulp difference of a pre-activation that sits
-    at the kink into a finite jump of one gradient element (observed: 1 element in 262144 at 5.6e-5)."""
+    |mine-ref|/max|ref| must be below `tol` and the WORST element below 10*tol.  The slack on isolated elements exists
+    because ReLU / hardswish / delta-threshold kinks turn a 1-ulp difference of a pre-activation that sits at the kink
+    into a finite jump of one gradient element (observed: 1 element in 262144 at 5.6e-5).  The achieved figures are logged."""
     a = np.asarray(mine, dtype=np.float64); b = np.asarray(ref, dtype=np.float64)
     e = np.abs(a - b) / (np.max(np.abs(b)) + 1e-300)
     q = float(np.quantile(e, 0.9999)) if e.size >= 10000 else float(e.max())
-    assert q < tol, f"{what}: p99.99 rel err {q:.3e} >= {tol:.1e}"
-    assert float(e.max()) < 100 * tol, f"{what}: max rel err {float(e.max()):.3e} >= {100 * tol:.1e}"
+    worst = float(e.max())
+    note_achieved(what, p9999=q, worst=worst, worst_index=int(e.argmax()), tol=tol, n=int(e.size))
+    assert q < tol, f"{what}: p99.99 rel err {q:.3e} >= {tol:.1e} (worst {worst:.3e})"
+    assert worst < 10 * tol, f"{what}: max rel err {worst:.3e} (element {int(e.argmax())}) >= {10 * tol:.1e}"
