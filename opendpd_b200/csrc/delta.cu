@@ -53,7 +53,7 @@ __device__ __forceinline__ void tcn_point(IqRow x2, int T, int t, const float *w
 template <int HT, bool TRES>
 struct DFwdSmem {
     static constexpr int HP = Pad4<HT>::value, ROW = DRow<HT>::value;
-    static constexpr int XP = CH * 3 * HP, FT = CH * 8, ACT = CH * ROW, PO = CH * 33, SK = CH * 2;
+    static constexpr int XP = (CH + 1) * 3 * HP /* +1 spare row for the chain's last-step prefetch */, FT = CH * 8, ACT = CH * ROW, PO = CH * 33, SK = CH * 2;
     __host__ __device__ static constexpr int total(int Ppad) { return 16 + Ppad + HP + 2 * XP + 3 * FT + 3 * SK + 2 * ACT + 2 * PO + 2 * HP; }
 };
 template <int HT, bool TRES>

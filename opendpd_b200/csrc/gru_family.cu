@@ -39,7 +39,8 @@ template <int HT, int HEAD> struct Row { static constexpr int NS = HEAD ? 6 : 5;
 template <int HT, int HEAD>
 struct FwdSmem {
     static constexpr int HP = Pad4<HT>::value, ROW = Row<HT, HEAD>::value;
-    static constexpr int XP = CH * 3 * HP;     // input projection of one chunk
+    static constexpr int XP = (CH + 1) * 3 * HP;   // input projection of one chunk (+1 row: the chain's last-step prefetch reads one row past
+                                                   // the chunk; the spare row keeps that read inside its own buffer, away from the pre warp's writes)
     static constexpr int FT = CH * 8;          // features of one chunk
     static constexpr int ACT = CH * ROW;       // activation rows of one chunk
     static constexpr int PO = CH * 33;
@@ -160,8 +161,8 @@ __global__ void __launch_bounds__(96, 1) gru_fwd_kernel(GruArgs a) {
                     const float *hrow = (c == 0) ? zero : sact + ((c - 1) & 1) * SM::ACT + (CH - 1) * ROW + 4 * HP;
                     float xa = xpA[0], xn = xpN[0];
                     float pr_ = 0.f, pz_ = 0.f, pn_ = 0.f, phg_ = 0.f;
-                    // pointer-increment form: the loop body carries no index arithmetic.  Reading one row past the chunk's
-                    // projections (last step's prefetch) stays inside the shared-memory carve-up and the value is never used.
+                    // pointer-increment form: the loop body carries no index arithmetic.  The last step's prefetch reads the spare
+                    // row (CH) of this chunk's own projection buffer; the value is never used.
                     const bool wr = lane < HP;
                     float *row = ac + lane;                 // row[k*HP] = slot k of this lane's unit
                     const float *xa_p = xpA, *xn_p = xpN;

@@ -83,8 +83,12 @@ def test_chunked_matches_serial_and_oracle(kind, H, B, T, tchunks, twarm):
     def q(a, b):
         e = np.abs(a.astype(np.float64) - b) / (np.abs(b).max() + 1e-300)
         return float(np.quantile(e, 0.9999)) if e.size >= 10000 else float(e.max())
+    # DVRJANET's magnitude filter is sum_k c_k |p - k/K| (dvrjanet.py:32-41): where p sits within an ulp of a knot k/K the fp32 GPU,
+    # the fp32 oracle and the fp64 oracle can take different signs, which moves ONE dL/dx element by a finite amount (seen: 1 element
+    # of 1 048 576 at 3.8e-4 of max|gx|, p99.99 at 9e-6) — only that cell gets the wider bound on the single worst element
+    wf = 100.0 if kind == "dvrjanet" else 10.0
     for key, mine in (("out", chk["out"]), ("gx", chk["gx"]), ("gparams", chk["gp"])):
-        assert_close(mine, r64[key], max(1e-5, 3 * q(r32[key], r64[key])), key)
+        assert_close(mine, r64[key], max(1e-5, 3 * q(r32[key], r64[key])), key, worst_factor=wf if key == "gx" else 10.0)
     assert abs(chk["loss"] - r64["loss"]) <= 1e-5 * abs(r64["loss"])
 
 

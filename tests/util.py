@@ -53,9 +53,9 @@ def tol_for(g, key, base=1e-5):
     return max(base, 5.0 * cond)
 
 
-def assert_close(mine, ref, tol, what=""):
+def assert_close(mine, ref, tol, what="", worst_factor=10.0):
     """Parity criterion for fp32 implementations of piecewise-smooth networks: the 99.99th percentile of
-    |mine-ref|/max|ref| must be below `tol` and the WORST element below 10*tol.  The slack on isolated elements exists
+    |mine-ref|/max|ref| must be below `tol` and the WORST element below worst_factor*tol (10 by default).  The slack on isolated elements exists
     because ReLU / hardswish / delta-threshold kinks turn a 1-ulp difference of a pre-activation that sits at the kink
     into a finite jump of one gradient element (observed: 1 element in 262144 at 5.6e-5).  The achieved figures are logged."""
     a = np.asarray(mine, dtype=np.float64); b = np.asarray(ref, dtype=np.float64)
@@ -64,4 +64,4 @@ def assert_close(mine, ref, tol, what=""):
     worst = float(e.max())
     note_achieved(what, p9999=q, worst=worst, worst_index=int(e.argmax()), tol=tol, n=int(e.size))
     assert q < tol, f"{what}: p99.99 rel err {q:.3e} >= {tol:.1e} (worst {worst:.3e})"
-    assert worst < 10 * tol, f"{what}: max rel err {worst:.3e} (element {int(e.argmax())}) >= {10 * tol:.1e}"
+    assert worst < worst_factor * tol, f"{what}: max rel err {worst:.3e} (element {int(e.argmax())}) >= {worst_factor * tol:.1e}"
