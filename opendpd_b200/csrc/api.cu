@@ -147,7 +147,7 @@ int64_t odpd_saved_bytes(const OdpdDims *d) {
 int64_t odpd_bwd_workspace_bytes(const OdpdDims *d) {
     if (check_dims(d)) return -1;
     if (is_gru_family(d->cell)) {
-        const int64_t n = gru_family_workspace_floats(d->cell, d->B, d->H, d->tchunks);
+        const int64_t n = gru_family_workspace_floats(d->cell, d->B, d->T, d->H, d->tchunks);
         if (n < 0) { set_error("GRU-family kernels support hidden_size <= 32 (got %d)", d->H); return -1; }
         return 4 * n + 64;
     }

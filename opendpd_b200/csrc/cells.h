@@ -30,12 +30,14 @@ struct GruArgs {
     int *sc_fail;
     float tol;
     int tchunks_req, twarm_req, twarm_default;
+    int wt_blocks;   // split backward: 32-step blocks per CTA of the weights kernel
+    float *gbuf;     // split backward (gru_family.cu): per-step gate gradients [B][T][4*HP+4], written by the chain kernel, read by the weights kernel
 };
 
 // gru_family.cu : GRU / DGRU / QGRU / QGRU_AMP1
 int64_t gru_family_nparams(int cell, int H);
 int64_t gru_family_saved_floats(int cell, int B, int T, int H, bool save, int tchunks_req);
-int64_t gru_family_workspace_floats(int cell, int B, int H, int tchunks_req);
+int64_t gru_family_workspace_floats(int cell, int B, int T, int H, int tchunks_req);
 int gru_family_run(int cell, const GruArgs &a, int dir, bool dw, cudaStream_t st, int *rows_out);
 int gru_family_plan(int cell, int B, int T, int H, int tchunks_req, int twarm_req, int dir, bool dw, bool save, int out[4]);
 

@@ -15,6 +15,7 @@
 //     warp 2 "post"  : output head + squared error + TMA bulk store of the activations (forward);
 //                      weight-gradient accumulation in registers, dL/dfeatures -> dL/dx (backward)
 // The flat parameter block is staged once per CTA into shared memory by a TMA bulk copy.
+#include <cstdlib>
 #include "cells.h"
 #include "pipeline.cuh"
 #include "chunking.cuh"
@@ -731,6 +732,538 @@ __global__ void __launch_bounds__(128, 1) gru_bwd_kernel(GruArgs a) {
     }
 }
 
+// ================================================================ backward, split form (default)
+// The fused backward above keeps four warps per sequence busy, but three of them do TIME-PARALLEL work (weight gradients,
+// dL/dx) with lanes = hidden units inside the latency-critical chain kernel: 323 instructions per timestep and CTA, 219
+// registers, 74 KB of shared memory => 2 CTAs per SM, 4 time chunks.  The split form separates the two kinds of work:
+//   gru_bwdc_kernel  ("chain"): 2 working warps (+1 placement spacer) per (sequence, chunk).  Warp 1 loads the saved rows (TMA) and back-projects the output
+//                    head with lanes = TIMESTEPS (32 steps at once instead of a 32-step loop); warp 0 runs the reverse
+//                    recurrence and streams the per-step gate gradients G_t = (ar | az | an*r | an) to global memory with one
+//                    TMA bulk store per 32-step block.  ~110 instructions per step, ~50 KB => 4 CTAs per SM, 8 chunks.
+//   gru_bwdw_kernel  ("weights"): fully time-parallel, one CTA per (sequence, 256-step tile), no dependence between tiles:
+//                    dL/dW_hh, dL/dW_ih, biases, head gradients (lanes = units, register accumulators) and dL/dx (lanes =
+//                    timesteps) from G_t, the saved rows and the IQ samples; one gradient-partial row per tile.
+// Chunk verification (mode 2) works on the chain kernel exactly as before; the weights kernel runs after it on the final G.
+// floats per timestep of G in shared AND global memory: 4*HP + 4, so that (GS/4) is odd and one-timestep-per-lane LDS.128 reads of a
+// block are bank-conflict free (the chain's own broadcast reads do not care)
+template <int HT> struct GStride { static constexpr int value = 4 * Pad4<HT>::value + 4; };
+template <int HT, int HEAD>
+struct BwdcSmem {
+    static constexpr int HP = Pad4<HT>::value, ROW = Row<HT, HEAD>::value;
+    static constexpr int ACT = (CH + 1) * ROW, DH = CH * HP, G = CH * GStride<HT>::value;
+    __host__ __device__ static constexpr int total(int Ppad) { return 16 + Ppad + 2 * ACT + 2 * DH + 2 * G + DH + 2 * CH; }
+};
+
+template <int HT, int FM, int HEAD>
+__global__ void __launch_bounds__(96, 1) gru_bwdc_kernel(GruArgs a) {
+    constexpr int HP = Pad4<HT>::value, ROW = Row<HT, HEAD>::value, GS = GStride<HT>::value;
+    using SM = BwdcSmem<HT, HEAD>;
+    const GruLayout<FM, HEAD> L(a.H);
+    const int H = a.H, T = a.T;
+    extern __shared__ __align__(128) float smem[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem);   // [0] params, [1..2] activation slots
+    float *sp = smem + 16;
+    const int Ppad = (L.P + 3) & ~3;
+    float *sact = sp + Ppad;                 // [2][(CH+1)][ROW]   row 0 = step t0-1
+    float *sdh = sact + 2 * SM::ACT;         // [2][CH][HP]        dL/dh_t from the head
+    float *sG = sdh + 2 * SM::DH;            // [2][CH][GS]        ar | az | an*r | an | pad
+    float *sdpre = sG + 2 * SM::G;           // [CH][HP]           dpre of the DGRU head (pre warp only)
+    float2 *sgo = reinterpret_cast<float2 *>(sdpre + SM::DH);   // [CH] dLoss/dout (pre warp only)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const BwdRange R = bwd_range(a);
+    const bool spec = R.spec;
+    const int b = R.b, t_elo = R.t_elo, t_ehi = R.t_ehi, t_hi = R.t_hi;
+    if (a.mode == 2 && bwd_verify_pass(a, b, HP, HP, H)) return;
+
+    if (threadIdx.x == 0) { mbar_init(bars + 1, 1); mbar_init(bars + 2, 1); }
+    stage_params(sp, a.params, L.P, bars);
+    const bool act = lane < H;
+    const int j = act ? lane : 0;
+    const int lp = lane < HP ? lane : 0;
+    const int cb = t_elo / CH, ce = (t_hi + CH - 1) / CH, nchunks = ce - cb, ce_emit = (t_ehi + CH - 1) / CH;
+    const float *svg = a.saved + (size_t)b * T * ROW;
+    float *gbuf = a.gbuf + (size_t)b * T * GS;
+    // Warp 2 is a placement spacer and leaves here.  Warps go to sub-partition (warp slot % 4): with 2-warp CTAs the chain warps of the
+    // four co-resident CTAs would pile up on two of the four sub-partitions; with 3-warp CTAs they land on four different ones.
+    if (warp == 2) return;
+    auto stage_sync = [] { asm volatile("bar.sync 1, 64;" ::: "memory"); };
+
+    if (warp == 1) {
+        // =============================== pre: saved rows (TMA) + head back-projection, one timestep per lane
+        const float2 *go2 = a.gout ? reinterpret_cast<const float2 *>(a.gout) + (size_t)b * T : nullptr;
+        const float2 *oi2 = a.out_in ? reinterpret_cast<const float2 *>(a.out_in) + (size_t)b * T : nullptr;
+        const IqRow y2 = iq_row(a.target, a.target_bf16, a.target_starts, b, T);
+        const float gs = a.gscale * (a.gscale_dev ? __ldg(a.gscale_dev) : 1.0f);
+        float whT[HEAD ? HT : 1];
+        if constexpr (HEAD) {
+#pragma unroll
+            for (int k = 0; k < HT; ++k) whT[k] = (act && k < H) ? sp[L.oWh + k * H + j] : 0.f;
+        }
+        const float wo0 = act ? sp[L.oWo + j] : 0.f, wo1 = act ? sp[L.oWo + L.O + j] : 0.f;
+        for (int s = 0; s < nchunks + 1; ++s) {
+            if (s < nchunks) {
+                const int c = ce - 1 - s, t0 = c * CH, nt = min(CH, t_hi - t0), slot = s & 1;
+                float *ac = sact + slot * SM::ACT;
+                float *dh = sdh + slot * SM::DH;
+                uint64_t *bar = bars + 1 + slot;
+                load_rows_with_prev(ac, svg, ROW, t0, nt, lane, bar);
+                if (lane < nt) sgo[lane] = load_gout(go2, oi2, y2, t0 + lane, gs);     // one timestep per lane (coalesced)
+                __syncwarp();
+                mbar_wait(bar, (uint32_t)((s >> 1) & 1));
+                // back-projection of the head with lane = unit: consecutive lanes read consecutive words (no bank conflicts — a
+                // one-timestep-per-lane version needs 8x fewer instructions but its 32-way conflicted row reads stall the chain
+                // warps of all co-resident CTAs, which share the SM's shared-memory pipe)
+                if constexpr (HEAD) {
+                    if (lane < HP) {
+                        for (int tl = 0; tl < nt; ++tl) {
+                            const float2 go = sgo[tl];
+                            const float g = ac[(tl + 1) * ROW + 5 * HP + lane];
+                            sdpre[tl * HP + lane] = g > 0.f ? fmaf(wo0, go.x, wo1 * go.y) : 0.f;
+                        }
+                    }
+                    __syncwarp();
+                    if (lane < HP) {
+#pragma unroll 2
+                        for (int tl = 0; tl < nt; ++tl) {
+                            float d0 = 0.f, d1 = 0.f;
+                            const float4 *dp4 = reinterpret_cast<const float4 *>(sdpre + tl * HP);
+#pragma unroll
+                            for (int k4 = 0; k4 < HP / 4; ++k4) {
+                                const float4 dv = dp4[k4];
+                                const float dk[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const int k = k4 * 4 + e;
+                                    if (k < HT) { if (k & 1) d1 = fmaf(whT[k], dk[e], d1); else d0 = fmaf(whT[k], dk[e], d0); }
+                                }
+                            }
+                            dh[tl * HP + lane] = d0 + d1;
+                        }
+                    }
+                } else {
+                    if (lane < HP) {
+                        for (int tl = 0; tl < nt; ++tl) {
+                            const float2 go = sgo[tl];
+                            dh[tl * HP + lane] = fmaf(wo0, go.x, wo1 * go.y);
+                        }
+                    }
+                }
+            }
+            stage_sync();
+        }
+    } else {
+        // =============================== chain: reverse-time recurrence of dL/dh (identical arithmetic to the fused kernel)
+        float wcol[3 * HT];   // column j of W_hh
+#pragma unroll
+        for (int g = 0; g < 3; ++g)
+#pragma unroll
+            for (int k = 0; k < HT; ++k) wcol[g * HT + k] = (act && k < H) ? sp[L.oWhh + (g * H + k) * H + j] : 0.f;
+        float gH = 0.f;
+        int stores = 0;
+        for (int s = 0; s < nchunks + 1; ++s) {
+            const int sc = s - 1;
+            if (sc >= 0) {
+                const int c = ce - 1 - sc, t0 = c * CH, nt = min(CH, t_hi - t0);
+                if (spec && c == ce_emit - 1 && t_ehi < T && lane < HP) a.sc_guess[(size_t)blockIdx.x * HP + lane] = gH;
+                const float *ac = sact + (sc & 1) * SM::ACT + lp;
+                const float *dh = sdh + (sc & 1) * SM::DH + lp;
+                float *Gb = sG + (sc & 1) * SM::G;
+                // the bulk store issued two blocks ago read this buffer: it must have finished reading before we overwrite it
+                if (stores >= 2) { if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); __syncwarp(); }
+                const float *row = ac + nt * ROW;   // step t0+nt-1
+                float r = row[0], z = row[HP], n = row[2 * HP], hgn = row[3 * HP], hp = row[4 * HP - ROW], dht = dh[(nt - 1) * HP];
+                for (int tl = nt - 1; tl >= 0; --tl) {
+                    const int tp = tl > 0 ? tl - 1 : 0;
+                    const float *rown = ac + (tp + 1) * ROW;
+                    const float r_n = rown[0], z_n = rown[HP], n_n = rown[2 * HP], hgn_n = rown[3 * HP], hp_n = rown[4 * HP - ROW],
+                                dh_n = dh[tp * HP];
+                    gH += dht;
+                    const float gz = gH * (hp - n), gn = gH * (1.f - z), ghp = gH * z;
+                    const float an = gn * (1.f - n * n);
+                    const float az = gz * z * (1.f - z);
+                    const float anr = an * r;
+                    const float ar = anr * hgn * (1.f - r);
+                    float *G = Gb + tl * GS;
+                    if (lane < HP) { G[lane] = ar; G[HP + lane] = az; G[2 * HP + lane] = anr; G[3 * HP + lane] = an; }
+                    __syncwarp();
+                    // six accumulators: three 3H-term dot products as chains of depth ~H/2 (the fused kernel ran depth ~H)
+                    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f, acc4 = 0.f, acc5 = 0.f;
+                    const float4 *G4 = reinterpret_cast<const float4 *>(G);
+                    float4 gv[3 * (HP / 4)];
+#pragma unroll
+                    for (int q = 0; q < 3 * (HP / 4); ++q) gv[q] = G4[q];
+#pragma unroll
+                    for (int k4 = 0; k4 < HP / 4; ++k4) {
+                        const float kr[4] = {gv[k4].x, gv[k4].y, gv[k4].z, gv[k4].w};
+                        const float kz[4] = {gv[HP / 4 + k4].x, gv[HP / 4 + k4].y, gv[HP / 4 + k4].z, gv[HP / 4 + k4].w};
+                        const float kn[4] = {gv[2 * (HP / 4) + k4].x, gv[2 * (HP / 4) + k4].y, gv[2 * (HP / 4) + k4].z, gv[2 * (HP / 4) + k4].w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int k = k4 * 4 + e;
+                            if (k < HT) {
+                                if (k & 1) { acc1 = fmaf(wcol[k], kr[e], acc1); acc3 = fmaf(wcol[HT + k], kz[e], acc3); acc5 = fmaf(wcol[2 * HT + k], kn[e], acc5); }
+                                else       { acc0 = fmaf(wcol[k], kr[e], acc0); acc2 = fmaf(wcol[HT + k], kz[e], acc2); acc4 = fmaf(wcol[2 * HT + k], kn[e], acc4); }
+                            }
+                        }
+                    }
+                    gH = (ghp + (acc0 + acc1)) + ((acc2 + acc3) + (acc4 + acc5));
+                    r = r_n; z = z_n; n = n_n; hgn = hgn_n; hp = hp_n; dht = dh_n;
+                }
+                if (c < ce_emit) {       // warm-up blocks emit nothing
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) tma_store_1d(gbuf + (size_t)t0 * GS, Gb, (uint32_t)(nt * GS * 4));
+                    ++stores;
+                }
+            }
+            stage_sync();
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if (spec && lane < HP) a.sc_end[(size_t)blockIdx.x * HP + lane] = gH;
+    }
+}
+
+template <int HT, int FM, int HEAD>
+struct BwdwSmem {
+    static constexpr int HP = Pad4<HT>::value, ROW = Row<HT, HEAD>::value;
+    static constexpr int ACT = (CH + 1) * ROW, G = CH * GStride<HT>::value, PRE = CH * 12, DP = CH * HP;
+    __host__ __device__ static constexpr int total(int Ppad) { return 16 + Ppad + 3 * ACT + 3 * G + 2 * PRE + 2 * DP + 16; }
+};
+
+// N consecutive floats from shared memory with the widest loads the tile geometry guarantees (p is 4*gcd(N,4)-byte aligned)
+template <int N>
+__device__ __forceinline__ void lds_vec(const float *p, float (&v)[N]) {
+    if constexpr (N % 4 == 0) {
+#pragma unroll
+        for (int q = 0; q < N / 4; ++q) { const float4 t = reinterpret_cast<const float4 *>(p)[q]; v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w; }
+    } else if constexpr (N % 2 == 0) {
+#pragma unroll
+        for (int q = 0; q < N / 2; ++q) { const float2 t = reinterpret_cast<const float2 *>(p)[q]; v[2 * q] = t.x; v[2 * q + 1] = t.y; }
+    } else {
+#pragma unroll
+        for (int q = 0; q < N; ++q) v[q] = p[q];
+    }
+}
+// acc[i][c] += a[i] * b[c]
+template <int TR, int TC>
+__device__ __forceinline__ void outer_acc(float (&acc)[TR * TC], const float (&av)[TR], const float (&bv)[TC]) {
+#pragma unroll
+    for (int i = 0; i < TR; ++i)
+#pragma unroll
+        for (int c = 0; c < TC; ++c) acc[i * TC + c] = fmaf(av[i], bv[c], acc[i * TC + c]);
+}
+
+// One CTA = one (sequence, tile of a.wt_blocks 32-step blocks); tiles are independent.  Every weight gradient is a sum over time of
+// an outer product of two per-timestep vectors, so the kernel is organised as small register-tiled GEMMs whose K dimension is time:
+// each lane owns a TR x TC tile of the output, reads TR + TC operands per timestep (vector LDS, mostly broadcast) and issues TR*TC
+// FMAs — all 32 lanes busy, instead of lanes = hidden units (13 of 32 busy for the headline model).
+//   warp 0 "prep" : TMA loads of the saved rows and of G one block ahead; per timestep (one per lane) features (+ a ones column),
+//                   dLoss/dout and, for the DGRU head, dpre = relu'(.) * (W_o^T dLoss/dout)
+//   warp 1 "hh"   : dL/dW_hh            = sum_t [ar|az|an*r]_t (x) h_{t-1}            lanes 8 x 4, tile ceil(3HP/8) x HP/4
+//   warp 2 "ih"   : dL/dW_ih, all biases = sum_t [ar|az|an*r|an]_t (x) [feat_t, 1]     lanes 16 x 2 (32 x 1 for 2 features), tile x 4
+//                   head: dL/dfc_hid.W  = sum_t dpre_t (x) h_t (lanes 8 x 4);  dL/dfc_out.W[:, :H] = sum_t dLoss/dout_t (x) g_t (lane = column)
+//   warp 3 "dx"   : one timestep per lane: dL/dfeatures = W_ih^T [ar|az|an] (+ head) -> dL/dx; per-timestep sums (fc_out bias and
+//                   feature columns, fc_hid bias)
+template <int HT, int FM, int HEAD, bool DW>
+__global__ void __launch_bounds__(128, 1) gru_bwdw_kernel(GruArgs a) {
+    constexpr int F = FeatN<FM>::value, HP = Pad4<HT>::value, ROW = Row<HT, HEAD>::value, GS = GStride<HT>::value;
+    using SM = BwdwSmem<HT, FM, HEAD>;
+    const GruLayout<FM, HEAD> L(a.H);
+    const int H = a.H, T = a.T;
+    extern __shared__ __align__(128) float smem[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem);   // [0] params, [1..3] block slots
+    float *sp = smem + 16;
+    const int Ppad = (L.P + 3) & ~3;
+    float *sact = sp + Ppad;                 // [3][(CH+1)][ROW]
+    float *sG = sact + 3 * SM::ACT;          // [3][CH][GS]
+    float *spre = sG + 3 * SM::G;            // [2][CH][12]   feat(F) | 1 | 0.. (8) | go(2) | -
+    float *sdp = spre + 2 * SM::PRE;         // [2][CH][HP]   dpre (DGRU head)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.y, tile = blockIdx.x;
+    const int WTs = a.wt_blocks * CH;
+    const int t_lo = tile * WTs, t_hi = min(T, t_lo + WTs);
+    const int nblk = (t_hi - t_lo + CH - 1) / CH;
+    if (threadIdx.x == 0) { mbar_init(bars + 1, 1); mbar_init(bars + 2, 1); mbar_init(bars + 3, 1); }
+    stage_params(sp, a.params, L.P, bars);
+    const IqRow x2 = iq_row(a.x, a.x_bf16, a.x_starts, b, T);
+    const float *svg = a.saved + (size_t)b * T * ROW;
+    const float *gbuf = a.gbuf + (size_t)b * T * GS;
+    float *prt = (DW && a.partials) ? a.partials + ((size_t)b * gridDim.x + tile) * L.P : nullptr;
+
+    if (warp == 0) {
+        // =============================== prep
+        const float2 *go2 = a.gout ? reinterpret_cast<const float2 *>(a.gout) + (size_t)b * T : nullptr;
+        const float2 *oi2 = a.out_in ? reinterpret_cast<const float2 *>(a.out_in) + (size_t)b * T : nullptr;
+        const IqRow y2 = iq_row(a.target, a.target_bf16, a.target_starts, b, T);
+        const float gs = a.gscale * (a.gscale_dev ? __ldg(a.gscale_dev) : 1.0f);
+        auto issue = [&](int q) {      // TMA loads of block q into slot q % 3
+            const int t0 = t_lo + q * CH, nt = min(CH, t_hi - t0), slot = q % 3;
+            float *ac = sact + slot * SM::ACT;
+            uint64_t *bar = bars + 1 + slot;
+            if (lane == 0) {
+                const uint32_t gbytes = (uint32_t)(nt * GS * 4);
+                if (t0 > 0) {
+                    const uint32_t bytes = (uint32_t)((nt + 1) * ROW * 4);
+                    mbar_expect_tx(bar, bytes + gbytes);
+                    tma_load_1d(ac, svg + (size_t)(t0 - 1) * ROW, bytes, bar);
+                } else {
+                    const uint32_t bytes = (uint32_t)(nt * ROW * 4);
+                    mbar_expect_tx(bar, bytes + gbytes);
+                    tma_load_1d(ac + ROW, svg, bytes, bar);
+                }
+                tma_load_1d(sG + slot * SM::G, gbuf + (size_t)t0 * GS, gbytes, bar);
+            }
+            if (t0 == 0) { for (int i = lane; i < ROW; i += 32) ac[i] = 0.f; }   // h_{-1} = 0
+        };
+        // global loads of a block (x, and out/target or dLoss/dout) are issued one block ahead and held in registers, so that their
+        // latency overlaps the previous block's work instead of heading every stage
+        auto fetch = [&](int q, float2 &v, float2 &go) {
+            const int t0 = t_lo + q * CH, nt = min(CH, t_hi - t0);
+            v = make_float2(0.f, 0.f); go = make_float2(0.f, 0.f);
+            if (q < nblk && lane < nt) { v = __ldg(x2 + t0 + lane); go = load_gout(go2, oi2, y2, t0 + lane, gs); }
+        };
+        const float wo0 = (HEAD && lane < H) ? sp[L.oWo + lane] : 0.f, wo1 = (HEAD && lane < H) ? sp[L.oWo + L.O + lane] : 0.f;
+        issue(0);
+        float2 v_n, go_n;
+        fetch(0, v_n, go_n);
+        for (int s = 0; s < nblk + 1; ++s) {
+            if (s < nblk) {
+                if (s + 1 < nblk) issue(s + 1);
+                const float2 v = v_n, go = go_n;
+                fetch(s + 1, v_n, go_n);
+                const int t0 = t_lo + s * CH, nt = min(CH, t_hi - t0), slot = s % 3;
+                float *pr = spre + (s & 1) * SM::PRE, *dp = sdp + (s & 1) * SM::DP;
+                float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                if (lane < nt) {
+                    features_fwd<FM>(v.x, v.y, 0.f, 0.f, f);
+                    f[F] = 1.0f;                                                  // the ones column: bias gradients fall out of the same GEMM
+                }
+                // lanes >= nt (ragged last block) contribute zeros: the GEMM warps always run all 32 timesteps of a block
+                float4 *d = reinterpret_cast<float4 *>(pr + lane * 12);
+                d[0] = make_float4(f[0], f[1], f[2], f[3]);
+                d[1] = make_float4(f[4], f[5], f[6], f[7]);
+                d[2] = make_float4(go.x, go.y, 0.f, 0.f);
+                __syncwarp();
+                mbar_wait(bars + 1 + slot, (uint32_t)((s / 3) & 1));
+                if (nt < CH) {      // ragged block: zero the G rows and the h rows of the missing timesteps so that they add nothing
+                    float *Gz = sG + slot * SM::G + nt * GS;
+                    for (int i = lane; i < (CH - nt) * GS; i += 32) Gz[i] = 0.f;
+                    float *az = sact + slot * SM::ACT + (nt + 1) * ROW;
+                    for (int i = lane; i < (CH - nt) * ROW; i += 32) az[i] = 0.f;
+                    __syncwarp();
+                }
+                if constexpr (HEAD) {
+                    // dpre with lane = unit (conflict-free): relu'(fc_hid) * (W_o^T dLoss/dout); zero rows for a ragged tail
+                    if (lane < HP) {
+                        const float *grow = sact + slot * SM::ACT + ROW + 5 * HP + lane;
+#pragma unroll 4
+                        for (int tl = 0; tl < CH; ++tl) {
+                            const float2 g2 = *reinterpret_cast<const float2 *>(pr + tl * 12 + 8);
+                            dp[tl * HP + lane] = (tl < nt && grow[tl * ROW] > 0.f) ? fmaf(wo0, g2.x, wo1 * g2.y) : 0.f;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    } else if (warp == 1) {
+        // =============================== dL/dW_hh
+        constexpr int TR = (3 * HP + 7) / 8, TC = HP / 4;
+        const int rg = lane >> 2, cg = lane & 3;
+        float acc[DW ? TR * TC : 1];
+        if constexpr (DW) {
+#pragma unroll
+            for (int q = 0; q < TR * TC; ++q) acc[q] = 0.f;
+        }
+        for (int s = 0; s < nblk + 1; ++s) {
+            const int sc = s - 1;
+            if (sc >= 0) {
+                if constexpr (DW) {
+                    const float *Ap = sG + (sc % 3) * SM::G + TR * rg;
+                    const float *Bp = sact + (sc % 3) * SM::ACT + 4 * HP + TC * cg;      // row tl = step t-1: h_{t-1}
+#pragma unroll 4
+                    for (int tl = 0; tl < CH; ++tl) {
+                        float av[TR], bv[TC];
+                        lds_vec<TR>(Ap + tl * GS, av);
+                        lds_vec<TC>(Bp + tl * ROW, bv);
+                        outer_acc<TR, TC>(acc, av, bv);
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        if constexpr (DW) {
+            if (prt) {
+#pragma unroll
+                for (int i = 0; i < TR; ++i) {
+                    const int r = TR * rg + i, g = r / HP, k = r - g * HP;
+#pragma unroll
+                    for (int c = 0; c < TC; ++c) {
+                        const int jj = TC * cg + c;
+                        if (r < 3 * HP && k < H && jj < H) prt[L.oWhh + (g * H + k) * H + jj] = acc[i * TC + c];
+                    }
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // =============================== dL/dW_ih + every bias (ones column), head weights
+        constexpr int NC = (F + 1 + 3) & ~3;                 // feature columns + the ones column, padded to 4
+        constexpr int LC = NC / 4, LR = 32 / LC, TR = (4 * HP + LR - 1) / LR, TC = 4;
+        constexpr int TR3 = (HP + 7) / 8, TC3 = HP / 4;       // head: dpre (x) h_t
+        const int rg = lane / LC, cg = lane % LC;
+        const int rg3 = lane >> 2, cg3 = lane & 3;
+        const int lp = lane < HP ? lane : 0;
+        float acc[DW ? TR * TC : 1], acc3[(DW && HEAD) ? TR3 * TC3 : 1];
+        float gwo0 = 0.f, gwo1 = 0.f;
+        if constexpr (DW) {
+#pragma unroll
+            for (int q = 0; q < TR * TC; ++q) acc[q] = 0.f;
+            if constexpr (HEAD) {
+#pragma unroll
+                for (int q = 0; q < TR3 * TC3; ++q) acc3[q] = 0.f;
+            }
+        }
+        for (int s = 0; s < nblk + 1; ++s) {
+            const int sc = s - 1;
+            if (sc >= 0) {
+                if constexpr (DW) {
+                    const float *Ap = sG + (sc % 3) * SM::G + TR * rg;
+                    const float *Bp = spre + (sc & 1) * SM::PRE + TC * cg;
+                    const float *ac = sact + (sc % 3) * SM::ACT;
+                    const float *pr = spre + (sc & 1) * SM::PRE;
+                    const float *A3 = sdp + (sc & 1) * SM::DP + TR3 * rg3;
+                    const float *B3 = ac + ROW + 4 * HP + TC3 * cg3;                      // row tl+1 = step t: h_t
+                    const float *hcol = ac + ROW + (HEAD ? 5 : 4) * HP + lp;             // g_t (DGRU) or h_t feeds fc_out
+#pragma unroll 4
+                    for (int tl = 0; tl < CH; ++tl) {
+                        float av[TR], bv[TC];
+                        lds_vec<TR>(Ap + tl * GS, av);
+                        lds_vec<TC>(Bp + tl * 12, bv);
+                        outer_acc<TR, TC>(acc, av, bv);
+                        if constexpr (HEAD) {
+                            float a3[TR3], b3[TC3];
+                            lds_vec<TR3>(A3 + tl * HP, a3);
+                            lds_vec<TC3>(B3 + tl * ROW, b3);
+                            outer_acc<TR3, TC3>(acc3, a3, b3);
+                        }
+                        const float2 go = *reinterpret_cast<const float2 *>(pr + tl * 12 + 8);
+                        const float hv = hcol[tl * ROW];
+                        gwo0 = fmaf(go.x, hv, gwo0); gwo1 = fmaf(go.y, hv, gwo1);
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        if constexpr (DW) {
+            if (prt) {
+#pragma unroll
+                for (int i = 0; i < TR; ++i) {
+                    const int r = TR * rg + i, blk = r / HP, k = r - blk * HP;     // blk: 0 ar, 1 az, 2 an*r, 3 an
+                    if (r < 4 * HP && k < H) {
+#pragma unroll
+                        for (int c = 0; c < TC; ++c) {
+                            const int col = TC * cg + c;
+                            const float v = acc[i * TC + c];
+                            if (col < F && blk != 2) prt[L.oWih + ((blk == 3 ? 2 : blk) * H + k) * F + col] = v;
+                            if (col == F) {
+                                if (blk < 2) { prt[L.obih + blk * H + k] = v; prt[L.obhh + blk * H + k] = v; }
+                                else if (blk == 3) prt[L.obih + 2 * H + k] = v;
+                                else prt[L.obhh + 2 * H + k] = v;
+                            }
+                        }
+                    }
+                }
+                if constexpr (HEAD) {
+#pragma unroll
+                    for (int i = 0; i < TR3; ++i) {
+                        const int k = TR3 * rg3 + i;
+#pragma unroll
+                        for (int c = 0; c < TC3; ++c) {
+                            const int jj = TC3 * cg3 + c;
+                            if (k < H && jj < H) prt[L.oWh + k * H + jj] = acc3[i * TC3 + c];
+                        }
+                    }
+                }
+                if (lane < H) { prt[L.oWo + lane] = gwo0; prt[L.oWo + L.O + lane] = gwo1; }
+            }
+        }
+    } else {
+        // =============================== dL/dfeatures -> dL/dx and the per-timestep sums: one timestep per lane
+        float gbo0 = 0.f, gbo1 = 0.f;
+        float gwof[(DW && HEAD) ? 2 * F : 1], gbh[(DW && HEAD) ? HP : 1];
+        if constexpr (DW && HEAD) {
+#pragma unroll
+            for (int q = 0; q < 2 * F; ++q) gwof[q] = 0.f;
+#pragma unroll
+            for (int q = 0; q < HP; ++q) gbh[q] = 0.f;
+        }
+        float2 *gx2 = (a.need_dx && a.gx) ? reinterpret_cast<float2 *>(a.gx) + (size_t)b * T : nullptr;
+        for (int s = 0; s < nblk + 1; ++s) {
+            const int sc = s - 1;
+            if (sc >= 0) {
+                const int t0 = t_lo + sc * CH, nt = min(CH, t_hi - t0);
+                const float *Gb = sG + (sc % 3) * SM::G;
+                const float *p = spre + (sc & 1) * SM::PRE + lane * 12;
+                const float g0 = p[8], g1 = p[9];          // zero for lanes >= nt
+                if constexpr (DW) {
+                    gbo0 += g0; gbo1 += g1;
+                    if constexpr (HEAD) {
+                        float fv[8];
+                        lds_vec<8>(p, fv);
+#pragma unroll
+                        for (int q = 0; q < F; ++q) { gwof[q] = fmaf(g0, fv[q], gwof[q]); gwof[F + q] = fmaf(g1, fv[q], gwof[F + q]); }
+                        float dv[HP];
+                        lds_vec<HP>(sdp + (sc & 1) * SM::DP + lane * HP, dv);
+#pragma unroll
+                        for (int q = 0; q < HP; ++q) gbh[q] += dv[q];
+                    }
+                }
+                if (gx2 && lane < nt) {
+                    // dL/dfeat[q] = sum_k W_ih[r,k][q] ar_k + W_ih[z,k][q] az_k + W_ih[n,k][q] an_k  (+ head: wof[.][q] . go)
+                    float gf[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    float gv[4 * HP];          // ar | az | an*r | an of this lane's timestep (GS/4 odd: conflict-free LDS.128)
+                    lds_vec<4 * HP>(Gb + lane * GS, gv);
+#pragma unroll
+                    for (int k = 0; k < HT; ++k) {
+                        if (k < H) {
+                            const float ar = gv[k], az = gv[HP + k], an = gv[3 * HP + k];
+                            const float *wr = sp + L.oWih + (0 * H + k) * F, *wz = sp + L.oWih + (1 * H + k) * F, *wn = sp + L.oWih + (2 * H + k) * F;
+#pragma unroll
+                            for (int q = 0; q < F; ++q) gf[q] = fmaf(wn[q], an, fmaf(wz[q], az, fmaf(wr[q], ar, gf[q])));
+                        }
+                    }
+                    if constexpr (HEAD) {
+#pragma unroll
+                        for (int q = 0; q < F; ++q) gf[q] += fmaf(sp[L.oWo + H + q], g0, sp[L.oWo + L.O + H + q] * g1);
+                    }
+                    float gi, gq;
+                    features_bwd<FM>(p[0], p[1], gf, gi, gq);          // features 0,1 are the raw (I,Q) sample in every feature mode
+                    gx2[t0 + lane] = make_float2(gi, gq);
+                }
+            }
+            __syncthreads();
+        }
+        if constexpr (DW) {
+            if (prt) {
+                gbo0 = warp_sum(gbo0); gbo1 = warp_sum(gbo1);
+                if (lane == 0) { prt[L.obo] = gbo0; prt[L.obo + 1] = gbo1; }
+                if constexpr (HEAD) {
+#pragma unroll
+                    for (int q = 0; q < 2 * F; ++q) {
+                        const float sum = warp_sum(gwof[q]);
+                        if (lane == 0) prt[L.oWo + (q / F) * L.O + H + (q % F)] = sum;
+                    }
+#pragma unroll
+                    for (int q = 0; q < HP; ++q) {
+                        const float sum = warp_sum(gbh[q]);
+                        if (lane == 0 && q < H) prt[L.obh + q] = sum;
+                    }
+                }
+            }
+        }
+    }
+}
+
 // ================================================================ host dispatch
 template <int FM, int HEAD> static int64_t gru_nparams(int H) { return GruLayout<FM, HEAD>(H).P; }
 
@@ -754,15 +1287,62 @@ static int launch_fwd(GruArgs a, cudaStream_t st, bool plan_only, int *info) {
     return chunk_launch(gru_fwd_kernel<HT, FM, HEAD>, 96, smem, &occ, a, 0, a.saved ? a.saved + soff : nullptr, soff, HP, st, plan_only, info,
                         "gru_fwd_kernel");
 }
+// backward workspace (floats):  [rowsP][P] gradient partials (4-aligned) | chunk scratch | G buffer [B][T][GS]
+//   rowsP = max(rows of the fused kernel (one per (sequence, chunk)), rows of the weights kernel (one per (sequence, WT-step tile)))
+static constexpr int WTILES_MAX = 16;   // weights-kernel tiles per sequence (upper bound: sizes the gradient-partial rows)
+static inline int64_t bwd_partial_rows(int B, int T, int tchunks_req) {
+    const int64_t nblk = (T + CH - 1) / CH;
+    const int64_t a = chunk_rows(B, tchunks_req), b = (int64_t)(B > 0 ? B : 1) * (nblk < WTILES_MAX ? (nblk > 0 ? nblk : 1) : WTILES_MAX);
+    return a > b ? a : b;
+}
+static inline bool bwd_split_enabled() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("ODPD_BWD_SPLIT"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v != 0;
+}
+
 template <int HT, int FM, int HEAD, bool DW>
 static int launch_bwd_t(GruArgs a, cudaStream_t st, bool plan_only, int *info) {
-    constexpr int HP = Pad4<HT>::value;
+    constexpr int HP = Pad4<HT>::value, GS = GStride<HT>::value;
     const GruLayout<FM, HEAD> L(a.H);
-    const size_t smem = (size_t)BwdSmem<HT, HEAD>::total((L.P + 3) & ~3) * sizeof(float);
-    static OccCache occ{};
-    const int64_t woff = (chunk_rows(a.B, a.tchunks_req) * L.P + 3) & ~(int64_t)3;   // workspace = [rows][P] partials | chunk scratch
-    return chunk_launch(gru_bwd_kernel<HT, FM, HEAD, DW>, 128, smem, &occ, a, 1, a.partials ? a.partials + woff : nullptr, woff, HP, st,
-                        plan_only, info, "gru_bwd_kernel");
+    const int Ppad = (L.P + 3) & ~3;
+    const int64_t rows = chunk_rows(a.B, a.tchunks_req);
+    const int64_t woff = (bwd_partial_rows(a.B, a.T, a.tchunks_req) * L.P + 3) & ~(int64_t)3;
+    float *scr = a.partials ? a.partials + woff : nullptr;
+    if (!bwd_split_enabled() || (!plan_only && !a.partials)) {
+        // fused form: one kernel (kept for A/B comparison, ODPD_BWD_SPLIT=0, and for a dX-only backward without workspace)
+        const size_t smem = (size_t)BwdSmem<HT, HEAD>::total(Ppad) * sizeof(float);
+        static OccCache occ{};
+        const int rc = chunk_launch(gru_bwd_kernel<HT, FM, HEAD, DW>, 128, smem, &occ, a, 1, scr, woff, HP, st, plan_only, info, "gru_bwd_kernel");
+        if (info) info[4] = a.B * info[0];
+        return rc;
+    }
+    a.gbuf = scr ? scr + chunk_bwd_scratch_floats(rows, HP) : nullptr;
+    const size_t smem_c = (size_t)BwdcSmem<HT, HEAD>::total(Ppad) * sizeof(float);
+    static OccCache occ_c{};
+    int rc = chunk_launch(gru_bwdc_kernel<HT, FM, HEAD>, 96, smem_c, &occ_c, a, 1, scr, woff, HP, st, plan_only, info, "gru_bwdc_kernel");
+    // weights kernel: tiles per sequence chosen so that all CTAs are resident at once (one wave), at most WTILES_MAX
+    const size_t smem_w = (size_t)BwdwSmem<HT, FM, HEAD>::total(Ppad) * sizeof(float);
+    static OccCache occ_w{};
+    auto kw = gru_bwdw_kernel<HT, FM, HEAD, DW>;
+    int *ow = &occ_w.v[cur_dev_slot()];
+    if (!*ow) {
+        cudaFuncSetAttribute(kw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w);
+        int o = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kw, 128, smem_w) != cudaSuccess || o <= 0) o = 1;
+        *ow = o;
+    }
+    const int nblk = (a.T + CH - 1) / CH;
+    int tiles = (*ow * num_sms()) / (a.B > 0 ? a.B : 1);
+    tiles = tiles < 1 ? 1 : (tiles > WTILES_MAX ? WTILES_MAX : tiles);
+    if (tiles > nblk) tiles = nblk;
+    a.wt_blocks = (nblk + tiles - 1) / tiles;
+    tiles = (nblk + a.wt_blocks - 1) / a.wt_blocks;
+    if (info) info[4] = a.B * tiles;
+    if (rc || plan_only) return rc;
+    kw<<<dim3((unsigned)tiles, (unsigned)a.B), 128, smem_w, st>>>(a);
+    (void)GS;
+    return check_launch("gru_bwdw_kernel");
 }
 
 template <int FM, int HEAD>
@@ -795,10 +1375,12 @@ int64_t gru_family_saved_floats(int cell, int B, int T, int H, bool save, int tc
     const int64_t rowsz = save ? (int64_t)B * T * (cell == ODPD_CELL_DGRU ? 6 : 5) * HP : 0;
     return rowsz + chunk_fwd_scratch_floats(chunk_rows(B, tchunks_req), HP);
 }
-int64_t gru_family_workspace_floats(int cell, int B, int H, int tchunks_req) {
+int64_t gru_family_workspace_floats(int cell, int B, int T, int H, int tchunks_req) {
     const int ht = gru_tier(H);
     if (ht < 0) return -1;
-    return chunk_workspace_floats(chunk_rows(B, tchunks_req), gru_family_nparams(cell, H), (ht + 3) & ~3);
+    const int HP = (ht + 3) & ~3;
+    const int64_t partials = (bwd_partial_rows(B, T, tchunks_req) * gru_family_nparams(cell, H) + 3) & ~(int64_t)3;
+    return partials + chunk_bwd_scratch_floats(chunk_rows(B, tchunks_req), HP) + (int64_t)(B > 0 ? B : 1) * (T > 0 ? T : 1) * (4 * HP + 4);
 }
 
 static int run_or_plan(int cell, const GruArgs &a, int dir, bool dw, cudaStream_t st, int *info) {
@@ -814,16 +1396,19 @@ static int run_or_plan(int cell, const GruArgs &a, int dir, bool dw, cudaStream_
 
 // rows_out: number of gradient-partial rows the backward wrote (B * chunks), for the ordered reduction that follows
 int gru_family_run(int cell, const GruArgs &a, int dir, bool dw, cudaStream_t st, int *rows_out) {
-    int info[4] = {1, 0, 0, 0};
+    int info[5] = {1, 0, 0, 0, 0};
     const int rc = run_or_plan(cell, a, dir, dw, st, info);
-    if (rows_out) *rows_out = a.B * info[0];
+    if (rows_out) *rows_out = info[4] > 0 ? info[4] : a.B * info[0];
     return rc;
 }
 
 int gru_family_plan(int cell, int B, int T, int H, int tchunks_req, int twarm_req, int dir, bool dw, bool save, int out[4]) {
     GruArgs a{};
     a.B = B; a.T = T; a.H = H; a.tchunks_req = tchunks_req; a.twarm_req = twarm_req; a.save = save;
-    return run_or_plan(cell, a, 2 + (dir & 1), dw, nullptr, out);
+    int info[5] = {1, 0, 0, -1, 0};
+    const int rc = run_or_plan(cell, a, 2 + (dir & 1), dw, nullptr, info);
+    for (int i = 0; i < 4; ++i) out[i] = info[i];
+    return rc;
 }
 
 }  // namespace odpd
