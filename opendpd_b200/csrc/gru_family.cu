@@ -1264,6 +1264,390 @@ __global__ void __launch_bounds__(128, 1) gru_bwdw_kernel(GruArgs a) {
     }
 }
 
+// ================================================================ backward, lean fused form (default)
+// Measured (B200, C2a): the split form above does not pay — its chain kernel runs 8 chunks at 54 us, but the weights kernel needs
+// ~45 us to stream G and the saved rows back in (170 MB of extra traffic; 21 KB bulk copies with one block of look-ahead).  The lean
+// fused form keeps everything in one kernel like the original, so G never leaves shared memory, but borrows the two things that
+// made the split attractive: the register-tiled GEMM warps (every lane busy) instead of lane = hidden unit, and a footprint small
+// enough (5 warps, <= 136 registers, ~75 KB) for 3 CTAs per SM => 6 time chunks instead of 4.
+//   warp 0 chain | warp 1 pre (TMA rows, features, dLoss/dout, head back-projection) | warp 2 dW_hh | warp 3 dW_ih + biases + head
+//   weights | warp 4 dL/dx + per-timestep sums.   Stage s: pre works on block s, chain on block s-1, the three GEMM warps on block s-2.
+template <int HT, int FM, int HEAD>
+struct BwdfSmem {
+    static constexpr int HP = Pad4<HT>::value, ROW = Row<HT, HEAD>::value;
+    static constexpr int ACT = (CH + 1) * ROW, DH = CH * HP, G = CH * GStride<HT>::value, PRE = CH * 12;
+    __host__ __device__ static constexpr int total(int Ppad) { return 16 + Ppad + 3 * ACT + 2 * DH + 2 * G + 3 * PRE + 3 * DH; }
+};
+
+template <int HT, int FM, int HEAD, bool DW>
+__global__ void __launch_bounds__(160, 1) gru_bwdf_kernel(GruArgs a) {
+    constexpr int F = FeatN<FM>::value, HP = Pad4<HT>::value, ROW = Row<HT, HEAD>::value, GS = GStride<HT>::value;
+    using SM = BwdfSmem<HT, FM, HEAD>;
+    const GruLayout<FM, HEAD> L(a.H);
+    const int H = a.H, T = a.T;
+    extern __shared__ __align__(128) float smem[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem);   // [0] params, [1..3] activation slots
+    float *sp = smem + 16;
+    const int Ppad = (L.P + 3) & ~3;
+    float *sact = sp + Ppad;                 // [3][(CH+1)][ROW]   row 0 = step t0-1
+    float *sdh = sact + 3 * SM::ACT;         // [2][CH][HP]        dL/dh_t from the head
+    float *sG = sdh + 2 * SM::DH;            // [2][CH][GS]        ar | az | an*r | an | pad
+    float *spre = sG + 2 * SM::G;            // [3][CH][12]        feat(F) | 1 | 0.. (8) | go(2) | -
+    float *sdp = spre + 3 * SM::PRE;         // [3][CH][HP]        dpre (DGRU head)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const BwdRange R = bwd_range(a);
+    const bool spec = R.spec;
+    const int b = R.b, t_elo = R.t_elo, t_ehi = R.t_ehi, t_hi = R.t_hi;
+    if (a.mode == 2 && bwd_verify_pass(a, b, HP, HP, H)) return;
+
+    if (threadIdx.x == 0) { mbar_init(bars + 1, 1); mbar_init(bars + 2, 1); mbar_init(bars + 3, 1); }
+    stage_params(sp, a.params, L.P, bars);
+    const bool act = lane < H;
+    const int j = act ? lane : 0;
+    const int lp = lane < HP ? lane : 0;
+    const int cb = t_elo / CH, ce = (t_hi + CH - 1) / CH, nchunks = ce - cb, ce_emit = (t_ehi + CH - 1) / CH;
+    const IqRow x2 = iq_row(a.x, a.x_bf16, a.x_starts, b, T);
+    const float *svg = a.saved + (size_t)b * T * ROW;
+    float *prt = nullptr;
+    if constexpr (DW) {
+        if (a.partials && warp >= 2) prt = chunk_partial_row(a, spec, b, L.P, (warp - 2) * 32 + lane, 96);
+    }
+
+    if (warp == 1) {
+        // =============================== pre
+        const float2 *go2 = a.gout ? reinterpret_cast<const float2 *>(a.gout) + (size_t)b * T : nullptr;
+        const float2 *oi2 = a.out_in ? reinterpret_cast<const float2 *>(a.out_in) + (size_t)b * T : nullptr;
+        const IqRow y2 = iq_row(a.target, a.target_bf16, a.target_starts, b, T);
+        const float gs = a.gscale * (a.gscale_dev ? __ldg(a.gscale_dev) : 1.0f);
+        float whT[HEAD ? HT : 1];
+        if constexpr (HEAD) {
+#pragma unroll
+            for (int k = 0; k < HT; ++k) whT[k] = (act && k < H) ? sp[L.oWh + k * H + j] : 0.f;
+        }
+        const float wo0 = act ? sp[L.oWo + j] : 0.f, wo1 = act ? sp[L.oWo + L.O + j] : 0.f;
+        for (int s = 0; s < nchunks + 2; ++s) {
+            if (s < nchunks) {
+                const int c = ce - 1 - s, t0 = c * CH, nt = min(CH, t_hi - t0), slot = s % 3;
+                float *ac = sact + slot * SM::ACT;
+                float *pr = spre + slot * SM::PRE, *dp = sdp + slot * SM::DH;
+                float *dh = sdh + (s & 1) * SM::DH;
+                uint64_t *bar = bars + 1 + slot;
+                load_rows_with_prev(ac, svg, ROW, t0, nt, lane, bar);
+                {   // one timestep per lane: features (+ the ones column) and dLoss/dout; zeros for a ragged tail
+                    float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    float2 go = make_float2(0.f, 0.f);
+                    if (lane < nt) {
+                        const float2 v = __ldg(x2 + t0 + lane);
+                        features_fwd<FM>(v.x, v.y, 0.f, 0.f, f);
+                        f[F] = 1.0f;
+                        go = load_gout(go2, oi2, y2, t0 + lane, gs);
+                    }
+                    float4 *d = reinterpret_cast<float4 *>(pr + lane * 12);
+                    d[0] = make_float4(f[0], f[1], f[2], f[3]);
+                    d[1] = make_float4(f[4], f[5], f[6], f[7]);
+                    d[2] = make_float4(go.x, go.y, 0.f, 0.f);
+                }
+                __syncwarp();
+                mbar_wait(bar, (uint32_t)((s / 3) & 1));
+                if (nt < CH) {      // ragged block: the GEMM warps run all 32 timesteps, the missing ones must add nothing
+                    float *az = ac + (nt + 1) * ROW;
+                    for (int i = lane; i < (CH - nt) * ROW; i += 32) az[i] = 0.f;
+                    __syncwarp();
+                }
+                if constexpr (HEAD) {
+                    if (lane < HP) {
+                        const float *grow = ac + ROW + 5 * HP + lane;
+#pragma unroll 4
+                        for (int tl = 0; tl < CH; ++tl) {
+                            const float2 g2 = *reinterpret_cast<const float2 *>(pr + tl * 12 + 8);
+                            dp[tl * HP + lane] = (tl < nt && grow[tl * ROW] > 0.f) ? fmaf(wo0, g2.x, wo1 * g2.y) : 0.f;
+                        }
+                    }
+                    __syncwarp();
+                    if (lane < HP) {
+#pragma unroll 2
+                        for (int tl = 0; tl < nt; ++tl) {
+                            float d0 = 0.f, d1 = 0.f;
+                            const float4 *dp4 = reinterpret_cast<const float4 *>(dp + tl * HP);
+#pragma unroll
+                            for (int k4 = 0; k4 < HP / 4; ++k4) {
+                                const float4 dv = dp4[k4];
+                                const float dk[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const int k = k4 * 4 + e;
+                                    if (k < HT) { if (k & 1) d1 = fmaf(whT[k], dk[e], d1); else d0 = fmaf(whT[k], dk[e], d0); }
+                                }
+                            }
+                            dh[tl * HP + lane] = d0 + d1;
+                        }
+                    }
+                } else {
+                    if (lane < HP) {
+                        for (int tl = 0; tl < nt; ++tl) {
+                            const float2 g2 = *reinterpret_cast<const float2 *>(pr + tl * 12 + 8);
+                            dh[tl * HP + lane] = fmaf(wo0, g2.x, wo1 * g2.y);
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    } else if (warp == 0) {
+        // =============================== chain: reverse-time recurrence of dL/dh
+        float wcol[3 * HT];   // column j of W_hh
+#pragma unroll
+        for (int g = 0; g < 3; ++g)
+#pragma unroll
+            for (int k = 0; k < HT; ++k) wcol[g * HT + k] = (act && k < H) ? sp[L.oWhh + (g * H + k) * H + j] : 0.f;
+        float gH = 0.f;
+        for (int s = 0; s < nchunks + 2; ++s) {
+            const int sc = s - 1;
+            if (sc >= 0 && sc < nchunks) {
+                const int c = ce - 1 - sc, t0 = c * CH, nt = min(CH, t_hi - t0);
+                if (spec && c == ce_emit - 1 && t_ehi < T && lane < HP) a.sc_guess[(size_t)blockIdx.x * HP + lane] = gH;
+                const float *ac = sact + (sc % 3) * SM::ACT + lp;
+                const float *dh = sdh + (sc & 1) * SM::DH + lp;
+                float *Gb = sG + (sc & 1) * SM::G;
+                if (nt < CH) { for (int i = lane; i < (CH - nt) * GS; i += 32) Gb[nt * GS + i] = 0.f; }
+                const float *row = ac + nt * ROW;   // step t0+nt-1
+                float r = row[0], z = row[HP], n = row[2 * HP], hgn = row[3 * HP], hp = row[4 * HP - ROW], dht = dh[(nt - 1) * HP];
+                for (int tl = nt - 1; tl >= 0; --tl) {
+                    const int tp = tl > 0 ? tl - 1 : 0;
+                    const float *rown = ac + (tp + 1) * ROW;
+                    const float r_n = rown[0], z_n = rown[HP], n_n = rown[2 * HP], hgn_n = rown[3 * HP], hp_n = rown[4 * HP - ROW],
+                                dh_n = dh[tp * HP];
+                    gH += dht;
+                    const float gz = gH * (hp - n), gn = gH * (1.f - z), ghp = gH * z;
+                    const float an = gn * (1.f - n * n);
+                    const float az = gz * z * (1.f - z);
+                    const float anr = an * r;
+                    const float ar = anr * hgn * (1.f - r);
+                    float *G = Gb + tl * GS;
+                    if (lane < HP) { G[lane] = ar; G[HP + lane] = az; G[2 * HP + lane] = anr; G[3 * HP + lane] = an; }
+                    __syncwarp();
+                    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f, acc4 = 0.f, acc5 = 0.f;
+                    const float4 *G4 = reinterpret_cast<const float4 *>(G);
+                    float4 gv[3 * (HP / 4)];
+#pragma unroll
+                    for (int q = 0; q < 3 * (HP / 4); ++q) gv[q] = G4[q];
+#pragma unroll
+                    for (int k4 = 0; k4 < HP / 4; ++k4) {
+                        const float kr[4] = {gv[k4].x, gv[k4].y, gv[k4].z, gv[k4].w};
+                        const float kz[4] = {gv[HP / 4 + k4].x, gv[HP / 4 + k4].y, gv[HP / 4 + k4].z, gv[HP / 4 + k4].w};
+                        const float kn[4] = {gv[2 * (HP / 4) + k4].x, gv[2 * (HP / 4) + k4].y, gv[2 * (HP / 4) + k4].z, gv[2 * (HP / 4) + k4].w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int k = k4 * 4 + e;
+                            if (k < HT) {
+                                if (k & 1) { acc1 = fmaf(wcol[k], kr[e], acc1); acc3 = fmaf(wcol[HT + k], kz[e], acc3); acc5 = fmaf(wcol[2 * HT + k], kn[e], acc5); }
+                                else       { acc0 = fmaf(wcol[k], kr[e], acc0); acc2 = fmaf(wcol[HT + k], kz[e], acc2); acc4 = fmaf(wcol[2 * HT + k], kn[e], acc4); }
+                            }
+                        }
+                    }
+                    gH = (ghp + (acc0 + acc1)) + ((acc2 + acc3) + (acc4 + acc5));
+                    r = r_n; z = z_n; n = n_n; hgn = hgn_n; hp = hp_n; dht = dh_n;
+                }
+            }
+            __syncthreads();
+        }
+        if (spec && lane < HP) a.sc_end[(size_t)blockIdx.x * HP + lane] = gH;
+    } else if (warp == 2) {
+        // =============================== dL/dW_hh = sum_t [ar|az|an*r]_t (x) h_{t-1}: lanes 8 x 4, register tile TR x TC
+        constexpr int TR = (3 * HP + 7) / 8, TC = HP / 4;
+        const int rg = lane >> 2, cg = lane & 3;
+        float acc[DW ? TR * TC : 1];
+        if constexpr (DW) {
+#pragma unroll
+            for (int q = 0; q < TR * TC; ++q) acc[q] = 0.f;
+        }
+        for (int s = 0; s < nchunks + 2; ++s) {
+            const int sc = s - 2;
+            if (sc >= 0 && ce - 1 - sc < ce_emit) {
+                if constexpr (DW) {
+                    const float *Ap = sG + (sc & 1) * SM::G + TR * rg;
+                    const float *Bp = sact + (sc % 3) * SM::ACT + 4 * HP + TC * cg;      // row tl = step t-1: h_{t-1}
+#pragma unroll 4
+                    for (int tl = 0; tl < CH; ++tl) {
+                        float av[TR], bv[TC];
+                        lds_vec<TR>(Ap + tl * GS, av);
+                        lds_vec<TC>(Bp + tl * ROW, bv);
+                        outer_acc<TR, TC>(acc, av, bv);
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        if constexpr (DW) {
+            if (prt) {
+#pragma unroll
+                for (int i = 0; i < TR; ++i) {
+                    const int r = TR * rg + i, g = r / HP, k = r - g * HP;
+#pragma unroll
+                    for (int c = 0; c < TC; ++c) {
+                        const int jj = TC * cg + c;
+                        if (r < 3 * HP && k < H && jj < H) prt[L.oWhh + (g * H + k) * H + jj] = acc[i * TC + c];
+                    }
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // =============================== dL/dW_ih + every bias (ones column) = sum_t [ar|az|an*r|an]_t (x) [feat_t, 1]; head weights
+        constexpr int NC = (F + 1 + 3) & ~3;
+        constexpr int LC = NC / 4, LR = 32 / LC, TR = (4 * HP + LR - 1) / LR, TC = 4;
+        constexpr int TR3 = (HP + 7) / 8, TC3 = HP / 4;
+        const int rg = lane / LC, cg = lane % LC;
+        const int rg3 = lane >> 2, cg3 = lane & 3;
+        float acc[DW ? TR * TC : 1], acc3[(DW && HEAD) ? TR3 * TC3 : 1];
+        float gwo0 = 0.f, gwo1 = 0.f;
+        if constexpr (DW) {
+#pragma unroll
+            for (int q = 0; q < TR * TC; ++q) acc[q] = 0.f;
+            if constexpr (HEAD) {
+#pragma unroll
+                for (int q = 0; q < TR3 * TC3; ++q) acc3[q] = 0.f;
+            }
+        }
+        for (int s = 0; s < nchunks + 2; ++s) {
+            const int sc = s - 2;
+            if (sc >= 0 && ce - 1 - sc < ce_emit) {
+                if constexpr (DW) {
+                    const float *Ap = sG + (sc & 1) * SM::G + TR * rg;
+                    const float *pr = spre + (sc % 3) * SM::PRE;
+                    const float *Bp = pr + TC * cg;
+                    const float *ac = sact + (sc % 3) * SM::ACT;
+                    const float *A3 = sdp + (sc % 3) * SM::DH + TR3 * rg3;
+                    const float *B3 = ac + ROW + 4 * HP + TC3 * cg3;                      // row tl+1 = step t: h_t
+                    const float *hcol = ac + ROW + (HEAD ? 5 : 4) * HP + lp;             // g_t (DGRU) or h_t feeds fc_out
+#pragma unroll 4
+                    for (int tl = 0; tl < CH; ++tl) {
+                        float av[TR], bv[TC];
+                        lds_vec<TR>(Ap + tl * GS, av);
+                        lds_vec<TC>(Bp + tl * 12, bv);
+                        outer_acc<TR, TC>(acc, av, bv);
+                        if constexpr (HEAD) {
+                            float a3[TR3], b3[TC3];
+                            lds_vec<TR3>(A3 + tl * HP, a3);
+                            lds_vec<TC3>(B3 + tl * ROW, b3);
+                            outer_acc<TR3, TC3>(acc3, a3, b3);
+                        }
+                        const float2 go = *reinterpret_cast<const float2 *>(pr + tl * 12 + 8);
+                        const float hv = hcol[tl * ROW];
+                        gwo0 = fmaf(go.x, hv, gwo0); gwo1 = fmaf(go.y, hv, gwo1);
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        if constexpr (DW) {
+            if (prt) {
+#pragma unroll
+                for (int i = 0; i < TR; ++i) {
+                    const int r = TR * rg + i, blk = r / HP, k = r - blk * HP;     // blk: 0 ar, 1 az, 2 an*r, 3 an
+                    if (r < 4 * HP && k < H) {
+#pragma unroll
+                        for (int c = 0; c < TC; ++c) {
+                            const int col = TC * cg + c;
+                            const float v = acc[i * TC + c];
+                            if (col < F && blk != 2) prt[L.oWih + ((blk == 3 ? 2 : blk) * H + k) * F + col] = v;
+                            if (col == F) {
+                                if (blk < 2) { prt[L.obih + blk * H + k] = v; prt[L.obhh + blk * H + k] = v; }
+                                else if (blk == 3) prt[L.obih + 2 * H + k] = v;
+                                else prt[L.obhh + 2 * H + k] = v;
+                            }
+                        }
+                    }
+                }
+                if constexpr (HEAD) {
+#pragma unroll
+                    for (int i = 0; i < TR3; ++i) {
+                        const int k = TR3 * rg3 + i;
+#pragma unroll
+                        for (int c = 0; c < TC3; ++c) {
+                            const int jj = TC3 * cg3 + c;
+                            if (k < H && jj < H) prt[L.oWh + k * H + jj] = acc3[i * TC3 + c];
+                        }
+                    }
+                }
+                if (lane < H) { prt[L.oWo + lane] = gwo0; prt[L.oWo + L.O + lane] = gwo1; }
+            }
+        }
+    } else {
+        // =============================== dL/dfeatures -> dL/dx and the per-timestep sums: one timestep per lane
+        float gbo0 = 0.f, gbo1 = 0.f;
+        float gwof[(DW && HEAD) ? 2 * F : 1], gbh[(DW && HEAD) ? HP : 1];
+        if constexpr (DW && HEAD) {
+#pragma unroll
+            for (int q = 0; q < 2 * F; ++q) gwof[q] = 0.f;
+#pragma unroll
+            for (int q = 0; q < HP; ++q) gbh[q] = 0.f;
+        }
+        float2 *gx2 = (a.need_dx && a.gx) ? reinterpret_cast<float2 *>(a.gx) + (size_t)b * T : nullptr;
+        for (int s = 0; s < nchunks + 2; ++s) {
+            const int sc = s - 2;
+            if (sc >= 0 && ce - 1 - sc < ce_emit) {
+                const int c = ce - 1 - sc, t0 = c * CH, nt = min(CH, t_hi - t0);
+                const float *Gb = sG + (sc & 1) * SM::G;
+                const float *p = spre + (sc % 3) * SM::PRE + lane * 12;
+                const float g0 = p[8], g1 = p[9];          // zero for lanes >= nt
+                if constexpr (DW) {
+                    gbo0 += g0; gbo1 += g1;
+                    if constexpr (HEAD) {
+                        float fv[8];
+                        lds_vec<8>(p, fv);
+#pragma unroll
+                        for (int q = 0; q < F; ++q) { gwof[q] = fmaf(g0, fv[q], gwof[q]); gwof[F + q] = fmaf(g1, fv[q], gwof[F + q]); }
+                        float dv[HP];
+                        lds_vec<HP>(sdp + (sc % 3) * SM::DH + lane * HP, dv);
+#pragma unroll
+                        for (int q = 0; q < HP; ++q) gbh[q] += dv[q];
+                    }
+                }
+                if (gx2 && lane < nt) {
+                    float gf[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    float gv[4 * HP];          // ar | az | an*r | an of this lane's timestep (GS/4 odd: conflict-free LDS.128)
+                    lds_vec<4 * HP>(Gb + lane * GS, gv);
+#pragma unroll
+                    for (int k = 0; k < HT; ++k) {
+                        if (k < H) {
+                            const float ar = gv[k], az = gv[HP + k], an = gv[3 * HP + k];
+                            const float *wr = sp + L.oWih + (0 * H + k) * F, *wz = sp + L.oWih + (1 * H + k) * F, *wn = sp + L.oWih + (2 * H + k) * F;
+#pragma unroll
+                            for (int q = 0; q < F; ++q) gf[q] = fmaf(wn[q], an, fmaf(wz[q], az, fmaf(wr[q], ar, gf[q])));
+                        }
+                    }
+                    if constexpr (HEAD) {
+#pragma unroll
+                        for (int q = 0; q < F; ++q) gf[q] += fmaf(sp[L.oWo + H + q], g0, sp[L.oWo + L.O + H + q] * g1);
+                    }
+                    float gi, gq;
+                    features_bwd<FM>(p[0], p[1], gf, gi, gq);          // features 0,1 are the raw (I,Q) sample in every feature mode
+                    gx2[t0 + lane] = make_float2(gi, gq);
+                }
+            }
+            __syncthreads();
+        }
+        if constexpr (DW) {
+            if (prt) {
+                gbo0 = warp_sum(gbo0); gbo1 = warp_sum(gbo1);
+                if (lane == 0) { prt[L.obo] = gbo0; prt[L.obo + 1] = gbo1; }
+                if constexpr (HEAD) {
+#pragma unroll
+                    for (int q = 0; q < 2 * F; ++q) {
+                        const float sum = warp_sum(gwof[q]);
+                        if (lane == 0) prt[L.oWo + (q / F) * L.O + H + (q % F)] = sum;
+                    }
+#pragma unroll
+                    for (int q = 0; q < HP; ++q) {
+                        const float sum = warp_sum(gbh[q]);
+                        if (lane == 0 && q < H) prt[L.obh + q] = sum;
+                    }
+                }
+            }
+        }
+    }
+}
+
 // ================================================================ host dispatch
 template <int FM, int HEAD> static int64_t gru_nparams(int H) { return GruLayout<FM, HEAD>(H).P; }
 
@@ -1295,10 +1679,11 @@ static inline int64_t bwd_partial_rows(int B, int T, int tchunks_req) {
     const int64_t a = chunk_rows(B, tchunks_req), b = (int64_t)(B > 0 ? B : 1) * (nblk < WTILES_MAX ? (nblk > 0 ? nblk : 1) : WTILES_MAX);
     return a > b ? a : b;
 }
-static inline bool bwd_split_enabled() {
+// backward form: 2 = lean fused (default), 1 = split (chain kernel + weights kernel), 0 = original fused.  env ODPD_BWD_FORM
+static inline int bwd_form() {
     static int v = -1;
-    if (v < 0) { const char *e = getenv("ODPD_BWD_SPLIT"); v = (e && e[0] == '0') ? 0 : 1; }
-    return v != 0;
+    if (v < 0) { const char *e = getenv("ODPD_BWD_FORM"); v = e ? atoi(e) : 2; if (v < 0 || v > 2) v = 2; }
+    return v;
 }
 
 template <int HT, int FM, int HEAD, bool DW>
@@ -1309,7 +1694,14 @@ static int launch_bwd_t(GruArgs a, cudaStream_t st, bool plan_only, int *info) {
     const int64_t rows = chunk_rows(a.B, a.tchunks_req);
     const int64_t woff = (bwd_partial_rows(a.B, a.T, a.tchunks_req) * L.P + 3) & ~(int64_t)3;
     float *scr = a.partials ? a.partials + woff : nullptr;
-    if (!bwd_split_enabled() || (!plan_only && !a.partials)) {
+    if (bwd_form() == 2) {
+        const size_t smem = (size_t)BwdfSmem<HT, FM, HEAD>::total(Ppad) * sizeof(float);
+        static OccCache occ{};
+        const int rc = chunk_launch(gru_bwdf_kernel<HT, FM, HEAD, DW>, 160, smem, &occ, a, 1, scr, woff, HP, st, plan_only, info, "gru_bwdf_kernel");
+        if (info) info[4] = a.B * info[0];
+        return rc;
+    }
+    if (bwd_form() == 0 || (!plan_only && !a.partials)) {
         // fused form: one kernel (kept for A/B comparison, ODPD_BWD_SPLIT=0, and for a dX-only backward without workspace)
         const size_t smem = (size_t)BwdSmem<HT, HEAD>::total(Ppad) * sizeof(float);
         static OccCache occ{};
