@@ -54,7 +54,7 @@ template <int HT, bool TRES>
 struct DFwdSmem {
     static constexpr int HP = Pad4<HT>::value, ROW = DRow<HT>::value;
     static constexpr int XP = (CH + 1) * 3 * HP /* +1 spare row for the chain's last-step prefetch */, FT = CH * 8, ACT = CH * ROW, PO = CH * 33, SK = CH * 2;
-    __host__ __device__ static constexpr int total(int Ppad) { return 16 + Ppad + HP + 2 * XP + 3 * FT + 3 * SK + 2 * ACT + 2 * PO + 2 * HP; }
+    __host__ __device__ static constexpr int total(int Ppad) { return 16 + Ppad + HP + 2 * XP + 3 * FT + 3 * SK + 2 * ACT + 2 * PO + 2 * HP + CH * 8 + ROW; }
 };
 template <int HT, bool TRES>
 struct DBwdSmem {
@@ -82,6 +82,8 @@ __global__ void __launch_bounds__(96, 1) delta_fwd_kernel(GruArgs a) {
     float *sact = ssk + 3 * SM::SK;          // [2][CH][ROW]
     float *spo = sact + 2 * SM::ACT;         // [2][CH][33]
     float *sdl = spo + 2 * SM::PO;           // [2][HP]        delta_h broadcast line (double buffered)
+    float *sraw = sdl + 2 * HP;              // [CH][8]        raw features of the block (pre warp only)
+    float *sdump = sraw + CH * 8;            // [ROW]          dump row for the chain's first deferred store
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, b = blockIdx.x;
     stage_params(sp, a.params, L.P, bars);
     if (threadIdx.x < HP) zero[threadIdx.x] = 0.f;
@@ -105,44 +107,67 @@ __global__ void __launch_bounds__(96, 1) delta_fwd_kernel(GruArgs a) {
         float Mr = (!TRES && act) ? sp[L.obih + j] + sp[L.obhh + j] : 0.f;
         float Mz = (!TRES && act) ? sp[L.obih + H + j] + sp[L.obhh + H + j] : 0.f;
         float Mn = (!TRES && act) ? sp[L.obih + 2 * H + j] : 0.f;
-        float xh[F] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // x_hat (uniform across lanes)
+        // Three phases per 32-step block, each with the lane mapping that suits it (the first version ran everything in one loop over
+        // the timesteps with lane = unit and broadcast every feature with a shuffle: ~350 cycles per step, as slow as the chain warp):
+        //   (i)   lane = timestep: load the samples, features (IEEE, no contraction), TCN skip
+        //   (ii)  lane = feature : the x_hat recurrence |f - x_hat| >= thx (serial over time, 6 lanes, ~4 dependent ops per step);
+        //                          masked delta_x, keep mask and zero count via ballots
+        //   (iii) lane = unit    : running sums M += W_ih delta_x_t (the dot product first, then one add: the reference's order,
+        //                          deltagru.py:196-199 `mm(delta_x, W^T) + M`), no cross-lane traffic
+        float xh = 0.f;                              // x_hat of feature `lane` (lanes 0..5)
+        const bool fl = lane < F;
         long long zx = 0;
         for (int s = 0; s < nchunks + 2; ++s) {
             if (s < nchunks) {
                 const int t0 = s * CH, nt = min(CH, T - t0);
                 float *ft = sft + (s % 3) * SM::FT, *xp = sxp + (s & 1) * SM::XP, *sk = ssk + (s % 3) * SM::SK;
-                float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                 if (lane < nt) {
                     const int t = t0 + lane;
                     const float2 v = __ldg(x2 + t);
                     float2 vn = make_float2(0.f, 0.f);
                     if (TRES) vn = __ldg(x2 + ((t + 1 < T) ? t + 1 : 0));    // torch.roll(x,-1): wraps to x[0]
+                    float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                     features_fwd<FM>(v.x, v.y, vn.x, vn.y, f);
+                    float4 *r4 = reinterpret_cast<float4 *>(sraw + lane * 8);
+                    r4[0] = make_float4(f[0], f[1], f[2], f[3]);
+                    r4[1] = make_float4(f[4], f[5], 0.f, 0.f);
                     if (TRES) {
                         float c1[3], c2[2];
                         tcn_point(x2, T, t, sp + L.oc0, sp + L.oc2, c1, c2);
                         *reinterpret_cast<float2 *>(sk + lane * 2) = make_float2(hswish(c2[0]), hswish(c2[1]));
                     }
                 }
+                __syncwarp();
+                unsigned zc = 0;
+                const float *rawq = sraw + (fl ? lane : 0);
+                float *ftq = ft + (fl ? lane : 7);
+#pragma unroll 4
                 for (int tl = 0; tl < nt; ++tl) {
-                    float dx[F];
-                    unsigned mx = 0;
-#pragma unroll
-                    for (int q = 0; q < F; ++q) {
-                        const float fv = __shfl_sync(ODPD_FULL, f[q], tl);
-                        const float d = __fsub_rn(fv, xh[q]);
-                        const float ad = fabsf(d);
-                        dx[q] = (ad < thx) ? 0.f : d;                 // masked_fill(|d| < th, 0)
-                        if (ad >= thx) { xh[q] = fv; mx |= 1u << q; } // where(|d| >= th, x, x_hat)
-                        zx += (dx[q] == 0.f);
-                    }
-#pragma unroll
-                    for (int q = 0; q < F; ++q) { Mr = fmaf(wir[q], dx[q], Mr); Mz = fmaf(wiz[q], dx[q], Mz); Mn = fmaf(win[q], dx[q], Mn); }
-                    if (lane < HP) { float *o = xp + tl * 3 * HP + lane; o[0] = Mr; o[HP] = Mz; o[2 * HP] = Mn; }
-                    if (lane == 0) {
-                        float4 *d4 = reinterpret_cast<float4 *>(ft + tl * 8);
-                        d4[0] = make_float4(dx[0], dx[1], dx[2], dx[3]);
-                        d4[1] = make_float4(dx[4], dx[5], __uint_as_float(mx), 0.f);
+                    const float fv = rawq[tl * 8];
+                    const float d = __fsub_rn(fv, xh);
+                    const float ad = fabsf(d);
+                    const float dxv = (ad < thx) ? 0.f : d;          // masked_fill(|d| < th, 0)
+                    const bool keep = ad >= thx;                      // where(|d| >= th, x, x_hat)
+                    xh = keep ? fv : xh;
+                    const unsigned mx = __ballot_sync(ODPD_FULL, keep && fl);
+                    zc += __popc(__ballot_sync(ODPD_FULL, dxv == 0.f && fl));
+                    ftq[tl * 8] = fl ? dxv : 0.f;                     // lanes >= 6 all write the unused word 7
+                    if (lane == 0) ft[tl * 8 + 6] = __uint_as_float(mx);
+                }
+                zx += zc;
+                __syncwarp();
+                if (lane < HP) {
+#pragma unroll 4
+                    for (int tl = 0; tl < nt; ++tl) {
+                        const float4 *d4 = reinterpret_cast<const float4 *>(ft + tl * 8);
+                        const float4 d0 = d4[0], d1 = d4[1];
+                        const float dx[F] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y};
+                        const float pr = fmaf(wir[2], dx[2], fmaf(wir[1], dx[1], wir[0] * dx[0])) + fmaf(wir[5], dx[5], fmaf(wir[4], dx[4], wir[3] * dx[3]));
+                        const float pz = fmaf(wiz[2], dx[2], fmaf(wiz[1], dx[1], wiz[0] * dx[0])) + fmaf(wiz[5], dx[5], fmaf(wiz[4], dx[4], wiz[3] * dx[3]));
+                        const float pn = fmaf(win[2], dx[2], fmaf(win[1], dx[1], win[0] * dx[0])) + fmaf(win[5], dx[5], fmaf(win[4], dx[4], win[3] * dx[3]));
+                        Mr += pr; Mz += pz; Mn += pn;
+                        float *o = xp + tl * 3 * HP + lane;
+                        o[0] = Mr; o[HP] = Mz; o[2 * HP] = Mn;
                     }
                 }
             }
@@ -168,7 +193,6 @@ __global__ void __launch_bounds__(96, 1) delta_fwd_kernel(GruArgs a) {
             }
             float h = 0.f, hh = 0.f, MhA = 0.f;
             float Mnh = (!TRES && au && lo) ? sp[L.obhh + 2 * H + ju] : 0.f;
-            long long zh = 0;
             int cur = 0;
             for (int s = 0; s < nchunks + 2; ++s) {
                 const int c = s - 1;
@@ -177,51 +201,63 @@ __global__ void __launch_bounds__(96, 1) delta_fwd_kernel(GruArgs a) {
                     const float *xa_p = sxp + (c & 1) * SM::XP + (half ? HP : 0) + up;
                     const float *xn_p = sxp + (c & 1) * SM::XP + 2 * HP + up;
                     float *row = sact + (c & 1) * SM::ACT + lane;
-                    float *rowm = sact + (c & 1) * SM::ACT + 6 * HP + 7;
                     const bool wr = lane < HP;
                     float xa = *xa_p, xn = *xn_p;
-#pragma unroll 1
+                    // The gate values of a step are stored one iteration late, while the next step's broadcast loads are in flight; the
+                    // first iteration "stores" into a dump row so that the loop body carries no branch.  The keep mask and the zero
+                    // count are NOT produced here: the post warp derives both from the stored delta_h (vote + popc on the chain warp cost
+                    // ~35 cycles per step: issue is in order, so even off-path consumers of a slow result stall the chain).
+                    float p_s = 0.f, p_z = 0.f, p_n = 0.f, p_m = 0.f, p_h = 0.f, p_d = 0.f;
+                    float *prow = sdump + lane;
+#pragma unroll 2
                     for (int tl = 0; tl < nt; ++tl) {
                         xa_p += 3 * HP; xn_p += 3 * HP;
-                        const float nxa = *xa_p, nxn = *xn_p;       // one row past the chunk on the last step: in-bounds, unused
-                        const float d = h - hh, ad = fabsf(d);
-                        const float dh = (ad < thh) ? 0.f : d;
-                        const bool keep = ad >= thh;
-                        if (keep) hh = h;
-                        if (au && lo) zh += (dh == 0.f);
-                        const unsigned mh = __ballot_sync(ODPD_FULL, keep && au && lo);
+                        const float nxa = *xa_p, nxn = *xn_p;       // the last step reads the spare row of its own buffer: unused
+                        const float d = h - hh;
+                        const bool keep = fabsf(d) >= thh;
+                        const float dh = keep ? d : 0.f;
+                        hh = keep ? h : hh;
                         float *line = sdl + cur * HP;
-                        if (wr) line[lane] = au ? dh : 0.f;
+                        if (wr) line[lane] = dh;
                         __syncwarp();
-                        float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
-                        bcast_dot<HT>(line, wA, a0, a1);
-                        bcast_dot<HT>(line, wB, b0, b1);
-                        MhA += a0 + a1; Mnh += b0 + b1;
-                        const float sA = sigmoidf_(xa + MhA);                     // r (lanes 0..15) / z (lanes 16..31)
+                        const float4 *l4 = reinterpret_cast<const float4 *>(line);
+                        float4 lv[HP / 4];
+#pragma unroll
+                        for (int q = 0; q < HP / 4; ++q) lv[q] = l4[q];
+                        if (wr) { prow[0] = p_s; prow[HP] = p_z; prow[2 * HP] = p_n; prow[3 * HP] = p_m; prow[4 * HP] = p_h; prow[5 * HP] = p_d; }
+                        const float base = xa + MhA;
+                        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;   // 4 chains per dot product
+#pragma unroll
+                        for (int q = 0; q < HP / 4; ++q) {
+                            const float e[4] = {lv[q].x, lv[q].y, lv[q].z, lv[q].w};
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int k = q * 4 + i;
+                                if (k < HT) {
+                                    if (i == 0) { a0 = fmaf(wA[k], e[i], a0); b0 = fmaf(wB[k], e[i], b0); }
+                                    else if (i == 1) { a1 = fmaf(wA[k], e[i], a1); b1 = fmaf(wB[k], e[i], b1); }
+                                    else if (i == 2) { a2 = fmaf(wA[k], e[i], a2); b2 = fmaf(wB[k], e[i], b2); }
+                                    else { a3 = fmaf(wA[k], e[i], a3); b3 = fmaf(wB[k], e[i], b3); }
+                                }
+                            }
+                        }
+                        const float dA = (a0 + a1) + (a2 + a3), dB = (b0 + b1) + (b2 + b3);
+                        const float sA = sigmoidf_(base + dA);                    // r (lanes 0..15) / z (lanes 16..31)
+                        MhA += dA; Mnh += dB;
                         const float z = __shfl_down_sync(ODPD_FULL, sA, 16);
                         const float n = tanhf_(fmaf(sA, Mnh, xn));
-                        h = fmaf(z, h, (1.f - z) * n);
-                        if (wr) {
-                            row[0] = sA; row[HP] = z; row[2 * HP] = n; row[3 * HP] = Mnh; row[4 * HP] = h; row[5 * HP] = au ? dh : 0.f;
-                        }
-                        if (lane == 0) *rowm = __uint_as_float(mh);
-                        row += ROW; rowm += ROW;
+                        h = fmaf(z, h - n, n);                                    // z*h + (1-z)*n
+                        p_s = sA; p_z = z; p_n = n; p_m = Mnh; p_h = h; p_d = dh;
+                        prow = row;
+                        row += ROW;
                         cur ^= 1;
                         xa = nxa; xn = nxn;
                     }
+                    if (wr) { prow[0] = p_s; prow[HP] = p_z; prow[2 * HP] = p_n; prow[3 * HP] = p_m; prow[4 * HP] = p_h; prow[5 * HP] = p_d; }
                     __syncwarp();
                     fence_async_smem();
                 }
                 __syncthreads();
-            }
-            if (a.stats) {
-                unsigned long long tot = (unsigned long long)zh;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(ODPD_FULL, tot, o);
-                if (lane == 0) {
-                    atomicAdd(reinterpret_cast<unsigned long long *>(a.stats) + 2, tot);
-                    atomicAdd(reinterpret_cast<unsigned long long *>(a.stats) + 3, (unsigned long long)T * H);
-                }
             }
         } else {
         float whr[HT], whz[HT], whn[HT];
@@ -297,6 +333,7 @@ __global__ void __launch_bounds__(96, 1) delta_fwd_kernel(GruArgs a) {
         float2 *o2 = reinterpret_cast<float2 *>(a.out) + (size_t)b * T;
         float *svg = a.save ? a.saved + (size_t)b * T * ROW : nullptr;
         float lsum = 0.f;
+        long long zh_post = 0;
         for (int s = 0; s < nchunks + 2; ++s) {
             const int c = s - 2;
             if (c >= 0) {
@@ -309,6 +346,21 @@ __global__ void __launch_bounds__(96, 1) delta_fwd_kernel(GruArgs a) {
                     float *row = ac + lane * ROW + 6 * HP;
                     *reinterpret_cast<float4 *>(row) = d0;
                     row[4] = d1.x; row[5] = d1.y; row[6] = d1.z;
+                }
+                if constexpr (HP <= 16) {
+                    // keep mask and zero count of delta_h, derived from the stored masked delta_h (lane = unit): with thh > 0 a unit is
+                    // kept iff its masked delta is non-zero (|d| >= thh > 0); with thh <= 0 every unit is kept (deltagru.py:176-183)
+                    const bool valid = lane < H;
+                    const float *dcol = ac + 5 * HP + (valid ? lane : 0);
+                    unsigned zc = 0;
+#pragma unroll 4
+                    for (int tl = 0; tl < nt; ++tl) {
+                        const float dv = dcol[tl * ROW];
+                        const unsigned mh = __ballot_sync(ODPD_FULL, valid && (thh > 0.f ? dv != 0.f : true));
+                        zc += __popc(__ballot_sync(ODPD_FULL, valid && dv == 0.f));
+                        if (lane == 0) ac[tl * ROW + 6 * HP + 7] = __uint_as_float(mh);
+                    }
+                    zh_post += zc;
                 }
                 fence_async_smem();
                 __syncwarp();
@@ -323,6 +375,12 @@ __global__ void __launch_bounds__(96, 1) delta_fwd_kernel(GruArgs a) {
         if (a.loss && y2) {
             lsum = warp_sum(lsum);
             if (lane == 0) atomicAdd(a.loss, (double)lsum * (double)a.loss_scale);
+        }
+        if constexpr (HP <= 16) {
+            if (a.stats && lane == 0) {
+                atomicAdd(reinterpret_cast<unsigned long long *>(a.stats) + 2, (unsigned long long)zh_post);
+                atomicAdd(reinterpret_cast<unsigned long long *>(a.stats) + 3, (unsigned long long)T * H);
+            }
         }
     }
 }
@@ -486,11 +544,11 @@ __global__ void __launch_bounds__(128, 1) delta_bwd_kernel(GruArgs a) {
                     float *G = Gb + tl * 4 * HP;
                     if (lane < HP) { G[lane] = act ? gMr : 0.f; G[HP + lane] = act ? gMz : 0.f; G[2 * HP + lane] = act ? gMnh : 0.f; G[3 * HP + lane] = act ? gMn : 0.f; }
                     __syncwarp();
-                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, a5 = 0.f;     // three H-term dots as six chains of depth H/2
                     bcast_dot<HT>(G, wcr, a0, a1);
                     bcast_dot<HT>(G + HP, wcz, a2, a3);
-                    bcast_dot<HT>(G + 2 * HP, wcn, a0, a1);
-                    const float gdh = (a0 + a1) + (a2 + a3);
+                    bcast_dot<HT>(G + 2 * HP, wcn, a4, a5);
+                    const float gdh = ((a0 + a1) + (a2 + a3)) + (a4 + a5);
                     if ((mh >> lane) & 1u) { ghp += ghh + gdh; ghh = -gdh; }
                     gH = ghp;
                     r = r_n; z = z_n; n = n_n; mnh = mnh_n; hp = hp_n; dht = dh_n; mh = mh_n;
