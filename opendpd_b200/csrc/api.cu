@@ -159,16 +159,16 @@ int64_t odpd_bwd_workspace_bytes(const OdpdDims *d) {
 int odpd_backbone_fwd(const OdpdDims *d, const float *x, const float *target, const float *params, float *out, double *loss,
                       double loss_scale, void *saved, int64_t *stats, void *stream) {
     if (check_dims(d)) return -1;
-    ODPD_CHECK(params && out, "params/out must not be NULL");
-    ODPD_CHECK(((uintptr_t)params & 15) == 0, "params must be 16-byte aligned");
-    const bool save = (d->flags & ODPD_F_SAVE) != 0;
-    ODPD_CHECK(!save || saved, "ODPD_F_SAVE set but saved==NULL");
     cudaStream_t st = (cudaStream_t)stream;
     if (loss && (d->flags & ODPD_F_ZERO_LOSS)) {
         cudaError_t e = cudaMemsetAsync(loss, 0, sizeof(double), st);
         ODPD_CHECK(e == cudaSuccess, "cudaMemsetAsync(loss): %s", cudaGetErrorString(e));
     }
-    if (d->B == 0 || d->T == 0) return 0;
+    if (d->B == 0 || d->T == 0) return 0;       // an empty batch (e.g. a data-parallel rank's empty shard): nothing to read or write
+    ODPD_CHECK(params && out, "params/out must not be NULL");
+    ODPD_CHECK(((uintptr_t)params & 15) == 0, "params must be 16-byte aligned");
+    const bool save = (d->flags & ODPD_F_SAVE) != 0;
+    ODPD_CHECK(!save || saved, "ODPD_F_SAVE set but saved==NULL");
     ODPD_CHECK(x != nullptr, "x must not be NULL");
     if (is_gru_family(d->cell)) {
         GruArgs a{};
@@ -187,13 +187,9 @@ int odpd_backbone_bwd(const OdpdDims *d, const float *x, const float *params, co
                       void *stream) {
     if (check_dims(d)) return -1;
     const bool dx = (d->flags & ODPD_F_NEED_DX) != 0, dw = (d->flags & ODPD_F_NEED_DW) != 0;
-    ODPD_CHECK(params != nullptr, "params must not be NULL");
-    ODPD_CHECK(((uintptr_t)params & 15) == 0, "params must be 16-byte aligned");
-    ODPD_CHECK(!dx || gx, "ODPD_F_NEED_DX set but gx==NULL");
-    ODPD_CHECK(!dw || (gparams && workspace), "ODPD_F_NEED_DW set but gparams/workspace==NULL");
-    ODPD_CHECK(gout || (out && target), "need gout, or out+target for the fused MSE gradient");
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t P = odpd_n_params(d->cell, d->H, d->K);
+    ODPD_CHECK(!dw || gparams, "ODPD_F_NEED_DW set but gparams==NULL");
     if (d->B == 0 || d->T == 0) {
         // an empty shard (data-parallel rank whose share of the last partial batch is empty) contributes a ZERO gradient: with
         // OVERWRITE_DW the caller's buffer must not keep the previous step's values
@@ -203,6 +199,11 @@ int odpd_backbone_bwd(const OdpdDims *d, const float *x, const float *params, co
         }
         return 0;
     }
+    ODPD_CHECK(params != nullptr, "params must not be NULL");
+    ODPD_CHECK(((uintptr_t)params & 15) == 0, "params must be 16-byte aligned");
+    ODPD_CHECK(!dx || gx, "ODPD_F_NEED_DX set but gx==NULL");
+    ODPD_CHECK(!dw || workspace, "ODPD_F_NEED_DW set but workspace==NULL");
+    ODPD_CHECK(gout || (out && target), "need gout, or out+target for the fused MSE gradient");
     if (!dx && !dw) return 0;
     ODPD_CHECK(x && (saved || d->cell == ODPD_CELL_GMP), "x/saved must not be NULL");
     int rc, rows = d->B;

@@ -250,8 +250,8 @@ def test_delta_oracle_parity_with_mask_accounting(kind, H, B, T, thx, thh):
         assert abs(loss.item() - r64["loss"]) <= 1e-5 * abs(r64["loss"])
 
 
-@pytest.mark.parametrize("bits", [8, 16])
-def test_qat_oracle_parity_with_flip_accounting(bits):
+@pytest.mark.parametrize("bits,H", [(8, 10), (16, 10), (8, 20), (8, 30)])     # H = 20 / 30: bash_scripts/quant_qgru_dpd_regr.sh:74
+def test_qat_oracle_parity_with_flip_accounting(bits, H):
     """Fake-quantised GRU at BASELINE config-5 scale (B=512 would be 4 GPUs x 128; here 128 x T=50).  A value that lands within
     rounding of a quantisation boundary can round the other way than on the CPU (one quantum = 2^(2-bits)); such sequences are
     counted, must be rare, and are excluded from the tight comparison."""
@@ -264,7 +264,7 @@ def test_qat_oracle_parity_with_flip_accounting(bits):
 
     class _Proj:
         quant, n_bits_w, n_bits_a, pretrained_model = True, bits, bits, ""
-    net = get_quant_model(_Proj(), models.CoreModel(2, 10, 1, "qgru")).cuda().train()
+    net = get_quant_model(_Proj(), models.CoreModel(2, H, 1, "qgru")).cuda().train()
     B, T = 128, 50
     gen = torch.Generator().manual_seed(3)
     xc = (0.25 * torch.randn(B, T, 2, generator=gen)).clamp(-0.8, 0.8)
@@ -275,7 +275,7 @@ def test_qat_oracle_parity_with_flip_accounting(bits):
     torch.cuda.synchronize()
     params = np.concatenate([p.detach().cpu().numpy().ravel() for _, p in net.backbone.named_parameters()])
     K = bits | (bits << 8)
-    r32 = oracle.run("qgru_qat", xc.numpy(), params, target=yc.numpy(), H=10, K=K, dtype=np.float32, nthreads=8)
+    r32 = oracle.run("qgru_qat", xc.numpy(), params, target=yc.numpy(), H=H, K=K, dtype=np.float32, nthreads=8)
     o = out.detach().cpu().numpy()
     quantum = 2.0 ** (2 - bits)
     if bits >= 12:
@@ -299,7 +299,7 @@ def test_qat_oracle_parity_with_flip_accounting(bits):
     net.eval()
     with torch.no_grad():
         oe = net(xc.cuda()).cpu().numpy()
-    re = oracle.run("qgru_qat", xc.numpy(), params, H=10, K=K | (1 << 16), dtype=np.float32, nthreads=8, want_grads=False)
+    re = oracle.run("qgru_qat", xc.numpy(), params, H=H, K=K | (1 << 16), dtype=np.float32, nthreads=8, want_grads=False)
     if bits >= 12:
         assert np.abs(oe - re["out"]).max() <= 8 * quantum
     else:

@@ -260,3 +260,31 @@ def test_integration_snippet_matches_header():
         if decl:
             names += [v.strip().lstrip("*") for v in decl.split(None, 1)[1].replace("const int32_t", "").split(",")] if "," in decl else [decl.split()[-1].lstrip("*")]
     assert names == [n for n, _ in D._fields_], names
+
+
+def test_qat_pretrained_model_loads_weights_only(tmp_path):
+    """quant/quant_envs.py:173-182 + quant_layers.py:53-60: a --pretrained_model checkpoint of the GRU-swapped float model provides the
+    three weight matrices; the INT_Linear biases stay the wrapper's own fresh draws (same RNG positions as without a checkpoint)."""
+    from opendpd_b200.quant import get_quant_model
+    H = 10
+    sd = {"backbone.rnn.rnn_cell_list.0.x2h.weight": torch.full((3 * H, 4), 0.25), "backbone.rnn.rnn_cell_list.0.x2h.bias": torch.zeros(3 * H),
+          "backbone.rnn.rnn_cell_list.0.h2h.weight": torch.full((3 * H, H), -0.5), "backbone.rnn.rnn_cell_list.0.h2h.bias": torch.zeros(3 * H),
+          "backbone.fc_out.weight": torch.full((2, H), 0.125), "backbone.fc_out.bias": torch.zeros(2)}
+    path = str(tmp_path / "pre.pt")
+    torch.save(sd, path)
+
+    class _P:
+        quant, n_bits_w, n_bits_a = True, 8, 8
+        pretrained_model = ""
+    torch.manual_seed(3)
+    plain = get_quant_model(_P(), models.CoreModel(2, H, 1, "qgru"))
+    _P.pretrained_model = path
+    torch.manual_seed(3)
+    pre = get_quant_model(_P(), models.CoreModel(2, H, 1, "qgru"))
+    c0, c1 = plain.backbone.rnn.rnn_cell_list[0], pre.backbone.rnn.rnn_cell_list[0]
+    assert torch.equal(c1.x2h.weight, sd["backbone.rnn.rnn_cell_list.0.x2h.weight"]) and torch.equal(c1.h2h.weight, sd["backbone.rnn.rnn_cell_list.0.h2h.weight"])
+    assert torch.equal(pre.backbone.fc_out.weight, sd["backbone.fc_out.weight"])
+    assert torch.equal(c1.x2h.bias, c0.x2h.bias) and torch.equal(c1.h2h.bias, c0.h2h.bias) and torch.equal(pre.backbone.fc_out.bias, plain.backbone.fc_out.bias)
+    torch.save({"backbone.rnn.weight_ih_l0": torch.zeros(3 * H, 4)}, path)       # a float nn.GRU checkpoint: the reference silently trains in float
+    with pytest.raises(ValueError):
+        get_quant_model(_P(), models.CoreModel(2, H, 1, "qgru"))
