@@ -184,11 +184,17 @@ int odpd_dp_ipc_handle(void *ptr, unsigned char handle_out[64]);
 int odpd_dp_ipc_open(const unsigned char handle[64], void **out_peer_ptr);
 int odpd_dp_ipc_close(void *peer_ptr);
 /* bufs: HOST array of `world` device pointers (index = rank; bufs[rank] is the caller's own buffer).  grad_local: this rank's flat
- * gradient of the step (`gparams` of odpd_backbone_bwd), loss_local its loss (double, from odpd_backbone_fwd).  The slot parity is
+ * gradient of the step (`gparams` of odpd_backbone_bwd; NULL = already published by odpd_dp_publish_next_bwd), loss_local its loss
+ * (double, from odpd_backbone_fwd).  The slot parity is
  * (step_dev+1)&1, read on the device, so the launch is identical every step and can be replayed from a CUDA graph.  On return
  * (stream order) `param` is updated, loss_out[0] = sum of all ranks' losses, gnorm_out = pre-clip norm of the summed gradient.
  * status_dev[0] != 0 (= 1 + rank of a peer) reports a peer that did not publish within 2 s: the kernel then leaves the parameters
  * and the step counter untouched instead of hanging; the caller must poll status_dev and stop (NativeTrainStep does, and raises). */
+/* Optional: arm the NEXT odpd_backbone_bwd call of this host thread (one with ODPD_F_NEED_DW) to publish the gradient it reduces
+ * — and the loss `loss_local` — to every rank's receive buffer straight from the epilogue of its gradient reduction, so that the
+ * NVLink flight overlaps the launch of the optimiser kernel.  The matching odpd_dp_clip_adamw call then passes grad_local = NULL.
+ * One-shot, thread-local host state; an empty batch (B == 0) publishes a zero gradient. */
+int odpd_dp_publish_next_bwd(void *const *bufs, int world, int rank, int64_t n, const int64_t *step_dev, const double *loss_local);
 int odpd_dp_clip_adamw(float *param, void *const *bufs, int world, int rank, int64_t n, const float *grad_local, const double *loss_local,
                        float *exp_avg, float *exp_avg_sq, const float *lr_dev, float beta1, float beta2, float eps, float weight_decay,
                        float max_norm, int64_t *step_dev, float *gnorm_out, float *loss_out, int *status_dev, void *stream);

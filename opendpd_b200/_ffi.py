@@ -48,6 +48,7 @@ SYMBOLS = {
     "odpd_dp_ipc_handle": (ctypes.c_int, [_vp, ctypes.c_char_p]),
     "odpd_dp_ipc_open": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(_vp)]),
     "odpd_dp_ipc_close": (ctypes.c_int, [_vp]),
+    "odpd_dp_publish_next_bwd": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_int, ctypes.c_int, _i64, _vp, _vp]),
     "odpd_dp_clip_adamw": (ctypes.c_int, [_vp, ctypes.POINTER(_vp), ctypes.c_int, ctypes.c_int, _i64, _vp, _vp, _vp, _vp, _vp, _flt, _flt,
                                           _flt, _flt, _flt, _vp, _vp, _vp, _vp, _vp]),
 }

@@ -2,6 +2,7 @@
 // the ordered gradient-partials reduction and the fused clip+AdamW step.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include "cells.h"
 #include "chunking.cuh"
 
@@ -14,6 +15,12 @@ void set_error(const char *fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("ODPD_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v != 0;
 }
 
 int check_launch(const char *what) {
@@ -30,8 +37,9 @@ int check_launch(const char *what) {
 // is bit-reproducible run to run; no float atomics.
 static constexpr int RED_TY = 16;
 __global__ void __launch_bounds__(32 * RED_TY) reduce_partials_kernel(const float *__restrict__ part, int nrows, int64_t P, float *__restrict__ g,
-                                                                      int overwrite) {
+                                                                      int overwrite, DpPushArgs push) {
     __shared__ float red[RED_TY][33];
+    pdl_enter();
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int64_t p = (int64_t)blockIdx.x * 32 + tx;
     float acc = 0.f;
@@ -52,13 +60,30 @@ __global__ void __launch_bounds__(32 * RED_TY) reduce_partials_kernel(const floa
         float s = red[0][tx];
 #pragma unroll
         for (int k = 1; k < RED_TY; ++k) s += red[k][tx];
-        g[p] = overwrite ? s : g[p] + s;
+        s = overwrite ? s : g[p] + s;
+        g[p] = s;
+        if (push.world > 1) {      // data-parallel publish (dp.cu): {value, step tag} words into slot [parity][rank] of every rank
+            const int64_t step = *push.step_dev + 1;
+            const unsigned tag = (unsigned)step;
+            const int64_t off = ((int64_t)(step & 1) * push.world + push.rank) * push.stride;
+#pragma unroll
+            for (int r = 0; r < ODPD_DP_MAX_WORLD; ++r)
+                if (r < push.world) asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(push.buf[r] + off + p), "r"(__float_as_uint(s)), "r"(tag) : "memory");
+            if (p == 0) {           // the loss rides along as element P
+                const float lv = push.loss_local ? (float)(*push.loss_local) : 0.f;
+#pragma unroll
+                for (int r = 0; r < ODPD_DP_MAX_WORLD; ++r)
+                    if (r < push.world) asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(push.buf[r] + off + P), "r"(__float_as_uint(lv)), "r"(tag) : "memory");
+            }
+        }
     }
 }
 
-int reduce_partials(const float *part, int nrows, int64_t P, float *g, int overwrite, cudaStream_t st) {
+int reduce_partials(const float *part, int nrows, int64_t P, float *g, int overwrite, cudaStream_t st, const DpPushArgs *push) {
     if (P <= 0) return 0;
-    reduce_partials_kernel<<<(unsigned)((P + 31) / 32), 32 * RED_TY, 0, st>>>(part, nrows, P, g, overwrite);
+    DpPushArgs pa{};
+    if (push) pa = *push;
+    launch_pdl(reduce_partials_kernel, dim3((unsigned)((P + 31) / 32)), dim3(32 * RED_TY), 0, st, part, nrows, P, g, overwrite, pa);
     return check_launch("reduce_partials_kernel");
 }
 
@@ -72,6 +97,7 @@ __global__ void __launch_bounds__(1024) clip_adamw_kernel(float *__restrict__ p,
                                                           float *gnorm_out, int zero_grad) {
     __shared__ float red[32];
     __shared__ float s_coef;
+    pdl_enter();
     float ss = 0.f;
     for (int64_t i = threadIdx.x; i < n; i += blockDim.x) { const float x = g[i]; ss = fmaf(x, x, ss); }
     ss = warp_sum(ss);
@@ -194,6 +220,8 @@ int odpd_backbone_bwd(const OdpdDims *d, const float *x, const float *params, co
         // an empty shard (data-parallel rank whose share of the last partial batch is empty) contributes a ZERO gradient: with
         // OVERWRITE_DW the caller's buffer must not keep the previous step's values
         if (dw && (d->flags & ODPD_F_OVERWRITE_DW) && P > 0) {
+            DpPushArgs push{};
+            if (dp_take_armed_push(push)) return reduce_partials(nullptr, 0, P, gparams, 1, st, &push);   // zero gradient, still published
             cudaError_t e = cudaMemsetAsync(gparams, 0, (size_t)P * sizeof(float), st);
             ODPD_CHECK(e == cudaSuccess, "cudaMemsetAsync(gparams): %s", cudaGetErrorString(e));
         }
@@ -220,7 +248,11 @@ int odpd_backbone_bwd(const OdpdDims *d, const float *x, const float *params, co
         rc = other_bwd(d, x, params, saved, gout, out, target, gscale, gscale_dev, gx, (float *)workspace, st, &rows);
     }
     if (rc) return rc;
-    if (dw) return reduce_partials((const float *)workspace, rows, P, gparams, (d->flags & ODPD_F_OVERWRITE_DW) != 0, st);
+    if (dw) {
+        DpPushArgs push{};
+        const bool armed = dp_take_armed_push(push);
+        return reduce_partials((const float *)workspace, rows, P, gparams, (d->flags & ODPD_F_OVERWRITE_DW) != 0, st, armed ? &push : nullptr);
+    }
     return 0;
 }
 
@@ -260,8 +292,8 @@ int odpd_clip_adamw(float *param, float *grad, float *exp_avg, float *exp_avg_sq
     ODPD_CHECK(param && grad && exp_avg && exp_avg_sq && lr_dev && step_dev, "odpd_clip_adamw: NULL buffer");
     ODPD_CHECK(n >= 0, "odpd_clip_adamw: negative n");
     if (n == 0) return 0;
-    clip_adamw_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr_dev, beta1, beta2, eps, weight_decay,
-                                                            max_norm, step_dev, gnorm_out, zero_grad);
+    launch_pdl(clip_adamw_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream, param, grad, exp_avg, exp_avg_sq, n, lr_dev, beta1, beta2, eps,
+               weight_decay, max_norm, step_dev, gnorm_out, zero_grad);
     return check_launch("clip_adamw_kernel");
 }
 

@@ -110,12 +110,12 @@ inline int chunk_launch(K k, int nthreads, size_t smem, OccCache *occ_all, GruAr
         a.sc_fail = reinterpret_cast<int *>(scr + (dir == 0 ? rows * (2 * ss + 1) : rows * 2 * ss));
         a.tol = dir == 0 ? SPEC_TOL_FWD : SPEC_TOL_BWD;
         a.mode = 0;
-        k<<<a.B * a.C, nthreads, smem, st>>>(a);
+        launch_pdl(k, dim3(a.B * a.C), dim3(nthreads), smem, st, a);
         a.mode = 2;
-        k<<<a.B, nthreads, smem, st>>>(a);
+        launch_pdl(k, dim3(a.B), dim3(nthreads), smem, st, a);
     } else {
         a.mode = 0;
-        k<<<a.B, nthreads, smem, st>>>(a);
+        launch_pdl(k, dim3(a.B), dim3(nthreads), smem, st, a);
     }
     return check_launch(what);
 }

@@ -20,6 +20,28 @@ void set_error(const char *fmt, ...);
     } while (0)
 int check_launch(const char *what);
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// A train step is 6 small dependent kernels replayed from one CUDA graph; between two dependent kernels the GPU idles for the
+// launch latency (~2 us each, ~7 % of the 160 us step).  With the programmatic-stream-serialization launch attribute the next
+// kernel is launched while its predecessor still runs: its CTAs become resident as SMs drain and park in griddepcontrol.wait until
+// the predecessor grid has completed and its memory is visible.  Every kernel of the step path calls pdl_enter() first thing, so
+// nothing is ever read before the predecessor's results are final; kernels launched the ordinary way execute both as no-ops.
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+bool pdl_enabled();   // env ODPD_PDL != 0 (api.cu)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*k)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, k, static_cast<KArgs>(args)...);
+}
+
 // ---------------------------------------------------------------- math
 // Gate nonlinearities: 2 MUFU ops each (ex2 + rcp), ~2e-7 relative error — far inside the 1e-5 parity budget and
 // ~3x shorter dependent chain than expf()+IEEE divide; they sit on the serial critical path of every timestep.
@@ -187,7 +209,18 @@ __device__ __forceinline__ void stage_params(float *sdst, const float *gsrc, int
     __syncthreads();
 }
 
+// Data-parallel publish fused into the gradient reduction (csrc/dp.cu has the receive side): when world > 1 every reduced gradient
+// element (and the loss) is also pushed as an 8-byte {value, step tag} word into slot [parity][rank] of every rank's receive buffer
+// (own buffer included), straight from the reduction's epilogue — the NVLink flight overlaps the launch of the optimiser kernel.
+static constexpr int ODPD_DP_MAX_WORLD = 8;
+struct DpPushArgs {
+    uint2 *buf[ODPD_DP_MAX_WORLD];
+    int world, rank;
+    int64_t stride;
+    const int64_t *step_dev;
+    const double *loss_local;
+};
 // Deterministic second-stage reduction of per-sequence gradient partials:  g[p] += sum_b part[b][p]
-__global__ void reduce_partials_kernel(const float *__restrict__ part, int nrows, int64_t P, float *__restrict__ g, int overwrite);
+__global__ void reduce_partials_kernel(const float *__restrict__ part, int nrows, int64_t P, float *__restrict__ g, int overwrite, DpPushArgs push);
 
 }  // namespace odpd

@@ -542,7 +542,9 @@ __global__ void __launch_bounds__(128, 1) delta_bwd_kernel(GruArgs a) {
                     gMn += ga;
                     gMnh = fmaf(ga, r, gMnh);
                     float *G = Gb + tl * 4 * HP;
-                    if (lane < HP) { G[lane] = act ? gMr : 0.f; G[HP + lane] = act ? gMz : 0.f; G[2 * HP + lane] = act ? gMnh : 0.f; G[3 * HP + lane] = act ? gMn : 0.f; }
+                    // no `act ?` select here: lanes >= H carry exact zeros by construction (zero head and W_hh columns => gH == 0), and the
+                    // select made ptxas re-load H from the constant bank on the dependent chain of every step
+                    if (lane < HP) { G[lane] = gMr; G[HP + lane] = gMz; G[2 * HP + lane] = gMnh; G[3 * HP + lane] = gMn; }
                     __syncwarp();
                     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, a5 = 0.f;     // three H-term dots as six chains of depth H/2
                     bcast_dot<HT>(G, wcr, a0, a1);

@@ -14,7 +14,7 @@
 
 namespace odpd {
 
-static constexpr int DP_MAX_WORLD = 8;    // one NVSwitch node; keeps the per-thread gather arrays in registers
+static constexpr int DP_MAX_WORLD = ODPD_DP_MAX_WORLD;    // 8 = one NVSwitch node; keeps the per-thread gather arrays in registers
 struct DpPtrs { uint2 *buf[DP_MAX_WORLD]; };
 
 __host__ __device__ inline int64_t dp_stride(int64_t n) { return (n + 1 + 3) & ~(int64_t)3; }
@@ -42,6 +42,7 @@ __global__ void __launch_bounds__(1024) dp_clip_adamw_kernel(float *__restrict__
                                                              float *loss_out, int *status_dev) {
     __shared__ float red[32];
     __shared__ float s_coef;
+    pdl_enter();
     const int64_t step = *step_dev + 1;
     const int64_t stride = dp_stride(n);
     const int par = (int)(step & 1);
@@ -52,7 +53,7 @@ __global__ void __launch_bounds__(1024) dp_clip_adamw_kernel(float *__restrict__
     for (int e = 0; e < 4; ++e) {
         const int64_t i = threadIdx.x + (int64_t)e * blockDim.x;
         own[e] = 0.f;
-        if (i <= n) {
+        if (grad_local && i <= n) {      // grad_local == NULL: the backward's reduction already published (odpd_dp_publish_next_bwd)
             own[e] = (i < n) ? grad_local[i] : (loss_local ? (float)(*loss_local) : 0.f);
             const int64_t off = ((int64_t)par * world + rank) * stride + i;
 #pragma unroll
@@ -76,7 +77,7 @@ __global__ void __launch_bounds__(1024) dp_clip_adamw_kernel(float *__restrict__
 #pragma unroll
             for (int r = 0; r < DP_MAX_WORLD; ++r) {
                 pv[r] = 0.f;
-                if (r < world && r != rank) pending |= 1u << r;
+                if (r < world && (r != rank || !grad_local)) pending |= 1u << r;
             }
             while (pending && !bad) {
                 uint2 w[DP_MAX_WORLD];
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(1024) dp_clip_adamw_kernel(float *__restrict__
             }
 #pragma unroll
             for (int r = 0; r < DP_MAX_WORLD; ++r)
-                if (r < world) acc += (r == rank) ? own[e] : pv[r];
+                if (r < world) acc += (r == rank && grad_local) ? own[e] : pv[r];
         }
         g[e] = acc;
         if (i < n) ss = fmaf(acc, acc, ss);
@@ -140,9 +141,32 @@ __global__ void __launch_bounds__(1024) dp_clip_adamw_kernel(float *__restrict__
 
 }  // namespace odpd
 
+namespace odpd {
+static thread_local DpPushArgs g_armed_push;
+static thread_local bool g_armed = false;
+bool dp_take_armed_push(DpPushArgs &out) {
+    if (!g_armed) return false;
+    out = g_armed_push;
+    g_armed = false;
+    return true;
+}
+}  // namespace odpd
+
 using namespace odpd;
 
 extern "C" {
+
+int odpd_dp_publish_next_bwd(void *const *bufs, int world, int rank, int64_t n, const int64_t *step_dev, const double *loss_local) {
+    ODPD_CHECK(bufs && step_dev, "odpd_dp_publish_next_bwd: NULL buffer");
+    ODPD_CHECK(world >= 1 && world <= DP_MAX_WORLD && rank >= 0 && rank < world, "odpd_dp_publish_next_bwd: bad world/rank (%d,%d)", world, rank);
+    ODPD_CHECK(n >= 1 && n + 1 <= 4096, "odpd_dp_publish_next_bwd: n=%lld outside 1..4095", (long long)n);
+    DpPushArgs p{};
+    for (int r = 0; r < world; ++r) { ODPD_CHECK(bufs[r] != nullptr, "odpd_dp_publish_next_bwd: bufs[%d] is NULL", r); p.buf[r] = (uint2 *)bufs[r]; }
+    p.world = world; p.rank = rank; p.stride = dp_stride(n); p.step_dev = step_dev; p.loss_local = loss_local;
+    g_armed_push = p;
+    g_armed = true;
+    return 0;
+}
 
 int64_t odpd_dp_buffer_bytes(int64_t n_params) { return 2 * DP_MAX_WORLD * dp_stride(n_params) * (int64_t)sizeof(uint2); }
 
@@ -184,13 +208,13 @@ int odpd_dp_ipc_close(void *peer_ptr) {
 int odpd_dp_clip_adamw(float *param, void *const *bufs, int world, int rank, int64_t n, const float *grad_local, const double *loss_local, float *exp_avg,
                        float *exp_avg_sq, const float *lr_dev, float beta1, float beta2, float eps, float weight_decay, float max_norm,
                        int64_t *step_dev, float *gnorm_out, float *loss_out, int *status_dev, void *stream) {
-    ODPD_CHECK(param && bufs && grad_local && exp_avg && exp_avg_sq && lr_dev && step_dev, "odpd_dp_clip_adamw: NULL buffer");
+    ODPD_CHECK(param && bufs && exp_avg && exp_avg_sq && lr_dev && step_dev, "odpd_dp_clip_adamw: NULL buffer");
     ODPD_CHECK(world >= 1 && world <= DP_MAX_WORLD && rank >= 0 && rank < world, "odpd_dp_clip_adamw: bad world/rank (%d,%d)", world, rank);
     ODPD_CHECK(n >= 1 && n + 1 <= 4096, "odpd_dp_clip_adamw: n=%lld outside 1..4095", (long long)n);
     DpPtrs p{};
     for (int r = 0; r < world; ++r) { ODPD_CHECK(bufs[r] != nullptr, "odpd_dp_clip_adamw: bufs[%d] is NULL", r); p.buf[r] = (uint2 *)bufs[r]; }
-    dp_clip_adamw_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(param, p, world, rank, n, grad_local, loss_local, exp_avg, exp_avg_sq, lr_dev, beta1, beta2,
-                                                              eps, weight_decay, max_norm, step_dev, gnorm_out, loss_out, status_dev);
+    launch_pdl(dp_clip_adamw_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream, param, p, world, rank, n, grad_local, loss_local, exp_avg, exp_avg_sq,
+               lr_dev, beta1, beta2, eps, weight_decay, max_norm, step_dev, gnorm_out, loss_out, status_dev);
     return check_launch("dp_clip_adamw_kernel");
 }
 

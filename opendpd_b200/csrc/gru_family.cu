@@ -61,6 +61,7 @@ struct BwdSmem {
 // ================================================================ forward
 template <int HT, int FM, int HEAD>
 __global__ void __launch_bounds__(96, 1) gru_fwd_kernel(GruArgs a) {
+    pdl_enter();
     constexpr int F = FeatN<FM>::value, HP = Pad4<HT>::value, ROW = Row<HT, HEAD>::value;
     using SM = FwdSmem<HT, HEAD>;
     const GruLayout<FM, HEAD> L(a.H);
@@ -369,6 +370,7 @@ __global__ void __launch_bounds__(96, 1) gru_fwd_kernel(GruArgs a) {
 // bound by per-SM throughput, 6 chunks x 3 CTAs/SM takes as long as 4 chunks x 2 CTAs/SM, and the serial kernel gets 15 % slower)
 template <int HT, int FM, int HEAD, bool DW>
 __global__ void __launch_bounds__(128, 1) gru_bwd_kernel(GruArgs a) {
+    pdl_enter();
     constexpr int F = FeatN<FM>::value, HP = Pad4<HT>::value, ROW = Row<HT, HEAD>::value;
     constexpr bool SPLIT = (HT + F > 32);
     using SM = BwdSmem<HT, HEAD>;
@@ -756,6 +758,7 @@ struct BwdcSmem {
 
 template <int HT, int FM, int HEAD>
 __global__ void __launch_bounds__(96, 1) gru_bwdc_kernel(GruArgs a) {
+    pdl_enter();
     constexpr int HP = Pad4<HT>::value, ROW = Row<HT, HEAD>::value, GS = GStride<HT>::value;
     using SM = BwdcSmem<HT, HEAD>;
     const GruLayout<FM, HEAD> L(a.H);
@@ -966,6 +969,7 @@ __device__ __forceinline__ void outer_acc(float (&acc)[TR * TC], const float (&a
 //                   feature columns, fc_hid bias)
 template <int HT, int FM, int HEAD, bool DW>
 __global__ void __launch_bounds__(128, 1) gru_bwdw_kernel(GruArgs a) {
+    pdl_enter();
     constexpr int F = FeatN<FM>::value, HP = Pad4<HT>::value, ROW = Row<HT, HEAD>::value, GS = GStride<HT>::value;
     using SM = BwdwSmem<HT, FM, HEAD>;
     const GruLayout<FM, HEAD> L(a.H);
@@ -1281,6 +1285,7 @@ struct BwdfSmem {
 
 template <int HT, int FM, int HEAD, bool DW>
 __global__ void __launch_bounds__(160, 1) gru_bwdf_kernel(GruArgs a) {
+    pdl_enter();
     constexpr int F = FeatN<FM>::value, HP = Pad4<HT>::value, ROW = Row<HT, HEAD>::value, GS = GStride<HT>::value;
     using SM = BwdfSmem<HT, FM, HEAD>;
     const GruLayout<FM, HEAD> L(a.H);
@@ -1732,7 +1737,7 @@ static int launch_bwd_t(GruArgs a, cudaStream_t st, bool plan_only, int *info) {
     tiles = (nblk + a.wt_blocks - 1) / a.wt_blocks;
     if (info) info[4] = a.B * tiles;
     if (rc || plan_only) return rc;
-    kw<<<dim3((unsigned)tiles, (unsigned)a.B), 128, smem_w, st>>>(a);
+    launch_pdl(kw, dim3((unsigned)tiles, (unsigned)a.B), dim3(128), smem_w, st, a);
     (void)GS;
     return check_launch("gru_bwdw_kernel");
 }

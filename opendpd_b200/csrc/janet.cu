@@ -46,6 +46,7 @@ __device__ __forceinline__ void pg_features(float i, float q, float &a, float &c
 
 template <int HT>
 __global__ void __launch_bounds__(96, 1) pgjanet_fwd_kernel(GruArgs a) {
+    pdl_enter();   // launched through chunk_launch with the programmatic-serialization attribute (common.cuh)
     constexpr int HP = Pad4<HT>::value, ROW = PgRow<HT>::value;
     using SM = PgFwdSmem<HT>;
     const PgLayout L(a.H);
@@ -170,6 +171,7 @@ __global__ void __launch_bounds__(96, 1) pgjanet_fwd_kernel(GruArgs a) {
 
 template <int HT, bool DW>
 __global__ void __launch_bounds__(96, 1) pgjanet_bwd_kernel(GruArgs a) {
+    pdl_enter();   // launched through chunk_launch with the programmatic-serialization attribute (common.cuh)
     constexpr int HP = Pad4<HT>::value, ROW = PgRow<HT>::value;
     using SM = PgBwdSmem<HT>;
     const PgLayout L(a.H);
@@ -399,6 +401,7 @@ template <int HT> struct DvBwdSmem {
 
 template <int HT>
 __global__ void __launch_bounds__(96, 1) dvrjanet_fwd_kernel(GruArgs a) {
+    pdl_enter();   // launched through chunk_launch with the programmatic-serialization attribute (common.cuh)
     constexpr int HP = Pad4<HT>::value, ROW = DvRow<HT>::value;
     using SM = DvFwdSmem<HT>;
     const DvLayout L(a.H, a.K);
@@ -545,6 +548,7 @@ __global__ void __launch_bounds__(96, 1) dvrjanet_fwd_kernel(GruArgs a) {
 
 template <int HT, bool DW>
 __global__ void __launch_bounds__(96, 1) dvrjanet_bwd_kernel(GruArgs a) {
+    pdl_enter();   // launched through chunk_launch with the programmatic-serialization attribute (common.cuh)
     constexpr int HP = Pad4<HT>::value, ROW = DvRow<HT>::value;
     using SM = DvBwdSmem<HT>;
     const DvLayout L(a.H, a.K);

@@ -31,6 +31,7 @@ struct LBwdSmem {
 
 template <int HT>
 __global__ void __launch_bounds__(96, 1) lstm_fwd_kernel(GruArgs a) {
+    pdl_enter();   // launched through chunk_launch with the programmatic-serialization attribute (common.cuh)
     constexpr int HP = Pad4<HT>::value, ROW = LRow<HT>::value;
     using SM = LFwdSmem<HT>;
     const LstmLayout L(a.H);
@@ -162,6 +163,7 @@ __global__ void __launch_bounds__(96, 1) lstm_fwd_kernel(GruArgs a) {
 
 template <int HT, bool DW>
 __global__ void __launch_bounds__(96, 1) lstm_bwd_kernel(GruArgs a) {
+    pdl_enter();   // launched through chunk_launch with the programmatic-serialization attribute (common.cuh)
     constexpr int HP = Pad4<HT>::value, ROW = LRow<HT>::value;
     using SM = LBwdSmem<HT>;
     const LstmLayout L(a.H);

@@ -212,10 +212,17 @@ class NativeTrainStep:
         B, T = features.shape[0], features.shape[1]
         count = float(global_count) if global_count else float(2 * B * T * self.world)   # nn.MSELoss 'mean', GLOBAL batch
         gflat = self.gflat
+
+        def arm_publish(loss):
+            # data parallel: the backward that produces the weight gradient publishes it (and the loss) to every rank straight from
+            # the epilogue of its gradient reduction (csrc/api.cu reduce_partials_kernel, include/odpd.h odpd_dp_publish_next_bwd)
+            if self.px is not None:
+                _ffi.check(L.odpd_dp_publish_next_bwd(self.px.ptrs, self.world, self.px.rank, ctypes.c_int64(self.n), _ptr(self.step_dev), _ptr(loss)))
         if self.dpd is None:
             spec = tb._spec()
             out, loss, saved = backbone_forward_raw(spec, features, flat, targets, 1.0 / count, True, tb._stats_tensor(self.device),
                                                     self._bufs[0])
+            arm_publish(loss)
             backbone_backward_raw(spec, features, flat, saved, False, True, out=out, target=targets, gscale=2.0 / count,
                                   gflat=gflat, bufs=self._bufs[1])
         else:
@@ -226,10 +233,11 @@ class NativeTrainStep:
                                                       self._bufs[2])
             gmid, _ = backbone_backward_raw(sp, mid, paflat, saved_p, True, False, out=out, target=targets, gscale=2.0 / count,
                                             bufs=self._bufs[3])
+            arm_publish(loss)
             backbone_backward_raw(sd, features, flat, saved_d, False, True, gout=gmid, gflat=gflat, bufs=self._bufs[1])
         if self.px is not None:
-            # fused: NVLink peer reads + ordered sum + clip + AdamW in ONE kernel (csrc/dp.cu)
-            _ffi.check(L.odpd_dp_clip_adamw(_ptr(flat), self.px.ptrs, self.world, self.px.rank, ctypes.c_int64(self.n), _ptr(self.gflat), _ptr(loss),
+            # fused: gather of the pushed gradients from the LOCAL receive buffer + ordered sum + clip + AdamW in ONE kernel (csrc/dp.cu)
+            _ffi.check(L.odpd_dp_clip_adamw(_ptr(flat), self.px.ptrs, self.world, self.px.rank, ctypes.c_int64(self.n), None, _ptr(loss),
                                             _ptr(self.exp_avg), _ptr(self.exp_avg_sq), _ptr(self.lr_dev), self.betas[0], self.betas[1],
                                             self.eps, self.wd, self.clip, _ptr(self.step_dev), _ptr(self.gnorm), _ptr(self.px.loss_out),
                                             _ptr(self.px.status), _stream()))
