@@ -640,7 +640,8 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         fam = {"dgru": "gru", "gru": "gru", "qgru": "gru", "deltagru": "delta", "deltagru_tcnskip": "delta"}.get(bb.cell, bb.cell)
-        dom = (f"odpd::{fam}_bwd_kernel", bwd_ms) if bwd_ms >= fwd_ms else (f"odpd::{fam}_fwd_kernel", fwd_ms)
+        bwd_name = "odpd::gru_bwdf_kernel" if fam == "gru" else f"odpd::{fam}_bwd_kernel"      # GRU family: the lean fused backward (gru_family.cu)
+        dom = (bwd_name, bwd_ms) if bwd_ms >= fwd_ms else (f"odpd::{fam}_fwd_kernel", fwd_ms)
         achieved = ALGO_BYTES_PER_SAMPLE_PER_KERNEL * B * T / (dom[1] * 1e-3) / 1e9
         plan_i = (0, 1) if "pa" not in wl else (1, 2)
         tr_entry = traffic.get(args.workload, {}).get(dom[0], {})

@@ -29,6 +29,8 @@
  *   DVRJANET  (dvrjanet.py:14-30)   cs(K) W_ph.weight(H,H) W_ptheta.weight(H,1) W_ah.weight(H,H) W_ax.weight(H,1) W_f.weight(H,H) W_f.bias(H)
  *                                   W_ccos.weight(H,2H) W_ccos.bias(H) W_csin.* W_o1.weight(1,H) W_o1.bias(1) W_o2.weight(1,H) W_o2.bias(1)
  *   GMP       (gmp.py:11)           Weight(1,495)
+ *   VDLSTM    (vdlstm.py:28-41)     rnn.weight_ih_l0(4H,4) weight_hh_l0(4H,H) bias_ih_l0(4H) bias_hh_l0(4H) fc_lambda_1.weight(4,H) .bias(4)
+ *                                   fc_lambda_2.weight(4,H) .bias(4) fc_out.weight(2,8) fc_out.bias(2)
  *   QGRU_QAT  (quant_envs.py:215-305 applied to qgru.py) rnn.rnn_cell_list.0.x2h.weight(3H,4) .bias(3H) .weight_quantizer.scale .act_quantizer.scale
  *                                   .out_quantizer.scale | h2h.weight(3H,H) .bias(3H) + 3 scales | sigmoid/tanh/add/mul .quantizer.scale |
  *                                   fc_out.weight(2,H) .bias(2) + 3 scales.   For the QAT cells OdpdDims.K packs n_bits_w | n_bits_a<<8 | eval<<16.
@@ -58,7 +60,8 @@ enum {
     ODPD_CELL_QGRU_AMP1 = 9, /* backbones/qgru_amp1.py:59-76 */
     ODPD_CELL_QGRU_QAT = 10, /* qgru.py under --quant: quant/modules/gru.py:32-124 + quant/qmodules (fake-quant QAT) */
     ODPD_CELL_QGRU_AMP1_QAT = 11, /* qgru_amp1.py under --quant */
-    ODPD_CELL_COUNT = 12
+    ODPD_CELL_VDLSTM = 12,   /* backbones/vdlstm.py:58-82 */
+    ODPD_CELL_COUNT = 13
 };
 
 /* flags */

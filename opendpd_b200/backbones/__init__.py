@@ -3,8 +3,9 @@ from .gru import GRU
 from .dgru import DGRU
 from .qgru import QGRU, QGRUAmp1
 from .lstm import LSTM
+from .vdlstm import VDLSTM
 from .deltagru import DeltaGRU, TResDeltaGRU
 from .janet import PGJANET, DVRJANET
 from .gmp import GMP
 
-__all__ = ["GRU", "DGRU", "QGRU", "QGRUAmp1", "LSTM", "DeltaGRU", "TResDeltaGRU", "PGJANET", "DVRJANET", "GMP"]
+__all__ = ["GRU", "DGRU", "QGRU", "QGRUAmp1", "LSTM", "VDLSTM", "DeltaGRU", "TResDeltaGRU", "PGJANET", "DVRJANET", "GMP"]

@@ -31,6 +31,7 @@ struct GruArgs {
     float tol;
     int tchunks_req, twarm_req, twarm_default;
     int wt_blocks;   // split backward: 32-step blocks per CTA of the weights kernel
+    float *vd_contrib;   // VDLSTM backward: per-(step, window tap) dL/dx contributions [B][T][4] float2 (lstm.cu)
     float *gbuf;     // split backward (gru_family.cu): per-step gate gradients [B][T][4*HP+4], written by the chain kernel, read by the weights kernel
 };
 
@@ -46,7 +47,8 @@ int gru_family_plan(int cell, int B, int T, int H, int tchunks_req, int twarm_re
 #define ODPD_HAVE_GMP 1
 // lstm.cu
 int64_t lstm_saved_floats(int B, int T, int H, bool save, int tchunks_req);
-int64_t lstm_workspace_floats(int B, int H, int64_t P, int tchunks_req);
+int64_t lstm_workspace_floats(int B, int T, int H, int64_t P, int tchunks_req, bool vd);
+int64_t lstm_nparams(int H, bool vd);
 int lstm_run(const GruArgs &a, int dir, bool dw, cudaStream_t st, int *info);   // dir +2 = plan only; info[0..3] see chunking.cuh
 // delta.cu : DELTAGRU / TRES
 int64_t delta_saved_floats(int cell, int B, int T, int H);

@@ -38,7 +38,7 @@ inline int64_t chunk_workspace_floats(int64_t rows, int64_t P, int ss) { return 
 // Per-process caches are keyed by the CURRENT device: cudaFuncSetAttribute and occupancy are per device, and one process may
 // touch several GPUs (tests do).
 static constexpr int ODPD_MAX_DEV = 32;
-struct OccCache { int v[ODPD_MAX_DEV]; };
+struct OccCache { int v[ODPD_MAX_DEV]; size_t smem[ODPD_MAX_DEV]; };   // occupancy and the dynamic-smem limit it was taken at, per device
 inline int cur_dev_slot() {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= ODPD_MAX_DEV) dev = 0;
@@ -92,8 +92,11 @@ template <typename K>
 inline int chunk_launch(K k, int nthreads, size_t smem, OccCache *occ_all, GruArgs a, int dir, float *scr, int64_t scr_off, int ss,
                         cudaStream_t st, bool plan_only, int *info, const char *what, int warm = SPEC_WARM_DEFAULT) {
     a.twarm_default = warm;
-    int *occ_cache = &occ_all->v[cur_dev_slot()];
-    if (!*occ_cache) {
+    const int dev_slot = cur_dev_slot();
+    int *occ_cache = &occ_all->v[dev_slot];
+    // the footprint depends on the runtime hidden size inside a compiled tier (the parameter block): re-arm when a larger one shows up
+    if (!*occ_cache || smem > occ_all->smem[dev_slot]) {
+        occ_all->smem[dev_slot] = smem;
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int occ = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, nthreads, smem) != cudaSuccess || occ <= 0) occ = 1;

@@ -1723,7 +1723,8 @@ static int launch_bwd_t(GruArgs a, cudaStream_t st, bool plan_only, int *info) {
     static OccCache occ_w{};
     auto kw = gru_bwdw_kernel<HT, FM, HEAD, DW>;
     int *ow = &occ_w.v[cur_dev_slot()];
-    if (!*ow) {
+    if (!*ow || smem_w > occ_w.smem[cur_dev_slot()]) {
+        occ_w.smem[cur_dev_slot()] = smem_w;
         cudaFuncSetAttribute(kw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w);
         int o = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kw, 128, smem_w) != cudaSuccess || o <= 0) o = 1;

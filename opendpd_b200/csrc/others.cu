@@ -5,7 +5,8 @@ namespace odpd {
 
 int64_t other_nparams(int cell, int H, int K) {
     switch (cell) {
-    case ODPD_CELL_LSTM: return (int64_t)4 * H * 2 + 4 * H * H + 8 * H + 2 * H + 2;
+    case ODPD_CELL_LSTM: return lstm_nparams(H, false);
+    case ODPD_CELL_VDLSTM: return lstm_nparams(H, true);
     case ODPD_CELL_DELTAGRU: return (int64_t)3 * H * 6 + 3 * H * H + 6 * H + 2 * H + 2;
     case ODPD_CELL_TRES: return (int64_t)3 * H * 6 + 3 * H * H + 2 * H + 18 + 6;
     case ODPD_CELL_PGJANET: return (int64_t)3 * (H * (H + 1) + H) + 2 * (2 * H * H + H) + 2 * H + 2;
@@ -18,7 +19,7 @@ int64_t other_nparams(int cell, int H, int K) {
 
 static bool implemented(int cell) {
     switch (cell) {
-    case ODPD_CELL_LSTM: case ODPD_CELL_QGRU_QAT: case ODPD_CELL_QGRU_AMP1_QAT: return true;
+    case ODPD_CELL_LSTM: case ODPD_CELL_VDLSTM: case ODPD_CELL_QGRU_QAT: case ODPD_CELL_QGRU_AMP1_QAT: return true;
 #ifdef ODPD_HAVE_DELTA
     case ODPD_CELL_DELTAGRU: case ODPD_CELL_TRES: return true;
 #endif
@@ -32,14 +33,14 @@ static bool implemented(int cell) {
     return false;
 }
 
-static bool chunkable(int cell) { return cell == ODPD_CELL_LSTM || cell == ODPD_CELL_PGJANET || cell == ODPD_CELL_DVRJANET; }
+static bool chunkable(int cell) { return cell == ODPD_CELL_LSTM || cell == ODPD_CELL_VDLSTM || cell == ODPD_CELL_PGJANET || cell == ODPD_CELL_DVRJANET; }
 
 // bytes of `saved` for these dims: activations (with ODPD_F_SAVE) + the chunk scratch of the chunkable cells
 int64_t other_saved_bytes(const OdpdDims *d) {
     int64_t n = -1;
     const bool save = (d->flags & ODPD_F_SAVE) != 0;
     switch (d->cell) {
-    case ODPD_CELL_LSTM: n = lstm_saved_floats(d->B, d->T, d->H, save, d->tchunks); break;
+    case ODPD_CELL_LSTM: case ODPD_CELL_VDLSTM: n = lstm_saved_floats(d->B, d->T, d->H, save, d->tchunks); break;
     case ODPD_CELL_QGRU_QAT: case ODPD_CELL_QGRU_AMP1_QAT: n = qat_saved_floats(d->B, d->T, d->H); break;
 #ifdef ODPD_HAVE_DELTA
     case ODPD_CELL_DELTAGRU: case ODPD_CELL_TRES: n = delta_saved_floats(d->cell, d->B, d->T, d->H); break;
@@ -59,7 +60,7 @@ int64_t other_saved_bytes(const OdpdDims *d) {
 int64_t other_workspace_floats(const OdpdDims *d) {
     const int64_t P = other_nparams(d->cell, d->H, d->K);
     switch (d->cell) {
-    case ODPD_CELL_LSTM: return lstm_workspace_floats(d->B, d->H, P, d->tchunks);
+    case ODPD_CELL_LSTM: case ODPD_CELL_VDLSTM: return lstm_workspace_floats(d->B, d->T, d->H, P, d->tchunks, d->cell == ODPD_CELL_VDLSTM);
 #ifdef ODPD_HAVE_JANET
     case ODPD_CELL_PGJANET: case ODPD_CELL_DVRJANET: return janet_workspace_floats(d->cell, d->B, d->H, P, d->tchunks);
 #endif
@@ -72,7 +73,7 @@ static int run(const OdpdDims *d, const GruArgs &a, int dir, bool dw, cudaStream
     if (info) { info[0] = 1; info[1] = a.T; info[2] = 0; info[3] = -1; }
     if (dir >= 2 && !chunkable(d->cell)) return 0;
     switch (d->cell) {
-    case ODPD_CELL_LSTM: return lstm_run(a, dir, dw, st, info);
+    case ODPD_CELL_LSTM: case ODPD_CELL_VDLSTM: return lstm_run(a, dir, dw, st, info);
     case ODPD_CELL_QGRU_QAT: case ODPD_CELL_QGRU_AMP1_QAT: return qat_run(a, dir, dw, st);
 #ifdef ODPD_HAVE_DELTA
     case ODPD_CELL_DELTAGRU: case ODPD_CELL_TRES: return delta_run(a, dir, dw, st);

@@ -5,7 +5,7 @@ unchanged.  Backbones outside the hot-path scope (SURVEY.md §2
 import torch
 from torch import nn
 
-NATIVE_BACKBONES = ("gmp", "gru", "dgru", "qgru", "qgru_amp1", "lstm", "deltagru", "deltagru_tcnskip", "pgjanet", "dvrjanet")
+NATIVE_BACKBONES = ("gmp", "gru", "dgru", "qgru", "qgru_amp1", "lstm", "vdlstm", "deltagru", "deltagru_tcnskip", "pgjanet", "dvrjanet")
 
 
 class CoreModel(nn.Module):
@@ -28,6 +28,8 @@ class CoreModel(nn.Module):
             self.backbone = bb.QGRUAmp1(**kw)
         elif backbone_type == "lstm":
             self.backbone = bb.LSTM(input_size=input_size, **kw)
+        elif backbone_type == "vdlstm":
+            self.backbone = bb.VDLSTM(input_size=input_size, **kw)
         elif backbone_type == "deltagru":
             self.backbone = bb.DeltaGRU(input_size=6, hidden_size=hidden_size, output_size=2, num_layers=num_layers,
                                         thx=thx, thh=thh, bias=True)

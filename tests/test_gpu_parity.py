@@ -401,3 +401,53 @@ def test_integration_snippet_runs():
         ref = net(x)
     torch.cuda.synchronize()
     assert torch.equal(mine, ref)
+
+
+@pytest.mark.parametrize("name,seed", [("next_vdlstm_h8_b3_t40", 0), ("next_vdlstm_h12_b2_t129", 1)])
+def test_vdlstm_golden_parity(name, seed):
+    """VDLSTM (backbones/vdlstm.py) against vectors made by the unmodified reference's autograd in fp64."""
+    import os
+    from opendpd_b200 import models
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    H = int(g["H"])
+    torch.manual_seed(seed)
+    net = models.CoreModel(2, H, 1, "vdlstm")
+    assert [n for n, _ in net.backbone.named_parameters()] == list(g["names"])
+    mine0 = np.concatenate([p.detach().numpy().ravel() for _, p in net.backbone.named_parameters()])
+    assert np.array_equal(mine0, g["params"].astype(np.float32)), "initial weights differ from the reference's"
+    net = net.cuda()
+    for chunks in ((1, 1), None):
+        if chunks:
+            net.backbone.time_chunks = chunks
+        net.zero_grad()
+        x = torch.from_numpy(g["x"]).cuda().requires_grad_(True)
+        out, loss = net.forward_mse(x, torch.from_numpy(g["y"]).cuda())
+        loss.backward()
+        torch.cuda.synchronize()
+        errs = dict(out=rel_err(out.detach().cpu().numpy(), g["out"]), gx=rel_err(x.grad.cpu().numpy(), g["gx"]),
+                    gparams=rel_err(grads_flat(net), g["gparams"]), loss=abs(loss.item() - float(g["loss"])) / abs(float(g["loss"])))
+        note_achieved(name, **errs)
+        assert all(v < 1e-5 for v in errs.values()), errs
+
+
+@pytest.mark.parametrize("H,B,T,tchunks", [(9, 16, 1024, 1), (9, 16, 1024, (4, 3)), (16, 5, 300, 0), (9, 64, 2048, 0)])
+def test_vdlstm_oracle_parity_seeded(H, B, T, tchunks):
+    """VDLSTM at scale, serial and time-chunked, against the numpy fp64 restatement (oracle/next_cells.py, itself pinned to the goldens)."""
+    from oracle import next_cells
+    from opendpd_b200 import models
+    torch.manual_seed(77)
+    net = models.CoreModel(2, H, 1, "vdlstm").cuda()
+    net.backbone.time_chunks = tchunks
+    gen = torch.Generator().manual_seed(5)
+    xc = (0.2 * torch.randn(B, T, 2, generator=gen)).clamp(-0.7, 0.7)
+    yc = xc * (1 - 0.2 * (xc ** 2).sum(-1, keepdim=True))
+    x = xc.cuda().requires_grad_(True)
+    out, loss = net.forward_mse(x, yc.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    params = np.concatenate([p.detach().cpu().numpy().ravel() for _, p in net.backbone.named_parameters()])
+    ref = next_cells.vdlstm(xc.numpy(), params, H, target=yc.numpy())
+    assert_close(out.detach().cpu().numpy(), ref["out"], 1e-5, "vdlstm out")
+    assert_close(x.grad.cpu().numpy(), ref["gx"], 1e-5, "vdlstm gx")
+    assert_close(grads_flat(net), ref["gparams"], 1e-5, "vdlstm gparams")
+    assert abs(loss.item() - ref["loss"]) <= 1e-5 * abs(ref["loss"])

@@ -72,6 +72,16 @@ def test_cpu_tensor_is_rejected_loudly():
         net(torch.zeros(1, 4, 2))
 
 
+def test_vdlstm_container_matches_reference_golden():
+    """Row f-4, first cell: names, count and initial weights of the native VDLSTM equal the reference's (fixture from its own ctor)."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "next_vdlstm_h8_b3_t40.npz"))
+    torch.manual_seed(0)
+    net = models.CoreModel(2, 8, 1, "vdlstm")
+    assert [n for n, _ in net.backbone.named_parameters()] == list(g["names"])
+    mine = np.concatenate([p.detach().numpy().ravel() for _, p in net.backbone.named_parameters()])
+    assert mine.size == 538 == _ffi.n_params("vdlstm", 8) and np.array_equal(mine, g["params"].astype(np.float32))
+
+
 def test_unsupported_configs_raise():
     with pytest.raises(NotImplementedError):
         models.CoreModel(2, 8, 2, "gru")            # num_layers=2
