@@ -16,7 +16,8 @@ CASES = [  # kind, H, B, T, tchunks (fwd,bwd), twarm
     ("lstm", 9, 2, 130, (1, 1), 0), ("lstm", 9, 2, 256, (2, 2), 64),
     ("deltagru", 15, 2, 100, (1, 1), 0), ("deltagru_tcnskip", 15, 3, 100, (1, 1), 0),
     ("pgjanet", 15, 2, 100, (1, 1), 0), ("pgjanet", 15, 2, 256, (2, 2), 64), ("dvrjanet", 15, 2, 100, (1, 1), 0), ("dvrjanet", 15, 2, 256, (2, 2), 64),
-    ("gmp", 1, 2, 60, (1, 1), 0), ("qgru_qat", 10, 2, 40, (1, 1), 0),
+    ("gmp", 1, 2, 60, (1, 1), 0), ("qgru_qat", 10, 2, 40, (1, 1), 0), ("qgru_qat", 20, 5, 70, (1, 1), 0),
+    ("vdlstm", 9, 2, 100, (1, 1), 0), ("vdlstm", 9, 2, 256, (2, 2), 64), ("dgru", 23, 2, 130, (1, 1), 0), ("gru", 8, 2, 70, (1, 1), 0),
 ]
 for kind, H, B, T, tch, tw in CASES:
     if only and kind not in only:
