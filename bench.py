@@ -291,7 +291,8 @@ def build_trainer(wl, dev, pg, world):
 
 def chunk_report(trainer, B, T):
     from opendpd_b200.functional import chunk_reruns, chunk_worst_mismatch
-    info, launches = [], 2                       # reduce_partials + clip_adamw
+    info = []
+    launches = 1 if (trainer.px is None and trainer.world == 1 and trainer.fuse_optimizer) else 2     # reduce_partials (+ clip_adamw in its last CTA) | + optimiser launch
     for mod, backward, bi, save, need_dw in trainer.chunk_calls():
         sp_ = mod._spec()
         plan = sp_.chunk_plan(B, T, backward, save, need_dw)
@@ -312,6 +313,7 @@ class Run:
         GB = wl["B"] * world if weak else wl["B"]
         assert GB % world == 0, (GB, world)
         self.GB, self.B, self.T = GB, GB // world, wl["T"]
+        self.multi = int(os.environ.get("ODPD_BENCH_STEPS_PER_REPLAY", "8"))
         B, T = self.B, self.T
         self.net, self.trainer = build_trainer(wl, dev, pg, world)
         self.feed = Feed(wl, dev, rank, world, B, GB)
@@ -353,20 +355,39 @@ class Run:
     def pool_step(self, i, loss_out):
         return self.trainer.step_indexed(self.px, self.py, self.ptable[i % self.POOL], self.T, loss_out=loss_out)
 
-    def timed(self, W, K, flush=None):
+    def timed(self, W, K, flush=None, multi=None):
         """W warm-up + EXACTLY K timed steps over the pool, every step's loss copied device->host (pinned) inside the region;
-        CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.  Returns (ms total, losses)."""
+        CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.  Returns (ms total, losses).
+        The steps are issued `multi` per CUDA-graph replay (NativeTrainStep.steps_indexed; 1 = one graph per step): one copy of the
+        frame starts in and one copy of the losses out per replay instead of per step, no launch gap between the steps inside."""
         torch = self.torch
+        multi = self.multi if multi is None else multi
         loss_pin = torch.zeros(K, dtype=torch.float64).pin_memory()
-        for i in range(W):
-            self.pool_step(i, self.sink)
+        order = (torch.arange(W + K) % self.POOL).to(self.dev)
+        tab = self.ptable[order].contiguous()              # (W+K, B) frame starts of the warm-up and the timed steps, in order
+
+        def issue(lo, n, out):
+            if multi <= 1:
+                for i in range(lo, lo + n):
+                    self.trainer.step_indexed(self.px, self.py, tab[i], self.T, loss_out=None if out is None else out[i - W:i - W + 1])
+            else:
+                i = lo
+                while i < lo + n:
+                    m = min(multi, lo + n - i)
+                    self.trainer.steps_indexed(self.px, self.py, tab[i:i + m], self.T, losses_out=None if out is None else out[i - W:i - W + m])
+                    i += m
+        # untimed: every replay shape the timed loop will use is run eagerly once, captured once and replayed once before the clock starts
+        if multi > 1:
+            for m in sorted({min(multi, K), K % multi} - {0}):
+                for _ in range(3):
+                    self.trainer.steps_indexed(self.px, self.py, tab[:m], self.T)
+        issue(0, W, None)
         if flush is not None:
             flush.zero_()                               # evict the pool from L2: every timed step reads a cold batch
         self.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for i in range(K):
-            self.pool_step(W + i, loss_pin[i:i + 1])
+        issue(W, K, loss_pin)
         e1.record()
         self.barrier()
         return self.max_over_ranks(e0.elapsed_time(e1)), loss_pin.numpy().copy()
@@ -504,10 +525,11 @@ def main():
 
     # ---- e2e: host (pinned) frames, H2D inside the step, loss read back every step
     xs_pin, ys_pin, POOL = run.xs_pin, run.ys_pin, run.POOL
-    trainer.run_host_batches((xs_pin[i], ys_pin[i]) for i in range(3))
+    for _ in range(3):      # untimed: the same block pattern as the timed call, so that every replay shape is run eagerly, captured and replayed once
+        trainer.run_host_batches(((xs_pin[i % POOL], ys_pin[i % POOL]) for i in range(K)), steps_per_replay=max(run.multi, 1))
     run.barrier()
     t0 = time.perf_counter()
-    e2e_losses = trainer.run_host_batches((xs_pin[(W + i) % POOL], ys_pin[(W + i) % POOL]) for i in range(K))
+    e2e_losses = trainer.run_host_batches(((xs_pin[(W + i) % POOL], ys_pin[(W + i) % POOL]) for i in range(K)), steps_per_replay=max(run.multi, 1))
     torch.cuda.synchronize()
     e2e_s = run.max_over_ranks(time.perf_counter() - t0)
     assert len(e2e_losses) == K and all(np.isfinite(e2e_losses))
@@ -519,22 +541,35 @@ def main():
     e2e_seq_ms = run.max_over_ranks((time.perf_counter() - t1) / ks * 1e3)
     # on-device framing (SURVEY f-2), the way a real epoch runs: the raw APA stream resident in HBM (472 KB: L2-resident by nature),
     # per step the host sends only the B frame start indices of the seeded permutation, the loss comes back every step
-    starts_pin = run.feed.table(run.settle + POOL, K + 3).pin_memory()
-    loss_pin = [torch.zeros(1, dtype=torch.float64).pin_memory() for _ in range(2)]
+    starts_pin = run.feed.table(run.settle + POOL, K + 8).pin_memory()
     ev_l = [torch.cuda.Event() for _ in range(2)]
 
+    MULTI = run.multi
+    loss_pin = [torch.zeros(max(MULTI, 1), dtype=torch.float64).pin_memory() for _ in range(2)]
+
     def indexed_steps(n, off):
-        pending = None
-        for i in range(n):
-            sl = i & 1
-            trainer.step_indexed(run.feed.x, run.feed.y, starts_pin[off + i], T, loss_out=loss_pin[sl])
+        """n steps, MULTI per graph replay: per replay the (m,B) frame starts go pinned host -> device and the m losses come back; the
+        host reads them one replay later."""
+        pending, i, sl = None, 0, 0
+        while i < n:
+            m = min(max(MULTI, 1), n - i)
+            if MULTI > 1:
+                trainer.steps_indexed(run.feed.x, run.feed.y, starts_pin[off + i:off + i + m], T, losses_out=loss_pin[sl][:m])
+            else:
+                trainer.step_indexed(run.feed.x, run.feed.y, starts_pin[off + i], T, loss_out=loss_pin[sl][:1])
             ev_l[sl].record()
             if pending is not None:
-                ev_l[pending].synchronize()
-                assert np.isfinite(float(loss_pin[pending][0]))
-            pending = sl
-        ev_l[pending].synchronize()
-    indexed_steps(3, 0)
+                ev_l[pending[0]].synchronize()
+                assert np.all(np.isfinite(loss_pin[pending[0]][:pending[1]].numpy()))
+            pending = (sl, m)
+            sl ^= 1
+            i += m
+        ev_l[pending[0]].synchronize()
+    for _ in range(3):
+        indexed_steps(min(K, max(MULTI, 1)), 0)          # eager, capture, replay of the replay shape
+    if K % max(MULTI, 1):
+        for _ in range(3):
+            indexed_steps(K % MULTI, 0)
     run.barrier()
     t2 = time.perf_counter()
     indexed_steps(K, 3)
@@ -598,6 +633,7 @@ def main():
         replicas_ok = bool(all(torch.equal(allp[0], q) for q in allp))
     run.close()
     final_loss = float(losses[-1])
+    run_multi = MULTI
     settle_steps = run.settle
     del run, xd, yd, xs_pin, ys_pin, saved, out, kb0, kb1
     torch.cuda.empty_cache()
@@ -653,7 +689,7 @@ def main():
             "config": config_of(wl, world, True),
             "run": {"untimed_settle_steps": settle_steps, "untimed_settle": f"{settle_steps} real training steps over the seeded epoch permutation of the "
                     f"{wl['dataset']} stream (on-device framing) + {plan_settle} steps over the timed pool until the chunk controller made no change",
-                    "pool_batches": POOL, "pool_mb": POOL * 2 * B * T * 8 / 2**20, "cuda_graphs": bool(getattr(trainer, "use_graphs", False)),
+                    "steps_per_graph_replay": run_multi, "pool_batches": POOL, "pool_mb": POOL * 2 * B * T * 8 / 2**20, "cuda_graphs": bool(getattr(trainer, "use_graphs", False)),
                     "final_loss": final_loss, "loss_readback": "every timed step copies its loss device->host (pinned, async) inside the timed region; "
                     "value_sync_loss is the strict variant with loss.item() (host sync) after every step"},
             "value_sync_loss": {"value": world * B * T / (sync_ms * 1e-3), "ms_per_step": sync_ms},
@@ -663,7 +699,8 @@ def main():
             "e2e": {"value": world * B * T * K / e2e_s, "unit": "IQ samples/s", "ms_per_step": e2e_s / K * 1e3,
                     "h2d_bytes_per_step": 2 * B * T * 2 * 4, "d2h_bytes_per_step": 8,
                     "path": "NativeTrainStep.run_host_batches: per step pinned host (B,T,2) features+targets (real frames) -> cudaMemcpyAsync (side stream, "
-                            "overlapping the previous step) -> fwd/bwd/optimizer kernels -> async D2H of the loss, read one step later",
+                            "overlapping the previous block) -> fwd/bwd/optimizer kernels (blocks of run.steps_per_graph_replay steps per CUDA-graph "
+                            "replay) -> async D2H of every step's loss, read one block later",
                     "ms_per_step_sequential": e2e_seq_ms},
             "e2e_indexed": {"value": world * B * T * K / e2e_idx_s, "unit": "IQ samples/s", "ms_per_step": e2e_idx_s / K * 1e3,
                             "h2d_bytes_per_step": 4 * B, "d2h_bytes_per_step": 8,
@@ -671,9 +708,9 @@ def main():
                                     "L2-resident by nature); per step the B frame start indices of the seeded permutation go pinned host -> device, "
                                     "the kernels read the stride-1 windows in place (OdpdDims.x_starts), the loss is read back one step later"},
             "kernels_per_step": (["<cell>_fwd_kernel (chunks)", "<cell>_fwd_kernel (verify)", "<cell>_bwd_kernel<DW> (chunks)", "<cell>_bwd_kernel<DW> (verify)",
-                                  "reduce_partials_kernel", "clip_adamw_kernel"] if "pa" not in wl else
-                                 ["dpd_fwd", "pa_fwd(+MSE)", "pa_bwd<dX>", "dpd_bwd<DW>", "(+1 verify launch per chunked call)", "reduce_partials_kernel",
-                                  "clip_adamw_kernel", "(gmp: +1)"]),
+                                  "reduce_partials_kernel (clip + AdamW in its last CTA at N=1; + dp_clip_adamw_kernel at N>1)"] if "pa" not in wl else
+                                 ["dpd_fwd", "pa_fwd(+MSE)", "pa_bwd<dX>", "dpd_bwd<DW>", "(+1 verify launch per chunked call)",
+                                  "reduce_partials_kernel (+ optimiser)", "(gmp: +1)"]),
             "time_chunks": chunk_info, "time_chunk_events": events_at_timed,
             "kernel_ms": {"fwd": fwd_ms, "bwd": bwd_ms},
             "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -168,6 +168,14 @@ int odpd_clip_adamw(float *param, float *grad, float *exp_avg, float *exp_avg_sq
                     float beta1, float beta2, float eps, float weight_decay, float max_norm, int64_t *step_dev,
                     float *gnorm_out, int zero_grad, void *stream);
 
+/* Optional fusion of the optimiser into the backward (single GPU): arms the NEXT odpd_backbone_bwd call of this host thread (one with
+ * ODPD_F_NEED_DW | ODPD_F_OVERWRITE_DW) to run clip_grad_norm_ + AdamW — same arithmetic and arguments as odpd_clip_adamw, on the
+ * `gparams` that call produces — inside its gradient-reduction kernel (last CTA to finish), saving one launch per train step; the caller
+ * then does NOT call odpd_clip_adamw for that step.  ticket_dev: device int32, zero before first use (the kernel resets it).
+ * One-shot, thread-local host state. */
+int odpd_fuse_next_bwd_with_adamw(float *param, float *exp_avg, float *exp_avg_sq, const float *lr_dev, float beta1, float beta2, float eps,
+                                  float weight_decay, float max_norm, int64_t *step_dev, float *gnorm_out, int32_t *ticket_dev);
+
 /*
  * Data-parallel exchange over NVLink peer memory (ONE exchange per train step, the flat [grad | loss] buffer).
  * The all-reduce is fused into the optimiser kernel and is PUSH based: every rank stores its gradient as 8-byte words

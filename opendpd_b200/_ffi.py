@@ -40,6 +40,7 @@ SYMBOLS = {
     "odpd_backbone_bwd": (ctypes.c_int, [_DP, _vp, _vp, _vp, _vp, _vp, _vp, _dbl, _vp, _vp, _vp, _vp, _vp]),
     "odpd_clip_adamw": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _flt, _flt, _flt, _flt, _flt, _vp, _vp,
                                        ctypes.c_int, _vp]),
+    "odpd_fuse_next_bwd_with_adamw": (ctypes.c_int, [_vp, _vp, _vp, _vp, _flt, _flt, _flt, _flt, _flt, _vp, _vp, _vp]),
     "odpd_nmse_sums": (ctypes.c_int, [_vp, _vp, _i32, _i32, _vp, _vp]),
     "odpd_dft_magnitude": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "odpd_dp_buffer_bytes": (_i64, [_i64]),

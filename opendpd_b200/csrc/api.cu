@@ -32,12 +32,54 @@ int check_launch(const char *what) {
     return 0;
 }
 
+// clip_grad_norm_ + AdamW on the flat buffers, executed by ONE CTA of any size (train_funcs.py:41-44, project.py:283):
+// p *= 1-lr*wd;  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+// `g` is read with L1-bypassing loads: in the fused form other CTAs of the same kernel wrote it.
+__device__ __forceinline__ void clip_adamw_body(float *__restrict__ p, float *g, float *__restrict__ m, float *__restrict__ v, int64_t n,
+                                                const float *__restrict__ lr_dev, float b1, float b2, float eps, float wd, float max_norm,
+                                                int64_t *step_dev, float *gnorm_out, int zero_grad, float *red, float *s_coef) {
+    float ss = 0.f;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) { const float x = __ldcg(g + i); ss = fmaf(x, x, ss); }
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+        t = warp_sum(t);
+        if (threadIdx.x == 0) {
+            const float norm = sqrtf(t);
+            float coef = 1.f;
+            if (max_norm > 0.f) { coef = max_norm / (norm + 1e-6f); coef = coef < 1.f ? coef : 1.f; }
+            *s_coef = coef;
+            if (gnorm_out) *gnorm_out = norm;
+        }
+    }
+    __syncthreads();
+    const float coef = *s_coef;
+    const int64_t step = *step_dev + 1;
+    const float lr = *lr_dev;
+    const float bc1 = 1.f - powf(b1, (float)step), bc2 = 1.f - powf(b2, (float)step);
+    const float step_size = lr / bc1, bc2s = sqrtf(bc2);
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const float gi = __ldcg(g + i) * coef;
+        float pi = p[i] * (1.f - lr * wd);
+        const float mi = fmaf(b1, m[i], (1.f - b1) * gi);
+        const float vi = fmaf(b2, v[i], (1.f - b2) * gi * gi);
+        const float denom = sqrtf(vi) / bc2s + eps;
+        pi -= step_size * (mi / denom);
+        p[i] = pi; m[i] = mi; v[i] = vi;
+        if (zero_grad) g[i] = 0.f; else g[i] = gi;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *step_dev = step;
+}
+
 // g[p] (+)= sum_{b=0..nrows-1} part[b][p].  Block = 32 parameters x RED_TY row groups: thread (tx,ty) sums rows ty, ty+RED_TY, ... in
 // row order (8 independent loads in flight), the RED_TY group sums are then added in group order — a fixed summation tree, so the result
 // is bit-reproducible run to run; no float atomics.
 static constexpr int RED_TY = 16;
 __global__ void __launch_bounds__(32 * RED_TY) reduce_partials_kernel(const float *__restrict__ part, int nrows, int64_t P, float *__restrict__ g,
-                                                                      int overwrite, DpPushArgs push) {
+                                                                      int overwrite, DpPushArgs push, AdamFuseArgs adam) {
     __shared__ float red[RED_TY][33];
     pdl_enter();
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -77,20 +119,33 @@ __global__ void __launch_bounds__(32 * RED_TY) reduce_partials_kernel(const floa
             }
         }
     }
+    if (adam.p) {       // optimiser fused into the reduction: the last CTA to arrive sees every g[] (fence + atomic ticket)
+        __shared__ int s_last;
+        __shared__ float s_coef;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) s_last = (atomicAdd(adam.ticket, 1) == (int)gridDim.x - 1);
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            clip_adamw_body(adam.p, g, adam.m, adam.v, P, adam.lr_dev, adam.b1, adam.b2, adam.eps, adam.wd, adam.max_norm, adam.step_dev, adam.gnorm_out,
+                            0, &red[0][0], &s_coef);
+            if (threadIdx.x == 0) *adam.ticket = 0;
+        }
+    }
 }
 
-int reduce_partials(const float *part, int nrows, int64_t P, float *g, int overwrite, cudaStream_t st, const DpPushArgs *push) {
+int reduce_partials(const float *part, int nrows, int64_t P, float *g, int overwrite, cudaStream_t st, const DpPushArgs *push, const AdamFuseArgs *adam) {
     if (P <= 0) return 0;
     DpPushArgs pa{};
     if (push) pa = *push;
-    launch_pdl(reduce_partials_kernel, dim3((unsigned)((P + 31) / 32)), dim3(32 * RED_TY), 0, st, part, nrows, P, g, overwrite, pa);
+    AdamFuseArgs aa{};
+    if (adam) aa = *adam;
+    launch_pdl(reduce_partials_kernel, dim3((unsigned)((P + 31) / 32)), dim3(32 * RED_TY), 0, st, part, nrows, P, g, overwrite, pa, aa);
     return check_launch("reduce_partials_kernel");
 }
 
-// ---------------------------------------------------------------- fused clip_grad_norm_ + AdamW, single CTA (n is ~1e3)
-// train_funcs.py:41-44: nn.utils.clip_grad_norm_(params, max_norm) then optimizer.step() with torch.optim.AdamW
-// defaults (project.py:283): p *= 1-lr*wd;  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;
-// p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+// ---------------------------------------------------------------- clip_grad_norm_ + AdamW as its own launch (single CTA; n is ~1e3)
 __global__ void __launch_bounds__(1024) clip_adamw_kernel(float *__restrict__ p, float *__restrict__ g, float *__restrict__ m,
                                                           float *__restrict__ v, int64_t n, const float *__restrict__ lr_dev, float b1,
                                                           float b2, float eps, float wd, float max_norm, int64_t *step_dev,
@@ -98,40 +153,17 @@ __global__ void __launch_bounds__(1024) clip_adamw_kernel(float *__restrict__ p,
     __shared__ float red[32];
     __shared__ float s_coef;
     pdl_enter();
-    float ss = 0.f;
-    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) { const float x = g[i]; ss = fmaf(x, x, ss); }
-    ss = warp_sum(ss);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
-        t = warp_sum(t);
-        if (threadIdx.x == 0) {
-            const float norm = sqrtf(t);
-            float coef = 1.f;
-            if (max_norm > 0.f) { coef = max_norm / (norm + 1e-6f); coef = coef < 1.f ? coef : 1.f; }
-            s_coef = coef;
-            if (gnorm_out) *gnorm_out = norm;
-        }
-    }
-    __syncthreads();
-    const float coef = s_coef;
-    const int64_t step = *step_dev + 1;
-    const float lr = *lr_dev;
-    const float bc1 = 1.f - powf(b1, (float)step), bc2 = 1.f - powf(b2, (float)step);
-    const float step_size = lr / bc1, bc2s = sqrtf(bc2);
-    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-        const float gi = g[i] * coef;
-        float pi = p[i] * (1.f - lr * wd);
-        const float mi = fmaf(b1, m[i], (1.f - b1) * gi);
-        const float vi = fmaf(b2, v[i], (1.f - b2) * gi * gi);
-        const float denom = sqrtf(vi) / bc2s + eps;
-        pi -= step_size * (mi / denom);
-        p[i] = pi; m[i] = mi; v[i] = vi;
-        if (zero_grad) g[i] = 0.f; else g[i] = gi;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) *step_dev = step;
+    clip_adamw_body(p, g, m, v, n, lr_dev, b1, b2, eps, wd, max_norm, step_dev, gnorm_out, zero_grad, red, &s_coef);
+}
+
+// one-shot, thread-local: arms the next weight-gradient reduction of this host thread to run the optimiser in its last CTA
+static thread_local AdamFuseArgs g_armed_adam;
+static thread_local bool g_adam_armed = false;
+static bool take_armed_adam(AdamFuseArgs &out) {
+    if (!g_adam_armed) return false;
+    out = g_armed_adam;
+    g_adam_armed = false;
+    return true;
 }
 
 static int check_dims(const OdpdDims *d) {
@@ -221,7 +253,9 @@ int odpd_backbone_bwd(const OdpdDims *d, const float *x, const float *params, co
         // OVERWRITE_DW the caller's buffer must not keep the previous step's values
         if (dw && (d->flags & ODPD_F_OVERWRITE_DW) && P > 0) {
             DpPushArgs push{};
-            if (dp_take_armed_push(push)) return reduce_partials(nullptr, 0, P, gparams, 1, st, &push);   // zero gradient, still published
+            AdamFuseArgs adam{};
+            const bool ap = dp_take_armed_push(push), aa = take_armed_adam(adam);
+            if (ap || aa) return reduce_partials(nullptr, 0, P, gparams, 1, st, ap ? &push : nullptr, aa ? &adam : nullptr);   // zero gradient, still published / applied
             cudaError_t e = cudaMemsetAsync(gparams, 0, (size_t)P * sizeof(float), st);
             ODPD_CHECK(e == cudaSuccess, "cudaMemsetAsync(gparams): %s", cudaGetErrorString(e));
         }
@@ -250,8 +284,10 @@ int odpd_backbone_bwd(const OdpdDims *d, const float *x, const float *params, co
     if (rc) return rc;
     if (dw) {
         DpPushArgs push{};
-        const bool armed = dp_take_armed_push(push);
-        return reduce_partials((const float *)workspace, rows, P, gparams, (d->flags & ODPD_F_OVERWRITE_DW) != 0, st, armed ? &push : nullptr);
+        AdamFuseArgs adam{};
+        const bool armed = dp_take_armed_push(push), aa = take_armed_adam(adam);
+        return reduce_partials((const float *)workspace, rows, P, gparams, (d->flags & ODPD_F_OVERWRITE_DW) != 0, st, armed ? &push : nullptr,
+                               aa ? &adam : nullptr);
     }
     return 0;
 }
@@ -283,6 +319,17 @@ int odpd_chunk_plan(const OdpdDims *d, int32_t backward, int32_t out[4]) {
     if (rc) return rc;
     for (int i = 0; i < 4; ++i) out[i] = info[i];
     if (d->tchunks == 1) out[3] = -1;
+    return 0;
+}
+
+int odpd_fuse_next_bwd_with_adamw(float *param, float *exp_avg, float *exp_avg_sq, const float *lr_dev, float beta1, float beta2, float eps,
+                                  float weight_decay, float max_norm, int64_t *step_dev, float *gnorm_out, int32_t *ticket_dev) {
+    ODPD_CHECK(param && exp_avg && exp_avg_sq && lr_dev && step_dev && ticket_dev, "odpd_fuse_next_bwd_with_adamw: NULL buffer");
+    AdamFuseArgs a{};
+    a.p = param; a.m = exp_avg; a.v = exp_avg_sq; a.lr_dev = lr_dev; a.step_dev = step_dev; a.gnorm_out = gnorm_out; a.ticket = ticket_dev;
+    a.b1 = beta1; a.b2 = beta2; a.eps = eps; a.wd = weight_decay; a.max_norm = max_norm;
+    g_armed_adam = a;
+    g_adam_armed = true;
     return 0;
 }
 

@@ -74,7 +74,8 @@ int other_fwd(const OdpdDims *d, const float *x, const float *target, const floa
 int other_bwd(const OdpdDims *d, const float *x, const float *params, const void *saved, const float *gout, const float *out,
               const float *target, double gscale, const float *gscale_dev, float *gx, float *partials, cudaStream_t st, int *rows_out);
 
-int reduce_partials(const float *part, int nrows, int64_t P, float *g, int overwrite, cudaStream_t st, const DpPushArgs *push = nullptr);
+int reduce_partials(const float *part, int nrows, int64_t P, float *g, int overwrite, cudaStream_t st, const DpPushArgs *push = nullptr,
+                    const AdamFuseArgs *adam = nullptr);
 // one-shot data-parallel publish context armed by odpd_dp_publish_next_bwd (dp.cu) and consumed by the next weight-gradient reduction
 bool dp_take_armed_push(DpPushArgs &out);
 

@@ -220,7 +220,18 @@ struct DpPushArgs {
     const int64_t *step_dev;
     const double *loss_local;
 };
+// Optimiser fused into the gradient reduction (single GPU): the last CTA of reduce_partials_kernel to finish (atomic ticket) runs
+// clip_grad_norm_ + AdamW on the flat buffers, saving one launch per train step.  p == nullptr disables it.
+struct AdamFuseArgs {
+    float *p, *m, *v;
+    const float *lr_dev;
+    int64_t *step_dev;
+    float *gnorm_out;
+    int *ticket;            // device int, zero before the first use; the last CTA resets it
+    float b1, b2, eps, wd, max_norm;
+};
 // Deterministic second-stage reduction of per-sequence gradient partials:  g[p] += sum_b part[b][p]
-__global__ void reduce_partials_kernel(const float *__restrict__ part, int nrows, int64_t P, float *__restrict__ g, int overwrite, DpPushArgs push);
+__global__ void reduce_partials_kernel(const float *__restrict__ part, int nrows, int64_t P, float *__restrict__ g, int overwrite, DpPushArgs push,
+                                       AdamFuseArgs adam);
 
 }  // namespace odpd

@@ -128,6 +128,8 @@ class NativeTrainStep:
         if self.world > 1 and self.pg is not None and use_p2p and self.n + 1 <= 4096:
             self.px = PeerExchange(self.n, dev, self.pg, self.world, torch.distributed.get_rank(self.pg))
             self._px_pin, self._px_ev = torch.zeros(1, dtype=torch.int32).pin_memory(), None
+        self._ticket = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.fuse_optimizer = os.environ.get("ODPD_FUSE_ADAMW", "1") != "0"     # clip + AdamW inside the gradient-reduction kernel (single GPU)
         self._host_step = 0
         self._stage = None
         self._bufs = [dict() for _ in range(4)]
@@ -205,6 +207,60 @@ class NativeTrainStep:
         st.copy_(starts.reshape(-1), non_blocking=True)
         return self.step(IqStream(stream_x, st, T), IqStream(stream_y, st, T), global_count, loss_out)
 
+    def steps_indexed(self, stream_x, stream_y, starts, T, global_count=None, losses_out=None):
+        """K consecutive train steps in ONE graph replay: `starts` is a (K, B) int32 tensor (device or pinned host), row k = the frame
+        starts of step k (same framing as step_indexed).  Returns the K losses (device float64; or `losses_out`, a K-element float64
+        tensor on the device or in pinned host memory, filled with one stream-ordered copy).
+        Why: a step is ~5 kernels and ~160 us; launched one graph per step, the stream also carries a copy of the starts before and of the
+        loss after every step and the GPU idles between consecutive graph launches.  K steps per replay carry one copy in, one copy out
+        and no gap between the steps inside — the steps themselves are unchanged and still strictly sequential (step k+1 reads the
+        parameters step k wrote).  The chunk controller is consulted once per call."""
+        if starts.dim() != 2 or starts.dtype != torch.int32:
+            raise _ffi.OdpdError("steps_indexed wants a (K, B) int32 tensor of frame starts")
+        K, B = int(starts.shape[0]), int(starts.shape[1])
+        st = self._starts_stage.get((K, B))
+        if st is None:
+            st = self._starts_stage[(K, B)] = (torch.empty(K, B, dtype=torch.int32, device=self.device),
+                                               torch.zeros(K, dtype=torch.float64, device=self.device))
+        stage, losses = st
+        stage.copy_(starts, non_blocking=True)
+        items = [(IqStream(stream_x, stage[k], T), IqStream(stream_y, stage[k], T)) for k in range(K)]
+        self._run_multi(("idx", stream_x.data_ptr(), stream_y.data_ptr(), K, B, int(T), stream_x.dtype, stream_y.dtype), items, losses, global_count,
+                        keep=(stream_x, stream_y))
+        if losses_out is not None:
+            losses_out.copy_(losses, non_blocking=True)
+            out = losses_out
+        else:
+            out = losses.clone()
+        before = self._host_step
+        self._host_step += K
+        if self.chunk_check_every > 0 and before // self.chunk_check_every != self._host_step // self.chunk_check_every:
+            self._chunk_control(B, T)
+            self._check_exchange()
+        return out
+
+    def _run_multi(self, key, items, losses, global_count, keep=()):
+        """len(items) consecutive train steps on (features, targets) pairs whose ADDRESSES are fixed across calls with the same `key`,
+        loss k -> losses[k]; eager on the first call of a key shape, captured into one CUDA graph on the second, replayed afterwards."""
+        def run_all():
+            for k, (f, t) in enumerate(items):
+                losses[k:k + 1].copy_(self._step_impl(f, t, global_count))
+        if not self.use_graphs:
+            return run_all()
+        key = ("multi",) + tuple(key) + (global_count,)
+        g = self._graphs.get(key)
+        if g is None and key not in self._graph_warm:
+            self._graph_warm.add(key)
+            return run_all()
+        if g is None:
+            if len(self._graphs) >= 256:
+                self._graphs.pop(next(iter(self._graphs)))
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                run_all()
+            g = self._graphs[key] = (graph, losses, items, keep)       # keeps the captured buffers alive
+        g[0].replay()
+
     def _step_impl(self, features, targets, global_count=None):
         L = _ffi.lib()
         tb = self.train_bb
@@ -213,11 +269,19 @@ class NativeTrainStep:
         count = float(global_count) if global_count else float(2 * B * T * self.world)   # nn.MSELoss 'mean', GLOBAL batch
         gflat = self.gflat
 
+        single = not (self.pg is not None and self.world > 1)
+        fuse_opt = single and self.fuse_optimizer
+
         def arm_publish(loss):
             # data parallel: the backward that produces the weight gradient publishes it (and the loss) to every rank straight from
-            # the epilogue of its gradient reduction (csrc/api.cu reduce_partials_kernel, include/odpd.h odpd_dp_publish_next_bwd)
+            # the epilogue of its gradient reduction (csrc/api.cu reduce_partials_kernel, include/odpd.h odpd_dp_publish_next_bwd);
+            # single GPU: the same reduction kernel runs clip + AdamW in its last CTA (odpd_fuse_next_bwd_with_adamw): one launch less
             if self.px is not None:
                 _ffi.check(L.odpd_dp_publish_next_bwd(self.px.ptrs, self.world, self.px.rank, ctypes.c_int64(self.n), _ptr(self.step_dev), _ptr(loss)))
+            elif fuse_opt:
+                _ffi.check(L.odpd_fuse_next_bwd_with_adamw(_ptr(flat), _ptr(self.exp_avg), _ptr(self.exp_avg_sq), _ptr(self.lr_dev), self.betas[0],
+                                                           self.betas[1], self.eps, self.wd, self.clip, _ptr(self.step_dev), _ptr(self.gnorm),
+                                                           _ptr(self._ticket)))
         if self.dpd is None:
             spec = tb._spec()
             out, loss, saved = backbone_forward_raw(spec, features, flat, targets, 1.0 / count, True, tb._stats_tensor(self.device),
@@ -242,6 +306,8 @@ class NativeTrainStep:
                                             self.eps, self.wd, self.clip, _ptr(self.step_dev), _ptr(self.gnorm), _ptr(self.px.loss_out),
                                             _ptr(self.px.status), _stream()))
             return self.px.loss_out.to(torch.float64)
+        if fuse_opt:
+            return loss
         if self.pg is not None and self.world > 1:
             self.gbuf[-4] = loss.to(torch.float32)[0]
             allreduce_flat_(self.gbuf, self.pg)
@@ -334,59 +400,85 @@ class NativeTrainStep:
         fy.copy_(targets_cpu, non_blocking=True)
         return float(self.step(fx, fy).item())
 
-    def run_host_batches(self, batches):
-        """Train on an iterable of HOST (pinned) (features, targets) batches — the reference's `for features, targets in
-        dataloader` loop (train_funcs.py:28-48) as a 2-deep pipeline: batch i+1 is copied host->device on a side stream while step i
-        computes, and the loss of step i is read back (async D2H, pinned) while step i+1 is already queued.  Every step still does
-        its own H2D copy and its own loss read-back; they just no longer serialise with the kernels.  Returns the list of losses."""
+    def run_host_batches(self, batches, steps_per_replay=None):
+        """Train on an iterable of HOST (pinned) (features, targets) batches — the reference's `for features, targets in dataloader`
+        loop (train_funcs.py:28-48) as a 2-deep pipeline of BLOCKS of `steps_per_replay` (default 8, env ODPD_STEPS_PER_REPLAY) steps:
+        block j+1 is copied host->device on a side stream while block j computes as ONE CUDA-graph replay of its steps (block sizes ramp
+        1, 2, 4 ... so that only one batch copy is ever exposed), and the losses
+        of block j are read back (async D2H, pinned) while block j+1 is already queued.  Every step still has its own H2D copy of its
+        batch and its own loss read-back inside the region; they no longer serialise with the kernels, and there is no launch gap
+        between the steps of a block.  Returns the list of losses."""
+        K = int(steps_per_replay or os.environ.get("ODPD_STEPS_PER_REPLAY", "8"))
         cur = torch.cuda.current_stream()
         if not hasattr(self, "_cs"):
             self._cs = torch.cuda.Stream(device=self.device)
             self._pipe = None
         cs = self._cs
         it = iter(batches)
-        nxt = next(it, None)
-        if nxt is None:
+
+        ramp = [1]       # block sizes 1, 2, 4, ... K: the first block's copy is the only one nothing overlaps, so it is kept to one batch
+
+        def take_block():
+            size = min(ramp[0], K)
+            ramp[0] = min(2 * ramp[0], K)
+            blk = []
+            for b_ in it:
+                blk.append(b_)
+                if len(blk) == size:
+                    break
+            return blk
+        nxt = take_block()
+        if not nxt:
             return []
-        shp = (tuple(nxt[0].shape), tuple(nxt[1].shape), nxt[0].dtype, nxt[1].dtype)
+        shp = (tuple(nxt[0][0].shape), tuple(nxt[0][1].shape), nxt[0][0].dtype, nxt[0][1].dtype, K)
         if self._pipe is None or self._pipe["shape"] != shp:
-            mk = lambda s, dt: torch.empty(s, dtype=dt, device=self.device)
-            self._pipe = dict(shape=shp, stage=[(mk(shp[0], shp[2]), mk(shp[1], shp[3])) for _ in range(2)],
-                              loss=[torch.zeros(1, dtype=torch.float64).pin_memory() for _ in range(2)],
+            mk = lambda s_, dt: torch.empty(s_, dtype=dt, device=self.device)
+            self._pipe = dict(shape=shp, stage=[[(mk(shp[0], shp[2]), mk(shp[1], shp[3])) for _ in range(K)] for _ in range(2)],
+                              dloss=[torch.zeros(K, dtype=torch.float64, device=self.device) for _ in range(2)],
+                              loss=[torch.zeros(K, dtype=torch.float64).pin_memory() for _ in range(2)],
                               ev_copy=[torch.cuda.Event() for _ in range(2)], ev_free=[torch.cuda.Event() for _ in range(2)],
                               ev_loss=[torch.cuda.Event() for _ in range(2)])
         P = self._pipe
         used = [False, False]
 
-        def enqueue_copy(slot, batch):
+        def enqueue_copy(slot, blk):
             with torch.cuda.stream(cs):
                 if used[slot]:
                     cs.wait_event(P["ev_free"][slot])
                 else:
                     cs.wait_stream(cur)
-                P["stage"][slot][0].copy_(batch[0], non_blocking=True)
-                P["stage"][slot][1].copy_(batch[1], non_blocking=True)
+                for k, (f, t) in enumerate(blk):
+                    P["stage"][slot][k][0].copy_(f, non_blocking=True)
+                    P["stage"][slot][k][1].copy_(t, non_blocking=True)
                 P["ev_copy"][slot].record(cs)
 
         enqueue_copy(0, nxt)
         losses, pending, i = [], None, 0
-        while nxt is not None:
-            slot = i & 1
-            nxt = next(it, None)
-            if nxt is not None:
+        while nxt:
+            slot, blk = i & 1, nxt
+            nxt = take_block()
+            if nxt:
                 enqueue_copy(slot ^ 1, nxt)
             cur.wait_event(P["ev_copy"][slot])
-            self.step(*P["stage"][slot], loss_out=P["loss"][slot])      # async D2H of the loss into the slot's pinned scalar
+            n = len(blk)
+            B, T = blk[0][0].shape[0], blk[0][0].shape[1]
+            self._run_multi(("host", slot, n) + shp[:4], P["stage"][slot][:n], P["dloss"][slot], None)
             P["ev_free"][slot].record(cur)
             used[slot] = True
+            P["loss"][slot][:n].copy_(P["dloss"][slot][:n], non_blocking=True)      # async D2H of the block's losses
             P["ev_loss"][slot].record(cur)
+            before = self._host_step
+            self._host_step += n
+            if self.chunk_check_every > 0 and before // self.chunk_check_every != self._host_step // self.chunk_check_every:
+                self._chunk_control(B, T)
+                self._check_exchange()
             if pending is not None:
-                P["ev_loss"][pending].synchronize()
-                losses.append(float(P["loss"][pending][0]))
-            pending = slot
+                P["ev_loss"][pending[0]].synchronize()
+                losses += [float(v) for v in P["loss"][pending[0]][:pending[1]]]
+            pending = (slot, n)
             i += 1
-        P["ev_loss"][pending].synchronize()
-        losses.append(float(P["loss"][pending][0]))
+        P["ev_loss"][pending[0]].synchronize()
+        losses += [float(v) for v in P["loss"][pending[0]][:pending[1]]]
         return losses
 
     def grads_as_param_grads(self):
