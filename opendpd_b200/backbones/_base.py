@@ -12,17 +12,23 @@ class RNNParams(nn.Module):
     has no forward; the arithmetic runs in libodpd.so.  Ref: nn.RNNBase.__init__/reset_parameters
     (uniform(-1/sqrt(H), 1/sqrt(H)) over weight_ih, weight_hh, bias_ih, bias_hh in that order)."""
 
+    MAX_LAYERS = 8      # csrc/wide.cu WLMAX
+
     def __init__(self, input_size, hidden_size, gates, num_layers=1, bias=True):
         super().__init__()
-        if num_layers != 1:
-            raise NotImplementedError("native backbones implement num_layers=1 (every script of record; SURVEY App. A.10)")
+        if not 1 <= num_layers <= self.MAX_LAYERS:
+            raise NotImplementedError(f"native RNN backbones implement num_layers 1..{self.MAX_LAYERS} (got {num_layers})")
         if not bias:
             raise NotImplementedError("native RNN containers assume bias=True (models.py:23)")
         self.input_size, self.hidden_size, self.num_layers, self.bias = input_size, hidden_size, num_layers, bias
-        self.weight_ih_l0 = nn.Parameter(torch.empty(gates * hidden_size, input_size))
-        self.weight_hh_l0 = nn.Parameter(torch.empty(gates * hidden_size, hidden_size))
-        self.bias_ih_l0 = nn.Parameter(torch.empty(gates * hidden_size))
-        self.bias_hh_l0 = nn.Parameter(torch.empty(gates * hidden_size))
+        # nn.RNNBase registers, per layer k: weight_ih_l{k} (layer 0 reads the features, layer k > 0 the hidden sequence of layer
+        # k-1), weight_hh_l{k}, bias_ih_l{k}, bias_hh_l{k} — in that order, which is also the flat layout the kernels read
+        for k in range(num_layers):
+            fin = input_size if k == 0 else hidden_size
+            setattr(self, f"weight_ih_l{k}", nn.Parameter(torch.empty(gates * hidden_size, fin)))
+            setattr(self, f"weight_hh_l{k}", nn.Parameter(torch.empty(gates * hidden_size, hidden_size)))
+            setattr(self, f"bias_ih_l{k}", nn.Parameter(torch.empty(gates * hidden_size)))
+            setattr(self, f"bias_hh_l{k}", nn.Parameter(torch.empty(gates * hidden_size)))
         self.reset_parameters()
 
     def reset_parameters(self):
@@ -60,7 +66,11 @@ class NativeBackbone(nn.Module, FlatParams):
     cell = None
 
     def _spec(self):
-        return CellSpec(self.cell, getattr(self, "hidden_size", 0), getattr(self, "num_dvr_units", 0),
+        # OdpdDims.K: DVRJANET's num_dvr_units; for the nn.GRU / nn.LSTM based backbones the number of stacked layers
+        K = getattr(self, "num_dvr_units", 0)
+        if self.cell in ("gru", "lstm", "dgru", "qgru", "qgru_amp1") and getattr(self, "num_layers", 1) > 1:
+            K = self.num_layers
+        return CellSpec(self.cell, getattr(self, "hidden_size", 0), K,
                         getattr(self, "thx", 0.0), getattr(self, "thh", 0.0), getattr(self, "time_chunks", None),
                         getattr(self, "time_warmup", None))
 

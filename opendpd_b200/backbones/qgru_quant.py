@@ -95,6 +95,8 @@ class QGRUQuant(NativeBackbone):
     def from_float(cls, float_backbone, n_bits_w=8, n_bits_a=8):
         """Same construction order — hence the same RNG consumption — as Base_GRUQuantEnv.__init__ (quant_envs.py:139-171)."""
         H = float_backbone.hidden_size
+        if getattr(float_backbone, "num_layers", 1) != 1 or H > 32:
+            raise NotImplementedError("native QAT QGRU: num_layers=1, hidden_size <= 32 (quant_qgru_dpd_regr.sh uses 1 layer, H <= 30)")
         amp1 = float_backbone.cell == "qgru_amp1"
         # (1) create_pygru_model: GRUCell.__init__ (quant/modules/gru.py:9-30) draws two nn.Linear inits, then uniform(-1/sqrt(H), 1/sqrt(H))
         x2h, h2h = nn.Linear(4, 3 * H, bias=True), nn.Linear(H, 3 * H, bias=True)

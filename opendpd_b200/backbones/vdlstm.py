@@ -14,6 +14,8 @@ class VDLSTM(NativeBackbone):
         if bidirectional or not batch_first or output_size != 2 or window_length != 4 or stride != 1:
             raise NotImplementedError("native VDLSTM: unidirectional, batch_first, window_length=4, stride=1, 2 outputs (vdlstm.py defaults; "
                                       "models.py:71-79 never passes others)")
+        if num_layers != 1 or hidden_size > 32:
+            raise NotImplementedError("native VDLSTM: num_layers=1, hidden_size <= 32 (the layered kernels cover GRU/LSTM/DGRU/QGRU only)")
         self.hidden_size, self.input_size, self.output_size = hidden_size, window_length, output_size      # vdlstm.py:19: input_size = window
         self.num_layers, self.bidirectional, self.batch_first, self.bias = num_layers, bidirectional, batch_first, bias
         self.window_length, self.stride, self.pad_size = window_length, stride, window_length - 1

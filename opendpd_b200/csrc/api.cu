@@ -170,9 +170,26 @@ static int check_dims(const OdpdDims *d) {
     ODPD_CHECK(d != nullptr, "dims is NULL");
     ODPD_CHECK(d->cell >= 0 && d->cell < ODPD_CELL_COUNT, "unknown cell %d", d->cell);
     ODPD_CHECK(d->B >= 0 && d->T >= 0, "negative B/T (%d,%d)", d->B, d->T);
-    if (d->cell != ODPD_CELL_GMP) ODPD_CHECK(d->H >= 1 && d->H <= 32, "hidden_size %d outside the fused range 1..32", d->H);
+    if (wide_supported(d->cell)) {
+        ODPD_CHECK(d->H >= 1 && d->H <= 64, "hidden_size %d outside 1..64", d->H);
+        ODPD_CHECK(d->K >= 0 && d->K <= 8, "num_layers %d outside 1..8", d->K);
+    } else if (d->cell != ODPD_CELL_GMP) {
+        ODPD_CHECK(d->H >= 1 && d->H <= 32, "hidden_size %d outside the fused range 1..32", d->H);
+    }
     if (d->cell == ODPD_CELL_DVRJANET) ODPD_CHECK(d->K >= 1 && d->K <= 8, "num_dvr_units %d outside 1..8", d->K);
     return 0;
+}
+
+// GRU / LSTM / DGRU / QGRU / QGRU_AMP1: OdpdDims.K = num_layers (0 or 1 = one layer).  Hidden sizes above the fused tiers and stacked
+// layers take the layered kernels of wide.cu.
+static int wide_layers(int cell, int K) { return wide_supported(cell) && K > 1 ? K : 1; }
+static bool is_wide(int cell, int H, int K) { return wide_supported(cell) && (H > 32 || K > 1); }
+static GruArgs wide_args(const OdpdDims *d) {
+    GruArgs a{};
+    a.B = d->B; a.T = d->T; a.H = d->H; a.cell = d->cell;
+    a.x_bf16 = (d->flags & ODPD_F_X_BF16) != 0; a.target_bf16 = (d->flags & ODPD_F_TARGET_BF16) != 0;
+    a.x_starts = d->x_starts; a.target_starts = d->target_starts;
+    return a;
 }
 
 static bool is_gru_family(int c) { return c == ODPD_CELL_GRU || c == ODPD_CELL_DGRU || c == ODPD_CELL_QGRU || c == ODPD_CELL_QGRU_AMP1; }
@@ -187,6 +204,7 @@ int odpd_version(void) { return ODPD_VERSION; }
 const char *odpd_last_error(void) { return g_err; }
 
 int64_t odpd_n_params(int32_t cell, int32_t H, int32_t K) {
+    if (is_wide(cell, H, K)) return (H >= 1 && H <= 64 && K <= 8) ? wide_nparams(cell, H, wide_layers(cell, K)) : -1;
     if (is_gru_family(cell)) return gru_family_nparams(cell, H);
     return other_nparams(cell, H, K);
 }
@@ -194,6 +212,7 @@ int64_t odpd_n_params(int32_t cell, int32_t H, int32_t K) {
 int64_t odpd_saved_bytes(const OdpdDims *d) {
     if (check_dims(d)) return -1;
     const bool save = (d->flags & ODPD_F_SAVE) != 0;
+    if (is_wide(d->cell, d->H, d->K)) return 4 * wide_saved_floats(d->cell, d->B, d->T, d->H, wide_layers(d->cell, d->K), save);
     if (is_gru_family(d->cell)) {
         const int64_t n = gru_family_saved_floats(d->cell, d->B, d->T, d->H, save, d->tchunks);
         if (n < 0) { set_error("GRU-family kernels support hidden_size <= 32 (got %d)", d->H); return -1; }
@@ -204,6 +223,7 @@ int64_t odpd_saved_bytes(const OdpdDims *d) {
 
 int64_t odpd_bwd_workspace_bytes(const OdpdDims *d) {
     if (check_dims(d)) return -1;
+    if (is_wide(d->cell, d->H, d->K)) return 4 * wide_workspace_floats(d->cell, d->B, d->T, d->H, wide_layers(d->cell, d->K)) + 64;
     if (is_gru_family(d->cell)) {
         const int64_t n = gru_family_workspace_floats(d->cell, d->B, d->T, d->H, d->tchunks);
         if (n < 0) { set_error("GRU-family kernels support hidden_size <= 32 (got %d)", d->H); return -1; }
@@ -228,6 +248,12 @@ int odpd_backbone_fwd(const OdpdDims *d, const float *x, const float *target, co
     const bool save = (d->flags & ODPD_F_SAVE) != 0;
     ODPD_CHECK(!save || saved, "ODPD_F_SAVE set but saved==NULL");
     ODPD_CHECK(x != nullptr, "x must not be NULL");
+    if (is_wide(d->cell, d->H, d->K)) {
+        GruArgs a = wide_args(d);
+        a.x = x; a.target = target; a.params = params; a.out = out; a.loss = loss;
+        a.loss_scale = (float)loss_scale; a.saved = (float *)saved; a.save = save;
+        return wide_run(d->cell, a, wide_layers(d->cell, d->K), 0, false, st, nullptr);
+    }
     if (is_gru_family(d->cell)) {
         GruArgs a{};
         a.B = d->B; a.T = d->T; a.H = d->H; a.x = x; a.target = target; a.params = params; a.out = out; a.loss = loss;
@@ -269,7 +295,13 @@ int odpd_backbone_bwd(const OdpdDims *d, const float *x, const float *params, co
     if (!dx && !dw) return 0;
     ODPD_CHECK(x && (saved || d->cell == ODPD_CELL_GMP), "x/saved must not be NULL");
     int rc, rows = d->B;
-    if (is_gru_family(d->cell)) {
+    if (is_wide(d->cell, d->H, d->K)) {
+        GruArgs a = wide_args(d);
+        a.x = x; a.params = params; a.saved = (float *)saved; a.gout = gout; a.out_in = out; a.target = target;
+        a.gscale = (float)gscale; a.gscale_dev = gscale_dev; a.gx = gx; a.partials = (float *)workspace; a.need_dx = dx;
+        ODPD_CHECK(workspace != nullptr, "the layered RNN backward needs the workspace (odpd_bwd_workspace_bytes)");
+        rc = wide_run(d->cell, a, wide_layers(d->cell, d->K), 1, dw, st, &rows);
+    } else if (is_gru_family(d->cell)) {
         GruArgs a{};
         a.B = d->B; a.T = d->T; a.H = d->H; a.x = x; a.params = params; a.saved = (float *)saved; a.gout = gout; a.out_in = out;
         a.target = target; a.gscale = (float)gscale; a.gscale_dev = gscale_dev; a.gx = gx; a.partials = (float *)workspace;
@@ -305,7 +337,7 @@ int odpd_chunk_plan(const OdpdDims *d, int32_t backward, int32_t out[4]) {
     if (check_dims(d)) return -1;
     ODPD_CHECK(out != nullptr, "out is NULL");
     out[0] = 1; out[1] = d->T; out[2] = 0; out[3] = -1;
-    if (d->B == 0 || d->T == 0 || d->cell == ODPD_CELL_GMP) return 0;
+    if (d->B == 0 || d->T == 0 || d->cell == ODPD_CELL_GMP || is_wide(d->cell, d->H, d->K)) return 0;
     int info[4];
     if (!is_gru_family(d->cell)) {
         const int rc = other_plan(d, backward, info);

@@ -64,6 +64,13 @@ int qat_run(const GruArgs &a, int dir, bool dw, cudaStream_t st);
 // gmp.cu
 int gmp_run(const GruArgs &a, int dir, bool dw, cudaStream_t st);
 
+// wide.cu : GRU / LSTM / DGRU / QGRU / QGRU_AMP1 with hidden_size 33..64 and/or num_layers > 1 (layered, unchunked)
+bool wide_supported(int cell);
+int64_t wide_nparams(int cell, int H, int layers);
+int64_t wide_saved_floats(int cell, int B, int T, int H, int layers, bool save);
+int64_t wide_workspace_floats(int cell, int B, int T, int H, int layers);
+int wide_run(int cell, const GruArgs &a, int layers, int dir, bool dw, cudaStream_t st, int *rows_out);
+
 // remaining families (lstm.cu, delta.cu, janet.cu, gmp.cu) behind one dispatcher in others.cu
 int64_t other_nparams(int cell, int H, int K);
 int64_t other_saved_bytes(const OdpdDims *d);

@@ -46,7 +46,7 @@ def frames(X, Y, B, T, seed):
     return x, y
 
 
-def build(kind, H, seed, thx=0.0, thh=0.0, K=3):
+def build(kind, H, seed, thx=0.0, thh=0.0, K=3, L=1):
     torch.manual_seed(seed)
     if kind.endswith("_qat"):
         # config 5: the reference's own QAT environment (quant/__init__.py:20-37 -> quant_envs.py Base_GRUQuantEnv) around the float QGRU
@@ -66,7 +66,7 @@ def build(kind, H, seed, thx=0.0, thh=0.0, K=3):
         nn.Module.__init__(net)
         net.num_layers, net.hidden_size, net.backbone = 1, H, bb
         return net
-    return models.CoreModel(input_size=2, hidden_size=H, num_layers=1, backbone_type=kind,
+    return models.CoreModel(input_size=2, hidden_size=H, num_layers=L, backbone_type=kind,
                             num_dvr_units=K, thx=thx, thh=thh)
 
 
@@ -174,6 +174,15 @@ CASES = [
     ("qgruqat_w8a8_h10_b4_t50", "qgru_qat", 10, 4, 50, 24, 0, 0, 8 | (8 << 8)),
     ("qgruqat_w16a16_h10_b3_t33", "qgru_qat", 10, 3, 33, 25, 0, 0, 16 | (16 << 8)),
     ("qgruamp1qat_w8a8_h8_b2_t20", "qgru_amp1_qat", 8, 2, 20, 26, 0, 0, 8 | (8 << 8)),
+    # hidden sizes above the fused tiers and stacked layers (arguments.py:51,60 -> nn.GRU/nn.LSTM num_layers): 10th field = num_layers
+    ("wide_gru_h48_b3_t70",        "gru",  48, 3, 70, 40, 0, 0, 3, 1),
+    ("wide_gru_h16_l2_b3_t40",     "gru",  16, 3, 40, 41, 0, 0, 3, 2),
+    ("wide_dgru_h40_l2_b2_t70",    "dgru", 40, 2, 70, 42, 0, 0, 3, 2),
+    ("wide_dgru_h64_b2_t33",       "dgru", 64, 2, 33, 43, 0, 0, 3, 1),
+    ("wide_lstm_h64_b2_t40",       "lstm", 64, 2, 40, 44, 0, 0, 3, 1),
+    ("wide_lstm_h12_l3_b3_t37",    "lstm", 12, 3, 37, 45, 0, 0, 3, 3),
+    ("wide_qgru_h36_b2_t50",       "qgru", 36, 2, 50, 46, 0, 0, 3, 1),
+    ("wide_qgru_amp1_h20_l2_b2_t45", "qgru_amp1", 20, 2, 45, 47, 0, 0, 3, 2),
 ]
 
 
@@ -185,10 +194,11 @@ def main():
     for case in CASES:
         name, kind, H, B, T, seed, thx, thh = case[:8]
         K = case[8] if len(case) > 8 else 3
+        L = case[9] if len(case) > 9 else 1
         if only and name not in only:
             continue
         x, y = frames(X, Y, B, T, seed)
-        net = build(kind, max(H, 1), seed, thx, thh, K)
+        net = build(kind, max(H, 1), seed, thx, thh, K, L)
         tap_cls = None
         if kind == "deltagru":
             from backbones.deltagru import DeltaGRULayer as tap_cls
@@ -200,7 +210,7 @@ def main():
         net.float()
         rec = dict(x=x, y=y, params=params.astype(np.float32), kind=np.array(kind), H=np.array(H),
                    thx=np.array(thx, dtype=np.float64), thh=np.array(thh, dtype=np.float64),
-                   K=np.array(K), param_index=np.array(json.dumps(param_index(net))))
+                   K=np.array(K), L=np.array(L), param_index=np.array(json.dumps(param_index(net))))
         for k, v in r32.items():
             rec[k] = v
         for k, v in r64.items():

@@ -84,8 +84,47 @@ def _delta_layer(f, p, H, thx, thh, bias):
     return torch.stack(hs, 1)
 
 
-def forward(kind, x, flat, H, K=3, thx=0.0, thh=0.0):
+def _rnn_stack_split(kind, flat, H, L):
+    """Flat vector of an L-layer nn.GRU / nn.LSTM backbone -> (per-layer [w_ih, w_hh, b_ih, b_hh] list in nn.RNNBase's flat order,
+    dict of the head tensors).  named_parameters() order: rnn.weight_ih_l0 .. bias_hh_l{L-1}, fc_out.*, (dgru) fc_hid.*."""
+    G = 4 if kind == "lstm" else 3
+    F = {"gru": 2, "lstm": 2, "dgru": 6, "qgru": 4, "qgru_amp1": 4}[kind]
+    ws, off = [], 0
+    for l in range(L):
+        fin = F if l == 0 else H
+        for shp in ((G * H, fin), (G * H, H), (G * H,), (G * H,)):
+            n = math.prod(shp)
+            ws.append(flat[off:off + n].view(shp)); off += n
+    O = H + 6 if kind == "dgru" else H
+    head = {}
+    for name, shp in (("wo", (2, O)), ("bo", (2,))) + ((("wh", (H, H)), ("bh", (H,))) if kind == "dgru" else ()):
+        n = math.prod(shp)
+        head[name] = flat[off:off + n].view(shp); off += n
+    assert off == flat.numel(), (kind, H, L, off, flat.numel())
+    return ws, head
+
+
+def forward_layers(kind, x, flat, H, L):
+    """gru / lstm / dgru / qgru / qgru_amp1 with num_layers = L (the reference passes --*_num_layers straight to nn.GRU / nn.LSTM:
+    gru.py:17-24, lstm.py:17-24, dgru.py:22-28, qgru.py:22-28), any hidden size."""
+    ws, p = _rnn_stack_split(kind, flat, H, L)
+    B = x.shape[0]
+    f = _feat(kind, x)
+    h0 = x.new_zeros(L, B, H)
+    if kind == "lstm":
+        hseq, _, _ = torch._VF.lstm(f, (h0, h0), ws, True, L, 0.0, x.is_cuda, False, True)
+    else:
+        hseq, _ = torch._VF.gru(f, h0, ws, True, L, 0.0, x.is_cuda, False, True)
+    if kind == "dgru":
+        g = torch.relu(Fn.linear(hseq, p["wh"], p["bh"]))
+        return Fn.linear(torch.cat((g, f), -1), p["wo"], p["bo"])
+    return Fn.linear(hseq, p["wo"], p["bo"])
+
+
+def forward(kind, x, flat, H, K=3, thx=0.0, thh=0.0, L=1):
     """x (B,T,2) -> out (B,T,2), differentiable w.r.t. x and flat."""
+    if L > 1:
+        return forward_layers(kind, x, flat, H, L)
     p = split_params(kind, flat, H, K)
     B, T, _ = x.shape
     if kind in ("gru", "qgru", "qgru_amp1", "dgru"):

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests.util import ROOT, golden_cases, load_golden
+from tests.util import ROOT, dims_K, golden_cases, load_golden, wide_cases
 from opendpd_b200 import _ffi, models
 
 
@@ -26,11 +26,15 @@ def test_error_reporting_without_gpu_work():
     d = _ffi.OdpdDims(99, 1, 1, 8, 0, 0, 0.0, 0.0)
     assert L.odpd_saved_bytes(ctypes.byref(d)) < 0
     assert b"unknown cell" in L.odpd_last_error()
-    d = _ffi.OdpdDims(_ffi.CELLS["gru"], 1, 1, 64, 0, 0, 0.0, 0.0)
+    d = _ffi.OdpdDims(_ffi.CELLS["gru"], 1, 1, 65, 0, 0, 0.0, 0.0)          # the layered path stops at 64
     assert L.odpd_saved_bytes(ctypes.byref(d)) < 0 and b"hidden_size" in L.odpd_last_error()
+    d = _ffi.OdpdDims(_ffi.CELLS["pgjanet"], 1, 1, 64, 0, 0, 0.0, 0.0)      # cells without a layered path stop at the fused tiers
+    assert L.odpd_saved_bytes(ctypes.byref(d)) < 0 and b"hidden_size" in L.odpd_last_error()
+    d = _ffi.OdpdDims(_ffi.CELLS["lstm"], 1, 1, 16, 9, 0, 0.0, 0.0)         # K = num_layers for the nn.GRU / nn.LSTM backbones
+    assert L.odpd_saved_bytes(ctypes.byref(d)) < 0 and b"num_layers" in L.odpd_last_error()
 
 
-@pytest.mark.parametrize("name", golden_cases())
+@pytest.mark.parametrize("name", golden_cases() + wide_cases())
 def test_param_count_and_flat_layout_match_reference(name):
     g = load_golden(name)
     if g["kind"].endswith("_qat"):
@@ -40,12 +44,12 @@ def test_param_count_and_flat_layout_match_reference(name):
             quant, n_bits_w, n_bits_a, pretrained_model = True, g["K"] & 255, (g["K"] >> 8) & 255, ""
         net = get_quant_model(_Proj(), models.CoreModel(2, g["H"], 1, g["kind"][:-4]))
     else:
-        net = models.CoreModel(2, max(g["H"], 1), 1, g["kind"], num_dvr_units=g["K"], thx=g["thx"], thh=g["thh"])
+        net = models.CoreModel(2, max(g["H"], 1), g["L"], g["kind"], num_dvr_units=g["K"], thx=g["thx"], thh=g["thh"])
     names = [n for n, _ in net.backbone.named_parameters()]
     assert names == [n for n, _ in g["param_index"]]
     assert [list(p.shape) for _, p in net.backbone.named_parameters()] == [s for _, s in g["param_index"]]
     n = sum(p.numel() for p in net.backbone.parameters())
-    assert n == g["params"].size == _ffi.n_params(g["kind"], g["H"], g["K"])
+    assert n == g["params"].size == _ffi.n_params(g["kind"], g["H"], dims_K(g))
     flat, layout = net.backbone._flat_sync()
     off = 0
     for (o, cnt, shape), (_, p) in zip(layout, net.backbone.named_parameters()):
@@ -83,8 +87,13 @@ def test_vdlstm_container_matches_reference_golden():
 
 
 def test_unsupported_configs_raise():
+    assert models.CoreModel(2, 8, 2, "gru").backbone._spec().K == 2     # stacked layers: the layered path (csrc/wide.cu), K = num_layers
     with pytest.raises(NotImplementedError):
-        models.CoreModel(2, 8, 2, "gru")            # num_layers=2
+        models.CoreModel(2, 8, 9, "gru")            # more layers than the layered path holds
+    with pytest.raises(NotImplementedError):
+        models.CoreModel(2, 8, 2, "vdlstm")         # cells outside the layered path stay single-layer
+    with pytest.raises(NotImplementedError):
+        models.CoreModel(2, 8, 2, "deltagru")
     with pytest.raises(ValueError):
         models.CoreModel(2, 8, 1, "rvtdcnn")         # out of the hot-path scope
 
@@ -221,7 +230,7 @@ def _manifest():
     return json.load(open(os.path.join(ROOT, "tests", "golden", "MANIFEST.json")))
 
 
-@pytest.mark.parametrize("name", golden_cases())
+@pytest.mark.parametrize("name", golden_cases() + wide_cases())
 def test_init_is_bit_identical_to_the_reference(name):
     """`reset_parameters` is kept in Python on the same RNG stream, so for the seed the reference-made fixture
     was built with (oracle/make_golden.py: torch.manual_seed(seed) then the reference constructor) the native model must start
@@ -236,7 +245,7 @@ def test_init_is_bit_identical_to_the_reference(name):
             quant, n_bits_w, n_bits_a, pretrained_model = True, g["K"] & 255, (g["K"] >> 8) & 255, ""
         net = get_quant_model(_Proj(), models.CoreModel(2, g["H"], 1, g["kind"][:-4]))
     else:
-        net = models.CoreModel(2, max(g["H"], 1), 1, g["kind"], num_dvr_units=g["K"], thx=g["thx"], thh=g["thh"])
+        net = models.CoreModel(2, max(g["H"], 1), g["L"], g["kind"], num_dvr_units=g["K"], thx=g["thx"], thh=g["thh"])
     mine = np.concatenate([p.detach().numpy().ravel() for _, p in net.backbone.named_parameters()])
     assert mine.dtype == np.float32 and np.array_equal(mine, g["params"]), f"{name}: initial weights differ from the reference's"
 

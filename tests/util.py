@@ -9,17 +9,33 @@ def golden_cases(kinds=None):
     out = []
     for f in sorted(glob.glob(os.path.join(GOLDEN, "*.npz"))):
         name = os.path.basename(f)[:-4]
-        if name.startswith(("metrics_", "next_", "iq_streams", "full_")):   # evaluation-metric goldens (tests/test_metrics_oracle.py); cells without a CUDA path yet
+        if name.startswith(("metrics_", "next_", "iq_streams", "full_", "wide_")):   # evaluation-metric goldens (tests/test_metrics_oracle.py); full-size and wide / stacked cases have their own tests
             continue
         if kinds is None or any(name.startswith(k) for k in kinds):
             out.append(name)
     return out
 
 
+def wide_cases():
+    """Goldens of the layered path (csrc/wide.cu): hidden sizes 33..64 and / or num_layers > 1, from the unmodified reference."""
+    return [os.path.basename(f)[:-4] for f in sorted(glob.glob(os.path.join(GOLDEN, "wide_*.npz")))]
+
+
+RNN_KINDS = ("gru", "lstm", "dgru", "qgru", "qgru_amp1")
+
+
+def dims_K(g):
+    """OdpdDims.K for a golden case: num_layers for the nn.GRU / nn.LSTM based backbones (0 = one layer), else the stored K
+    (DVRJANET units, QAT bit widths)."""
+    if g["kind"] in RNN_KINDS:
+        return g["L"] if g["L"] > 1 else 0
+    return g["K"]
+
+
 def load_golden(name):
     d = np.load(os.path.join(GOLDEN, name + ".npz"))
     g = {k: d[k] for k in d.files}
-    g["kind"] = str(g["kind"]); g["H"] = int(g["H"]); g["K"] = int(g["K"])
+    g["kind"] = str(g["kind"]); g["H"] = int(g["H"]); g["K"] = int(g["K"]); g["L"] = int(g["L"]) if "L" in g else 1
     g["thx"] = float(g["thx"]); g["thh"] = float(g["thh"])
     g["param_index"] = json.loads(str(g["param_index"]))
     return g
