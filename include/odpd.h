@@ -31,9 +31,17 @@
  *   GMP       (gmp.py:11)           Weight(1,495)
  *   VDLSTM    (vdlstm.py:28-41)     rnn.weight_ih_l0(4H,4) weight_hh_l0(4H,H) bias_ih_l0(4H) bias_hh_l0(4H) fc_lambda_1.weight(4,H) .bias(4)
  *                                   fc_lambda_2.weight(4,H) .bias(4) fc_out.weight(2,8) fc_out.bias(2)
+ *   RVTDCNN   (rvtdcnn.py:20-33)    Conv2d.weight(3,1,3,3) Conv2d.bias(3) fc_hid.weight(H,36) fc_hid.bias(H) fc_out.weight(2,H) fc_out.bias(2)
  *   QGRU_QAT  (quant_envs.py:215-305 applied to qgru.py) rnn.rnn_cell_list.0.x2h.weight(3H,4) .bias(3H) .weight_quantizer.scale .act_quantizer.scale
  *                                   .out_quantizer.scale | h2h.weight(3H,H) .bias(3H) + 3 scales | sigmoid/tanh/add/mul .quantizer.scale |
  *                                   fc_out.weight(2,H) .bias(2) + 3 scales.   For the QAT cells OdpdDims.K packs n_bits_w | n_bits_a<<8 | eval<<16.
+ *   num_layers = L > 1 (GRU, LSTM, DGRU, QGRU, QGRU_AMP1; OdpdDims.K = L): the rnn.* block repeats per layer in nn.RNNBase's order —
+ *                                   weight_ih_l{k}(G*H, F for k = 0 else H) weight_hh_l{k}(G*H,H) bias_ih_l{k}(G*H) bias_hh_l{k}(G*H), k = 0..L-1 —
+ *                                   followed by the head tensors as above.
+ *
+ * Two implementations sit behind the GRU / LSTM / DGRU / QGRU entries: the fused warp-specialised kernels (H <= 32, one layer: every
+ * script of record) and a layered path (H 33..64 and/or stacked layers: time-parallel projections around a per-layer chain kernel,
+ * not time-chunked).  The library picks by (H, K); the calls, buffers and results have the same meaning.
  */
 #ifndef ODPD_H_
 #define ODPD_H_
@@ -61,7 +69,8 @@ enum {
     ODPD_CELL_QGRU_QAT = 10, /* qgru.py under --quant: quant/modules/gru.py:32-124 + quant/qmodules (fake-quant QAT) */
     ODPD_CELL_QGRU_AMP1_QAT = 11, /* qgru_amp1.py under --quant */
     ODPD_CELL_VDLSTM = 12,   /* backbones/vdlstm.py:58-82 */
-    ODPD_CELL_COUNT = 13
+    ODPD_CELL_RVTDCNN = 13,  /* backbones/rvtdcnn.py:36-62 (row f-4): H = fc_hid_size (1..64); frame_length >= 3 */
+    ODPD_CELL_COUNT = 14
 };
 
 /* flags */
@@ -77,8 +86,9 @@ typedef struct OdpdDims {
     int32_t cell;   /* ODPD_CELL_* */
     int32_t B;      /* sequences in this call (>=0)                        */
     int32_t T;      /* frame length (>=0)                                  */
-    int32_t H;      /* hidden size (1..32 on the fused path; ignored by GMP) */
-    int32_t K;      /* DVRJANET num_dvr_units (dvrjanet.py:6); QAT cells: bit widths */
+    int32_t H;      /* hidden size: 1..32 on the fused kernels; GRU/LSTM/DGRU/QGRU/QGRU_AMP1 also 33..64 (layered kernels); ignored by GMP */
+    int32_t K;      /* DVRJANET num_dvr_units (dvrjanet.py:6); QAT cells: bit widths; GRU/LSTM/DGRU/QGRU/QGRU_AMP1: num_layers
+                       (0 or 1 = one layer, up to 8: nn.GRU / nn.LSTM stacking, gru.py:17-24, arguments.py:51,60) */
     uint32_t flags; /* ODPD_F_*                                            */
     float thx, thh; /* delta thresholds (deltagru.py:216-217)              */
     int32_t tchunks; /* GRU/DGRU/QGRU/LSTM/PGJANET/DVRJANET: time chunks a sequence is cut into and run concurrently (see below).

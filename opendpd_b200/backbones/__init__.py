@@ -7,5 +7,6 @@ from .vdlstm import VDLSTM
 from .deltagru import DeltaGRU, TResDeltaGRU
 from .janet import PGJANET, DVRJANET
 from .gmp import GMP
+from .rvtdcnn import RVTDCNN
 
-__all__ = ["GRU", "DGRU", "QGRU", "QGRUAmp1", "LSTM", "VDLSTM", "DeltaGRU", "TResDeltaGRU", "PGJANET", "DVRJANET", "GMP"]
+__all__ = ["GRU", "DGRU", "QGRU", "QGRUAmp1", "LSTM", "VDLSTM", "DeltaGRU", "TResDeltaGRU", "PGJANET", "DVRJANET", "GMP", "RVTDCNN"]

@@ -71,6 +71,11 @@ int64_t wide_saved_floats(int cell, int B, int T, int H, int layers, bool save);
 int64_t wide_workspace_floats(int cell, int B, int T, int H, int layers);
 int wide_run(int cell, const GruArgs &a, int layers, int dir, bool dw, cudaStream_t st, int *rows_out);
 
+// rvtdcnn.cu : RVTDCNN (feed-forward over a 4-sample wrap-around window; nothing saved, the backward recomputes)
+int64_t rvtdcnn_nparams(int H);
+int64_t rvtdcnn_workspace_floats(int B, int T, int H);
+int rvtdcnn_run(const GruArgs &a, int dir, bool dw, cudaStream_t st, int *rows_out);
+
 // remaining families (lstm.cu, delta.cu, janet.cu, gmp.cu) behind one dispatcher in others.cu
 int64_t other_nparams(int cell, int H, int K);
 int64_t other_saved_bytes(const OdpdDims *d);

@@ -174,6 +174,10 @@ CASES = [
     ("qgruqat_w8a8_h10_b4_t50", "qgru_qat", 10, 4, 50, 24, 0, 0, 8 | (8 << 8)),
     ("qgruqat_w16a16_h10_b3_t33", "qgru_qat", 10, 3, 33, 25, 0, 0, 16 | (16 << 8)),
     ("qgruamp1qat_w8a8_h8_b2_t20", "qgru_amp1_qat", 8, 2, 20, 26, 0, 0, 8 | (8 << 8)),
+    # row f-4: RVTDCNN (H = fc_hid_size, models.py:80-81)
+    ("rvtdcnn_h6_b3_t40",          "rvtdcnn", 6, 3, 40, 50, 0, 0),
+    ("rvtdcnn_h20_b2_t70",         "rvtdcnn", 20, 2, 70, 51, 0, 0),
+    ("rvtdcnn_h64_b2_t3",          "rvtdcnn", 64, 2, 3, 52, 0, 0),
     # hidden sizes above the fused tiers and stacked layers (arguments.py:51,60 -> nn.GRU/nn.LSTM num_layers): 10th field = num_layers
     ("wide_gru_h48_b3_t70",        "gru",  48, 3, 70, 40, 0, 0, 3, 1),
     ("wide_gru_h16_l2_b3_t40",     "gru",  16, 3, 40, 41, 0, 0, 3, 2),

@@ -54,7 +54,7 @@
 #endif
 
 enum { CELL_GRU = 0, CELL_LSTM = 1, CELL_DGRU = 2, CELL_DELTAGRU = 3, CELL_TRES = 4, CELL_PGJANET = 5,
-       CELL_DVRJANET = 6, CELL_GMP = 7, CELL_QGRU = 8, CELL_QGRU_AMP1 = 9, CELL_QGRU_QAT = 10, CELL_QGRU_AMP1_QAT = 11 };
+       CELL_DVRJANET = 6, CELL_GMP = 7, CELL_QGRU = 8, CELL_QGRU_AMP1 = 9, CELL_QGRU_QAT = 10, CELL_QGRU_AMP1_QAT = 11, CELL_RVTDCNN = 13 };
 
 typedef struct {
     int cell, B, T, H, K;
@@ -797,6 +797,79 @@ static void seq_qgru_qat(const Ctx *c, const REAL *x, const REAL *gout, REAL *ou
     }
 }
 
+/* ================================================================ RVTDCNN: rvtdcnn.py:36-62
+ * features (I,Q,a,a^2,a^3) (:41-46); window of timestep t = samples (t-3+r) mod T, r = 0..3 (`pad = x[:, -(window_size-1):, :]`, :51-53);
+ * Conv2d(1->3, 3x3, padding (1,0)) on the 4x5 image -> tanh -> 36 values in (channel,row,column) order (:57-58); fc_hid(36->H) tanh (:59);
+ * fc_out(H->2) (:60).  params: Conv2d.weight(3,1,3,3) Conv2d.bias(3) fc_hid.weight(H,36) fc_hid.bias(H) fc_out.weight(2,H) fc_out.bias(2). */
+static void seq_rvtdcnn(const Ctx *c, const REAL *x, const REAL *gout, REAL *out, REAL *gx, REAL *gp, int phase) {
+    const int T = c->T, H = c->H;
+    const REAL *Wc = c->params, *bc = Wc + 27, *Wh = bc + 3, *bh = Wh + 36 * H, *Wo = bh + H, *bo = Wo + 2 * H;
+    for (int t = 0; t < T; ++t) {
+        REAL w[4][5], z[36], hk[64];
+        int sidx[4];
+        for (int r = 0; r < 4; ++r) {
+            int s = ((t - 3 + r) % T + T) % T;
+            sidx[r] = s;
+            volatile REAL i = x[2 * s], q = x[2 * s + 1];
+            volatile REAL ii = i * i, qq = q * q;
+            volatile REAL a2 = ii + qq;
+            volatile REAL a = R_SQRT(a2);
+            volatile REAL aa = a * a;
+            volatile REAL a3 = aa * a;
+            w[r][0] = i; w[r][1] = q; w[r][2] = a; w[r][3] = a2; w[r][4] = a3;
+        }
+        for (int ch = 0; ch < 3; ++ch)
+            for (int r = 0; r < 4; ++r)
+                for (int cc = 0; cc < 3; ++cc) {
+                    REAL acc = bc[ch];
+                    for (int dr = 0; dr < 3; ++dr) {
+                        int rr = r + dr - 1;
+                        if (rr < 0 || rr > 3) continue;
+                        for (int dc = 0; dc < 3; ++dc) acc += Wc[ch * 9 + dr * 3 + dc] * w[rr][cc + dc];
+                    }
+                    z[ch * 12 + r * 3 + cc] = R_TANH(acc);
+                }
+        REAL o0 = bo[0], o1 = bo[1];
+        for (int k = 0; k < H; ++k) {
+            hk[k] = R_TANH(bh[k] + dotv(Wh + 36 * k, z, 36));
+            o0 += Wo[k] * hk[k]; o1 += Wo[H + k] * hk[k];
+        }
+        if (!phase) { out[2 * t] = o0; out[2 * t + 1] = o1; continue; }
+        const REAL g0 = gout[2 * t], g1 = gout[2 * t + 1];
+        REAL dz[36] = {0}, dw[4][5] = {{0}};
+        gp[30 + 37 * H + 2 * H] += g0; gp[30 + 37 * H + 2 * H + 1] += g1;
+        for (int k = 0; k < H; ++k) {
+            gp[30 + 37 * H + k] += g0 * hk[k]; gp[30 + 37 * H + H + k] += g1 * hk[k];
+            const REAL da = (g0 * Wo[k] + g1 * Wo[H + k]) * ((REAL)1 - hk[k] * hk[k]);
+            gp[30 + 36 * H + k] += da;
+            for (int m = 0; m < 36; ++m) { gp[30 + 36 * k + m] += da * z[m]; dz[m] += da * Wh[36 * k + m]; }
+        }
+        for (int ch = 0; ch < 3; ++ch)
+            for (int r = 0; r < 4; ++r)
+                for (int cc = 0; cc < 3; ++cc) {
+                    const int m = ch * 12 + r * 3 + cc;
+                    const REAL d = dz[m] * ((REAL)1 - z[m] * z[m]);
+                    gp[27 + ch] += d;
+                    for (int dr = 0; dr < 3; ++dr) {
+                        int rr = r + dr - 1;
+                        if (rr < 0 || rr > 3) continue;
+                        for (int dc = 0; dc < 3; ++dc) {
+                            gp[ch * 9 + dr * 3 + dc] += d * w[rr][cc + dc];
+                            dw[rr][cc + dc] += d * Wc[ch * 9 + dr * 3 + dc];
+                        }
+                    }
+                }
+        if (gx)
+            for (int r = 0; r < 4; ++r) {
+                const REAL i = w[r][0], q = w[r][1], a = w[r][2], a2 = w[r][3];
+                const REAL ga = dw[r][2] + (REAL)3 * a2 * dw[r][4];
+                const REAL sc = (REAL)2 * dw[r][3] + ga / a;
+                gx[2 * sidx[r]] += dw[r][0] + i * sc;
+                gx[2 * sidx[r] + 1] += dw[r][1] + q * sc;
+            }
+    }
+}
+
 static size_t n_params(int cell, int H, int K) {
     switch (cell) {
     case CELL_GRU: return (size_t)3 * H * 2 + 3 * H * H + 6 * H + 2 * H + 2;
@@ -808,6 +881,7 @@ static size_t n_params(int cell, int H, int K) {
     case CELL_PGJANET: return (size_t)3 * (H * (H + 1) + H) + 2 * (2 * H * H + H) + 2 * H + 2;
     case CELL_DVRJANET: return (size_t)K + 3 * H * H + 2 * H + H + 2 * (2 * H * H + H) + 2 * (H + 1);
     case CELL_GMP: return 495;
+    case CELL_RVTDCNN: return (size_t)32 + 39 * H;
     case CELL_QGRU_QAT: case CELL_QGRU_AMP1_QAT: return (size_t)3 * H * 4 + 3 * H * H + 6 * H + 2 * H + 2 + 13;
     }
     return 0;
@@ -822,6 +896,7 @@ static void seq_dispatch(const Ctx *c, const REAL *x, const REAL *gout, REAL *ou
     case CELL_PGJANET: seq_pgjanet(c, x, gout, out, gx, gp, phase); break;
     case CELL_DVRJANET: seq_dvrjanet(c, x, gout, out, gx, gp, phase); break;
     case CELL_GMP: seq_gmp(c, x, gout, out, gx, gp, phase); break;
+    case CELL_RVTDCNN: seq_rvtdcnn(c, x, gout, out, gx, gp, phase); break;
     case CELL_QGRU_QAT: case CELL_QGRU_AMP1_QAT: seq_qgru_qat(c, x, gout, out, gx, gp, phase); break;
     }
 }

@@ -28,6 +28,7 @@ def split_params(kind, flat, H, K=3):
                      ("wc", (H, 2 * H)), ("bc", (H,)), ("ws", (H, 2 * H)), ("bs", (H,)), ("wo1", (1, H)), ("bo1", (1,)),
                      ("wo2", (1, H)), ("bo2", (1,))],
         "gmp": [("w", (1, 495))],
+        "rvtdcnn": [("wc", (3, 1, 3, 3)), ("bc", (3,)), ("wh", (H, 36)), ("bh", (H,)), ("wo", (2, H)), ("bo", (2,))],
     }
     shapes["qgru_amp1"] = shapes["qgru"]
     shapes["tres"] = shapes["deltagru_tcnskip"]
@@ -179,6 +180,16 @@ def forward(kind, x, flat, H, K=3, thx=0.0, thh=0.0, L=1):
             hI = f * hI + (1 - f) * gc; hQ = f * hQ + (1 - f) * gs
             ys.append(torch.cat((Fn.linear(hI, p["wo1"], p["bo1"]), Fn.linear(hQ, p["wo2"], p["bo2"])), -1))
         return torch.stack(ys, 1)
+    if kind == "rvtdcnn":     # rvtdcnn.py:36-62
+        i, q = x[..., 0:1], x[..., 1:2]
+        amp2 = torch.pow(i, 2) + torch.pow(q, 2)
+        amp = torch.sqrt(amp2)
+        f = torch.cat((i, q, amp, amp2, torch.pow(amp, 3)), -1)
+        xx = torch.cat((f[:, -3:, :], f), 1)
+        win = xx.unfold(1, 4, 1).transpose(2, 3).contiguous().view(-1, 1, 4, 5)
+        o = torch.tanh(Fn.conv2d(win, p["wc"], p["bc"], 1, (1, 0))).view(-1, 36)
+        o = torch.tanh(Fn.linear(o, p["wh"], p["bh"]))
+        return Fn.linear(o, p["wo"], p["bo"]).view(B, T, 2)
     if kind == "gmp":
         xc = torch.complex(x[..., 0], x[..., 1])
         xp = torch.cat((xc.new_zeros(B, 20), xc), 1)              # xp[n] = x[n-20]

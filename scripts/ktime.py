@@ -16,7 +16,7 @@ def main():
     plans = [tuple(int(v) for v in p.split(",")) for p in sys.argv[5:]] or [(0, 0, 0)]
     torch.manual_seed(0)
     dev = torch.device("cuda", 0)
-    net = models.CoreModel(2, H, 1, kind, num_dvr_units=3, thx=0.01, thh=0.05).to(dev)
+    net = models.CoreModel(2, H, int(os.environ.get("KT_LAYERS", "1")), kind, num_dvr_units=3, thx=0.01, thh=0.05).to(dev)   # KT_LAYERS: stacked layers (layered path)
     bb = net.backbone
     flat, _ = bb._flat_sync()
     wl = dict(kind=kind, H=H, B=B, T=T, dataset="APA_200MHz")
