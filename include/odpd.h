@@ -32,6 +32,8 @@
  *   VDLSTM    (vdlstm.py:28-41)     rnn.weight_ih_l0(4H,4) weight_hh_l0(4H,H) bias_ih_l0(4H) bias_hh_l0(4H) fc_lambda_1.weight(4,H) .bias(4)
  *                                   fc_lambda_2.weight(4,H) .bias(4) fc_out.weight(2,8) fc_out.bias(2)
  *   RVTDCNN   (rvtdcnn.py:20-33)    Conv2d.weight(3,1,3,3) Conv2d.bias(3) fc_hid.weight(H,36) fc_hid.bias(H) fc_out.weight(2,H) fc_out.bias(2)
+ *   BOJANET   (bojanet.py:14-26)    fir_I.weight(6,16) fir_Q.weight(6,16) W_fi.weight(H,12) W_fi.bias(H) W_fh.weight(H,H) W_gi.weight(H,12) W_gi.bias(H)
+ *                                   W_gh.weight(H,H) W_out_I.weight(1,H) W_out_I.bias(1) W_out_Q.weight(1,H) W_out_Q.bias(1)
  *   QGRU_QAT  (quant_envs.py:215-305 applied to qgru.py) rnn.rnn_cell_list.0.x2h.weight(3H,4) .bias(3H) .weight_quantizer.scale .act_quantizer.scale
  *                                   .out_quantizer.scale | h2h.weight(3H,H) .bias(3H) + 3 scales | sigmoid/tanh/add/mul .quantizer.scale |
  *                                   fc_out.weight(2,H) .bias(2) + 3 scales.   For the QAT cells OdpdDims.K packs n_bits_w | n_bits_a<<8 | eval<<16.
@@ -70,7 +72,8 @@ enum {
     ODPD_CELL_QGRU_AMP1_QAT = 11, /* qgru_amp1.py under --quant */
     ODPD_CELL_VDLSTM = 12,   /* backbones/vdlstm.py:58-82 */
     ODPD_CELL_RVTDCNN = 13,  /* backbones/rvtdcnn.py:36-62 (row f-4): H = fc_hid_size (1..64); frame_length >= 3 */
-    ODPD_CELL_COUNT = 14
+    ODPD_CELL_BOJANET = 14,  /* backbones/bojanet.py:54-106 (row f-4): hidden_size 1..18 (the reference's pr_block covers 3 x 6 units) */
+    ODPD_CELL_COUNT = 15
 };
 
 /* flags */

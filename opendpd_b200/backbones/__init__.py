@@ -8,5 +8,6 @@ from .deltagru import DeltaGRU, TResDeltaGRU
 from .janet import PGJANET, DVRJANET
 from .gmp import GMP
 from .rvtdcnn import RVTDCNN
+from .bojanet import BOJANET
 
-__all__ = ["GRU", "DGRU", "QGRU", "QGRUAmp1", "LSTM", "VDLSTM", "DeltaGRU", "TResDeltaGRU", "PGJANET", "DVRJANET", "GMP", "RVTDCNN"]
+__all__ = ["GRU", "DGRU", "QGRU", "QGRUAmp1", "LSTM", "VDLSTM", "DeltaGRU", "TResDeltaGRU", "PGJANET", "DVRJANET", "GMP", "RVTDCNN", "BOJANET"]

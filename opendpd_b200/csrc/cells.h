@@ -76,6 +76,12 @@ int64_t rvtdcnn_nparams(int H);
 int64_t rvtdcnn_workspace_floats(int B, int T, int H);
 int rvtdcnn_run(const GruArgs &a, int dir, bool dw, cudaStream_t st, int *rows_out);
 
+// bojanet.cu : BOJANET (FIR front end + vector demodulator + f/g recurrence + phase rotation)
+int64_t bojanet_nparams(int H);
+int64_t bojanet_saved_floats(int B, int T, int H);
+int64_t bojanet_workspace_floats(int B, int T, int H);
+int bojanet_run(const GruArgs &a, int dir, bool dw, cudaStream_t st, int *rows_out);
+
 // remaining families (lstm.cu, delta.cu, janet.cu, gmp.cu) behind one dispatcher in others.cu
 int64_t other_nparams(int cell, int H, int K);
 int64_t other_saved_bytes(const OdpdDims *d);

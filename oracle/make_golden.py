@@ -178,6 +178,9 @@ CASES = [
     ("rvtdcnn_h6_b3_t40",          "rvtdcnn", 6, 3, 40, 50, 0, 0),
     ("rvtdcnn_h20_b2_t70",         "rvtdcnn", 20, 2, 70, 51, 0, 0),
     ("rvtdcnn_h64_b2_t3",          "rvtdcnn", 64, 2, 3, 52, 0, 0),
+    ("bojanet_h10_b3_t50",         "bojanet", 10, 3, 50, 53, 0, 0),
+    ("bojanet_h18_b2_t70",         "bojanet", 18, 2, 70, 54, 0, 0),
+    ("bojanet_h4_b2_t15",          "bojanet", 4, 2, 15, 55, 0, 0),
     # hidden sizes above the fused tiers and stacked layers (arguments.py:51,60 -> nn.GRU/nn.LSTM num_layers): 10th field = num_layers
     ("wide_gru_h48_b3_t70",        "gru",  48, 3, 70, 40, 0, 0, 3, 1),
     ("wide_gru_h16_l2_b3_t40",     "gru",  16, 3, 40, 41, 0, 0, 3, 2),

@@ -54,7 +54,7 @@
 #endif
 
 enum { CELL_GRU = 0, CELL_LSTM = 1, CELL_DGRU = 2, CELL_DELTAGRU = 3, CELL_TRES = 4, CELL_PGJANET = 5,
-       CELL_DVRJANET = 6, CELL_GMP = 7, CELL_QGRU = 8, CELL_QGRU_AMP1 = 9, CELL_QGRU_QAT = 10, CELL_QGRU_AMP1_QAT = 11, CELL_RVTDCNN = 13 };
+       CELL_DVRJANET = 6, CELL_GMP = 7, CELL_QGRU = 8, CELL_QGRU_AMP1 = 9, CELL_QGRU_QAT = 10, CELL_QGRU_AMP1_QAT = 11, CELL_RVTDCNN = 13, CELL_BOJANET = 14 };
 
 typedef struct {
     int cell, B, T, H, K;
@@ -870,6 +870,101 @@ static void seq_rvtdcnn(const Ctx *c, const REAL *x, const REAL *gout, REAL *out
     }
 }
 
+/* ================================================================ BOJANET: bojanet.py:54-106
+ * window t = samples t+m-15, m = 0..15, zero before the frame (:73-77); I_fir = fir_I(I)-fir_Q(Q), Q_fir = fir_Q(I)+fir_I(Q) (:80-83);
+ * mag = sqrt(I_fir^2+Q_fir^2)+1e-8, sin = Q_fir/mag, cos = I_fir/mag (:30-39); L = [mag(6) | mag^2(6)] (:85-86);
+ * f = sigm(W_fi L + b + W_fh h), g = tanh(W_gi L + b + W_gh h), h = f h + (1-f) g (:87-94); unit j rotated by filter j mod 6 (:41-52);
+ * out_I = W_out_I(h cos) - W_out_Q(h sin), out_Q = W_out_Q(h sin) + W_out_I(h cos) (:98-102).
+ * params: fir_I(6,16) fir_Q(6,16) W_fi(H,12) b_fi(H) W_fh(H,H) W_gi(H,12) b_gi(H) W_gh(H,H) W_out_I(1,H) b(1) W_out_Q(1,H) b(1). */
+static void seq_bojanet(const Ctx *c, const REAL *x, const REAL *gout, REAL *out, REAL *gx, REAL *gp, int phase) {
+    const int T = c->T, H = c->H;
+    const REAL eps = (REAL)1e-8;
+    const REAL *FI = c->params, *FQ = FI + 96, *Wfi = FQ + 96, *bfi = Wfi + 12 * H, *Wfh = bfi + H, *Wgi = Wfh + H * H, *bgi = Wgi + 12 * H,
+               *Wgh = bgi + H, *WoI = Wgh + H * H, *boI = WoI + H, *WoQ = boI + 1, *boQ = WoQ + H;
+    const size_t oWfi = 192, obfi = oWfi + 12 * H, oWfh = obfi + H, oWgi = oWfh + (size_t)H * H, obgi = oWgi + 12 * H, oWgh = obgi + H,
+                 oWoI = oWgh + (size_t)H * H, oboI = oWoI + H, oWoQ = oboI + 1, oboQ = oWoQ + H;
+    REAL *fir = (REAL *)malloc(sizeof(REAL) * (size_t)T * 12), *fr = (REAL *)malloc(sizeof(REAL) * (size_t)T * 24);
+    REAL *act = (REAL *)malloc(sizeof(REAL) * (size_t)T * 3 * H);     /* f | g | h per step */
+    REAL h[64] = {0};
+    for (int t = 0; t < T; ++t) {
+        for (int p = 0; p < 6; ++p) {
+            REAL a = 0, b = 0, cI = 0, d = 0;     /* fir_I(I), fir_Q(Q), fir_Q(I), fir_I(Q) */
+            for (int m = 0; m < 16; ++m) {
+                int s = t + m - 15; if (s < 0) continue;
+                a += FI[p * 16 + m] * x[2 * s]; b += FQ[p * 16 + m] * x[2 * s + 1];
+                cI += FQ[p * 16 + m] * x[2 * s]; d += FI[p * 16 + m] * x[2 * s + 1];
+            }
+            const REAL fi = a - b, fq = cI + d;
+            const REAL mag = R_SQRT(fi * fi + fq * fq) + eps;
+            fir[12 * t + p] = fi; fir[12 * t + 6 + p] = fq;
+            fr[24 * t + p] = mag; fr[24 * t + 6 + p] = mag * mag; fr[24 * t + 12 + p] = fq / mag; fr[24 * t + 18 + p] = fi / mag;
+        }
+        REAL hn[64];
+        for (int j = 0; j < H; ++j) {
+            const REAL f = sigm(bfi[j] + dotv(Wfi + 12 * j, fr + 24 * t, 12) + dotv(Wfh + H * j, h, H));
+            const REAL g = R_TANH(bgi[j] + dotv(Wgi + 12 * j, fr + 24 * t, 12) + dotv(Wgh + H * j, h, H));
+            hn[j] = f * h[j] + ((REAL)1 - f) * g;
+            act[3 * H * t + j] = f; act[3 * H * t + H + j] = g; act[3 * H * t + 2 * H + j] = hn[j];
+        }
+        memcpy(h, hn, sizeof(REAL) * H);
+        if (!phase) {
+            REAL a = boI[0], q = boQ[0];
+            for (int j = 0; j < H; ++j) { a += WoI[j] * (h[j] * fr[24 * t + 18 + j % 6]); q += WoQ[j] * (h[j] * fr[24 * t + 12 + j % 6]); }
+            out[2 * t] = a - q; out[2 * t + 1] = q + a;
+        }
+    }
+    if (phase) {
+        REAL rec[64] = {0};
+        REAL *dfir = (REAL *)calloc((size_t)T * 12, sizeof(REAL));
+        for (int t = T - 1; t >= 0; --t) {
+            const REAL da = gout[2 * t] + gout[2 * t + 1], dq = gout[2 * t + 1] - gout[2 * t];
+            const REAL *ft = fr + 24 * t, *at = act + 3 * H * t;
+            REAL dsn[6] = {0}, dcs[6] = {0}, dL[12] = {0}, af[64], ag[64], nrec[64] = {0};
+            gp[oboI] += da; gp[oboQ] += dq;
+            for (int j = 0; j < H; ++j) {
+                const REAL hv = at[2 * H + j], cs = ft[18 + j % 6], sn = ft[12 + j % 6];
+                gp[oWoI + j] += da * hv * cs; gp[oWoQ + j] += dq * hv * sn;
+                const REAL dI = da * WoI[j], dQ = dq * WoQ[j];
+                dcs[j % 6] += dI * hv; dsn[j % 6] += dQ * hv;
+                const REAL dh = dI * cs + dQ * sn + rec[j];
+                const REAL f = at[j], g = at[H + j], hp = t > 0 ? at[-3 * H + 2 * H + j] : 0;
+                af[j] = dh * (hp - g) * f * ((REAL)1 - f);
+                ag[j] = dh * ((REAL)1 - f) * ((REAL)1 - g * g);
+                nrec[j] = dh * f;
+            }
+            for (int j = 0; j < H; ++j) {
+                gp[obfi + j] += af[j]; gp[obgi + j] += ag[j];
+                for (int k = 0; k < 12; ++k) { gp[oWfi + 12 * j + k] += af[j] * ft[k]; gp[oWgi + 12 * j + k] += ag[j] * ft[k]; dL[k] += af[j] * Wfi[12 * j + k] + ag[j] * Wgi[12 * j + k]; }
+                for (int k = 0; k < H; ++k) {
+                    const REAL hp = t > 0 ? at[-3 * H + 2 * H + k] : 0;
+                    gp[oWfh + (size_t)H * j + k] += af[j] * hp; gp[oWgh + (size_t)H * j + k] += ag[j] * hp;
+                    nrec[k] += af[j] * Wfh[H * j + k] + ag[j] * Wgh[H * j + k];
+                }
+            }
+            memcpy(rec, nrec, sizeof(REAL) * H);
+            for (int p = 0; p < 6; ++p) {
+                const REAL mag = ft[p], sn = ft[12 + p], cs = ft[18 + p], fi = fir[12 * t + p], fq = fir[12 * t + 6 + p];
+                const REAL dmag = dL[p] + (REAL)2 * mag * dL[6 + p] - (dsn[p] * sn + dcs[p] * cs) / mag;
+                const REAL root = mag - eps;
+                dfir[12 * t + p] = dcs[p] / mag + dmag * fi / root;
+                dfir[12 * t + 6 + p] = dsn[p] / mag + dmag * fq / root;
+            }
+        }
+        for (int t = 0; t < T; ++t)
+            for (int p = 0; p < 6; ++p) {
+                const REAL di = dfir[12 * t + p], dq = dfir[12 * t + 6 + p];
+                for (int m = 0; m < 16; ++m) {
+                    int s = t + m - 15; if (s < 0) continue;
+                    gp[p * 16 + m] += di * x[2 * s] + dq * x[2 * s + 1];
+                    gp[96 + p * 16 + m] += dq * x[2 * s] - di * x[2 * s + 1];
+                    if (gx) { gx[2 * s] += di * FI[p * 16 + m] + dq * FQ[p * 16 + m]; gx[2 * s + 1] += dq * FI[p * 16 + m] - di * FQ[p * 16 + m]; }
+                }
+            }
+        free(dfir);
+    }
+    free(fir); free(fr); free(act);
+}
+
 static size_t n_params(int cell, int H, int K) {
     switch (cell) {
     case CELL_GRU: return (size_t)3 * H * 2 + 3 * H * H + 6 * H + 2 * H + 2;
@@ -882,6 +977,7 @@ static size_t n_params(int cell, int H, int K) {
     case CELL_DVRJANET: return (size_t)K + 3 * H * H + 2 * H + H + 2 * (2 * H * H + H) + 2 * (H + 1);
     case CELL_GMP: return 495;
     case CELL_RVTDCNN: return (size_t)32 + 39 * H;
+    case CELL_BOJANET: return (size_t)2 * H * H + 28 * H + 194;
     case CELL_QGRU_QAT: case CELL_QGRU_AMP1_QAT: return (size_t)3 * H * 4 + 3 * H * H + 6 * H + 2 * H + 2 + 13;
     }
     return 0;
@@ -897,6 +993,7 @@ static void seq_dispatch(const Ctx *c, const REAL *x, const REAL *gout, REAL *ou
     case CELL_DVRJANET: seq_dvrjanet(c, x, gout, out, gx, gp, phase); break;
     case CELL_GMP: seq_gmp(c, x, gout, out, gx, gp, phase); break;
     case CELL_RVTDCNN: seq_rvtdcnn(c, x, gout, out, gx, gp, phase); break;
+    case CELL_BOJANET: seq_bojanet(c, x, gout, out, gx, gp, phase); break;
     case CELL_QGRU_QAT: case CELL_QGRU_AMP1_QAT: seq_qgru_qat(c, x, gout, out, gx, gp, phase); break;
     }
 }

@@ -28,6 +28,8 @@ def split_params(kind, flat, H, K=3):
                      ("wc", (H, 2 * H)), ("bc", (H,)), ("ws", (H, 2 * H)), ("bs", (H,)), ("wo1", (1, H)), ("bo1", (1,)),
                      ("wo2", (1, H)), ("bo2", (1,))],
         "gmp": [("w", (1, 495))],
+        "bojanet": [("fi", (6, 16)), ("fq", (6, 16)), ("wfi", (H, 12)), ("bfi", (H,)), ("wfh", (H, H)), ("wgi", (H, 12)), ("bgi", (H,)),
+                    ("wgh", (H, H)), ("woi", (1, H)), ("boi", (1,)), ("woq", (1, H)), ("boq", (1,))],
         "rvtdcnn": [("wc", (3, 1, 3, 3)), ("bc", (3,)), ("wh", (H, 36)), ("bh", (H,)), ("wo", (2, H)), ("bo", (2,))],
     }
     shapes["qgru_amp1"] = shapes["qgru"]
@@ -180,6 +182,26 @@ def forward(kind, x, flat, H, K=3, thx=0.0, thh=0.0, L=1):
             hI = f * hI + (1 - f) * gc; hQ = f * hQ + (1 - f) * gs
             ys.append(torch.cat((Fn.linear(hI, p["wo1"], p["bo1"]), Fn.linear(hQ, p["wo2"], p["bo2"])), -1))
         return torch.stack(ys, 1)
+    if kind == "bojanet":     # bojanet.py:54-106
+        xx = torch.cat((torch.zeros_like(x[:, -15:, :]), x), 1)
+        win = xx.unfold(1, 16, 1).transpose(2, 3)                   # (B,T,16,2): tap m of window t = sample t+m-15
+        wi, wq = win[..., 0], win[..., 1]
+        i_fir = Fn.linear(wi, p["fi"]) - Fn.linear(wq, p["fq"])
+        q_fir = Fn.linear(wi, p["fq"]) + Fn.linear(wq, p["fi"])
+        mag = torch.sqrt(torch.pow(i_fir, 2) + torch.pow(q_fir, 2)) + 1e-8
+        sin, cos = q_fir / mag, i_fir / mag
+        Lf = torch.cat((mag, mag ** 2), -1)
+        h = x.new_zeros(B, H); hs = []
+        for t in range(T):
+            f = torch.sigmoid(Fn.linear(Lf[:, t], p["wfi"], p["bfi"]) + Fn.linear(h, p["wfh"]))
+            g = torch.tanh(Fn.linear(Lf[:, t], p["wgi"], p["bgi"]) + Fn.linear(h, p["wgh"]))
+            h = f * h + (1 - f) * g
+            hs.append(h)
+        hseq = torch.stack(hs, 1)
+        idx = torch.arange(H) % 6                                  # pr_block :41-52 for hidden_size <= 18
+        a = Fn.linear(hseq * cos[..., idx], p["woi"], p["boi"])
+        qq = Fn.linear(hseq * sin[..., idx], p["woq"], p["boq"])
+        return torch.cat((a - qq, qq + a), -1)
     if kind == "rvtdcnn":     # rvtdcnn.py:36-62
         i, q = x[..., 0:1], x[..., 1:2]
         amp2 = torch.pow(i, 2) + torch.pow(q, 2)

@@ -8,7 +8,7 @@ from tests.util import GOLDEN, golden_cases, load_golden, rel_err, tol_for, asse
 
 pytestmark = pytest.mark.gpu
 
-IMPLEMENTED = ("gru", "dgru", "qgru", "lstm", "deltagru", "tres", "pgjanet", "dvrjanet", "gmp", "qgruqat", "qgruamp1qat", "rvtdcnn")
+IMPLEMENTED = ("gru", "dgru", "qgru", "lstm", "deltagru", "tres", "pgjanet", "dvrjanet", "gmp", "qgruqat", "qgruamp1qat", "rvtdcnn", "bojanet")
 
 
 def _native_kinds():
@@ -19,7 +19,7 @@ def _native_kinds():
     have = set()
     for k, cell in (("gru", "gru"), ("dgru", "dgru"), ("qgru", "qgru"), ("lstm", "lstm"), ("deltagru", "deltagru"),
                     ("tres", "deltagru_tcnskip"), ("pgjanet", "pgjanet"), ("dvrjanet", "dvrjanet"), ("gmp", "gmp"),
-                    ("qgruqat", "qgru_qat"), ("qgruamp1qat", "qgru_amp1_qat"), ("rvtdcnn", "rvtdcnn")):
+                    ("qgruqat", "qgru_qat"), ("qgruamp1qat", "qgru_amp1_qat"), ("rvtdcnn", "rvtdcnn"), ("bojanet", "bojanet")):
         d = _ffi.OdpdDims(_ffi.CELLS[cell], 1, 1, 10, 3, 0, 0.0, 0.0)
         if L.odpd_saved_bytes(ctypes.byref(d)) >= 0:
             have.add(k)
@@ -106,7 +106,8 @@ def test_golden_parity(name, fused):
 @pytest.mark.parametrize("kind,H,B,T", [("dgru", 13, 64, 2048), ("gru", 32, 8, 1024), ("dgru", 13, 5, 100), ("gru", 16, 33, 64),
                                         ("qgru", 10, 16, 50), ("qgru_amp1", 10, 16, 50), ("lstm", 9, 16, 200), ("lstm", 32, 4, 70),
                                         ("pgjanet", 15, 8, 100), ("dvrjanet", 15, 8, 100), ("gmp", 0, 8, 100),
-                                        ("rvtdcnn", 6, 16, 200), ("rvtdcnn", 64, 5, 1000), ("rvtdcnn", 20, 64, 2048)])
+                                        ("rvtdcnn", 6, 16, 200), ("rvtdcnn", 64, 5, 1000), ("rvtdcnn", 20, 64, 2048),
+                                        ("bojanet", 10, 16, 200), ("bojanet", 18, 5, 1000), ("bojanet", 6, 64, 2048)])
 def test_oracle_parity_seeded(kind, H, B, T):
     """Same seeded inputs through the CUDA path and the CPU oracle (fp32 and fp64 arbiter)."""
     from oracle import oracle
