@@ -34,6 +34,9 @@
  *   RVTDCNN   (rvtdcnn.py:20-33)    Conv2d.weight(3,1,3,3) Conv2d.bias(3) fc_hid.weight(H,36) fc_hid.bias(H) fc_out.weight(2,H) fc_out.bias(2)
  *   BOJANET   (bojanet.py:14-26)    fir_I.weight(6,16) fir_Q.weight(6,16) W_fi.weight(H,12) W_fi.bias(H) W_fh.weight(H,H) W_gi.weight(H,12) W_gi.bias(H)
  *                                   W_gh.weight(H,H) W_out_I.weight(1,H) W_out_I.bias(1) W_out_Q.weight(1,H) W_out_Q.bias(1)
+ *   TCNN      (tcnn.py:15-31)       network.0.weight(H,6,1) network.0.bias(H) network.{2,4,6,8}.weight(H,1,5) network.10.weight(2,H,1)
+ *   NEURALTX  (neuraltx.py:19-38)   conv_I.weight(1,1,5) conv_Q.weight(1,1,5) network.0.weight(H,4,1) network.0.bias(H) network.{2,4,6,8}.weight(H,1,5)
+ *                                   network.10.weight(2,H,1) IQ_match.weight(2,2)
  *   QGRU_QAT  (quant_envs.py:215-305 applied to qgru.py) rnn.rnn_cell_list.0.x2h.weight(3H,4) .bias(3H) .weight_quantizer.scale .act_quantizer.scale
  *                                   .out_quantizer.scale | h2h.weight(3H,H) .bias(3H) + 3 scales | sigmoid/tanh/add/mul .quantizer.scale |
  *                                   fc_out.weight(2,H) .bias(2) + 3 scales.   For the QAT cells OdpdDims.K packs n_bits_w | n_bits_a<<8 | eval<<16.
@@ -73,7 +76,9 @@ enum {
     ODPD_CELL_VDLSTM = 12,   /* backbones/vdlstm.py:58-82 */
     ODPD_CELL_RVTDCNN = 13,  /* backbones/rvtdcnn.py:36-62 (row f-4): H = fc_hid_size (1..64); frame_length >= 3 */
     ODPD_CELL_BOJANET = 14,  /* backbones/bojanet.py:54-106 (row f-4): hidden_size 1..18 (the reference's pr_block covers 3 x 6 units) */
-    ODPD_CELL_COUNT = 15
+    ODPD_CELL_TCNN = 15,     /* backbones/tcnn.py:83-97 (row f-4): H = hidden_channels (1..64) */
+    ODPD_CELL_NEURALTX = 16, /* backbones/neuraltx.py:107-124 (row f-4): H = hidden_channels (1..64) */
+    ODPD_CELL_COUNT = 17
 };
 
 /* flags */

@@ -9,5 +9,6 @@ from .janet import PGJANET, DVRJANET
 from .gmp import GMP
 from .rvtdcnn import RVTDCNN
 from .bojanet import BOJANET
+from .tcnn import TCNN, NeuralTX
 
-__all__ = ["GRU", "DGRU", "QGRU", "QGRUAmp1", "LSTM", "VDLSTM", "DeltaGRU", "TResDeltaGRU", "PGJANET", "DVRJANET", "GMP", "RVTDCNN", "BOJANET"]
+__all__ = ["GRU", "DGRU", "QGRU", "QGRUAmp1", "LSTM", "VDLSTM", "DeltaGRU", "TResDeltaGRU", "PGJANET", "DVRJANET", "GMP", "RVTDCNN", "BOJANET", "TCNN", "NeuralTX"]

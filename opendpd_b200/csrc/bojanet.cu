@@ -438,29 +438,35 @@ __global__ void __launch_bounds__(BJ_TT) boja_front_bwd_kernel(GruArgs a, BjBufs
 // ================================================================ backward: transposed FIR.  dL/dx[s] gathers the windows t = s .. s+15 that hold sample s
 __global__ void __launch_bounds__(BJ_TT) boja_dx_kernel(GruArgs a, BjBufs u, int nts, int ntiles) {
     pdl_enter();
-    const BjLayout L(a.H);
     const int T = a.T, tid = threadIdx.x;
     __shared__ float sF[192];
+    __shared__ float sD[(BJ_TT + BJ_M - 1) * 13];        // dL/dFIR of the windows s0 .. s0+78 (pitch 13)
     for (int i = tid; i < 192; i += BJ_TT) sF[i] = __ldg(a.params + i);
     __syncthreads();
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         int b, s;
         bj_tile(tile, nts, T, tid, b, s);
-        if (s >= T) continue;
-        float gi = 0.f, gq = 0.f;
-#pragma unroll
-        for (int m = 0; m < BJ_M; ++m) {
-            const int t = s + (BJ_M - 1) - m;           // window t holds sample s at tap m
-            if (t >= T) continue;
-            const float *df = u.dfir + ((size_t)b * T + t) * 12;
-#pragma unroll
-            for (int p = 0; p < BJ_P; ++p) {
-                const float di = df[p], dq = df[BJ_P + p], wi = sF[p * BJ_M + m], wq = sF[96 + p * BJ_M + m];
-                gi = fmaf(di, wi, fmaf(dq, wq, gi));     // I_fir = wi I - wq Q,  Q_fir = wq I + wi Q
-                gq = fmaf(dq, wi, fmaf(-di, wq, gq));
-            }
+        const int s0 = s - tid;
+        for (int i = tid; i < (BJ_TT + BJ_M - 1) * 12; i += BJ_TT) {
+            const int r = i / 12, c = i - r * 12, t = s0 + r;
+            sD[r * 13 + c] = t < T ? __ldg(u.dfir + ((size_t)b * T + t) * 12 + c) : 0.f;
         }
-        reinterpret_cast<float2 *>(a.gx)[(size_t)b * T + s] = make_float2(gi, gq);
+        __syncthreads();
+        if (s < T) {
+            float gi = 0.f, gq = 0.f;
+#pragma unroll
+            for (int m = 0; m < BJ_M; ++m) {
+                const float *df = sD + (tid + (BJ_M - 1) - m) * 13;      // window t = s+15-m holds sample s at tap m (zero rows beyond the frame)
+#pragma unroll
+                for (int p = 0; p < BJ_P; ++p) {
+                    const float di = df[p], dq = df[BJ_P + p], wi = sF[p * BJ_M + m], wq = sF[96 + p * BJ_M + m];
+                    gi = fmaf(di, wi, fmaf(dq, wq, gi));     // I_fir = wi I - wq Q,  Q_fir = wq I + wi Q
+                    gq = fmaf(dq, wi, fmaf(-di, wq, gq));
+                }
+            }
+            reinterpret_cast<float2 *>(a.gx)[(size_t)b * T + s] = make_float2(gi, gq);
+        }
+        __syncthreads();
     }
 }
 

@@ -5,7 +5,7 @@ unchanged.  Backbones outside the hot-path scope (SURVEY.md §2
 import torch
 from torch import nn
 
-NATIVE_BACKBONES = ("gmp", "gru", "dgru", "qgru", "qgru_amp1", "lstm", "vdlstm", "deltagru", "deltagru_tcnskip", "pgjanet", "dvrjanet", "rvtdcnn", "bojanet")
+NATIVE_BACKBONES = ("gmp", "gru", "dgru", "qgru", "qgru_amp1", "lstm", "vdlstm", "deltagru", "deltagru_tcnskip", "pgjanet", "dvrjanet", "rvtdcnn", "bojanet", "tcnn", "neuraltx")
 
 
 class CoreModel(nn.Module):
@@ -45,6 +45,10 @@ class CoreModel(nn.Module):
             self.backbone = bb.GMP()
         elif backbone_type == "bojanet":
             self.backbone = bb.BOJANET(hidden_size=hidden_size, output_size=2, bias=True)      # models.py:86-90
+        elif backbone_type == "tcnn":
+            self.backbone = bb.TCNN(hidden_channels=hidden_size)          # models.py:130-132
+        elif backbone_type == "neuraltx":
+            self.backbone = bb.NeuralTX(hidden_channels=hidden_size)      # models.py:133-135
         elif backbone_type == "rvtdcnn":
             self.backbone = bb.RVTDCNN(fc_hid_size=hidden_size)       # models.py:80-81
         else:

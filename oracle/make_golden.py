@@ -181,6 +181,12 @@ CASES = [
     ("bojanet_h10_b3_t50",         "bojanet", 10, 3, 50, 53, 0, 0),
     ("bojanet_h18_b2_t70",         "bojanet", 18, 2, 70, 54, 0, 0),
     ("bojanet_h4_b2_t15",          "bojanet", 4, 2, 15, 55, 0, 0),
+    ("tcnn_h8_b3_t70",             "tcnn", 8, 3, 70, 56, 0, 0),
+    ("tcnn_h20_b2_t150",           "tcnn", 20, 2, 150, 57, 0, 0),
+    ("tcnn_h64_b2_t9",             "tcnn", 64, 2, 9, 58, 0, 0),
+    ("neuraltx_h8_b3_t70",         "neuraltx", 8, 3, 70, 59, 0, 0),
+    ("neuraltx_h24_b2_t131",       "neuraltx", 24, 2, 131, 60, 0, 0),
+    ("neuraltx_h3_b2_t4",          "neuraltx", 3, 2, 4, 61, 0, 0),
     # hidden sizes above the fused tiers and stacked layers (arguments.py:51,60 -> nn.GRU/nn.LSTM num_layers): 10th field = num_layers
     ("wide_gru_h48_b3_t70",        "gru",  48, 3, 70, 40, 0, 0, 3, 1),
     ("wide_gru_h16_l2_b3_t40",     "gru",  16, 3, 40, 41, 0, 0, 3, 2),

@@ -54,7 +54,7 @@
 #endif
 
 enum { CELL_GRU = 0, CELL_LSTM = 1, CELL_DGRU = 2, CELL_DELTAGRU = 3, CELL_TRES = 4, CELL_PGJANET = 5,
-       CELL_DVRJANET = 6, CELL_GMP = 7, CELL_QGRU = 8, CELL_QGRU_AMP1 = 9, CELL_QGRU_QAT = 10, CELL_QGRU_AMP1_QAT = 11, CELL_RVTDCNN = 13, CELL_BOJANET = 14 };
+       CELL_DVRJANET = 6, CELL_GMP = 7, CELL_QGRU = 8, CELL_QGRU_AMP1 = 9, CELL_QGRU_QAT = 10, CELL_QGRU_AMP1_QAT = 11, CELL_RVTDCNN = 13, CELL_BOJANET = 14, CELL_TCNN = 15, CELL_NEURALTX = 16 };
 
 typedef struct {
     int cell, B, T, H, K;
@@ -965,6 +965,106 @@ static void seq_bojanet(const Ctx *c, const REAL *x, const REAL *gout, REAL *out
     free(fir); free(fr); free(act);
 }
 
+/* ================================================================ TCNN (tcnn.py:83-97) and NeuralTX (neuraltx.py:107-124)
+ * stack: Conv1d(F->C,k=1,bias) hardswish; 4 x [depthwise Conv1d(k=5, dilation d=1,2,4,8, zero padding 2d, no bias) hardswish]; Conv1d(C->2,k=1).
+ * TCNN: F=6 features (I,Q,a,a^3,sin,cos), out = stack + (I,Q).  NeuralTX (its fft over a length-1 axis is the identity): 5-tap FIR
+ * I_f = conv_I(I)-conv_Q(Q), Q_f = conv_Q(I)+conv_I(Q) (zero 'same' padding), F=4 features (I_f,Q_f,a,a^3), out = stack + IQ_match(I_f,Q_f) + (I_f,Q_f).
+ * hardswish'(v) = 0 (v<-3), v/3+1/2 (-3<=v<=3), 1 (v>3)  (ATen hardswish_backward). */
+static inline REAL hswf(REAL v) { REAL r = v + (REAL)3; r = r < 0 ? 0 : (r > (REAL)6 ? (REAL)6 : r); return v * r / (REAL)6; }
+static inline REAL hswg(REAL v) { return v < (REAL)-3 ? 0 : (v <= (REAL)3 ? v / (REAL)3 + (REAL)0.5 : (REAL)1); }
+static void seq_tcn(const Ctx *c, const REAL *x, const REAL *gout, REAL *out, REAL *gx, REAL *gp, int phase) {
+    const int T = c->T, C = c->H, ntx = c->cell == CELL_NEURALTX, F = ntx ? 4 : 6;
+    const size_t oW0 = ntx ? 10 : 0, ob0 = oW0 + (size_t)C * F, oDw = ob0 + C, oW10 = oDw + (size_t)20 * C, oIQ = oW10 + (size_t)2 * C;
+    const REAL *P = c->params, *W0 = P + oW0, *b0 = P + ob0, *W10 = P + oW10, *IQ = P + oIQ;
+    REAL *feat = (REAL *)calloc((size_t)T * 8, sizeof(REAL)), *iq = (REAL *)calloc((size_t)T * 2, sizeof(REAL));
+    REAL *pre = (REAL *)calloc((size_t)5 * C * T, sizeof(REAL));
+#define PRE(l, ch, t) pre[((size_t)(l) * C + (ch)) * T + (t)]
+    for (int t = 0; t < T; ++t) {
+        if (!ntx) { features_fwd(CELL_DGRU, x, T, t, feat + 8 * t); iq[2 * t] = x[2 * t]; iq[2 * t + 1] = x[2 * t + 1]; }
+        else {
+            REAL a = 0, b = 0;
+            for (int k = 0; k < 5; ++k) { int q = t + k - 2; if (q < 0 || q >= T) continue; a += P[k] * x[2 * q] - P[5 + k] * x[2 * q + 1]; b += P[5 + k] * x[2 * q] + P[k] * x[2 * q + 1]; }
+            const REAL am = R_SQRT(a * a + b * b);
+            feat[8 * t] = a; feat[8 * t + 1] = b; feat[8 * t + 2] = am; feat[8 * t + 3] = am * am * am; iq[2 * t] = a; iq[2 * t + 1] = b;
+        }
+    }
+    for (int ch = 0; ch < C; ++ch)
+        for (int t = 0; t < T; ++t) { REAL v = b0[ch]; for (int m = 0; m < F; ++m) v += W0[ch * F + m] * feat[8 * t + m]; PRE(0, ch, t) = v; }
+    for (int l = 0; l < 4; ++l) {
+        const int d = 1 << l; const REAL *w = P + oDw + (size_t)5 * C * l;
+        for (int ch = 0; ch < C; ++ch)
+            for (int t = 0; t < T; ++t) {
+                REAL v = 0;
+                for (int k = 0; k < 5; ++k) { int q = t + (k - 2) * d; if (q >= 0 && q < T) v += w[ch * 5 + k] * hswf(PRE(l, ch, q)); }
+                PRE(l + 1, ch, t) = v;
+            }
+    }
+    if (!phase) {
+        for (int t = 0; t < T; ++t)
+            for (int o = 0; o < 2; ++o) {
+                REAL v = 0;
+                for (int ch = 0; ch < C; ++ch) v += W10[o * C + ch] * hswf(PRE(4, ch, t));
+                v += iq[2 * t + o];
+                if (ntx) v += IQ[2 * o] * iq[2 * t] + IQ[2 * o + 1] * iq[2 * t + 1];
+                out[2 * t + o] = v;
+            }
+    } else {
+        REAL *ga = (REAL *)calloc((size_t)C * T, sizeof(REAL)), *gb = (REAL *)calloc((size_t)C * T, sizeof(REAL));
+        REAL *diq = (REAL *)calloc((size_t)T * 2, sizeof(REAL));
+        for (int ch = 0; ch < C; ++ch)
+            for (int t = 0; t < T; ++t) {
+                const REAL g0 = gout[2 * t], g1 = gout[2 * t + 1], a4 = hswf(PRE(4, ch, t));
+                gp[oW10 + ch] += g0 * a4; gp[oW10 + C + ch] += g1 * a4;
+                ga[(size_t)ch * T + t] = (g0 * W10[ch] + g1 * W10[C + ch]) * hswg(PRE(4, ch, t));
+            }
+        for (int l = 3; l >= 0; --l) {
+            const int d = 1 << l; const REAL *w = P + oDw + (size_t)5 * C * l;
+            memset(gb, 0, sizeof(REAL) * (size_t)C * T);
+            for (int ch = 0; ch < C; ++ch)
+                for (int t = 0; t < T; ++t) {
+                    const REAL g = ga[(size_t)ch * T + t];
+                    for (int k = 0; k < 5; ++k) {
+                        int q = t + (k - 2) * d; if (q < 0 || q >= T) continue;
+                        gp[oDw + (size_t)5 * C * l + ch * 5 + k] += g * hswf(PRE(l, ch, q));
+                        gb[(size_t)ch * T + q] += g * w[ch * 5 + k];
+                    }
+                }
+            for (int ch = 0; ch < C; ++ch)
+                for (int t = 0; t < T; ++t) ga[(size_t)ch * T + t] = gb[(size_t)ch * T + t] * hswg(PRE(l, ch, t));
+        }
+        for (int t = 0; t < T; ++t) {
+            REAL gf[8] = {0};
+            const REAL g0 = gout[2 * t], g1 = gout[2 * t + 1];
+            for (int ch = 0; ch < C; ++ch) {
+                const REAL g = ga[(size_t)ch * T + t];
+                gp[ob0 + ch] += g;
+                for (int m = 0; m < F; ++m) { gp[oW0 + ch * F + m] += g * feat[8 * t + m]; gf[m] += g * W0[ch * F + m]; }
+            }
+            if (!ntx) {
+                if (gx) { features_bwd(CELL_DGRU, x, T, t, gf, gx); gx[2 * t] += g0; gx[2 * t + 1] += g1; }
+            } else {
+                const REAL a = iq[2 * t], b = iq[2 * t + 1], am = feat[8 * t + 2];
+                gp[oIQ] += g0 * a; gp[oIQ + 1] += g0 * b; gp[oIQ + 2] += g1 * a; gp[oIQ + 3] += g1 * b;
+                const REAL gam = gf[2] + (REAL)3 * am * am * gf[3];
+                diq[2 * t] = gf[0] + g0 + g0 * IQ[0] + g1 * IQ[2] + gam * a / am;
+                diq[2 * t + 1] = gf[1] + g1 + g0 * IQ[1] + g1 * IQ[3] + gam * b / am;
+            }
+        }
+        if (ntx)
+            for (int t = 0; t < T; ++t)
+                for (int k = 0; k < 5; ++k) {
+                    int q = t + k - 2; if (q < 0 || q >= T) continue;
+                    const REAL di = diq[2 * t], dq = diq[2 * t + 1];
+                    gp[k] += di * x[2 * q] + dq * x[2 * q + 1];
+                    gp[5 + k] += dq * x[2 * q] - di * x[2 * q + 1];
+                    if (gx) { gx[2 * q] += di * P[k] + dq * P[5 + k]; gx[2 * q + 1] += dq * P[k] - di * P[5 + k]; }
+                }
+        free(ga); free(gb); free(diq);
+    }
+#undef PRE
+    free(feat); free(iq); free(pre);
+}
+
 static size_t n_params(int cell, int H, int K) {
     switch (cell) {
     case CELL_GRU: return (size_t)3 * H * 2 + 3 * H * H + 6 * H + 2 * H + 2;
@@ -978,6 +1078,8 @@ static size_t n_params(int cell, int H, int K) {
     case CELL_GMP: return 495;
     case CELL_RVTDCNN: return (size_t)32 + 39 * H;
     case CELL_BOJANET: return (size_t)2 * H * H + 28 * H + 194;
+    case CELL_TCNN: return (size_t)29 * H;
+    case CELL_NEURALTX: return (size_t)27 * H + 14;
     case CELL_QGRU_QAT: case CELL_QGRU_AMP1_QAT: return (size_t)3 * H * 4 + 3 * H * H + 6 * H + 2 * H + 2 + 13;
     }
     return 0;
@@ -994,6 +1096,7 @@ static void seq_dispatch(const Ctx *c, const REAL *x, const REAL *gout, REAL *ou
     case CELL_GMP: seq_gmp(c, x, gout, out, gx, gp, phase); break;
     case CELL_RVTDCNN: seq_rvtdcnn(c, x, gout, out, gx, gp, phase); break;
     case CELL_BOJANET: seq_bojanet(c, x, gout, out, gx, gp, phase); break;
+    case CELL_TCNN: case CELL_NEURALTX: seq_tcn(c, x, gout, out, gx, gp, phase); break;
     case CELL_QGRU_QAT: case CELL_QGRU_AMP1_QAT: seq_qgru_qat(c, x, gout, out, gx, gp, phase); break;
     }
 }

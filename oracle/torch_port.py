@@ -30,6 +30,9 @@ def split_params(kind, flat, H, K=3):
         "gmp": [("w", (1, 495))],
         "bojanet": [("fi", (6, 16)), ("fq", (6, 16)), ("wfi", (H, 12)), ("bfi", (H,)), ("wfh", (H, H)), ("wgi", (H, 12)), ("bgi", (H,)),
                     ("wgh", (H, H)), ("woi", (1, H)), ("boi", (1,)), ("woq", (1, H)), ("boq", (1,))],
+        "tcnn": [("w0", (H, 6, 1)), ("b0", (H,)), ("d1", (H, 1, 5)), ("d2", (H, 1, 5)), ("d4", (H, 1, 5)), ("d8", (H, 1, 5)), ("w10", (2, H, 1))],
+        "neuraltx": [("ci", (1, 1, 5)), ("cq", (1, 1, 5)), ("w0", (H, 4, 1)), ("b0", (H,)), ("d1", (H, 1, 5)), ("d2", (H, 1, 5)), ("d4", (H, 1, 5)),
+                     ("d8", (H, 1, 5)), ("w10", (2, H, 1)), ("iq", (2, 2))],
         "rvtdcnn": [("wc", (3, 1, 3, 3)), ("bc", (3,)), ("wh", (H, 36)), ("bh", (H,)), ("wo", (2, H)), ("bo", (2,))],
     }
     shapes["qgru_amp1"] = shapes["qgru"]
@@ -202,6 +205,21 @@ def forward(kind, x, flat, H, K=3, thx=0.0, thh=0.0, L=1):
         a = Fn.linear(hseq * cos[..., idx], p["woi"], p["boi"])
         qq = Fn.linear(hseq * sin[..., idx], p["woq"], p["boq"])
         return torch.cat((a - qq, qq + a), -1)
+    if kind in ("tcnn", "neuraltx"):     # tcnn.py:83-97, neuraltx.py:107-124
+        def stack(u):
+            u = Fn.hardswish(Fn.conv1d(u, p["w0"], p["b0"]))
+            for name, d in (("d1", 1), ("d2", 2), ("d4", 4), ("d8", 8)):
+                u = Fn.hardswish(Fn.conv1d(u, p[name], None, 1, 2 * d, d, H))
+            return Fn.conv1d(u, p["w10"])
+        if kind == "tcnn":
+            return stack(_feat("dgru", x).transpose(1, 2)).transpose(1, 2) + x
+        it, qt = x[..., 0:1].transpose(1, 2), x[..., 1:2].transpose(1, 2)
+        i_f = (Fn.conv1d(it, p["ci"], None, 1, 2) - Fn.conv1d(qt, p["cq"], None, 1, 2)).transpose(1, 2)
+        q_f = (Fn.conv1d(it, p["cq"], None, 1, 2) + Fn.conv1d(qt, p["ci"], None, 1, 2)).transpose(1, 2)
+        amp = torch.sqrt(torch.pow(i_f, 2) + torch.pow(q_f, 2))
+        iq = torch.cat((i_f, q_f), -1)
+        u = torch.cat((i_f, q_f, amp, torch.pow(amp, 3)), -1).transpose(1, 2)
+        return stack(u).transpose(1, 2) + Fn.linear(iq, p["iq"]) + iq
     if kind == "rvtdcnn":     # rvtdcnn.py:36-62
         i, q = x[..., 0:1], x[..., 1:2]
         amp2 = torch.pow(i, 2) + torch.pow(q, 2)

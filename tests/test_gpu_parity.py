@@ -8,7 +8,7 @@ from tests.util import GOLDEN, golden_cases, load_golden, rel_err, tol_for, asse
 
 pytestmark = pytest.mark.gpu
 
-IMPLEMENTED = ("gru", "dgru", "qgru", "lstm", "deltagru", "tres", "pgjanet", "dvrjanet", "gmp", "qgruqat", "qgruamp1qat", "rvtdcnn", "bojanet")
+IMPLEMENTED = ("gru", "dgru", "qgru", "lstm", "deltagru", "tres", "pgjanet", "dvrjanet", "gmp", "qgruqat", "qgruamp1qat", "rvtdcnn", "bojanet", "tcnn", "neuraltx")
 
 
 def _native_kinds():
@@ -19,7 +19,7 @@ def _native_kinds():
     have = set()
     for k, cell in (("gru", "gru"), ("dgru", "dgru"), ("qgru", "qgru"), ("lstm", "lstm"), ("deltagru", "deltagru"),
                     ("tres", "deltagru_tcnskip"), ("pgjanet", "pgjanet"), ("dvrjanet", "dvrjanet"), ("gmp", "gmp"),
-                    ("qgruqat", "qgru_qat"), ("qgruamp1qat", "qgru_amp1_qat"), ("rvtdcnn", "rvtdcnn"), ("bojanet", "bojanet")):
+                    ("qgruqat", "qgru_qat"), ("qgruamp1qat", "qgru_amp1_qat"), ("rvtdcnn", "rvtdcnn"), ("bojanet", "bojanet"), ("tcnn", "tcnn"), ("neuraltx", "neuraltx")):
         d = _ffi.OdpdDims(_ffi.CELLS[cell], 1, 1, 10, 3, 0, 0.0, 0.0)
         if L.odpd_saved_bytes(ctypes.byref(d)) >= 0:
             have.add(k)
@@ -107,7 +107,9 @@ def test_golden_parity(name, fused):
                                         ("qgru", 10, 16, 50), ("qgru_amp1", 10, 16, 50), ("lstm", 9, 16, 200), ("lstm", 32, 4, 70),
                                         ("pgjanet", 15, 8, 100), ("dvrjanet", 15, 8, 100), ("gmp", 0, 8, 100),
                                         ("rvtdcnn", 6, 16, 200), ("rvtdcnn", 64, 5, 1000), ("rvtdcnn", 20, 64, 2048),
-                                        ("bojanet", 10, 16, 200), ("bojanet", 18, 5, 1000), ("bojanet", 6, 64, 2048)])
+                                        ("bojanet", 10, 16, 200), ("bojanet", 18, 5, 1000), ("bojanet", 6, 64, 2048),
+                                        ("tcnn", 8, 16, 200), ("tcnn", 64, 5, 1000), ("tcnn", 15, 64, 2048),
+                                        ("neuraltx", 8, 16, 200), ("neuraltx", 64, 5, 1000), ("neuraltx", 15, 64, 2048)])
 def test_oracle_parity_seeded(kind, H, B, T):
     """Same seeded inputs through the CUDA path and the CPU oracle (fp32 and fp64 arbiter)."""
     from oracle import oracle
