@@ -37,15 +37,24 @@ struct GruLayout {
 template <int HT, int HEAD> struct Row { static constexpr int NS = HEAD ? 6 : 5; static constexpr int value = NS * Pad4<HT>::value; };
 
 // shared-memory carve-up (floats).  [0,16): 4 mbarriers (params + 3 activation slots)
-template <int HT, int HEAD>
+template <int HT, int FM, int HEAD>
 struct FwdSmem {
-    static constexpr int HP = Pad4<HT>::value, ROW = Row<HT, HEAD>::value;
-    static constexpr int XP = (CH + 1) * 3 * HP;   // input projection of one chunk (+1 row: the chain's last-step prefetch reads one row past
+    static constexpr int HP = Pad4<HT>::value, ROW = Row<HT, HEAD>::value, F = FeatN<FM>::value;
+    static constexpr int XPP = 3 * HP + 4;         // row pitch of the input projection: lane-per-timestep 16-byte stores hit distinct banks
+    static constexpr int XP = (CH + 1) * XPP;      // input projection of one chunk (+1 row: the chain's last-step prefetch reads one row past
                                                    // the chunk; the spare row keeps that read inside its own buffer, away from the pre warp's writes)
     static constexpr int FT = CH * 8;          // features of one chunk
     static constexpr int ACT = CH * ROW;       // activation rows of one chunk
-    static constexpr int PO = CH * 33;
-    __host__ __device__ static constexpr int total(int Ppad) { return 16 + Ppad + HP + 2 * XP + 3 * FT + 2 * ACT + 2 * PO; }
+    // zero-padded, 16-byte aligned copies of the weights the lane-per-timestep helper warps broadcast-read:
+    //   WI [F][3*HP] (k-major) | BI [3*HP] | WH [HT][HP] + BH [HP] (DGRU head) | WO [2][HP]
+    // LEAN (hidden tiers above 16): the helper warps work lane-per-timestep on these copies.  Up to 16 units the lane-per-unit helpers
+    // are kept — measured on the headline (DGRU H13, 8 chunks x 4 CTAs/SM): lean helpers 59.2 us, lane-per-unit 55.6 us per forward
+    // (their bursts of conflicting 16-byte row accesses cost the co-resident chain warps more than the shorter streams save); above
+    // 16 units the lane-per-unit sweeps get longer and the smaller footprint (no [CH][33] transposition buffers) buys a CTA per SM.
+    static constexpr bool LEAN = HP > 16;
+    static constexpr int WI = LEAN ? F * 3 * HP : 0, BI = LEAN ? 3 * HP : 0, WH = (LEAN && HEAD) ? HT * HP + HP : 0, WO = LEAN ? 2 * HP : 0;
+    static constexpr int PO = LEAN ? 0 : CH * 33;
+    __host__ __device__ static constexpr int total(int Ppad) { return 16 + Ppad + HP + 2 * XP + 3 * FT + 2 * ACT + WI + BI + WH + WO + 2 * PO; }
 };
 template <int HT, int HEAD>
 struct BwdSmem {
@@ -63,7 +72,9 @@ template <int HT, int FM, int HEAD>
 __global__ void __launch_bounds__(96, 1) gru_fwd_kernel(GruArgs a) {
     pdl_enter();
     constexpr int F = FeatN<FM>::value, HP = Pad4<HT>::value, ROW = Row<HT, HEAD>::value;
-    using SM = FwdSmem<HT, HEAD>;
+    using SM = FwdSmem<HT, FM, HEAD>;
+    constexpr int XPP = SM::XPP;
+    constexpr bool LEAN = SM::LEAN;
     const GruLayout<FM, HEAD> L(a.H);
     const int H = a.H, T = a.T;
     extern __shared__ __align__(128) float smem[];
@@ -71,10 +82,14 @@ __global__ void __launch_bounds__(96, 1) gru_fwd_kernel(GruArgs a) {
     float *sp = smem + 16;
     const int Ppad = (L.P + 3) & ~3;
     float *zero = sp + Ppad;                 // [HP] zeros: h_{-1}
-    float *sxp = zero + HP;                  // [2][CH][3*HP]
+    float *sxp = zero + HP;                  // [2][CH+1][XPP]
     float *sft = sxp + 2 * SM::XP;           // [3][CH][8]
     float *sact = sft + 3 * SM::FT;          // [2][CH][ROW]
-    float *spo = sact + 2 * SM::ACT;         // [2][CH][33]
+    float *sWi = sact + 2 * SM::ACT;         // [F][3*HP]   W_ih, k-major, gate-major columns g*HP + j
+    float *sbi = sWi + SM::WI;               // [3*HP]      b_ih (+ b_hh for r, z)
+    float *sWh = sbi + SM::BI;               // [HT][HP] + [HP]   fc_hid (DGRU)
+    float *sWo = sWh + SM::WH;               // [2][HP]     fc_out columns of the hidden part
+    float *spo = sWo + SM::WO;               // [2][CH][33] (lane-per-unit post warp only)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const FwdRange R = fwd_range(a);          // chunking.cuh: warm-up [t_lo, t_emit) from h = 0, emitted steps [t_emit, t_hi)
     const bool spec = R.spec;
@@ -83,6 +98,27 @@ __global__ void __launch_bounds__(96, 1) gru_fwd_kernel(GruArgs a) {
 
     stage_params(sp, a.params, L.P, bars);
     if (threadIdx.x < HP) zero[threadIdx.x] = 0.f;
+    if constexpr (SM::LEAN) {
+    for (int i = threadIdx.x; i < SM::WI; i += blockDim.x) {
+        const int k = i / (3 * HP), o = i - k * 3 * HP, g = o / HP, jj = o - g * HP;
+        sWi[i] = jj < H ? sp[L.oWih + (g * H + jj) * F + k] : 0.f;
+    }
+    for (int o = threadIdx.x; o < 3 * HP; o += blockDim.x) {
+        const int g = o / HP, jj = o - g * HP;
+        sbi[o] = jj < H ? sp[L.obih + g * H + jj] + (g < 2 ? sp[L.obhh + g * H + jj] : 0.f) : 0.f;
+    }
+    if constexpr (HEAD) {
+        for (int i = threadIdx.x; i < HT * HP; i += blockDim.x) {
+            const int jj = i / HP, k = i - jj * HP;
+            sWh[i] = (jj < H && k < H) ? sp[L.oWh + jj * H + k] : 0.f;
+        }
+        for (int i = threadIdx.x; i < HP; i += blockDim.x) sWh[HT * HP + i] = i < H ? sp[L.obh + i] : 0.f;
+    }
+    for (int i = threadIdx.x; i < 2 * HP; i += blockDim.x) {
+        const int c = i / HP, jj = i - c * HP;
+        sWo[i] = jj < H ? sp[L.oWo + c * L.O + jj] : 0.f;
+    }
+    }
     __syncthreads();
 
     const bool act = lane < H;
@@ -93,46 +129,80 @@ __global__ void __launch_bounds__(96, 1) gru_fwd_kernel(GruArgs a) {
     const int role = warp;
 
     if (role == 1) {
-        // =============================== pre: features + input projection, one chunk ahead of the chain
-        float wir[F], wiz[F], win[F];
-#pragma unroll
-        for (int f = 0; f < F; ++f) {
-            wir[f] = act ? sp[L.oWih + (0 * H + j) * F + f] : 0.f;
-            wiz[f] = act ? sp[L.oWih + (1 * H + j) * F + f] : 0.f;
-            win[f] = act ? sp[L.oWih + (2 * H + j) * F + f] : 0.f;
-        }
-        const float b_r = act ? sp[L.obih + j] + sp[L.obhh + j] : 0.f;
-        const float b_z = act ? sp[L.obih + H + j] + sp[L.obhh + H + j] : 0.f;
-        const float b_in = act ? sp[L.obih + 2 * H + j] : 0.f;
-        for (int s = 0; s < nchunks + 2; ++s) {
-            if (s < nchunks) {
-                const int t0 = (cb + s) * CH, nt = min(CH, t_hi - t0);
-                float *ft = sft + (s % 3) * SM::FT, *xp = sxp + (s & 1) * SM::XP;
-                if (lane < nt) {
-                    const float2 v = __ldg(x2 + t0 + lane);
+        if constexpr (LEAN) {
+            // =============================== pre: features + input projection, one chunk ahead of the chain.  Lane = timestep: every lane
+            // turns its sample into features and all 3*HP projections (weights broadcast from shared memory, 16 bytes at a time) — a
+            // quarter of the instructions of a lane-per-unit sweep over the 32 steps, which matters because this warp shares an issue
+            // port with the chain warps of the CTAs resident on the same SM.
+            for (int s = 0; s < nchunks + 2; ++s) {
+                if (s < nchunks) {
+                    const int t0 = (cb + s) * CH, nt = min(CH, t_hi - t0);
+                    float *ft = sft + (s % 3) * SM::FT, *xp = sxp + (s & 1) * SM::XP;
                     float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                    features_fwd<FM>(v.x, v.y, 0.f, 0.f, f);
+                    if (lane < nt) {
+                        const float2 v = __ldg(x2 + t0 + lane);
+                        features_fwd<FM>(v.x, v.y, 0.f, 0.f, f);
+                    }
                     float4 *d = reinterpret_cast<float4 *>(ft + lane * 8);
                     d[0] = make_float4(f[0], f[1], f[2], f[3]);
                     d[1] = make_float4(f[4], f[5], f[6], f[7]);
-                }
-                __syncwarp();
-                if (lane < HP) {
-#pragma unroll 4
-                    for (int tl = 0; tl < nt; ++tl) {
-                        const float4 *fp = reinterpret_cast<const float4 *>(ft + tl * 8);
-                        const float4 f0 = fp[0];
-                        float feat[8] = {f0.x, f0.y, f0.z, f0.w, 0.f, 0.f, 0.f, 0.f};
-                        if (F > 4) { const float4 f1 = fp[1]; feat[4] = f1.x; feat[5] = f1.y; feat[6] = f1.z; feat[7] = f1.w; }
-                        float xr = b_r, xz = b_z, xn = b_in;
-#pragma unroll
-                        for (int f = 0; f < F; ++f) { xr = fmaf(wir[f], feat[f], xr); xz = fmaf(wiz[f], feat[f], xz); xn = fmaf(win[f], feat[f], xn); }
-                        float *o = xp + tl * 3 * HP + lane;
-                        o[0] = xr; o[HP] = xz; o[2 * HP] = xn;
+                    float4 *o4 = reinterpret_cast<float4 *>(xp + lane * XPP);
+                    const float4 *b4 = reinterpret_cast<const float4 *>(sbi);
+    #pragma unroll
+                    for (int q = 0; q < 3 * HP / 4; ++q) {
+                        float4 acc = b4[q];
+    #pragma unroll
+                        for (int k = 0; k < F; ++k) {
+                            const float4 w = *reinterpret_cast<const float4 *>(sWi + k * 3 * HP + 4 * q);
+                            acc.x = fmaf(w.x, f[k], acc.x); acc.y = fmaf(w.y, f[k], acc.y); acc.z = fmaf(w.z, f[k], acc.z); acc.w = fmaf(w.w, f[k], acc.w);
+                        }
+                        o4[q] = acc;
                     }
                 }
+                __syncthreads();
             }
-            __syncthreads();
+        } else {
+            // =============================== pre: features + input projection, one chunk ahead of the chain
+            float wir[F], wiz[F], win[F];
+    #pragma unroll
+            for (int f = 0; f < F; ++f) {
+                wir[f] = act ? sp[L.oWih + (0 * H + j) * F + f] : 0.f;
+                wiz[f] = act ? sp[L.oWih + (1 * H + j) * F + f] : 0.f;
+                win[f] = act ? sp[L.oWih + (2 * H + j) * F + f] : 0.f;
+            }
+            const float b_r = act ? sp[L.obih + j] + sp[L.obhh + j] : 0.f;
+            const float b_z = act ? sp[L.obih + H + j] + sp[L.obhh + H + j] : 0.f;
+            const float b_in = act ? sp[L.obih + 2 * H + j] : 0.f;
+            for (int s = 0; s < nchunks + 2; ++s) {
+                if (s < nchunks) {
+                    const int t0 = (cb + s) * CH, nt = min(CH, t_hi - t0);
+                    float *ft = sft + (s % 3) * SM::FT, *xp = sxp + (s & 1) * SM::XP;
+                    if (lane < nt) {
+                        const float2 v = __ldg(x2 + t0 + lane);
+                        float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                        features_fwd<FM>(v.x, v.y, 0.f, 0.f, f);
+                        float4 *d = reinterpret_cast<float4 *>(ft + lane * 8);
+                        d[0] = make_float4(f[0], f[1], f[2], f[3]);
+                        d[1] = make_float4(f[4], f[5], f[6], f[7]);
+                    }
+                    __syncwarp();
+                    if (lane < HP) {
+    #pragma unroll 4
+                        for (int tl = 0; tl < nt; ++tl) {
+                            const float4 *fp = reinterpret_cast<const float4 *>(ft + tl * 8);
+                            const float4 f0 = fp[0];
+                            float feat[8] = {f0.x, f0.y, f0.z, f0.w, 0.f, 0.f, 0.f, 0.f};
+                            if (F > 4) { const float4 f1 = fp[1]; feat[4] = f1.x; feat[5] = f1.y; feat[6] = f1.z; feat[7] = f1.w; }
+                            float xr = b_r, xz = b_z, xn = b_in;
+    #pragma unroll
+                            for (int f = 0; f < F; ++f) { xr = fmaf(wir[f], feat[f], xr); xz = fmaf(wiz[f], feat[f], xz); xn = fmaf(win[f], feat[f], xn); }
+                            float *o = xp + tl * XPP + lane;
+                            o[0] = xr; o[HP] = xz; o[2 * HP] = xn;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
         }
     } else if (role == 0) {
         // =============================== chain: the serial recurrence
@@ -174,7 +244,7 @@ __global__ void __launch_bounds__(96, 1) gru_fwd_kernel(GruArgs a) {
                         float4 hv[HP / 4];
 #pragma unroll
                         for (int k4 = 0; k4 < HP / 4; ++k4) hv[k4] = hb4[k4];
-                        xa_p += 3 * HP; xn_p += 3 * HP;
+                        xa_p += XPP; xn_p += XPP;
                         const float nxa = *xa_p, nxn = *xn_p;
                         if (wr && tl > 0) { row[-ROW] = pr_; row[HP - ROW] = pz_; row[2 * HP - ROW] = pn_; row[3 * HP - ROW] = phg_; }
                         float a0 = xa, a1 = 0.f, b0 = b_hn, b1 = 0.f;
@@ -242,7 +312,7 @@ __global__ void __launch_bounds__(96, 1) gru_fwd_kernel(GruArgs a) {
                         for (int k4 = 0; k4 < HP / 4; ++k4) hv[k4] = hb4[k4];
                         // prefetch next step's input projection (independent of h)
                         const int tn = (tl + 1 < nt) ? tl + 1 : tl;
-                        const float nxr = xp[tn * 3 * HP], nxz = xp[tn * 3 * HP + HP], nxn = xp[tn * 3 * HP + 2 * HP];
+                        const float nxr = xp[tn * XPP], nxz = xp[tn * XPP + HP], nxn = xp[tn * XPP + 2 * HP];
                         // deferred activation stores of step tl-1 (off the dependent chain)
                         if (tl > 0 && lane < HP) {
                             float *prow = ac + (tl - 1) * ROW;
@@ -285,80 +355,162 @@ __global__ void __launch_bounds__(96, 1) gru_fwd_kernel(GruArgs a) {
             if (spec && lane < HP) a.sc_end[(size_t)blockIdx.x * HP + lane] = h;
         }
     } else {
-        // =============================== post: head, output, squared error, activation store
-        float wh[HEAD ? HT : 1];
-        if constexpr (HEAD) {
-#pragma unroll
-            for (int k = 0; k < HT; ++k) wh[k] = (act && k < H) ? sp[L.oWh + j * H + k] : 0.f;
-        }
-        const float wo0 = act ? sp[L.oWo + j] : 0.f, wo1 = act ? sp[L.oWo + L.O + j] : 0.f;
-        const float bh = (HEAD && act) ? sp[L.obh + j] : 0.f;
-        const float bo0 = sp[L.obo], bo1 = sp[L.obo + 1];
-        const IqRow y2 = iq_row(a.target, a.target_bf16, a.target_starts, b, T);
-        float2 *o2 = reinterpret_cast<float2 *>(a.out) + (size_t)b * T;
-        float *svg = a.save ? a.saved + (size_t)b * T * ROW : nullptr;
-        float *spo0 = spo, *spo1 = spo + SM::PO;
-        float lsum = 0.f;
-        for (int s = 0; s < nchunks + 2; ++s) {
-            const int c = s - 2;
-            if (c >= 0 && (cb + c) * CH >= t_emit) {       // warm-up blocks emit nothing
-                const int t0 = (cb + c) * CH, nt = min(CH, t_hi - t0);
-                float *ac = sact + (c & 1) * SM::ACT;
-                const float *ft = sft + (c % 3) * SM::FT;
-#pragma unroll 2
-                for (int tl = 0; tl < nt; ++tl) {
-                    float *row = ac + tl * ROW;
-                    float g;
-                    if constexpr (HEAD) {
-                        float p0 = bh, p1 = 0.f;
-                        const float4 *hn4 = reinterpret_cast<const float4 *>(row + 4 * HP);
-#pragma unroll
-                        for (int k4 = 0; k4 < HP / 4; ++k4) {
-                            const float4 hv = hn4[k4];
-                            const float hk[4] = {hv.x, hv.y, hv.z, hv.w};
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const int k = k4 * 4 + e;
-                                if (k < HT) { if (k & 1) p1 = fmaf(wh[k], hk[e], p1); else p0 = fmaf(wh[k], hk[e], p0); }
-                            }
-                        }
-                        g = fmaxf(p0 + p1, 0.f);
-                        if (lane < HP) row[5 * HP + lane] = g;
-                    } else {
-                        g = lane < HP ? row[4 * HP + lane] : 0.f;
+        if constexpr (LEAN) {
+            // =============================== post: head, output, squared error, activation store.  Lane = timestep: each lane reads the h
+            // row of its step once, runs the head on it with broadcast weights and writes g back into the row for the bulk store.
+            const float bo0 = sp[L.obo], bo1 = sp[L.obo + 1];
+            const IqRow y2 = iq_row(a.target, a.target_bf16, a.target_starts, b, T);
+            float2 *o2 = reinterpret_cast<float2 *>(a.out) + (size_t)b * T;
+            float *svg = a.save ? a.saved + (size_t)b * T * ROW : nullptr;
+            float lsum = 0.f;
+            for (int s = 0; s < nchunks + 2; ++s) {
+                const int c = s - 2;
+                if (c >= 0 && (cb + c) * CH >= t_emit) {       // warm-up blocks emit nothing
+                    const int t0 = (cb + c) * CH, nt = min(CH, t_hi - t0);
+                    float *ac = sact + (c & 1) * SM::ACT;
+                    const float *ft = sft + (c % 3) * SM::FT;
+                    float *row = ac + lane * ROW;              // rows nt..31 hold stale data: computed on, never emitted
+                    float hv[HP];
+    #pragma unroll
+                    for (int k4 = 0; k4 < HP / 4; ++k4) {
+                        const float4 v = *reinterpret_cast<const float4 *>(row + 4 * HP + 4 * k4);
+                        hv[4 * k4] = v.x; hv[4 * k4 + 1] = v.y; hv[4 * k4 + 2] = v.z; hv[4 * k4 + 3] = v.w;
                     }
-                    spo0[tl * 33 + lane] = wo0 * g;
-                    spo1[tl * 33 + lane] = wo1 * g;
-                }
-                fence_async_smem();
-                __syncwarp();
-                if (svg && lane == 0) tma_store_1d(svg + (size_t)t0 * ROW, ac, (uint32_t)(nt * ROW * 4));
-                if (lane < nt) {
                     float o0 = bo0, o1 = bo1;
-                    for (int k = 0; k < H; ++k) { o0 += spo0[lane * 33 + k]; o1 += spo1[lane * 33 + k]; }
                     if constexpr (HEAD) {
-#pragma unroll
+                        float g[HP];
+    #pragma unroll
+                        for (int jj = 0; jj < HP; ++jj) g[jj] = 0.f;
+    #pragma unroll
+                        for (int jj = 0; jj < HT; ++jj) {
+                            float p0 = sWh[HT * HP + jj], p1 = 0.f;
+    #pragma unroll
+                            for (int k4 = 0; k4 < HP / 4; ++k4) {
+                                const float4 w = *reinterpret_cast<const float4 *>(sWh + jj * HP + 4 * k4);
+                                p0 = fmaf(w.x, hv[4 * k4], p0); p1 = fmaf(w.y, hv[4 * k4 + 1], p1);
+                                p0 = fmaf(w.z, hv[4 * k4 + 2], p0); p1 = fmaf(w.w, hv[4 * k4 + 3], p1);
+                            }
+                            g[jj] = fmaxf(p0 + p1, 0.f);
+                        }
+    #pragma unroll
+                        for (int k4 = 0; k4 < HP / 4; ++k4)
+                            *reinterpret_cast<float4 *>(row + 5 * HP + 4 * k4) = make_float4(g[4 * k4], g[4 * k4 + 1], g[4 * k4 + 2], g[4 * k4 + 3]);
+    #pragma unroll
+                        for (int k4 = 0; k4 < HP / 4; ++k4) {
+                            const float4 w0 = *reinterpret_cast<const float4 *>(sWo + 4 * k4), w1 = *reinterpret_cast<const float4 *>(sWo + HP + 4 * k4);
+                            o0 = fmaf(w0.x, g[4 * k4], o0); o0 = fmaf(w0.y, g[4 * k4 + 1], o0); o0 = fmaf(w0.z, g[4 * k4 + 2], o0); o0 = fmaf(w0.w, g[4 * k4 + 3], o0);
+                            o1 = fmaf(w1.x, g[4 * k4], o1); o1 = fmaf(w1.y, g[4 * k4 + 1], o1); o1 = fmaf(w1.z, g[4 * k4 + 2], o1); o1 = fmaf(w1.w, g[4 * k4 + 3], o1);
+                        }
+    #pragma unroll
                         for (int f = 0; f < F; ++f) {
                             const float fv = ft[lane * 8 + f];
                             o0 = fmaf(sp[L.oWo + H + f], fv, o0);
                             o1 = fmaf(sp[L.oWo + L.O + H + f], fv, o1);
                         }
+                    } else {
+    #pragma unroll
+                        for (int k4 = 0; k4 < HP / 4; ++k4) {
+                            const float4 w0 = *reinterpret_cast<const float4 *>(sWo + 4 * k4), w1 = *reinterpret_cast<const float4 *>(sWo + HP + 4 * k4);
+                            o0 = fmaf(w0.x, hv[4 * k4], o0); o0 = fmaf(w0.y, hv[4 * k4 + 1], o0); o0 = fmaf(w0.z, hv[4 * k4 + 2], o0); o0 = fmaf(w0.w, hv[4 * k4 + 3], o0);
+                            o1 = fmaf(w1.x, hv[4 * k4], o1); o1 = fmaf(w1.y, hv[4 * k4 + 1], o1); o1 = fmaf(w1.z, hv[4 * k4 + 2], o1); o1 = fmaf(w1.w, hv[4 * k4 + 3], o1);
+                        }
                     }
-                    o2[t0 + lane] = make_float2(o0, o1);
-                    if (y2) {
-                        const float2 y = __ldg(y2 + t0 + lane);
-                        const float d0 = o0 - y.x, d1 = o1 - y.y;
-                        lsum = fmaf(d0, d0, fmaf(d1, d1, lsum));
+                    fence_async_smem();
+                    __syncwarp();
+                    if (svg && lane == 0) tma_store_1d(svg + (size_t)t0 * ROW, ac, (uint32_t)(nt * ROW * 4));
+                    if (lane < nt) {
+                        o2[t0 + lane] = make_float2(o0, o1);
+                        if (y2) {
+                            const float2 y = __ldg(y2 + t0 + lane);
+                            const float d0 = o0 - y.x, d1 = o1 - y.y;
+                            lsum = fmaf(d0, d0, fmaf(d1, d1, lsum));
+                        }
                     }
+                    if (svg && lane == 0) tma_store_wait_read();
+                    __syncwarp();
                 }
-                if (svg && lane == 0) tma_store_wait_read();
-                __syncwarp();
+                __syncthreads();
             }
-            __syncthreads();
-        }
-        if (y2) {
-            lsum = warp_sum(lsum);
-            if (lane == 0) chunk_store_loss(a, spec, lsum);
+            if (y2) {
+                lsum = warp_sum(lsum);
+                if (lane == 0) chunk_store_loss(a, spec, lsum);
+            }
+        } else {
+            // =============================== post: head, output, squared error, activation store
+            float wh[HEAD ? HT : 1];
+            if constexpr (HEAD) {
+    #pragma unroll
+                for (int k = 0; k < HT; ++k) wh[k] = (act && k < H) ? sp[L.oWh + j * H + k] : 0.f;
+            }
+            const float wo0 = act ? sp[L.oWo + j] : 0.f, wo1 = act ? sp[L.oWo + L.O + j] : 0.f;
+            const float bh = (HEAD && act) ? sp[L.obh + j] : 0.f;
+            const float bo0 = sp[L.obo], bo1 = sp[L.obo + 1];
+            const IqRow y2 = iq_row(a.target, a.target_bf16, a.target_starts, b, T);
+            float2 *o2 = reinterpret_cast<float2 *>(a.out) + (size_t)b * T;
+            float *svg = a.save ? a.saved + (size_t)b * T * ROW : nullptr;
+            float *spo0 = spo, *spo1 = spo + SM::PO;
+            float lsum = 0.f;
+            for (int s = 0; s < nchunks + 2; ++s) {
+                const int c = s - 2;
+                if (c >= 0 && (cb + c) * CH >= t_emit) {       // warm-up blocks emit nothing
+                    const int t0 = (cb + c) * CH, nt = min(CH, t_hi - t0);
+                    float *ac = sact + (c & 1) * SM::ACT;
+                    const float *ft = sft + (c % 3) * SM::FT;
+    #pragma unroll 2
+                    for (int tl = 0; tl < nt; ++tl) {
+                        float *row = ac + tl * ROW;
+                        float g;
+                        if constexpr (HEAD) {
+                            float p0 = bh, p1 = 0.f;
+                            const float4 *hn4 = reinterpret_cast<const float4 *>(row + 4 * HP);
+    #pragma unroll
+                            for (int k4 = 0; k4 < HP / 4; ++k4) {
+                                const float4 hv = hn4[k4];
+                                const float hk[4] = {hv.x, hv.y, hv.z, hv.w};
+    #pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const int k = k4 * 4 + e;
+                                    if (k < HT) { if (k & 1) p1 = fmaf(wh[k], hk[e], p1); else p0 = fmaf(wh[k], hk[e], p0); }
+                                }
+                            }
+                            g = fmaxf(p0 + p1, 0.f);
+                            if (lane < HP) row[5 * HP + lane] = g;
+                        } else {
+                            g = lane < HP ? row[4 * HP + lane] : 0.f;
+                        }
+                        spo0[tl * 33 + lane] = wo0 * g;
+                        spo1[tl * 33 + lane] = wo1 * g;
+                    }
+                    fence_async_smem();
+                    __syncwarp();
+                    if (svg && lane == 0) tma_store_1d(svg + (size_t)t0 * ROW, ac, (uint32_t)(nt * ROW * 4));
+                    if (lane < nt) {
+                        float o0 = bo0, o1 = bo1;
+                        for (int k = 0; k < H; ++k) { o0 += spo0[lane * 33 + k]; o1 += spo1[lane * 33 + k]; }
+                        if constexpr (HEAD) {
+    #pragma unroll
+                            for (int f = 0; f < F; ++f) {
+                                const float fv = ft[lane * 8 + f];
+                                o0 = fmaf(sp[L.oWo + H + f], fv, o0);
+                                o1 = fmaf(sp[L.oWo + L.O + H + f], fv, o1);
+                            }
+                        }
+                        o2[t0 + lane] = make_float2(o0, o1);
+                        if (y2) {
+                            const float2 y = __ldg(y2 + t0 + lane);
+                            const float d0 = o0 - y.x, d1 = o1 - y.y;
+                            lsum = fmaf(d0, d0, fmaf(d1, d1, lsum));
+                        }
+                    }
+                    if (svg && lane == 0) tma_store_wait_read();
+                    __syncwarp();
+                }
+                __syncthreads();
+            }
+            if (y2) {
+                lsum = warp_sum(lsum);
+                if (lane == 0) chunk_store_loss(a, spec, lsum);
+            }
         }
     }
 }
@@ -1670,7 +1822,7 @@ template <int HT, int FM, int HEAD>
 static int launch_fwd(GruArgs a, cudaStream_t st, bool plan_only, int *info) {
     constexpr int HP = Pad4<HT>::value, ROW = Row<HT, HEAD>::value;
     const GruLayout<FM, HEAD> L(a.H);
-    const size_t smem = (size_t)FwdSmem<HT, HEAD>::total((L.P + 3) & ~3) * sizeof(float);
+    const size_t smem = (size_t)FwdSmem<HT, FM, HEAD>::total((L.P + 3) & ~3) * sizeof(float);
     static OccCache occ{};
     const int64_t soff = a.save ? (int64_t)a.B * a.T * ROW : 0;     // `saved` = [B][T][ROW] rows (when saving) | chunk scratch
     return chunk_launch(gru_fwd_kernel<HT, FM, HEAD>, 96, smem, &occ, a, 0, a.saved ? a.saved + soff : nullptr, soff, HP, st, plan_only, info,
