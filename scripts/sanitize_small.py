@@ -18,8 +18,13 @@ CASES = [  # kind, H, B, T, tchunks (fwd,bwd), twarm
     ("pgjanet", 15, 2, 100, (1, 1), 0), ("pgjanet", 15, 2, 256, (2, 2), 64), ("dvrjanet", 15, 2, 100, (1, 1), 0), ("dvrjanet", 15, 2, 256, (2, 2), 64),
     ("gmp", 1, 2, 60, (1, 1), 0), ("qgru_qat", 10, 2, 40, (1, 1), 0), ("qgru_qat", 20, 5, 70, (1, 1), 0),
     ("vdlstm", 9, 2, 100, (1, 1), 0), ("vdlstm", 9, 2, 256, (2, 2), 64), ("dgru", 23, 2, 130, (1, 1), 0), ("gru", 8, 2, 70, (1, 1), 0),
+    ("dgru", 23, 2, 256, (2, 2), 64), ("gru", 32, 2, 100, (1, 1), 0),                      # lane-per-timestep forward helpers (tiers above 16)
+    ("gru", 40, 2, 70, (1, 1), 0, 1), ("dgru", 12, 2, 70, (1, 1), 0, 2), ("lstm", 36, 2, 45, (1, 1), 0, 2),   # layered path (7th field = num_layers)
+    ("rvtdcnn", 6, 2, 100, (1, 1), 0), ("bojanet", 10, 2, 100, (1, 1), 0), ("tcnn", 8, 2, 150, (1, 1), 0), ("neuraltx", 8, 2, 150, (1, 1), 0),
 ]
-for kind, H, B, T, tch, tw in CASES:
+for case in CASES:
+    kind, H, B, T, tch, tw = case[:6]
+    layers = case[6] if len(case) > 6 else 1
     if only and kind not in only:
         continue
     if kind == "qgru_qat":
@@ -29,7 +34,7 @@ for kind, H, B, T, tch, tw in CASES:
             quant, n_bits_w, n_bits_a, pretrained_model = True, 8, 8, ""
         net = get_quant_model(_Proj(), models.CoreModel(2, H, 1, "qgru")).cuda().train()
     else:
-        net = models.CoreModel(2, H, 1, kind, num_dvr_units=3, thx=0.01, thh=0.05).cuda()
+        net = models.CoreModel(2, H, layers, kind, num_dvr_units=3, thx=0.01, thh=0.05).cuda()
     bb = net.backbone
     flat, _ = bb._flat_sync()
     x = (0.2 * torch.randn(B, T, 2)).cuda(); y = (0.8 * x).contiguous()
