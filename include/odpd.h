@@ -37,6 +37,8 @@
  *   TCNN      (tcnn.py:15-31)       network.0.weight(H,6,1) network.0.bias(H) network.{2,4,6,8}.weight(H,1,5) network.10.weight(2,H,1)
  *   NEURALTX  (neuraltx.py:19-38)   conv_I.weight(1,1,5) conv_Q.weight(1,1,5) network.0.weight(H,4,1) network.0.bias(H) network.{2,4,6,8}.weight(H,1,5)
  *                                   network.10.weight(2,H,1) IQ_match.weight(2,2)
+ *   APNRRU    (apnrru.py:44-51,13-19) fir_I.weight(3,16) fir_Q.weight(3,16) rru.C(1) rru.Z(1,S) rru.W_u.weight(16,S+8) rru.W_u.bias(16) rru.W_h.weight(S,16)
+ *                                   rru.W_h.bias(S) output_layer_I.weight(1,H) output_layer_Q.weight(1,H),  S = 2H+3
  *   QGRU_QAT  (quant_envs.py:215-305 applied to qgru.py) rnn.rnn_cell_list.0.x2h.weight(3H,4) .bias(3H) .weight_quantizer.scale .act_quantizer.scale
  *                                   .out_quantizer.scale | h2h.weight(3H,H) .bias(3H) + 3 scales | sigmoid/tanh/add/mul .quantizer.scale |
  *                                   fc_out.weight(2,H) .bias(2) + 3 scales.   For the QAT cells OdpdDims.K packs n_bits_w | n_bits_a<<8 | eval<<16.
@@ -78,7 +80,8 @@ enum {
     ODPD_CELL_BOJANET = 14,  /* backbones/bojanet.py:54-106 (row f-4): hidden_size 1..18 (the reference's pr_block covers 3 x 6 units) */
     ODPD_CELL_TCNN = 15,     /* backbones/tcnn.py:83-97 (row f-4): H = hidden_channels (1..64) */
     ODPD_CELL_NEURALTX = 16, /* backbones/neuraltx.py:107-124 (row f-4): H = hidden_channels (1..64) */
-    ODPD_CELL_COUNT = 17
+    ODPD_CELL_APNRRU = 17,   /* backbones/apnrru.py:52-135 (row f-4): hidden_size 1..14 (2H+3 state values, one per warp lane) */
+    ODPD_CELL_COUNT = 18
 };
 
 /* flags */

@@ -10,5 +10,6 @@ from .gmp import GMP
 from .rvtdcnn import RVTDCNN
 from .bojanet import BOJANET
 from .tcnn import TCNN, NeuralTX
+from .apnrru import APNRRU
 
-__all__ = ["GRU", "DGRU", "QGRU", "QGRUAmp1", "LSTM", "VDLSTM", "DeltaGRU", "TResDeltaGRU", "PGJANET", "DVRJANET", "GMP", "RVTDCNN", "BOJANET", "TCNN", "NeuralTX"]
+__all__ = ["GRU", "DGRU", "QGRU", "QGRUAmp1", "LSTM", "VDLSTM", "DeltaGRU", "TResDeltaGRU", "PGJANET", "DVRJANET", "GMP", "RVTDCNN", "BOJANET", "TCNN", "NeuralTX", "APNRRU"]

@@ -88,6 +88,12 @@ int64_t tcnn_saved_floats(int B, int T, int C);
 int64_t tcnn_workspace_floats(int cell, int B, int T, int C);
 int tcnn_run(int cell, const GruArgs &a, int dir, bool dw, cudaStream_t st, int *rows_out);
 
+// apnrru.cu : APNRRU (phase-normalised recurrent unit)
+int64_t apnrru_nparams(int H);
+int64_t apnrru_saved_floats(int B, int T, int H);
+int64_t apnrru_workspace_floats(int B, int T, int H);
+int apnrru_run(const GruArgs &a, int dir, bool dw, cudaStream_t st, int *rows_out);
+
 // remaining families (lstm.cu, delta.cu, janet.cu, gmp.cu) behind one dispatcher in others.cu
 int64_t other_nparams(int cell, int H, int K);
 int64_t other_saved_bytes(const OdpdDims *d);

@@ -187,6 +187,9 @@ CASES = [
     ("neuraltx_h8_b3_t70",         "neuraltx", 8, 3, 70, 59, 0, 0),
     ("neuraltx_h24_b2_t131",       "neuraltx", 24, 2, 131, 60, 0, 0),
     ("neuraltx_h3_b2_t4",          "neuraltx", 3, 2, 4, 61, 0, 0),
+    ("apnrru_h8_b3_t50",           "apnrru", 8, 3, 50, 62, 0, 0),
+    ("apnrru_h14_b2_t70",          "apnrru", 14, 2, 70, 63, 0, 0),
+    ("apnrru_h3_b2_t15",           "apnrru", 3, 2, 15, 64, 0, 0),
     # hidden sizes above the fused tiers and stacked layers (arguments.py:51,60 -> nn.GRU/nn.LSTM num_layers): 10th field = num_layers
     ("wide_gru_h48_b3_t70",        "gru",  48, 3, 70, 40, 0, 0, 3, 1),
     ("wide_gru_h16_l2_b3_t40",     "gru",  16, 3, 40, 41, 0, 0, 3, 2),

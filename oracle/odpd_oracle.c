@@ -54,7 +54,7 @@
 #endif
 
 enum { CELL_GRU = 0, CELL_LSTM = 1, CELL_DGRU = 2, CELL_DELTAGRU = 3, CELL_TRES = 4, CELL_PGJANET = 5,
-       CELL_DVRJANET = 6, CELL_GMP = 7, CELL_QGRU = 8, CELL_QGRU_AMP1 = 9, CELL_QGRU_QAT = 10, CELL_QGRU_AMP1_QAT = 11, CELL_RVTDCNN = 13, CELL_BOJANET = 14, CELL_TCNN = 15, CELL_NEURALTX = 16 };
+       CELL_DVRJANET = 6, CELL_GMP = 7, CELL_QGRU = 8, CELL_QGRU_AMP1 = 9, CELL_QGRU_QAT = 10, CELL_QGRU_AMP1_QAT = 11, CELL_RVTDCNN = 13, CELL_BOJANET = 14, CELL_TCNN = 15, CELL_NEURALTX = 16, CELL_APNRRU = 17 };
 
 typedef struct {
     int cell, B, T, H, K;
@@ -1065,6 +1065,120 @@ static void seq_tcn(const Ctx *c, const REAL *x, const REAL *gout, REAL *out, RE
     free(feat); free(iq); free(pre);
 }
 
+/* ================================================================ APNRRU: apnrru.py:52-135 (RRU cell :5-31)
+ * 16-tap complex FIR with 3 real-weight filter pairs (windows zero before the frame, :67-71, :84-87) + the raw sample = 4 complex inputs;
+ * r = conj(x_t)/|x_t| (:74-77) rotates the inputs (:93-95) and, every step, the complex state h_I + j h_Q (:101-102);
+ * u = [inputs(8), h_I', h_Q', h_A(3)], hnew = [h_I', h_Q', h_A];  v = sigmoid(C hnew) + Z * tanh(W_h tanh(W_u u + b) + b) (:22-31);
+ * (v[:H] + j v[H:2H]) is rotated back by conj(r) (:115-119), h_A = v[2H:];  out_I = o_I(h_I) - o_Q(h_Q), out_Q = o_Q(h_Q) + o_I(h_I) (:123-125).
+ * params: fir_I(3,16) fir_Q(3,16) C(1) Z(1,S) W_u(16,S+8) b_u(16) W_h(S,16) b_h(S) o_I(1,H) o_Q(1,H),  S = 2H+3. */
+static void seq_apnrru(const Ctx *c, const REAL *x, const REAL *gout, REAL *out, REAL *gx, REAL *gp, int phase) {
+    const int T = c->T, H = c->H, S = 2 * H + 3, U = S + 8;
+    const size_t oC = 96, oZ = 97, oWu = oZ + S, obu = oWu + (size_t)16 * U, oWh = obu + 16, obh = oWh + (size_t)16 * S, oI = obh + S, oQ = oI + H;
+    const REAL *P = c->params, *FI = P, *FQ = P + 48, Cc = P[oC], *Z = P + oZ, *Wu = P + oWu, *bu = P + obu, *Wh = P + oWh, *bh = P + obh,
+               *WI = P + oI, *WQ = P + oQ;
+    /* per step: fir(6) rr ri mag | u(U) | v1(16) | v2(S) | sg(S) | vv(S) | hd(2H) */
+    const int ST = 9 + U + 16 + 3 * S + 2 * H;
+    REAL *sv = (REAL *)calloc((size_t)T * ST, sizeof(REAL));
+    REAL hI[32] = {0}, hQ[32] = {0}, hA[3] = {0};
+    for (int t = 0; t < T; ++t) {
+        REAL *q = sv + (size_t)t * ST, *u = q + 9, *v1 = u + U, *v2 = v1 + 16, *sg = v2 + S, *vv = sg + S, *hd = vv + S;
+        REAL a[4], b[4];
+        for (int p = 0; p < 3; ++p) {
+            REAL fi = 0, fq = 0;
+            for (int m = 0; m < 16; ++m) {
+                int s = t + m - 15; if (s < 0) continue;
+                fi += FI[p * 16 + m] * x[2 * s] - FQ[p * 16 + m] * x[2 * s + 1];
+                fq += FQ[p * 16 + m] * x[2 * s] + FI[p * 16 + m] * x[2 * s + 1];
+            }
+            a[p] = fi; b[p] = fq; q[p] = fi; q[3 + p] = fq;
+        }
+        a[3] = x[2 * t]; b[3] = x[2 * t + 1];
+        const REAL mag = R_SQRT(x[2 * t] * x[2 * t] + x[2 * t + 1] * x[2 * t + 1]);
+        const REAL rr = x[2 * t] / mag, ri = -x[2 * t + 1] / mag;
+        q[6] = rr; q[7] = ri; q[8] = mag;
+        for (int k = 0; k < 4; ++k) { u[2 * k] = rr * a[k] - ri * b[k]; u[2 * k + 1] = ri * a[k] + rr * b[k]; }
+        for (int j = 0; j < H; ++j) { u[8 + j] = hI[j] * rr - hQ[j] * ri; u[8 + H + j] = hI[j] * ri + hQ[j] * rr; }
+        for (int k = 0; k < 3; ++k) u[8 + 2 * H + k] = hA[k];
+        for (int i = 0; i < 16; ++i) v1[i] = R_TANH(bu[i] + dotv(Wu + (size_t)i * U, u, U));
+        for (int s = 0; s < S; ++s) {
+            v2[s] = R_TANH(bh[s] + dotv(Wh + (size_t)s * 16, v1, 16));
+            sg[s] = sigm(Cc * u[8 + s]);
+            vv[s] = sg[s] + Z[s] * v2[s];
+        }
+        REAL oi = 0, oq = 0;
+        for (int j = 0; j < H; ++j) {
+            hI[j] = rr * vv[j] + ri * vv[H + j]; hQ[j] = rr * vv[H + j] - ri * vv[j];
+            hd[j] = hI[j]; hd[H + j] = hQ[j];
+            oi += WI[j] * hI[j]; oq += WQ[j] * hQ[j];
+        }
+        for (int k = 0; k < 3; ++k) hA[k] = vv[2 * H + k];
+        if (!phase) { out[2 * t] = oi - oq; out[2 * t + 1] = oq + oi; }
+    }
+    if (phase) {
+        REAL ghI[32] = {0}, ghQ[32] = {0}, ghA[3] = {0};
+        REAL *dfir = (REAL *)calloc((size_t)T * 6, sizeof(REAL));
+        for (int t = T - 1; t >= 0; --t) {
+            const REAL *q = sv + (size_t)t * ST, *u = q + 9, *v1 = u + U, *v2 = v1 + 16, *sg = v2 + S, *vv = sg + S, *hd = vv + S;
+            const REAL *hp = t > 0 ? q - ST + (ST - 2 * H) : NULL;      /* de-rotated state of step t-1 */
+            const REAL rr = q[6], ri = q[7], mag = q[8];
+            const REAL da = gout[2 * t] + gout[2 * t + 1], dq = gout[2 * t + 1] - gout[2 * t];
+            REAL gv[80], ghn[80], ga2[80], gv1[16] = {0}, gu[96] = {0}, grr = 0, gri = 0;
+            for (int j = 0; j < H; ++j) {
+                gp[oI + j] += da * hd[j]; gp[oQ + j] += dq * hd[H + j];
+                const REAL gI = ghI[j] + da * WI[j], gQ = ghQ[j] + dq * WQ[j];
+                gv[j] = gI * rr - gQ * ri; gv[H + j] = gI * ri + gQ * rr;
+                grr += gI * vv[j] + gQ * vv[H + j]; gri += gI * vv[H + j] - gQ * vv[j];
+            }
+            for (int k = 0; k < 3; ++k) gv[2 * H + k] = ghA[k];
+            for (int s = 0; s < S; ++s) {
+                const REAL ds = sg[s] * ((REAL)1 - sg[s]);
+                gp[oC] += gv[s] * ds * u[8 + s];
+                ghn[s] = gv[s] * ds * Cc;
+                gp[oZ + s] += gv[s] * v2[s];
+                ga2[s] = gv[s] * Z[s] * ((REAL)1 - v2[s] * v2[s]);
+                gp[obh + s] += ga2[s];
+                for (int i = 0; i < 16; ++i) { gp[oWh + (size_t)s * 16 + i] += ga2[s] * v1[i]; gv1[i] += ga2[s] * Wh[(size_t)s * 16 + i]; }
+            }
+            for (int i = 0; i < 16; ++i) {
+                const REAL ga1 = gv1[i] * ((REAL)1 - v1[i] * v1[i]);
+                gp[obu + i] += ga1;
+                for (int k = 0; k < U; ++k) { gp[oWu + (size_t)i * U + k] += ga1 * u[k]; gu[k] += ga1 * Wu[(size_t)i * U + k]; }
+            }
+            for (int s = 0; s < S; ++s) ghn[s] += gu[8 + s];
+            for (int j = 0; j < H; ++j) {
+                const REAL gI = ghn[j], gQ = ghn[H + j], pI = hp ? hp[j] : 0, pQ = hp ? hp[H + j] : 0;
+                ghI[j] = gI * rr + gQ * ri; ghQ[j] = -gI * ri + gQ * rr;
+                grr += gI * pI + gQ * pQ; gri += -gI * pQ + gQ * pI;
+            }
+            for (int k = 0; k < 3; ++k) ghA[k] = ghn[2 * H + k];
+            REAL gxi = 0, gxq = 0;
+            for (int k = 0; k < 4; ++k) {
+                const REAL gre = gu[2 * k], gim = gu[2 * k + 1];
+                const REAL ak = k < 3 ? q[k] : x[2 * t], bk = k < 3 ? q[3 + k] : x[2 * t + 1];
+                const REAL gak = gre * rr + gim * ri, gbk = -gre * ri + gim * rr;
+                grr += gre * ak + gim * bk; gri += -gre * bk + gim * ak;
+                if (k < 3) { dfir[6 * t + k] = gak; dfir[6 * t + 3 + k] = gbk; } else { gxi += gak; gxq += gbk; }
+            }
+            const REAL I = x[2 * t], Q = x[2 * t + 1], m3 = mag * mag * mag;
+            gxi += grr * ((REAL)1 / mag - I * I / m3) + gri * (Q * I / m3);
+            gxq += grr * (-I * Q / m3) + gri * ((REAL)-1 / mag + Q * Q / m3);
+            if (gx) { gx[2 * t] += gxi; gx[2 * t + 1] += gxq; }
+        }
+        for (int t = 0; t < T; ++t)
+            for (int p = 0; p < 3; ++p) {
+                const REAL di = dfir[6 * t + p], dq = dfir[6 * t + 3 + p];
+                for (int m = 0; m < 16; ++m) {
+                    int s = t + m - 15; if (s < 0) continue;
+                    gp[p * 16 + m] += di * x[2 * s] + dq * x[2 * s + 1];
+                    gp[48 + p * 16 + m] += dq * x[2 * s] - di * x[2 * s + 1];
+                    if (gx) { gx[2 * s] += di * FI[p * 16 + m] + dq * FQ[p * 16 + m]; gx[2 * s + 1] += dq * FI[p * 16 + m] - di * FQ[p * 16 + m]; }
+                }
+            }
+        free(dfir);
+    }
+    free(sv);
+}
+
 static size_t n_params(int cell, int H, int K) {
     switch (cell) {
     case CELL_GRU: return (size_t)3 * H * 2 + 3 * H * H + 6 * H + 2 * H + 2;
@@ -1080,6 +1194,7 @@ static size_t n_params(int cell, int H, int K) {
     case CELL_BOJANET: return (size_t)2 * H * H + 28 * H + 194;
     case CELL_TCNN: return (size_t)29 * H;
     case CELL_NEURALTX: return (size_t)27 * H + 14;
+    case CELL_APNRRU: return (size_t)241 + 34 * (2 * H + 3) + 2 * H;
     case CELL_QGRU_QAT: case CELL_QGRU_AMP1_QAT: return (size_t)3 * H * 4 + 3 * H * H + 6 * H + 2 * H + 2 + 13;
     }
     return 0;
@@ -1097,6 +1212,7 @@ static void seq_dispatch(const Ctx *c, const REAL *x, const REAL *gout, REAL *ou
     case CELL_RVTDCNN: seq_rvtdcnn(c, x, gout, out, gx, gp, phase); break;
     case CELL_BOJANET: seq_bojanet(c, x, gout, out, gx, gp, phase); break;
     case CELL_TCNN: case CELL_NEURALTX: seq_tcn(c, x, gout, out, gx, gp, phase); break;
+    case CELL_APNRRU: seq_apnrru(c, x, gout, out, gx, gp, phase); break;
     case CELL_QGRU_QAT: case CELL_QGRU_AMP1_QAT: seq_qgru_qat(c, x, gout, out, gx, gp, phase); break;
     }
 }

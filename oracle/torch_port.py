@@ -33,6 +33,8 @@ def split_params(kind, flat, H, K=3):
         "tcnn": [("w0", (H, 6, 1)), ("b0", (H,)), ("d1", (H, 1, 5)), ("d2", (H, 1, 5)), ("d4", (H, 1, 5)), ("d8", (H, 1, 5)), ("w10", (2, H, 1))],
         "neuraltx": [("ci", (1, 1, 5)), ("cq", (1, 1, 5)), ("w0", (H, 4, 1)), ("b0", (H,)), ("d1", (H, 1, 5)), ("d2", (H, 1, 5)), ("d4", (H, 1, 5)),
                      ("d8", (H, 1, 5)), ("w10", (2, H, 1)), ("iq", (2, 2))],
+        "apnrru": [("fi", (3, 16)), ("fq", (3, 16)), ("C", (1,)), ("Z", (1, 2 * H + 3)), ("wu", (16, 2 * H + 11)), ("bu", (16,)),
+                   ("wh", (2 * H + 3, 16)), ("bh", (2 * H + 3,)), ("oi", (1, H)), ("oq", (1, H))],
         "rvtdcnn": [("wc", (3, 1, 3, 3)), ("bc", (3,)), ("wh", (H, 36)), ("bh", (H,)), ("wo", (2, H)), ("bo", (2,))],
     }
     shapes["qgru_amp1"] = shapes["qgru"]
@@ -185,6 +187,33 @@ def forward(kind, x, flat, H, K=3, thx=0.0, thh=0.0, L=1):
             hI = f * hI + (1 - f) * gc; hQ = f * hQ + (1 - f) * gs
             ys.append(torch.cat((Fn.linear(hI, p["wo1"], p["bo1"]), Fn.linear(hQ, p["wo2"], p["bo2"])), -1))
         return torch.stack(ys, 1)
+    if kind == "apnrru":      # apnrru.py:52-135
+        xx = torch.cat((torch.zeros_like(x[:, -15:, :]), x), 1)
+        win = xx.unfold(1, 16, 1).transpose(2, 3)                   # (B,T,16,2): tap m of window t = sample t+m-15
+        wi, wq = win[..., 0], win[..., 1]
+        i_fir = Fn.linear(wi, p["fi"]) - Fn.linear(wq, p["fq"])     # (B,T,3)
+        q_fir = Fn.linear(wi, p["fq"]) + Fn.linear(wq, p["fi"])
+        li, lq = x[..., 0], x[..., 1]
+        mag = torch.sqrt(li ** 2 + lq ** 2)
+        rr, ri = li / mag, -lq / mag                                 # r = conj(x)/|x|
+        a = torch.cat((i_fir, li.unsqueeze(-1)), -1)                 # (B,T,4) real parts
+        bq = torch.cat((q_fir, lq.unsqueeze(-1)), -1)
+        nre = rr.unsqueeze(-1) * a - ri.unsqueeze(-1) * bq
+        nim = ri.unsqueeze(-1) * a + rr.unsqueeze(-1) * bq
+        xin = torch.stack((nre, nim), -1).reshape(B, T, 8)
+        hI = x.new_zeros(B, H); hQ = x.new_zeros(B, H); hA = x.new_zeros(B, 3); outs = []
+        for t in range(T):
+            r0, r1 = rr[:, t:t + 1], ri[:, t:t + 1]
+            hI, hQ = hI * r0 - hQ * r1, hI * r1 + hQ * r0
+            hnew = torch.cat((hI, hQ, hA), -1)
+            v = torch.tanh(Fn.linear(torch.cat((xin[:, t], hnew), -1), p["wu"], p["bu"]))
+            v = torch.tanh(Fn.linear(v, p["wh"], p["bh"]))
+            v = torch.sigmoid(p["C"] * hnew) + p["Z"] * v
+            aI, aQ, hA = v[:, :H], v[:, H:2 * H], v[:, 2 * H:]
+            hI, hQ = r0 * aI + r1 * aQ, r0 * aQ - r1 * aI           # times conj(r)
+            oi, oq = Fn.linear(hI, p["oi"]), Fn.linear(hQ, p["oq"])
+            outs.append(torch.cat((oi - oq, oq + oi), -1))
+        return torch.stack(outs, 1)
     if kind == "bojanet":     # bojanet.py:54-106
         xx = torch.cat((torch.zeros_like(x[:, -15:, :]), x), 1)
         win = xx.unfold(1, 16, 1).transpose(2, 3)                   # (B,T,16,2): tap m of window t = sample t+m-15

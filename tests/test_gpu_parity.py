@@ -8,7 +8,7 @@ from tests.util import GOLDEN, golden_cases, load_golden, rel_err, tol_for, asse
 
 pytestmark = pytest.mark.gpu
 
-IMPLEMENTED = ("gru", "dgru", "qgru", "lstm", "deltagru", "tres", "pgjanet", "dvrjanet", "gmp", "qgruqat", "qgruamp1qat", "rvtdcnn", "bojanet", "tcnn", "neuraltx")
+IMPLEMENTED = ("gru", "dgru", "qgru", "lstm", "deltagru", "tres", "pgjanet", "dvrjanet", "gmp", "qgruqat", "qgruamp1qat", "rvtdcnn", "bojanet", "tcnn", "neuraltx", "apnrru")
 
 
 def _native_kinds():
@@ -19,7 +19,7 @@ def _native_kinds():
     have = set()
     for k, cell in (("gru", "gru"), ("dgru", "dgru"), ("qgru", "qgru"), ("lstm", "lstm"), ("deltagru", "deltagru"),
                     ("tres", "deltagru_tcnskip"), ("pgjanet", "pgjanet"), ("dvrjanet", "dvrjanet"), ("gmp", "gmp"),
-                    ("qgruqat", "qgru_qat"), ("qgruamp1qat", "qgru_amp1_qat"), ("rvtdcnn", "rvtdcnn"), ("bojanet", "bojanet"), ("tcnn", "tcnn"), ("neuraltx", "neuraltx")):
+                    ("qgruqat", "qgru_qat"), ("qgruamp1qat", "qgru_amp1_qat"), ("rvtdcnn", "rvtdcnn"), ("bojanet", "bojanet"), ("tcnn", "tcnn"), ("neuraltx", "neuraltx"), ("apnrru", "apnrru")):
         d = _ffi.OdpdDims(_ffi.CELLS[cell], 1, 1, 10, 3, 0, 0.0, 0.0)
         if L.odpd_saved_bytes(ctypes.byref(d)) >= 0:
             have.add(k)
@@ -109,7 +109,8 @@ def test_golden_parity(name, fused):
                                         ("rvtdcnn", 6, 16, 200), ("rvtdcnn", 64, 5, 1000), ("rvtdcnn", 20, 64, 2048),
                                         ("bojanet", 10, 16, 200), ("bojanet", 18, 5, 1000), ("bojanet", 6, 64, 2048),
                                         ("tcnn", 8, 16, 200), ("tcnn", 64, 5, 1000), ("tcnn", 15, 64, 2048),
-                                        ("neuraltx", 8, 16, 200), ("neuraltx", 64, 5, 1000), ("neuraltx", 15, 64, 2048)])
+                                        ("neuraltx", 8, 16, 200), ("neuraltx", 64, 5, 1000), ("neuraltx", 15, 64, 2048),
+                                        ("apnrru", 8, 16, 200), ("apnrru", 14, 5, 400), ("apnrru", 8, 64, 1024)])
 def test_oracle_parity_seeded(kind, H, B, T):
     """Same seeded inputs through the CUDA path and the CPU oracle (fp32 and fp64 arbiter)."""
     from oracle import oracle
@@ -119,6 +120,9 @@ def test_oracle_parity_seeded(kind, H, B, T):
         pytest.skip("backbone not built yet")
     thx, thh = (0.01, 0.05) if "delta" in kind else (0.0, 0.0)
     net = models.CoreModel(2, max(H, 1), 1, kind, num_dvr_units=3, thx=thx, thh=thh).cuda()
+    if kind == "apnrru":      # the reference starts Z at zero (apnrru.py:19), which silences the cell's two dense layers: exercise them
+        with torch.no_grad():
+            net.backbone.rru.Z.normal_(0.0, 0.5)
     gen = torch.Generator().manual_seed(7)
     xc = (0.2 * torch.randn(B, T, 2, generator=gen)).clamp(-0.7, 0.7)
     amp2 = (xc ** 2).sum(-1, keepdim=True)
