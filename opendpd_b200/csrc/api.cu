@@ -346,8 +346,6 @@ int odpd_backbone_bwd(const OdpdDims *d, const float *x, const float *params, co
         a.x = x; a.params = params; a.gout = gout; a.out_in = out; a.target = target;
         a.gscale = (float)gscale; a.gscale_dev = gscale_dev; a.gx = gx; a.partials = (float *)workspace; a.need_dx = dx;
         rc = rvtdcnn_run(a, 1, dw, st, &rows);
-    } else if (d->cell == ODPD_CELL_APNRRU) {
-        ODPD_CHECK(d->H >= 1 && d->H <= 14, "APNRRU hidden_size %d outside 1..14", d->H);
     } else if (d->cell == ODPD_CELL_BOJANET) {
         GruArgs a = wide_args(d);
         a.x = x; a.params = params; a.saved = (float *)saved; a.gout = gout; a.out_in = out; a.target = target;

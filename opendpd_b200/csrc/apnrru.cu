@@ -127,10 +127,29 @@ __global__ void __launch_bounds__(128) apn_chain_fwd_kernel(GruArgs a, ApBufs u)
     const int R = L.row();
     float *st = u.st + (size_t)b * T * R;
     float h = 0.f;                                    // lanes < H: h_I, H..2H-1: h_Q, 2H..2H+2: h_A
-    float qx = T > 0 ? __ldg(xp) : 0.f, qr = T > 0 ? __ldg(fr + 6) : 0.f, qi = T > 0 ? __ldg(fr + 7) : 0.f;
-    for (int t = 0; t < T; ++t) {
-        const float xpv = qx, rr = qr, ri = qi;
-        if (t + 1 < T) { qx = __ldg(xp + (size_t)(t + 1) * 16); qr = __ldg(fr + (size_t)(t + 1) * 12 + 6); qi = __ldg(fr + (size_t)(t + 1) * 12 + 7); }
+    // inputs of the next 4 steps are fetched while the current 4 run (a one-step-ahead register prefetch stalls on its own hand-over:
+    // ncu showed a third of all stall samples on the MOV that ends the iteration)
+    float cx[4], cr[4], ci[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        cx[i] = i < T ? __ldg(xp + (size_t)i * 16) : 0.f;
+        cr[i] = i < T ? __ldg(fr + (size_t)i * 12 + 6) : 0.f;
+        ci[i] = i < T ? __ldg(fr + (size_t)i * 12 + 7) : 0.f;
+    }
+    for (int t0 = 0; t0 < T; t0 += 4) {
+        float nx[4], nr[4], ni[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int tt = t0 + 4 + i;
+            nx[i] = tt < T ? __ldg(xp + (size_t)tt * 16) : 0.f;
+            nr[i] = tt < T ? __ldg(fr + (size_t)tt * 12 + 6) : 0.f;
+            ni[i] = tt < T ? __ldg(fr + (size_t)tt * 12 + 7) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+        const int t = t0 + i;
+        if (t < T) {
+        const float xpv = cx[i], rr = cr[i], ri = ci[i];
         // rotate the complex state by r
         const float hp = __shfl_sync(ODPD_FULL, h, partner);
         const float hn = lowI ? fmaf(h, rr, -hp * ri) : (upQ ? fmaf(hp, ri, h * rr) : h);
@@ -164,6 +183,10 @@ __global__ void __launch_bounds__(128) apn_chain_fwd_kernel(GruArgs a, ApBufs u)
         if (lane < 16) row[S + lane] = v1;
         if (lane < 2 * H) row[3 * S + 16 + lane] = h;
         __syncwarp();
+        }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { cx[i] = nx[i]; cr[i] = nr[i]; ci[i] = ni[i]; }
     }
 }
 
@@ -233,14 +256,22 @@ __global__ void __launch_bounds__(128) apn_chain_bwd_kernel(GruArgs a, ApBufs u)
     const int R = L.row();
     const float *st = u.st + (size_t)b * T * R;
     float gh = 0.f;                                   // adjoint of the state after step t (same lane layout as h)
-    for (int t = T - 1; t >= 0; --t) {
+    // everything a step reads from memory is fetched one step ahead: the serial loop never waits on a global load
+    struct StepIn { float rr, ri, da, dq, hn, v2, sg, v1, hprev; };
+    auto fetch = [&](int t) {
+        StepIn q{};
+        if (t < 0) return q;
         const float *row = st + (size_t)t * R;
-        const float rr = __ldg(fr + (size_t)t * 12 + 6), ri = __ldg(fr + (size_t)t * 12 + 7);
+        q.rr = __ldg(fr + (size_t)t * 12 + 6); q.ri = __ldg(fr + (size_t)t * 12 + 7);
         const float2 go = apn_go(a, b, t, gs);
-        const float da = go.x + go.y, dq = go.y - go.x;
-        const float hn = act ? __ldg(row + lane) : 0.f, v2 = act ? __ldg(row + S + 16 + lane) : 0.f, sg = act ? __ldg(row + 2 * S + 16 + lane) : 0.f;
-        const float v1 = lane < 16 ? __ldg(row + S + lane) : 0.f;
-        const float hprev = (lane < 2 * H && t > 0) ? __ldg(row - R + 3 * S + 16 + lane) : 0.f;
+        q.da = go.x + go.y; q.dq = go.y - go.x;
+        q.hn = act ? __ldg(row + lane) : 0.f; q.v2 = act ? __ldg(row + S + 16 + lane) : 0.f; q.sg = act ? __ldg(row + 2 * S + 16 + lane) : 0.f;
+        q.v1 = lane < 16 ? __ldg(row + S + lane) : 0.f;
+        q.hprev = (lane < 2 * H && t > 0) ? __ldg(row - R + 3 * S + 16 + lane) : 0.f;
+        return q;
+    };
+    auto step = [&](int t, const StepIn &c) {
+        const float rr = c.rr, ri = c.ri, da = c.da, dq = c.dq, v2 = c.v2, sg = c.sg, v1 = c.v1, hprev = c.hprev;
         const float vv = fmaf(Zs, v2, sg);
         // head + rotation back by conj(r):  h_I = rr aI + ri aQ,  h_Q = rr aQ - ri aI
         const float g = gh + (lowI ? da : dq) * wo;                         // lanes >= 2H: wo = 0
@@ -283,6 +314,14 @@ __global__ void __launch_bounds__(128) apn_chain_bwd_kernel(GruArgs a, ApBufs u)
         if (lane < 16) u.ga1[((size_t)b * T + t) * 16 + lane] = ga1;
         if (lane == 0) { u.grr[((size_t)b * T + t) * 2] = prr; u.grr[((size_t)b * T + t) * 2 + 1] = pri; }
         __syncwarp();
+    };
+    StepIn A = fetch(T - 1), Bq = fetch(T - 2);
+    for (int t = T - 1; t >= 0; t -= 2) {
+        const StepIn An = fetch(t - 2);
+        step(t, A);
+        const StepIn Bn = fetch(t - 3);
+        if (t - 1 >= 0) step(t - 1, Bq);
+        A = An; Bq = Bn;
     }
 }
 
