@@ -459,3 +459,27 @@ def test_vdlstm_oracle_parity_seeded(H, B, T, tchunks):
     assert_close(x.grad.cpu().numpy(), ref["gx"], 1e-5, "vdlstm gx")
     assert_close(grads_flat(net), ref["gparams"], 1e-5, "vdlstm gparams")
     assert abs(loss.item() - ref["loss"]) <= 1e-5 * abs(ref["loss"])
+
+
+@pytest.mark.parametrize("kind,H", [("rvtdcnn", 6), ("bojanet", 10), ("tcnn", 8), ("neuraltx", 8), ("apnrru", 8)])
+def test_f4_cells_inference_and_dx_only(kind, H):
+    """Row f-4 cells on the rest of the boundary: a forward under no_grad (net_eval, train_funcs.py:74: nothing saved) gives the same
+    output bit for bit, and with frozen parameters (the PA of a cascade, models.py:169-171) the dX-only backward equals the full one."""
+    from opendpd_b200 import models
+    torch.manual_seed(21)
+    net = models.CoreModel(2, H, 1, kind).cuda()
+    gen = torch.Generator().manual_seed(5)
+    xc = (0.25 * torch.randn(5, 150, 2, generator=gen)).clamp(-0.7, 0.7)
+    yc = 0.8 * xc
+    x = xc.cuda().requires_grad_(True)
+    out = net(x)
+    torch.nn.MSELoss()(out, yc.cuda()).backward()
+    gx_full = x.grad.clone()
+    with torch.no_grad():
+        out_inf = net(xc.cuda())
+    assert torch.equal(out_inf, out.detach())
+    for p in net.parameters():
+        p.requires_grad_(False)
+    x2 = xc.cuda().requires_grad_(True)
+    torch.nn.MSELoss()(net(x2), yc.cuda()).backward()
+    assert torch.equal(x2.grad, gx_full)
