@@ -11,5 +11,6 @@ from .rvtdcnn import RVTDCNN
 from .bojanet import BOJANET
 from .tcnn import TCNN, NeuralTX
 from .apnrru import APNRRU
+from .mcldnn import MCLDNN
 
-__all__ = ["GRU", "DGRU", "QGRU", "QGRUAmp1", "LSTM", "VDLSTM", "DeltaGRU", "TResDeltaGRU", "PGJANET", "DVRJANET", "GMP", "RVTDCNN", "BOJANET", "TCNN", "NeuralTX", "APNRRU"]
+__all__ = ["GRU", "DGRU", "QGRU", "QGRUAmp1", "LSTM", "VDLSTM", "DeltaGRU", "TResDeltaGRU", "PGJANET", "DVRJANET", "GMP", "RVTDCNN", "BOJANET", "TCNN", "NeuralTX", "APNRRU", "MCLDNN"]

@@ -94,6 +94,12 @@ int64_t apnrru_saved_floats(int B, int T, int H);
 int64_t apnrru_workspace_floats(int B, int T, int H);
 int apnrru_run(const GruArgs &a, int dir, bool dw, cudaStream_t st, int *rows_out);
 
+// mcldnn.cu : MCLDNN (linear convolutional front end composed in parameter space + LSTM(8) + two linear layers)
+int64_t mcldnn_nparams(int C);
+int64_t mcldnn_saved_floats(int B, int T, int C);
+int64_t mcldnn_workspace_floats(int B, int T, int C);
+int mcldnn_run(const GruArgs &a, int dir, bool dw, cudaStream_t st, int *rows_out);
+
 // remaining families (lstm.cu, delta.cu, janet.cu, gmp.cu) behind one dispatcher in others.cu
 int64_t other_nparams(int cell, int H, int K);
 int64_t other_saved_bytes(const OdpdDims *d);

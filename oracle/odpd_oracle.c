@@ -54,7 +54,7 @@
 #endif
 
 enum { CELL_GRU = 0, CELL_LSTM = 1, CELL_DGRU = 2, CELL_DELTAGRU = 3, CELL_TRES = 4, CELL_PGJANET = 5,
-       CELL_DVRJANET = 6, CELL_GMP = 7, CELL_QGRU = 8, CELL_QGRU_AMP1 = 9, CELL_QGRU_QAT = 10, CELL_QGRU_AMP1_QAT = 11, CELL_RVTDCNN = 13, CELL_BOJANET = 14, CELL_TCNN = 15, CELL_NEURALTX = 16, CELL_APNRRU = 17 };
+       CELL_DVRJANET = 6, CELL_GMP = 7, CELL_QGRU = 8, CELL_QGRU_AMP1 = 9, CELL_QGRU_QAT = 10, CELL_QGRU_AMP1_QAT = 11, CELL_RVTDCNN = 13, CELL_BOJANET = 14, CELL_TCNN = 15, CELL_NEURALTX = 16, CELL_APNRRU = 17, CELL_MCLDNN = 18 };
 
 typedef struct {
     int cell, B, T, H, K;
@@ -1179,6 +1179,173 @@ static void seq_apnrru(const Ctx *c, const REAL *x, const REAL *gout, REAL *out,
     free(sv);
 }
 
+/* ================================================================ MCLDNN: mcldnn.py:83-113
+ * features (I,Q,a,a^2,a^3) (:88-93); window of timestep t = samples (t-4+m) mod T, m = 0..4 (`pad = x[:, -(memory_length-1):, :]`, :96-99), laid out
+ * as a 5x5 image (feature, memory); conv2d_1 (1->C, 3x3, pad 1) (:101); conv1d over memory with the features as 5 groups (5 -> 5C, k=3, pad 1)
+ * re-viewed as (C,5,5): channel oc lands at [oc / 5][oc % 5] (:102-103); concatenated along the height (:104), transposed and convolved by
+ * conv2d_2 (10 -> 1, 3x3, pad 1) over (C,5) (:106); LSTM(5C -> 8) (:108); fc_out(8->16), fc_out_2(16->2), no activation in between (:109-110).
+ * params: conv2d_1.w(C,1,3,3) .b(C) conv1d.w(5C,1,3) .b(5C) conv2d_2.w(1,10,3,3) .b(1) lstm.w_ih(32,5C) w_hh(32,8) b_ih(32) b_hh(32)
+ *         fc_out.w(16,8) .b(16) fc_out_2.w(2,16) .b(2).   H = C (conv channels). */
+static void mcl_window(const REAL *x, int T, int t, REAL w[5][5], int sidx[5]) {
+    for (int m = 0; m < 5; ++m) {
+        int s = ((t - 4 + m) % T + T) % T;
+        sidx[m] = s;
+        volatile REAL i = x[2 * s], q = x[2 * s + 1];
+        volatile REAL ii = i * i, qq = q * q;
+        volatile REAL a2 = ii + qq;
+        volatile REAL a = R_SQRT(a2);
+        volatile REAL aa = a * a;
+        volatile REAL a3 = aa * a;
+        w[0][m] = i; w[1][m] = q; w[2][m] = a; w[3][m] = a2; w[4][m] = a3;
+    }
+}
+#define MZ(c, r, m) Zb[((c) * 10 + (r)) * 5 + (m)]
+static void mcl_front(const REAL *P, int C, REAL w[5][5], REAL *Zb, REAL *O) {
+    const REAL *W1 = P, *b1 = W1 + 9 * C, *Wc = b1 + C, *bc = Wc + 15 * C, *W2 = bc + 5 * C, *b2 = W2 + 90;
+    for (int c = 0; c < C; ++c)
+        for (int f = 0; f < 5; ++f)
+            for (int m = 0; m < 5; ++m) {
+                REAL v = b1[c];
+                for (int df = 0; df < 3; ++df)
+                    for (int dm = 0; dm < 3; ++dm) {
+                        int ff = f + df - 1, mm = m + dm - 1;
+                        if (ff < 0 || ff > 4 || mm < 0 || mm > 4) continue;
+                        v += W1[c * 9 + df * 3 + dm] * w[ff][mm];
+                    }
+                MZ(c, f, m) = v;
+            }
+    for (int oc = 0; oc < 5 * C; ++oc)
+        for (int m = 0; m < 5; ++m) {
+            REAL v = bc[oc];
+            for (int dm = 0; dm < 3; ++dm) { int mm = m + dm - 1; if (mm < 0 || mm > 4) continue; v += Wc[oc * 3 + dm] * w[oc / C][mm]; }
+            MZ(oc / 5, 5 + oc % 5, m) = v;
+        }
+    for (int c = 0; c < C; ++c)
+        for (int m = 0; m < 5; ++m) {
+            REAL v = b2[0];
+            for (int r = 0; r < 10; ++r)
+                for (int dc = 0; dc < 3; ++dc)
+                    for (int dm = 0; dm < 3; ++dm) {
+                        int cc = c + dc - 1, mm = m + dm - 1;
+                        if (cc < 0 || cc >= C || mm < 0 || mm > 4) continue;
+                        v += W2[r * 9 + dc * 3 + dm] * MZ(cc, r, mm);
+                    }
+            O[c * 5 + m] = v;
+        }
+}
+static void seq_mcldnn(const Ctx *c, const REAL *x, const REAL *gout, REAL *out, REAL *gx, REAL *gp, int phase) {
+    const int T = c->T, C = c->H, IN = 5 * C;
+    const size_t oW1 = 0, ob1 = 9 * C, oWc = ob1 + C, obc = oWc + 15 * C, oW2 = obc + 5 * C, ob2 = oW2 + 90, oWih = ob2 + 1, oWhh = oWih + (size_t)32 * IN,
+                 obih = oWhh + 256, obhh = obih + 32, oF1 = obhh + 32, oF1b = oF1 + 128, oF2 = oF1b + 16, oF2b = oF2 + 32;
+    const REAL *P = c->params, *Wih = P + oWih, *Whh = P + oWhh, *bih = P + obih, *bhh = P + obhh, *F1 = P + oF1, *F1b = P + oF1b, *F2 = P + oF2,
+               *F2b = P + oF2b;
+    REAL *Zb = (REAL *)malloc(sizeof(REAL) * (size_t)C * 50), *inp = (REAL *)malloc(sizeof(REAL) * (size_t)T * IN);
+    REAL *act = (REAL *)malloc(sizeof(REAL) * (size_t)T * 48);      /* i f g o c h per step */
+    REAL h[8] = {0}, cs[8] = {0};
+    for (int t = 0; t < T; ++t) {
+        REAL w[5][5]; int sidx[5];
+        mcl_window(x, T, t, w, sidx);
+        mcl_front(P, C, w, Zb, inp + (size_t)t * IN);
+        REAL g4[32];
+        for (int r = 0; r < 32; ++r) g4[r] = bih[r] + bhh[r] + dotv(Wih + (size_t)r * IN, inp + (size_t)t * IN, IN) + dotv(Whh + r * 8, h, 8);
+        REAL *a = act + 48 * t;
+        for (int j = 0; j < 8; ++j) {
+            const REAL ig = sigm(g4[j]), fg = sigm(g4[8 + j]), gg = R_TANH(g4[16 + j]), og = sigm(g4[24 + j]);
+            cs[j] = fg * cs[j] + ig * gg;
+            a[j] = ig; a[8 + j] = fg; a[16 + j] = gg; a[24 + j] = og; a[32 + j] = cs[j];
+        }
+        for (int j = 0; j < 8; ++j) { h[j] = a[24 + j] * R_TANH(cs[j]); a[40 + j] = h[j]; }
+        if (!phase) {
+            REAL y1[16];
+            for (int k = 0; k < 16; ++k) y1[k] = F1b[k] + dotv(F1 + 8 * k, h, 8);
+            out[2 * t] = F2b[0] + dotv(F2, y1, 16); out[2 * t + 1] = F2b[1] + dotv(F2 + 16, y1, 16);
+        }
+    }
+    if (phase) {
+        REAL dh[8] = {0}, dc[8] = {0};
+        REAL *dZ = (REAL *)malloc(sizeof(REAL) * (size_t)C * 50), *din = (REAL *)malloc(sizeof(REAL) * IN);
+        const REAL *W1 = P + oW1, *Wc = P + oWc, *W2 = P + oW2;
+        for (int t = T - 1; t >= 0; --t) {
+            const REAL *a = act + 48 * t, *ap = t > 0 ? a - 48 : NULL;
+            const REAL g0 = gout[2 * t], g1 = gout[2 * t + 1];
+            REAL y1[16], dy1[16], ga[32];
+            for (int k = 0; k < 16; ++k) { y1[k] = F1b[k] + dotv(F1 + 8 * k, a + 40, 8); dy1[k] = g0 * F2[k] + g1 * F2[16 + k]; }
+            gp[oF2b] += g0; gp[oF2b + 1] += g1;
+            for (int k = 0; k < 16; ++k) {
+                gp[oF2 + k] += g0 * y1[k]; gp[oF2 + 16 + k] += g1 * y1[k]; gp[oF1b + k] += dy1[k];
+                for (int j = 0; j < 8; ++j) { gp[oF1 + 8 * k + j] += dy1[k] * a[40 + j]; dh[j] += dy1[k] * F1[8 * k + j]; }
+            }
+            for (int j = 0; j < 8; ++j) {
+                const REAL ig = a[j], fg = a[8 + j], gg = a[16 + j], og = a[24 + j], tc = R_TANH(a[32 + j]), cp = ap ? ap[32 + j] : 0;
+                const REAL dcc = dc[j] + dh[j] * og * ((REAL)1 - tc * tc);
+                ga[j] = dcc * gg * ig * ((REAL)1 - ig);
+                ga[8 + j] = dcc * cp * fg * ((REAL)1 - fg);
+                ga[16 + j] = dcc * ig * ((REAL)1 - gg * gg);
+                ga[24 + j] = dh[j] * tc * og * ((REAL)1 - og);
+                dc[j] = dcc * fg;
+            }
+            for (int j = 0; j < 8; ++j) dh[j] = 0;
+            for (int k = 0; k < IN; ++k) din[k] = 0;
+            for (int r = 0; r < 32; ++r) {
+                gp[obih + r] += ga[r]; gp[obhh + r] += ga[r];
+                for (int k = 0; k < IN; ++k) { gp[oWih + (size_t)r * IN + k] += ga[r] * inp[(size_t)t * IN + k]; din[k] += ga[r] * Wih[(size_t)r * IN + k]; }
+                for (int j = 0; j < 8; ++j) { gp[oWhh + r * 8 + j] += ga[r] * (ap ? ap[40 + j] : 0); dh[j] += ga[r] * Whh[r * 8 + j]; }
+            }
+            /* front backward: recompute Z of this timestep */
+            REAL w[5][5], dw[5][5] = {{0}}, Otmp[64]; int sidx[5];
+            mcl_window(x, T, t, w, sidx);
+            mcl_front(P, C, w, Zb, Otmp);
+            memset(dZ, 0, sizeof(REAL) * (size_t)C * 50);
+            for (int cc = 0; cc < C; ++cc)
+                for (int m = 0; m < 5; ++m) {
+                    const REAL d = din[cc * 5 + m];
+                    gp[ob2] += d;
+                    for (int r = 0; r < 10; ++r)
+                        for (int dcx = 0; dcx < 3; ++dcx)
+                            for (int dm = 0; dm < 3; ++dm) {
+                                int c2 = cc + dcx - 1, mm = m + dm - 1;
+                                if (c2 < 0 || c2 >= C || mm < 0 || mm > 4) continue;
+                                gp[oW2 + r * 9 + dcx * 3 + dm] += d * MZ(c2, r, mm);
+                                dZ[(c2 * 10 + r) * 5 + mm] += d * W2[r * 9 + dcx * 3 + dm];
+                            }
+                }
+            for (int cc = 0; cc < C; ++cc)
+                for (int f = 0; f < 5; ++f)
+                    for (int m = 0; m < 5; ++m) {
+                        const REAL d = dZ[(cc * 10 + f) * 5 + m];
+                        gp[ob1 + cc] += d;
+                        for (int df = 0; df < 3; ++df)
+                            for (int dm = 0; dm < 3; ++dm) {
+                                int ff = f + df - 1, mm = m + dm - 1;
+                                if (ff < 0 || ff > 4 || mm < 0 || mm > 4) continue;
+                                gp[oW1 + cc * 9 + df * 3 + dm] += d * w[ff][mm];
+                                dw[ff][mm] += d * W1[cc * 9 + df * 3 + dm];
+                            }
+                    }
+            for (int oc = 0; oc < 5 * C; ++oc)
+                for (int m = 0; m < 5; ++m) {
+                    const REAL d = dZ[((oc / 5) * 10 + 5 + oc % 5) * 5 + m];
+                    gp[obc + oc] += d;
+                    for (int dm = 0; dm < 3; ++dm) {
+                        int mm = m + dm - 1; if (mm < 0 || mm > 4) continue;
+                        gp[oWc + oc * 3 + dm] += d * w[oc / C][mm];
+                        dw[oc / C][mm] += d * Wc[oc * 3 + dm];
+                    }
+                }
+            if (gx)
+                for (int m = 0; m < 5; ++m) {
+                    const REAL i = w[0][m], q = w[1][m], am = w[2][m], a2 = w[3][m];
+                    const REAL gam = dw[2][m] + (REAL)3 * a2 * dw[4][m];
+                    const REAL sc = (REAL)2 * dw[3][m] + gam / am;
+                    gx[2 * sidx[m]] += dw[0][m] + i * sc; gx[2 * sidx[m] + 1] += dw[1][m] + q * sc;
+                }
+        }
+        free(dZ); free(din);
+    }
+    free(Zb); free(inp); free(act);
+}
+#undef MZ
+
 static size_t n_params(int cell, int H, int K) {
     switch (cell) {
     case CELL_GRU: return (size_t)3 * H * 2 + 3 * H * H + 6 * H + 2 * H + 2;
@@ -1195,6 +1362,7 @@ static size_t n_params(int cell, int H, int K) {
     case CELL_TCNN: return (size_t)29 * H;
     case CELL_NEURALTX: return (size_t)27 * H + 14;
     case CELL_APNRRU: return (size_t)241 + 34 * (2 * H + 3) + 2 * H;
+    case CELL_MCLDNN: return (size_t)190 * H + 589;
     case CELL_QGRU_QAT: case CELL_QGRU_AMP1_QAT: return (size_t)3 * H * 4 + 3 * H * H + 6 * H + 2 * H + 2 + 13;
     }
     return 0;
@@ -1213,6 +1381,7 @@ static void seq_dispatch(const Ctx *c, const REAL *x, const REAL *gout, REAL *ou
     case CELL_BOJANET: seq_bojanet(c, x, gout, out, gx, gp, phase); break;
     case CELL_TCNN: case CELL_NEURALTX: seq_tcn(c, x, gout, out, gx, gp, phase); break;
     case CELL_APNRRU: seq_apnrru(c, x, gout, out, gx, gp, phase); break;
+    case CELL_MCLDNN: seq_mcldnn(c, x, gout, out, gx, gp, phase); break;
     case CELL_QGRU_QAT: case CELL_QGRU_AMP1_QAT: seq_qgru_qat(c, x, gout, out, gx, gp, phase); break;
     }
 }

@@ -35,6 +35,8 @@ def split_params(kind, flat, H, K=3):
                      ("d8", (H, 1, 5)), ("w10", (2, H, 1)), ("iq", (2, 2))],
         "apnrru": [("fi", (3, 16)), ("fq", (3, 16)), ("C", (1,)), ("Z", (1, 2 * H + 3)), ("wu", (16, 2 * H + 11)), ("bu", (16,)),
                    ("wh", (2 * H + 3, 16)), ("bh", (2 * H + 3,)), ("oi", (1, H)), ("oq", (1, H))],
+        "mcldnn": [("c1w", (H, 1, 3, 3)), ("c1b", (H,)), ("cdw", (5 * H, 1, 3)), ("cdb", (5 * H,)), ("c2w", (1, 10, 3, 3)), ("c2b", (1,)),
+                   ("wih", (32, 5 * H)), ("whh", (32, 8)), ("bih", (32,)), ("bhh", (32,)), ("f1w", (16, 8)), ("f1b", (16,)), ("f2w", (2, 16)), ("f2b", (2,))],
         "rvtdcnn": [("wc", (3, 1, 3, 3)), ("bc", (3,)), ("wh", (H, 36)), ("bh", (H,)), ("wo", (2, H)), ("bo", (2,))],
     }
     shapes["qgru_amp1"] = shapes["qgru"]
@@ -249,6 +251,20 @@ def forward(kind, x, flat, H, K=3, thx=0.0, thh=0.0, L=1):
         iq = torch.cat((i_f, q_f), -1)
         u = torch.cat((i_f, q_f, amp, torch.pow(amp, 3)), -1).transpose(1, 2)
         return stack(u).transpose(1, 2) + Fn.linear(iq, p["iq"]) + iq
+    if kind == "mcldnn":      # mcldnn.py:83-113  (H = conv channels; the LSTM is always 8 wide)
+        i, q = x[..., 0:1], x[..., 1:2]
+        amp2 = torch.pow(i, 2) + torch.pow(q, 2)
+        amp = torch.sqrt(amp2)
+        f = torch.cat((i, q, amp, amp2, torch.pow(amp, 3)), -1)
+        xx = torch.cat((f[:, -4:, :], f), 1)
+        win = xx.unfold(1, 5, 1).contiguous().view(-1, 1, 5, 5)      # (N, 1, feature, memory)
+        o2 = Fn.conv2d(win, p["c1w"], p["c1b"], 1, 1)                # (N, C, 5, 5)
+        o1 = Fn.conv1d(win.squeeze(1), p["cdw"], p["cdb"], 1, 1, 1, 5).view(-1, H, 5, 5)
+        o = torch.cat((o2, o1), 2)                                   # (N, C, 10, 5)
+        o = Fn.conv2d(o.transpose(1, 2), p["c2w"], p["c2b"], 1, 1).view(B, T, -1)
+        h0 = x.new_zeros(1, B, 8)
+        hseq, _, _ = torch._VF.lstm(o, (h0, h0), [p["wih"], p["whh"], p["bih"], p["bhh"]], True, 1, 0.0, x.is_cuda, False, True)
+        return Fn.linear(Fn.linear(hseq, p["f1w"], p["f1b"]), p["f2w"], p["f2b"])
     if kind == "rvtdcnn":     # rvtdcnn.py:36-62
         i, q = x[..., 0:1], x[..., 1:2]
         amp2 = torch.pow(i, 2) + torch.pow(q, 2)
