@@ -41,6 +41,7 @@
  *                                   rru.W_h.bias(S) output_layer_I.weight(1,H) output_layer_Q.weight(1,H),  S = 2H+3
  *   MCLDNN    (mcldnn.py:21-27)     conv2d_1.weight(H,1,3,3) .bias(H) conv1d.weight(5H,1,3) .bias(5H) conv2d_2.weight(1,10,3,3) .bias(1) lstm.weight_ih_l0(32,5H)
  *                                   weight_hh_l0(32,8) bias_ih_l0(32) bias_hh_l0(32) fc_out.weight(16,8) .bias(16) fc_out_2.weight(2,16) .bias(2)
+ *   DELTAJANET (deltajanet.py:97-105,27-29) rnn.weight_ih_l0(2H,6) weight_hh_l0(2H,H) bias_ih_l0(2H) bias_hh_l0(2H) fc_out.weight(2,H) fc_out.bias(2)
  *   QGRU_QAT  (quant_envs.py:215-305 applied to qgru.py) rnn.rnn_cell_list.0.x2h.weight(3H,4) .bias(3H) .weight_quantizer.scale .act_quantizer.scale
  *                                   .out_quantizer.scale | h2h.weight(3H,H) .bias(3H) + 3 scales | sigmoid/tanh/add/mul .quantizer.scale |
  *                                   fc_out.weight(2,H) .bias(2) + 3 scales.   For the QAT cells OdpdDims.K packs n_bits_w | n_bits_a<<8 | eval<<16.
@@ -84,7 +85,8 @@ enum {
     ODPD_CELL_NEURALTX = 16, /* backbones/neuraltx.py:107-124 (row f-4): H = hidden_channels (1..64) */
     ODPD_CELL_APNRRU = 17,   /* backbones/apnrru.py:52-135 (row f-4): hidden_size 1..14 (2H+3 state values, one per warp lane) */
     ODPD_CELL_MCLDNN = 18,   /* backbones/mcldnn.py:83-113 (row f-4): H = conv channels (1..12); the LSTM inside is always 8 wide; frame_length >= 4 */
-    ODPD_CELL_COUNT = 19
+    ODPD_CELL_DELTAJANET = 19, /* backbones/deltajanet.py:49-60, 203-262 (row f-4): hidden_size 1..16; thx / thh are ignored like in the reference (:22-26) */
+    ODPD_CELL_COUNT = 20
 };
 
 /* flags */

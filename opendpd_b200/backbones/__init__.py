@@ -12,5 +12,6 @@ from .bojanet import BOJANET
 from .tcnn import TCNN, NeuralTX
 from .apnrru import APNRRU
 from .mcldnn import MCLDNN
+from .deltajanet import DeltaJANET
 
-__all__ = ["GRU", "DGRU", "QGRU", "QGRUAmp1", "LSTM", "VDLSTM", "DeltaGRU", "TResDeltaGRU", "PGJANET", "DVRJANET", "GMP", "RVTDCNN", "BOJANET", "TCNN", "NeuralTX", "APNRRU", "MCLDNN"]
+__all__ = ["GRU", "DGRU", "QGRU", "QGRUAmp1", "LSTM", "VDLSTM", "DeltaGRU", "TResDeltaGRU", "PGJANET", "DVRJANET", "GMP", "RVTDCNN", "BOJANET", "TCNN", "NeuralTX", "APNRRU", "MCLDNN", "DeltaJANET"]

@@ -5,7 +5,7 @@ unchanged.  Backbones outside the hot-path scope (SURVEY.md §2
 import torch
 from torch import nn
 
-NATIVE_BACKBONES = ("gmp", "gru", "dgru", "qgru", "qgru_amp1", "lstm", "vdlstm", "deltagru", "deltagru_tcnskip", "pgjanet", "dvrjanet", "rvtdcnn", "bojanet", "tcnn", "neuraltx", "apnrru", "mcldnn")
+NATIVE_BACKBONES = ("gmp", "gru", "dgru", "qgru", "qgru_amp1", "lstm", "vdlstm", "deltagru", "deltagru_tcnskip", "pgjanet", "dvrjanet", "rvtdcnn", "bojanet", "tcnn", "neuraltx", "apnrru", "mcldnn", "deltajanet")
 
 
 class CoreModel(nn.Module):
@@ -43,6 +43,9 @@ class CoreModel(nn.Module):
             self.backbone = bb.DVRJANET(hidden_size=hidden_size, output_size=2, num_dvr_units=num_dvr_units, bias=True)
         elif backbone_type == "gmp":
             self.backbone = bb.GMP()
+        elif backbone_type == "deltajanet":
+            self.backbone = bb.DeltaJANET(input_size=6, hidden_size=hidden_size, output_size=2, num_layers=num_layers,
+                                          thx=thx, thh=thh, bias=True)                          # models.py:100-108
         elif backbone_type == "mcldnn":
             self.backbone = bb.MCLDNN(hidden_size=hidden_size)                                  # models.py:136-138
         elif backbone_type == "apnrru":

@@ -193,6 +193,9 @@ CASES = [
     ("mcldnn_h8_b3_t50",           "mcldnn", 8, 3, 50, 65, 0, 0),
     ("mcldnn_h12_b2_t70",          "mcldnn", 12, 2, 70, 66, 0, 0),
     ("mcldnn_h2_b2_t5",            "mcldnn", 2, 2, 5, 67, 0, 0),
+    ("deltajanet_h10_b3_t50",      "deltajanet", 10, 3, 50, 68, 0.01, 0.05),     # thx / thh are accepted and ignored by the reference (deltajanet.py:22-26)
+    ("deltajanet_h16_b2_t70",      "deltajanet", 16, 2, 70, 69, 0, 0),
+    ("deltajanet_h3_b2_t2",        "deltajanet", 3, 2, 2, 70, 0, 0),
     # hidden sizes above the fused tiers and stacked layers (arguments.py:51,60 -> nn.GRU/nn.LSTM num_layers): 10th field = num_layers
     ("wide_gru_h48_b3_t70",        "gru",  48, 3, 70, 40, 0, 0, 3, 1),
     ("wide_gru_h16_l2_b3_t40",     "gru",  16, 3, 40, 41, 0, 0, 3, 2),

@@ -54,7 +54,7 @@
 #endif
 
 enum { CELL_GRU = 0, CELL_LSTM = 1, CELL_DGRU = 2, CELL_DELTAGRU = 3, CELL_TRES = 4, CELL_PGJANET = 5,
-       CELL_DVRJANET = 6, CELL_GMP = 7, CELL_QGRU = 8, CELL_QGRU_AMP1 = 9, CELL_QGRU_QAT = 10, CELL_QGRU_AMP1_QAT = 11, CELL_RVTDCNN = 13, CELL_BOJANET = 14, CELL_TCNN = 15, CELL_NEURALTX = 16, CELL_APNRRU = 17, CELL_MCLDNN = 18 };
+       CELL_DVRJANET = 6, CELL_GMP = 7, CELL_QGRU = 8, CELL_QGRU_AMP1 = 9, CELL_QGRU_QAT = 10, CELL_QGRU_AMP1_QAT = 11, CELL_RVTDCNN = 13, CELL_BOJANET = 14, CELL_TCNN = 15, CELL_NEURALTX = 16, CELL_APNRRU = 17, CELL_MCLDNN = 18, CELL_DELTAJANET = 19 };
 
 typedef struct {
     int cell, B, T, H, K;
@@ -1346,6 +1346,72 @@ static void seq_mcldnn(const Ctx *c, const REAL *x, const REAL *gout, REAL *out,
 }
 #undef MZ
 
+/* ================================================================ DeltaJANET: deltajanet.py:49-60 (features), :203-262 (layer)
+ * The outer module builds its layer with thx = thh = 0 (:22-26), so every delta passes its threshold and the states track every step:
+ * dx_t = f_t - f_{t-1}, dh_t = h_{t-1} - h_{t-2} (zero states before the frame); M += W_ih dx + W_hh dh, M_0 = b_ih + b_hh (:160-167);
+ * f = sigm(M_f), g = sigm(M_g) (both sigmoids, :246-247), h = (1-f) g + f h (:248); out = fc_out(h).
+ * The accumulator is summed in the reference's order: (W_ih dx + M) + W_hh dh (:196-202).
+ * params: rnn.weight_ih_l0(2H,6) weight_hh_l0(2H,H) bias_ih_l0(2H) bias_hh_l0(2H) fc_out.weight(2,H) fc_out.bias(2). */
+static void seq_deltajanet(const Ctx *c, const REAL *x, const REAL *gout, REAL *out, REAL *gx, REAL *gp, int phase) {
+    const int T = c->T, H = c->H, G = 2 * H;
+    const size_t oWih = 0, oWhh = (size_t)G * 6, obih = oWhh + (size_t)G * H, obhh = obih + G, oWo = obhh + G, obo = oWo + 2 * H;
+    const REAL *P = c->params, *Wih = P, *Whh = P + oWhh, *bih = P + obih, *bhh = P + obhh, *Wo = P + oWo, *bo = P + obo;
+    REAL *ft = (REAL *)calloc((size_t)(T + 1) * 8, sizeof(REAL));          /* ft[t+1] = features of step t, ft[0] = 0 */
+    REAL *act = (REAL *)calloc((size_t)(T + 2) * 3 * H, sizeof(REAL));     /* rows t+2: f | g | h of step t; rows 0,1 = zero state */
+    REAL M[64];
+    for (int r = 0; r < G; ++r) M[r] = bih[r] + bhh[r];
+    for (int t = 0; t < T; ++t) {
+        features_fwd(CELL_DGRU, x, T, t, ft + 8 * (t + 1));
+        REAL dx[6], dh[32];
+        for (int k = 0; k < 6; ++k) dx[k] = ft[8 * (t + 1) + k] - ft[8 * t + k];
+        const REAL *h1 = act + (size_t)(t + 1) * 3 * H + 2 * H, *h2 = act + (size_t)t * 3 * H + 2 * H;
+        for (int k = 0; k < H; ++k) dh[k] = h1[k] - h2[k];
+        for (int r = 0; r < G; ++r) { REAL mx = dotv(Wih + 6 * r, dx, 6) + M[r]; M[r] = mx + dotv(Whh + (size_t)H * r, dh, H); }
+        REAL *a = act + (size_t)(t + 2) * 3 * H;
+        for (int j = 0; j < H; ++j) {
+            const REAL f = sigm(M[j]), g = sigm(M[H + j]);
+            a[j] = f; a[H + j] = g; a[2 * H + j] = ((REAL)1 - f) * g + f * h1[j];
+        }
+        if (!phase) { out[2 * t] = bo[0] + dotv(Wo, a + 2 * H, H); out[2 * t + 1] = bo[1] + dotv(Wo + H, a + 2 * H, H); }
+    }
+    if (phase) {
+        REAL gM[64] = {0}, gH[32] = {0}, pend[32] = {0};
+        REAL *GMs = (REAL *)calloc((size_t)(T + 1) * G, sizeof(REAL));      /* running adjoint of M at step t (row T = 0) */
+        for (int t = T - 1; t >= 0; --t) {
+            const REAL *a = act + (size_t)(t + 2) * 3 * H, *h1 = a - 3 * H + 2 * H, *h2 = a - 6 * H + 2 * H;
+            const REAL g0 = gout[2 * t], g1 = gout[2 * t + 1];
+            gp[obo] += g0; gp[obo + 1] += g1;
+            REAL at[32] = {0}, nH[32];
+            for (int j = 0; j < H; ++j) {
+                gp[oWo + j] += g0 * a[2 * H + j]; gp[oWo + H + j] += g1 * a[2 * H + j];
+                const REAL gh = gH[j] + g0 * Wo[j] + g1 * Wo[H + j];
+                const REAL f = a[j], g = a[H + j];
+                gM[j] += gh * (h1[j] - g) * f * ((REAL)1 - f);
+                gM[H + j] += gh * ((REAL)1 - f) * g * ((REAL)1 - g);
+                nH[j] = gh * f;
+            }
+            for (int r = 0; r < G; ++r) {
+                GMs[(size_t)t * G + r] = gM[r];
+                for (int k = 0; k < 6; ++k) gp[oWih + 6 * r + k] += gM[r] * (ft[8 * (t + 1) + k] - ft[8 * t + k]);
+                for (int k = 0; k < H; ++k) { gp[oWhh + (size_t)H * r + k] += gM[r] * (h1[k] - h2[k]); at[k] += gM[r] * Whh[(size_t)H * r + k]; }
+            }
+            for (int k = 0; k < H; ++k) { gH[k] = nH[k] + at[k] + pend[k]; pend[k] = -at[k]; }
+        }
+        for (int r = 0; r < G; ++r) { gp[obih + r] += gM[r]; gp[obhh + r] += gM[r]; }
+        if (gx)
+            for (int t = 0; t < T; ++t) {
+                REAL gf[8] = {0};
+                for (int r = 0; r < G; ++r) {
+                    const REAL d = GMs[(size_t)t * G + r] - GMs[(size_t)(t + 1) * G + r];
+                    for (int k = 0; k < 6; ++k) gf[k] += d * Wih[6 * r + k];
+                }
+                features_bwd(CELL_DGRU, x, T, t, gf, gx);
+            }
+        free(GMs);
+    }
+    free(ft); free(act);
+}
+
 static size_t n_params(int cell, int H, int K) {
     switch (cell) {
     case CELL_GRU: return (size_t)3 * H * 2 + 3 * H * H + 6 * H + 2 * H + 2;
@@ -1363,6 +1429,7 @@ static size_t n_params(int cell, int H, int K) {
     case CELL_NEURALTX: return (size_t)27 * H + 14;
     case CELL_APNRRU: return (size_t)241 + 34 * (2 * H + 3) + 2 * H;
     case CELL_MCLDNN: return (size_t)190 * H + 589;
+    case CELL_DELTAJANET: return (size_t)2 * H * H + 18 * H + 2;
     case CELL_QGRU_QAT: case CELL_QGRU_AMP1_QAT: return (size_t)3 * H * 4 + 3 * H * H + 6 * H + 2 * H + 2 + 13;
     }
     return 0;
@@ -1382,6 +1449,7 @@ static void seq_dispatch(const Ctx *c, const REAL *x, const REAL *gout, REAL *ou
     case CELL_TCNN: case CELL_NEURALTX: seq_tcn(c, x, gout, out, gx, gp, phase); break;
     case CELL_APNRRU: seq_apnrru(c, x, gout, out, gx, gp, phase); break;
     case CELL_MCLDNN: seq_mcldnn(c, x, gout, out, gx, gp, phase); break;
+    case CELL_DELTAJANET: seq_deltajanet(c, x, gout, out, gx, gp, phase); break;
     case CELL_QGRU_QAT: case CELL_QGRU_AMP1_QAT: seq_qgru_qat(c, x, gout, out, gx, gp, phase); break;
     }
 }

@@ -37,6 +37,7 @@ def split_params(kind, flat, H, K=3):
                    ("wh", (2 * H + 3, 16)), ("bh", (2 * H + 3,)), ("oi", (1, H)), ("oq", (1, H))],
         "mcldnn": [("c1w", (H, 1, 3, 3)), ("c1b", (H,)), ("cdw", (5 * H, 1, 3)), ("cdb", (5 * H,)), ("c2w", (1, 10, 3, 3)), ("c2b", (1,)),
                    ("wih", (32, 5 * H)), ("whh", (32, 8)), ("bih", (32,)), ("bhh", (32,)), ("f1w", (16, 8)), ("f1b", (16,)), ("f2w", (2, 16)), ("f2b", (2,))],
+        "deltajanet": [("w_ih", (2 * H, 6)), ("w_hh", (2 * H, H)), ("b_ih", (2 * H,)), ("b_hh", (2 * H,)), ("wo", (2, H)), ("bo", (2,))],
         "rvtdcnn": [("wc", (3, 1, 3, 3)), ("bc", (3,)), ("wh", (H, 36)), ("bh", (H,)), ("wo", (2, H)), ("bo", (2,))],
     }
     shapes["qgru_amp1"] = shapes["qgru"]
@@ -189,6 +190,21 @@ def forward(kind, x, flat, H, K=3, thx=0.0, thh=0.0, L=1):
             hI = f * hI + (1 - f) * gc; hQ = f * hQ + (1 - f) * gs
             ys.append(torch.cat((Fn.linear(hI, p["wo1"], p["bo1"]), Fn.linear(hQ, p["wo2"], p["bo2"])), -1))
         return torch.stack(ys, 1)
+    if kind == "deltajanet":  # deltajanet.py:49-60, 203-262 — the layer is built with thx = thh = 0 (:22-26): every delta passes
+        f = _feat("dgru", x)
+        xp = f.new_zeros(B, 6); h = f.new_zeros(B, H); hp = f.new_zeros(B, H)
+        M = f.new_zeros(B, 2 * H) + (p["b_ih"] + p["b_hh"])
+        hs = []
+        for t in range(T):
+            dx, dh = f[:, t] - xp, h - hp
+            xp, hp = f[:, t], h
+            mx = torch.mm(dx, p["w_ih"].t()) + M
+            mh = torch.mm(dh, p["w_hh"].t())
+            M = torch.cat((mx[:, :H] + mh[:, :H], mx[:, H:] + mh[:, H:]), 1)
+            gf, gg = torch.sigmoid(M[:, :H]), torch.sigmoid(M[:, H:])
+            h = (1 - gf) * gg + gf * h
+            hs.append(h)
+        return Fn.linear(torch.stack(hs, 1), p["wo"], p["bo"])
     if kind == "apnrru":      # apnrru.py:52-135
         xx = torch.cat((torch.zeros_like(x[:, -15:, :]), x), 1)
         win = xx.unfold(1, 16, 1).transpose(2, 3)                   # (B,T,16,2): tap m of window t = sample t+m-15

@@ -10,7 +10,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 KINDS = [("gru", 16), ("dgru", 13), ("dgru", 23), ("qgru", 10), ("lstm", 9), ("deltagru", 15), ("deltagru_tcnskip", 15), ("pgjanet", 15),
-         ("dvrjanet", 15), ("gmp", 1), ("vdlstm", 9), ("rvtdcnn", 6), ("gru", 40), ("bojanet", 10), ("tcnn", 8), ("neuraltx", 8), ("apnrru", 8), ("mcldnn", 8)]
+         ("dvrjanet", 15), ("gmp", 1), ("vdlstm", 9), ("rvtdcnn", 6), ("gru", 40), ("bojanet", 10), ("tcnn", 8), ("neuraltx", 8), ("apnrru", 8), ("mcldnn", 8), ("deltajanet", 10)]
 
 
 def _net(kind, H):

@@ -8,7 +8,7 @@ from tests.util import GOLDEN, golden_cases, load_golden, rel_err, tol_for, asse
 
 pytestmark = pytest.mark.gpu
 
-IMPLEMENTED = ("gru", "dgru", "qgru", "lstm", "deltagru", "tres", "pgjanet", "dvrjanet", "gmp", "qgruqat", "qgruamp1qat", "rvtdcnn", "bojanet", "tcnn", "neuraltx", "apnrru", "mcldnn")
+IMPLEMENTED = ("gru", "dgru", "qgru", "lstm", "deltagru", "tres", "pgjanet", "dvrjanet", "gmp", "qgruqat", "qgruamp1qat", "rvtdcnn", "bojanet", "tcnn", "neuraltx", "apnrru", "mcldnn", "deltajanet")
 
 
 def _native_kinds():
@@ -19,7 +19,7 @@ def _native_kinds():
     have = set()
     for k, cell in (("gru", "gru"), ("dgru", "dgru"), ("qgru", "qgru"), ("lstm", "lstm"), ("deltagru", "deltagru"),
                     ("tres", "deltagru_tcnskip"), ("pgjanet", "pgjanet"), ("dvrjanet", "dvrjanet"), ("gmp", "gmp"),
-                    ("qgruqat", "qgru_qat"), ("qgruamp1qat", "qgru_amp1_qat"), ("rvtdcnn", "rvtdcnn"), ("bojanet", "bojanet"), ("tcnn", "tcnn"), ("neuraltx", "neuraltx"), ("apnrru", "apnrru"), ("mcldnn", "mcldnn")):
+                    ("qgruqat", "qgru_qat"), ("qgruamp1qat", "qgru_amp1_qat"), ("rvtdcnn", "rvtdcnn"), ("bojanet", "bojanet"), ("tcnn", "tcnn"), ("neuraltx", "neuraltx"), ("apnrru", "apnrru"), ("mcldnn", "mcldnn"), ("deltajanet", "deltajanet")):
         d = _ffi.OdpdDims(_ffi.CELLS[cell], 1, 1, 10, 3, 0, 0.0, 0.0)
         if L.odpd_saved_bytes(ctypes.byref(d)) >= 0:
             have.add(k)
@@ -111,7 +111,8 @@ def test_golden_parity(name, fused):
                                         ("tcnn", 8, 16, 200), ("tcnn", 64, 5, 1000), ("tcnn", 15, 64, 2048),
                                         ("neuraltx", 8, 16, 200), ("neuraltx", 64, 5, 1000), ("neuraltx", 15, 64, 2048),
                                         ("apnrru", 8, 16, 200), ("apnrru", 14, 5, 400), ("apnrru", 8, 64, 1024),
-                                        ("mcldnn", 8, 16, 200), ("mcldnn", 12, 5, 400), ("mcldnn", 3, 64, 1024)])
+                                        ("mcldnn", 8, 16, 200), ("mcldnn", 12, 5, 400), ("mcldnn", 3, 64, 1024),
+                                        ("deltajanet", 10, 16, 200), ("deltajanet", 16, 5, 400), ("deltajanet", 8, 64, 1024)])
 def test_oracle_parity_seeded(kind, H, B, T):
     """Same seeded inputs through the CUDA path and the CPU oracle (fp32 and fp64 arbiter)."""
     from oracle import oracle
@@ -119,7 +120,7 @@ def test_oracle_parity_seeded(kind, H, B, T):
     torch.manual_seed(1234)
     if _kind_key(kind) not in _native_kinds():
         pytest.skip("backbone not built yet")
-    thx, thh = (0.01, 0.05) if "delta" in kind else (0.0, 0.0)
+    thx, thh = (0.01, 0.05) if ("delta" in kind and kind != "deltajanet") else (0.0, 0.0)
     net = models.CoreModel(2, max(H, 1), 1, kind, num_dvr_units=3, thx=thx, thh=thh).cuda()
     if kind == "apnrru":      # the reference starts Z at zero (apnrru.py:19), which silences the cell's two dense layers: exercise them
         with torch.no_grad():
@@ -462,7 +463,7 @@ def test_vdlstm_oracle_parity_seeded(H, B, T, tchunks):
     assert abs(loss.item() - ref["loss"]) <= 1e-5 * abs(ref["loss"])
 
 
-@pytest.mark.parametrize("kind,H", [("rvtdcnn", 6), ("bojanet", 10), ("tcnn", 8), ("neuraltx", 8), ("apnrru", 8), ("mcldnn", 8)])
+@pytest.mark.parametrize("kind,H", [("rvtdcnn", 6), ("bojanet", 10), ("tcnn", 8), ("neuraltx", 8), ("apnrru", 8), ("mcldnn", 8), ("deltajanet", 10)])
 def test_f4_cells_inference_and_dx_only(kind, H):
     """Row f-4 cells on the rest of the boundary: a forward under no_grad (net_eval, train_funcs.py:74: nothing saved) gives the same
     output bit for bit, and with frozen parameters (the PA of a cascade, models.py:169-171) the dX-only backward equals the full one."""

@@ -34,7 +34,7 @@ def _flat(net):
 
 
 @pytest.mark.parametrize("kind,H", [("dgru", 13), ("gru", 32), ("deltagru_tcnskip", 15), ("pgjanet", 10), ("gmp", 1), ("lstm", 9),
-                                    ("dvrjanet", 10), ("qgru_qat", 10), ("vdlstm", 9), ("rvtdcnn", 6), ("bojanet", 10), ("tcnn", 8), ("neuraltx", 8), ("apnrru", 8), ("mcldnn", 8)])
+                                    ("dvrjanet", 10), ("qgru_qat", 10), ("vdlstm", 9), ("rvtdcnn", 6), ("bojanet", 10), ("tcnn", 8), ("neuraltx", 8), ("apnrru", 8), ("mcldnn", 8), ("deltajanet", 10)])
 def test_fused_step_equals_stock_loop(kind, H):
     from opendpd_b200 import models
     from opendpd_b200.train import NativeTrainStep

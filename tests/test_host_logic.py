@@ -95,7 +95,7 @@ def test_unsupported_configs_raise():
     with pytest.raises(NotImplementedError):
         models.CoreModel(2, 8, 2, "deltagru")
     with pytest.raises(ValueError):
-        models.CoreModel(2, 8, 1, "deltajanet")      # not built
+        models.CoreModel(2, 8, 1, "mamba")           # a name arguments.py:46 lists but models.py has no branch for
 
 
 def test_dims_struct_matches_the_header_layout():
