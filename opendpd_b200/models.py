@@ -1,7 +1,7 @@
 """CoreModel / CascadedModel — mirror of reference models.py:10-176 that instantiates the native backbones.
 
 Same constructor signature, attributes and parameter names (`backbone.*`), so `project.py`/`steps/*.py` use it
-unchanged.  Backbones outside the hot-path scope are not provided here."""
+unchanged.  Every backbone the reference's CoreModel can build (models.py:26-141) has a native class here."""
 import torch
 from torch import nn
 
