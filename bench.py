@@ -40,7 +40,20 @@ WORKLOADS = {
     "c5q": dict(name="C5: QGRU H=10 W8A8 QAT (515 params) step, global B=512 x T=50, fp32 fake-quant", kind="qgru_qat", H=10, B=512, T=50,
                 dataset="DPA_200MHz"),
     "lstm": dict(name="LSTM H=9 (488 params) train_pa step, B=64 x T=2048, fp32", kind="lstm", H=9, B=64, T=2048, dataset="APA_200MHz"),
+    # SURVEY §8 row f-4 (every other backbone models.py can build) and the layered path, train_pa step, B=64 x T=2048 real frames
+    "f4_vdlstm": dict(name="VDLSTM H=9", kind="vdlstm", H=9, B=64, T=2048, dataset="APA_200MHz"),
+    "f4_bojanet": dict(name="BOJANET H=10", kind="bojanet", H=10, B=64, T=2048, dataset="APA_200MHz"),
+    "f4_apnrru": dict(name="APNRRU H=8", kind="apnrru", H=8, B=64, T=2048, dataset="APA_200MHz"),
+    "f4_deltajanet": dict(name="DeltaJANET H=10", kind="deltajanet", H=10, B=64, T=2048, dataset="APA_200MHz"),
+    "f4_mcldnn": dict(name="MCLDNN C=8", kind="mcldnn", H=8, B=64, T=2048, dataset="APA_200MHz"),
+    "f4_rvtdcnn": dict(name="RVTDCNN H=6", kind="rvtdcnn", H=6, B=64, T=2048, dataset="APA_200MHz"),
+    "f4_tcnn": dict(name="TCNN C=8", kind="tcnn", H=8, B=64, T=2048, dataset="APA_200MHz"),
+    "f4_neuraltx": dict(name="NeuralTX C=8", kind="neuraltx", H=8, B=64, T=2048, dataset="APA_200MHz"),
+    "wide_dgru64": dict(name="DGRU H=64 (layered path)", kind="dgru", H=64, B=64, T=2048, dataset="APA_200MHz"),
+    "wide_gru32x2": dict(name="GRU H=32, 2 layers (layered path)", kind="gru", H=32, L=2, B=64, T=2048, dataset="APA_200MHz"),
 }
+OTHER_BACKBONES = ("f4_vdlstm", "f4_bojanet", "f4_apnrru", "f4_deltajanet", "f4_mcldnn", "f4_rvtdcnn", "f4_tcnn", "f4_neuraltx", "wide_dgru64",
+                   "wide_gru32x2")   # 1-GPU lines only: coverage, ms per whole train step
 SECONDARY = ("c2a", "c3", "c4p", "c4d", "c5g", "c5q")   # extra keys of the line: fixed GLOBAL batch split over the ranks (strong scaling)
 ALGO_BYTES_PER_SAMPLE_PER_KERNEL = 16  # fwd reads x(8)+target(8); bwd re-reads x(8)+target/dout(8)  => 32 B/sample/step
 STREAMS = os.path.join(ROOT, "tests", "golden", "iq_streams.npz")
@@ -280,7 +293,7 @@ def build_trainer(wl, dev, pg, world):
             quant, n_bits_w, n_bits_a, pretrained_model = True, 8, 8, ""
         net = get_quant_model(_Proj(), models.CoreModel(2, wl["H"], 1, "qgru")).to(dev).train()
     else:
-        net = models.CoreModel(2, wl["H"], 1, wl["kind"], num_dvr_units=3, thx=0.01, thh=0.05).to(dev)
+        net = models.CoreModel(2, wl["H"], wl.get("L", 1), wl["kind"], num_dvr_units=3, thx=0.01, thh=0.05).to(dev)
     if "pa" in wl:                                      # train_dpd: DPD in front of a frozen PA (steps/train_dpd.py:60-63)
         torch.manual_seed(1)
         pa_net = models.CoreModel(2, wl["pa"][1], 1, wl["pa"][0]).to(dev)
@@ -663,6 +676,25 @@ def main():
                 secondary[name] = {"error": repr(e)[:300]}
                 if world > 1:
                     raise
+
+    # ---- every other backbone of the reference + the layered path: whole train step, short runs (single-GPU lines only)
+    if not args.no_secondary and args.workload == "c2a" and world == 1:
+        others = {}
+        for name in OTHER_BACKBONES:
+            w2 = WORKLOADS[name]
+            try:
+                r2 = Run(w2, dev, pg, world, rank, weak=False, settle=40)
+                K2 = 10
+                ms2, l2 = r2.timed(3, K2, flush)
+                others[name] = {"backbone": w2["name"], "ms_per_step": round(ms2 / K2, 4), "value": r2.GB * r2.T * K2 / (ms2 * 1e-3),
+                                "final_loss": float(l2[-1])}
+                r2.close()
+                del r2
+                torch.cuda.empty_cache()
+            except Exception as e:
+                others[name] = {"error": repr(e)[:300]}
+        secondary["other_backbones"] = {"what": "train_pa step (fwd + MSE + bwd + clip + AdamW), B=64 x T=2048 real APA_200MHz frames, 40 settle + 10 timed "
+                                                "steps; these cells are not time-chunked (DESIGN.md 4.3/4.4)", "unit": "IQ samples/s", **others}
 
     if rank == 0:
         peaks, traffic = {}, {}

@@ -9,7 +9,7 @@ python bench.py --steps 20 --warmup 5 > gpurun_out/r2_final_bench.json 2> gpurun
 python - <<'PY'
 import json
 d=json.loads(open('/root/repo/gpurun_out/r2_final_bench.json').read().strip().splitlines()[-1])
-print(d["ms_per_step"], d["value"], d["e2e"]["ms_per_step"], d["e2e"]["value"], d["kernel_ms"], d["clocks"], {k:round(v["ms_per_step"],4) for k,v in d["secondary"].items()})
+print(d["ms_per_step"], d["value"], d["e2e"]["ms_per_step"], d["e2e"]["value"], d["kernel_ms"], d["clocks"], {k:round(v["ms_per_step"],4) for k,v in d["secondary"].items() if "ms_per_step" in v}, {k:v.get("ms_per_step", v) for k,v in d["secondary"].get("other_backbones",{}).items() if isinstance(v,dict)})
 PY
 timeout 900 compute-sanitizer --tool memcheck --launch-timeout 900 python scripts/sanitize_small.py > gpurun_out/r2c_memcheck.log 2>&1; tail -2 gpurun_out/r2c_memcheck.log
 timeout 1500 compute-sanitizer --tool racecheck --launch-timeout 900 python scripts/sanitize_small.py > gpurun_out/r2c_racecheck.log 2>&1; tail -2 gpurun_out/r2c_racecheck.log
