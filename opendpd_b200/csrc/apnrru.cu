@@ -526,14 +526,14 @@ int apnrru_run(const GruArgs &a, int dir, bool dw, cudaStream_t st, int *rows_ou
     if (a.H < 1 || a.H > AP_HMAX) { set_error("APNRRU: hidden_size %d outside 1..%d (one warp lane per state value: 2H+3 <= 31)", a.H, AP_HMAX); return -1; }
     if (a.T < AP_M - 1) { set_error("APNRRU needs frame_length >= 15 (the reference pads with zeros_like(x[:, -15:]), apnrru.py:69-71; got %d)", a.T); return -1; }
     const ApLayout L(a.H);
-    const int nts = (a.T + AP_TT - 1) / AP_TT, ntiles = a.B * nts, grid = ap_grid(a.B, a.T), cgrid = (a.B + 3) / 4;
+    const int nts = (a.T + AP_TT - 1) / AP_TT, ntiles = a.B * nts, grid = ap_grid(a.B, a.T), wpc = a.B <= 2 * num_sms() ? 1 : 4 /* few sequences: one chain warp per CTA spreads them over the SMs */, cgrid = (a.B + wpc - 1) / wpc;
     const int64_t bt = (int64_t)a.B * a.T;
     if (!a.saved) { set_error("APNRRU needs the `saved` buffer (odpd_saved_bytes), also without ODPD_F_SAVE"); return -1; }
     ApBufs u{};
     u.fr = a.saved; u.xp = u.fr + bt * 12; u.st = u.xp + bt * 16;
     if (dir == 0) {
         launch_pdl(apn_front_kernel, dim3(grid), dim3(AP_TT), 0, st, a, u, nts, ntiles);
-        launch_pdl(apn_chain_fwd_kernel, dim3(cgrid), dim3(128), 0, st, a, u);
+        launch_pdl(apn_chain_fwd_kernel, dim3(cgrid), dim3(32 * wpc), 0, st, a, u);
         launch_pdl(apn_head_fwd_kernel, dim3(grid), dim3(AP_TT), 0, st, a, u, nts, ntiles);
         return check_launch("apnrru forward");
     }
@@ -541,7 +541,7 @@ int apnrru_run(const GruArgs &a, int dir, bool dw, cudaStream_t st, int *rows_ou
     if (a.need_dx && !a.gx) { set_error("APNRRU backward: ODPD_F_NEED_DX without gx"); return -1; }
     const int64_t poff = ((int64_t)grid * L.P + 3) & ~(int64_t)3;
     u.partials = a.partials; u.gv = a.partials + poff; u.ga1 = u.gv + bt * L.S; u.grr = u.ga1 + bt * 16; u.dfir = u.grr + bt * 2; u.gxd = u.dfir + bt * 6;
-    launch_pdl(apn_chain_bwd_kernel, dim3(cgrid), dim3(128), 0, st, a, u);
+    launch_pdl(apn_chain_bwd_kernel, dim3(cgrid), dim3(32 * wpc), 0, st, a, u);
     const size_t bsm = (size_t)(96 + 128 + 32 + AP_TT * (17 + (L.U | 1) + (L.S | 1) + 17 + (L.S | 1) + 1 + ((2 * a.H) | 1) + 3 + 7) + 2 * (AP_TT + AP_M - 1)) * sizeof(float);
     if (dw) {
         static std::mutex mu;

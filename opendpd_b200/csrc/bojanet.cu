@@ -509,12 +509,12 @@ int bojanet_run(const GruArgs &a, int dir, bool dw, cudaStream_t st, int *rows_o
     BjBufs u{};
     if (!a.saved) { set_error("BOJANET needs the `saved` buffer (odpd_saved_bytes), also without ODPD_F_SAVE"); return -1; }
     u.fr = a.saved; u.xp = u.fr + bt * 24; u.act = u.xp + bt * 2 * H;
-    const int cgrid = (a.B + 3) / 4;
+    const int wpc = a.B <= 2 * num_sms() ? 1 : 4 /* few sequences: one chain warp per CTA spreads them over the SMs */, cgrid = (a.B + wpc - 1) / wpc;
     if (dir == 0) {
         const size_t fsm = (size_t)L.oWgh * sizeof(float);
         bj_ensure_smem((const void *)boja_front_kernel, fsm);
         launch_pdl(boja_front_kernel, dim3(grid), dim3(BJ_TT), fsm, st, a, u, nts, ntiles);
-        launch_pdl(boja_chain_fwd_kernel, dim3(cgrid), dim3(128), 0, st, a, u);
+        launch_pdl(boja_chain_fwd_kernel, dim3(cgrid), dim3(32 * wpc), 0, st, a, u);
         launch_pdl(boja_head_fwd_kernel, dim3(grid), dim3(BJ_TT), 0, st, a, u, nts, ntiles);
         return check_launch("bojanet forward");
     }
@@ -524,12 +524,12 @@ int bojanet_run(const GruArgs &a, int dir, bool dw, cudaStream_t st, int *rows_o
     const size_t bsm = (size_t)(24 * BJ_HMAX + BJ_TT * (((2 * H) | 1) + 13 + (H | 1) + 13) + 2 * (BJ_TT + BJ_M - 1)) * sizeof(float);
     if (dw) {
         launch_pdl(boja_head_bwd_kernel<true>, dim3(grid), dim3(BJ_TT), 0, st, a, u, nts, ntiles);
-        launch_pdl(boja_chain_bwd_kernel, dim3(cgrid), dim3(128), 0, st, a, u);
+        launch_pdl(boja_chain_bwd_kernel, dim3(cgrid), dim3(32 * wpc), 0, st, a, u);
         bj_ensure_smem((const void *)boja_front_bwd_kernel<true>, bsm);
         launch_pdl(boja_front_bwd_kernel<true>, dim3(grid), dim3(BJ_TT), bsm, st, a, u, nts, ntiles);
     } else {
         launch_pdl(boja_head_bwd_kernel<false>, dim3(grid), dim3(BJ_TT), 0, st, a, u, nts, ntiles);
-        launch_pdl(boja_chain_bwd_kernel, dim3(cgrid), dim3(128), 0, st, a, u);
+        launch_pdl(boja_chain_bwd_kernel, dim3(cgrid), dim3(32 * wpc), 0, st, a, u);
         bj_ensure_smem((const void *)boja_front_bwd_kernel<false>, bsm);
         launch_pdl(boja_front_bwd_kernel<false>, dim3(grid), dim3(BJ_TT), bsm, st, a, u, nts, ntiles);
     }

@@ -337,13 +337,13 @@ int deltajanet_run(const GruArgs &a, int dir, bool dw, cudaStream_t st, int *row
     if (a.H < 1 || a.H > DJ_HMAX) { set_error("DeltaJANET: hidden_size %d outside 1..%d", a.H, DJ_HMAX); return -1; }
     if (!a.saved) { set_error("DeltaJANET needs the `saved` buffer (odpd_saved_bytes), also without ODPD_F_SAVE"); return -1; }
     const DjLayout L(a.H);
-    const int H = a.H, nts = (a.T + DJ_TT - 1) / DJ_TT, ntiles = a.B * nts, grid = dj_grid(a.B, a.T), cgrid = (a.B + 3) / 4;
+    const int H = a.H, nts = (a.T + DJ_TT - 1) / DJ_TT, ntiles = a.B * nts, grid = dj_grid(a.B, a.T), wpc = a.B <= 2 * num_sms() ? 1 : 4 /* few sequences: one chain warp per CTA spreads them over the SMs */, cgrid = (a.B + wpc - 1) / wpc;
     const int64_t bt = (int64_t)a.B * a.T;
     DjBufs u{};
     u.xd = a.saved; u.act = a.saved + bt * 2 * H;
     if (dir == 0) {
         launch_pdl(dj_front_kernel, dim3(grid), dim3(DJ_TT), 0, st, a, u, nts, ntiles);
-        launch_pdl(dj_chain_fwd_kernel, dim3(cgrid), dim3(128), 0, st, a, u);
+        launch_pdl(dj_chain_fwd_kernel, dim3(cgrid), dim3(32 * wpc), 0, st, a, u);
         launch_pdl(dj_head_fwd_kernel, dim3(grid), dim3(DJ_TT), 0, st, a, u, nts, ntiles);
         return check_launch("deltajanet forward");
     }
@@ -352,7 +352,7 @@ int deltajanet_run(const GruArgs &a, int dir, bool dw, cudaStream_t st, int *row
     const int64_t poff = ((int64_t)grid * L.P + 3) & ~(int64_t)3;
     u.partials = a.partials; u.dh = a.partials + poff; u.gm = u.dh + bt * H;
     launch_pdl(dj_head_bwd_kernel, dim3(grid), dim3(DJ_TT), 0, st, a, u, nts, ntiles);
-    launch_pdl(dj_chain_bwd_kernel, dim3(cgrid), dim3(128), 0, st, a, u);
+    launch_pdl(dj_chain_bwd_kernel, dim3(cgrid), dim3(32 * wpc), 0, st, a, u);
     const size_t psm = (size_t)(DJ_TT * (((2 * H) | 1) + 7 + 2 * (H | 1) + 3) + ((2 * H) | 1)) * sizeof(float);
     if (dw) launch_pdl(dj_post_kernel<true>, dim3(grid), dim3(DJ_TT), psm, st, a, u, nts, ntiles);
     else if (a.need_dx) launch_pdl(dj_post_kernel<false>, dim3(grid), dim3(DJ_TT), psm, st, a, u, nts, ntiles);

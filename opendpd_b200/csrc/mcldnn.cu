@@ -573,7 +573,7 @@ int mcldnn_run(const GruArgs &a, int dir, bool dw, cudaStream_t st, int *rows_ou
     if (a.T < 4) { set_error("MCLDNN needs frame_length >= 4 (the reference's wrap-around window, mcldnn.py:96-99; got %d)", a.T); return -1; }
     if (!a.saved) { set_error("MCLDNN needs the `saved` buffer (odpd_saved_bytes), also without ODPD_F_SAVE"); return -1; }
     const McLayout L(a.H);
-    const int nts = (a.T + MC_TT - 1) / MC_TT, ntiles = a.B * nts, grid = mc_grid(a.B, a.T), cgrid = (a.B + 3) / 4;
+    const int nts = (a.T + MC_TT - 1) / MC_TT, ntiles = a.B * nts, grid = mc_grid(a.B, a.T), wpc = a.B <= 2 * num_sms() ? 1 : 4 /* few sequences: one chain warp per CTA spreads them over the SMs */, cgrid = (a.B + wpc - 1) / wpc;
     const int64_t bt = (int64_t)a.B * a.T;
     McBufs u{};
     u.comp = a.saved; u.xp = a.saved + mc_comp_floats(a.H); u.act = u.xp + bt * 32;
@@ -581,7 +581,7 @@ int mcldnn_run(const GruArgs &a, int dir, bool dw, cudaStream_t st, int *rows_ou
     if (dir == 0) {
         launch_pdl(mcl_compose_kernel, dim3(1), dim3(256), csm, st, a, u);
         launch_pdl(mcl_xp_kernel, dim3(grid), dim3(MC_TT), 0, st, a, u, nts, ntiles);
-        launch_pdl(mcl_chain_fwd_kernel, dim3(cgrid), dim3(128), 0, st, a, u);
+        launch_pdl(mcl_chain_fwd_kernel, dim3(cgrid), dim3(32 * wpc), 0, st, a, u);
         launch_pdl(mcl_head_fwd_kernel, dim3(grid), dim3(MC_TT), 0, st, a, u, nts, ntiles);
         return check_launch("mcldnn forward");
     }
@@ -591,7 +591,7 @@ int mcldnn_run(const GruArgs &a, int dir, bool dw, cudaStream_t st, int *rows_ou
     u.contrib = reinterpret_cast<float2 *>(u.ga + bt * 32);       // even float offset from the (8-byte aligned) workspace base
     u.rows = grid;
     launch_pdl(mcl_head_bwd_kernel, dim3(grid), dim3(MC_TT), 0, st, a, u, nts, ntiles);
-    launch_pdl(mcl_chain_bwd_kernel, dim3(cgrid), dim3(128), 0, st, a, u);
+    launch_pdl(mcl_chain_bwd_kernel, dim3(cgrid), dim3(32 * wpc), 0, st, a, u);
     const size_t psm = (size_t)MC_TT * (33 + 25 + 9 + 9 + 3 + 17 + 17) * sizeof(float);
     if (dw) launch_pdl(mcl_post_kernel<true>, dim3(grid), dim3(MC_TT), psm, st, a, u, nts, ntiles);
     else if (a.need_dx) launch_pdl(mcl_post_kernel<false>, dim3(grid), dim3(MC_TT), psm, st, a, u, nts, ntiles);
