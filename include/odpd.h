@@ -42,6 +42,8 @@
  *   MCLDNN    (mcldnn.py:21-27)     conv2d_1.weight(H,1,3,3) .bias(H) conv1d.weight(5H,1,3) .bias(5H) conv2d_2.weight(1,10,3,3) .bias(1) lstm.weight_ih_l0(32,5H)
  *                                   weight_hh_l0(32,8) bias_ih_l0(32) bias_hh_l0(32) fc_out.weight(16,8) .bias(16) fc_out_2.weight(2,16) .bias(2)
  *   DELTAJANET (deltajanet.py:97-105,27-29) rnn.weight_ih_l0(2H,6) weight_hh_l0(2H,H) bias_ih_l0(2H) bias_hh_l0(2H) fc_out.weight(2,H) fc_out.bias(2)
+ *   TRES_QAT  (quant_envs.py:286-305 applied to deltagru_tcnskip.py) rnn.x2h.weight(3H,6) + weight/act/out scales | rnn.h2h.weight(3H,H) + 3 scales |
+ *                                   rnn.add / mul / sigmoid / tanh .quantizer.scale | fc_out.weight(2,H) + 3 scales | tcn.0.weight(3,2,3) tcn.2.weight(2,3,1)
  *   QGRU_QAT  (quant_envs.py:215-305 applied to qgru.py) rnn.rnn_cell_list.0.x2h.weight(3H,4) .bias(3H) .weight_quantizer.scale .act_quantizer.scale
  *                                   .out_quantizer.scale | h2h.weight(3H,H) .bias(3H) + 3 scales | sigmoid/tanh/add/mul .quantizer.scale |
  *                                   fc_out.weight(2,H) .bias(2) + 3 scales.   For the QAT cells OdpdDims.K packs n_bits_w | n_bits_a<<8 | eval<<16.
@@ -86,7 +88,9 @@ enum {
     ODPD_CELL_APNRRU = 17,   /* backbones/apnrru.py:52-135 (row f-4): hidden_size 1..14 (2H+3 state values, one per warp lane) */
     ODPD_CELL_MCLDNN = 18,   /* backbones/mcldnn.py:83-113 (row f-4): H = conv channels (1..12); the LSTM inside is always 8 wide; frame_length >= 4 */
     ODPD_CELL_DELTAJANET = 19, /* backbones/deltajanet.py:49-60, 203-262 (row f-4): hidden_size 1..16; thx / thh are ignored like in the reference (:22-26) */
-    ODPD_CELL_COUNT = 20
+    ODPD_CELL_TRES_QAT = 20, /* deltagru_tcnskip.py under --quant (quant/quant_envs.py:286-305; bash_scripts/OpenDPDv2.sh:47-49): hidden_size 1..16,
+                                K packs n_bits_w | n_bits_a<<8 | eval<<16 like the QAT GRU cells; thx / thh / stats as for ODPD_CELL_TRES */
+    ODPD_CELL_COUNT = 21
 };
 
 /* flags */

@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libodpd.so")
 
 CELLS = {"gru": 0, "lstm": 1, "dgru": 2, "deltagru": 3, "deltagru_tcnskip": 4, "pgjanet": 5, "dvrjanet": 6, "gmp": 7,
-         "qgru": 8, "qgru_amp1": 9, "qgru_qat": 10, "qgru_amp1_qat": 11, "vdlstm": 12, "rvtdcnn": 13, "bojanet": 14, "tcnn": 15, "neuraltx": 16, "apnrru": 17, "mcldnn": 18, "deltajanet": 19}
+         "qgru": 8, "qgru_amp1": 9, "qgru_qat": 10, "qgru_amp1_qat": 11, "vdlstm": 12, "rvtdcnn": 13, "bojanet": 14, "tcnn": 15, "neuraltx": 16, "apnrru": 17, "mcldnn": 18, "deltajanet": 19, "deltagru_tcnskip_qat": 20}
 F_NEED_DX, F_NEED_DW, F_SAVE, F_OVERWRITE_DW, F_ZERO_LOSS, F_X_BF16, F_TARGET_BF16 = 1, 2, 4, 8, 16, 32, 64
 
 

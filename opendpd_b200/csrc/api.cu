@@ -181,6 +181,8 @@ static int check_dims(const OdpdDims *d) {
         ODPD_CHECK(d->H >= 1 && d->H <= 12, "MCLDNN hidden size (conv channels) %d outside 1..12", d->H);
     } else if (d->cell == ODPD_CELL_DELTAJANET) {
         ODPD_CHECK(d->H >= 1 && d->H <= 16, "DeltaJANET hidden_size %d outside 1..16", d->H);
+    } else if (d->cell == ODPD_CELL_TRES_QAT) {
+        ODPD_CHECK(d->H >= 1 && d->H <= 16, "fake-quantised TRes-DeltaGRU hidden_size %d outside 1..16", d->H);
     } else if (d->cell == ODPD_CELL_BOJANET) {
         ODPD_CHECK(d->H >= 1 && d->H <= 18, "BOJANET hidden_size %d outside 1..18 (bojanet.py:41-52)", d->H);
     } else if (d->cell != ODPD_CELL_GMP) {
@@ -222,6 +224,7 @@ int64_t odpd_n_params(int32_t cell, int32_t H, int32_t K) {
     if (cell == ODPD_CELL_APNRRU) return apnrru_nparams(H);
     if (cell == ODPD_CELL_MCLDNN) return mcldnn_nparams(H);
     if (cell == ODPD_CELL_DELTAJANET) return deltajanet_nparams(H);
+    if (cell == ODPD_CELL_TRES_QAT) return tresq_nparams(H);
     if (is_gru_family(cell)) return gru_family_nparams(cell, H);
     return other_nparams(cell, H, K);
 }
@@ -235,6 +238,7 @@ int64_t odpd_saved_bytes(const OdpdDims *d) {
     if (d->cell == ODPD_CELL_APNRRU) return 4 * apnrru_saved_floats(d->B, d->T, d->H);
     if (d->cell == ODPD_CELL_MCLDNN) return 4 * mcldnn_saved_floats(d->B, d->T, d->H);
     if (d->cell == ODPD_CELL_DELTAJANET) return 4 * deltajanet_saved_floats(d->B, d->T, d->H);
+    if (d->cell == ODPD_CELL_TRES_QAT) return save ? 4 * tresq_saved_floats(d->B, d->T) : 0;
     if (d->cell == ODPD_CELL_RVTDCNN) return save ? 16 : 0;      // nothing is saved (the backward recomputes); a token buffer keeps callers uniform
     if (is_gru_family(d->cell)) {
         const int64_t n = gru_family_saved_floats(d->cell, d->B, d->T, d->H, save, d->tchunks);
@@ -253,6 +257,7 @@ int64_t odpd_bwd_workspace_bytes(const OdpdDims *d) {
     if (d->cell == ODPD_CELL_APNRRU) return 4 * apnrru_workspace_floats(d->B, d->T, d->H) + 64;
     if (d->cell == ODPD_CELL_MCLDNN) return 4 * mcldnn_workspace_floats(d->B, d->T, d->H) + 64;
     if (d->cell == ODPD_CELL_DELTAJANET) return 4 * deltajanet_workspace_floats(d->B, d->T, d->H) + 64;
+    if (d->cell == ODPD_CELL_TRES_QAT) return 4 * tresq_workspace_floats(d->B, d->T, d->H) + 64;
     if (is_gru_family(d->cell)) {
         const int64_t n = gru_family_workspace_floats(d->cell, d->B, d->T, d->H, d->tchunks);
         if (n < 0) { set_error("GRU-family kernels support hidden_size <= 32 (got %d)", d->H); return -1; }
@@ -313,6 +318,12 @@ int odpd_backbone_fwd(const OdpdDims *d, const float *x, const float *target, co
         GruArgs a = wide_args(d);
         a.x = x; a.target = target; a.params = params; a.out = out; a.loss = loss; a.loss_scale = (float)loss_scale; a.saved = (float *)saved;
         return deltajanet_run(a, 0, false, st, nullptr);
+    }
+    if (d->cell == ODPD_CELL_TRES_QAT) {
+        GruArgs a = wide_args(d);
+        a.x = x; a.target = target; a.params = params; a.out = out; a.loss = loss; a.loss_scale = (float)loss_scale; a.saved = (float *)saved;
+        a.save = save; a.K = d->K; a.thx = d->thx; a.thh = d->thh; a.stats = stats;
+        return tresq_run(a, 0, false, st, nullptr);
     }
     if (is_gru_family(d->cell)) {
         GruArgs a{};
@@ -395,6 +406,13 @@ int odpd_backbone_bwd(const OdpdDims *d, const float *x, const float *params, co
         a.gscale = (float)gscale; a.gscale_dev = gscale_dev; a.gx = gx; a.partials = (float *)workspace; a.need_dx = dx;
         ODPD_CHECK(workspace != nullptr, "the DeltaJANET backward needs the workspace (odpd_bwd_workspace_bytes)");
         rc = deltajanet_run(a, 1, dw, st, &rows);
+    } else if (d->cell == ODPD_CELL_TRES_QAT) {
+        GruArgs a = wide_args(d);
+        a.x = x; a.params = params; a.saved = (float *)saved; a.gout = gout; a.out_in = out; a.target = target;
+        a.gscale = (float)gscale; a.gscale_dev = gscale_dev; a.gx = gx; a.partials = (float *)workspace; a.need_dx = dx;
+        a.K = d->K; a.thx = d->thx; a.thh = d->thh;
+        ODPD_CHECK(workspace != nullptr, "the fake-quantised TRes-DeltaGRU backward needs the workspace (odpd_bwd_workspace_bytes)");
+        rc = tresq_run(a, 1, dw, st, &rows);
     } else if (is_gru_family(d->cell)) {
         GruArgs a{};
         a.B = d->B; a.T = d->T; a.H = d->H; a.x = x; a.params = params; a.saved = (float *)saved; a.gout = gout; a.out_in = out;
@@ -431,7 +449,7 @@ int odpd_chunk_plan(const OdpdDims *d, int32_t backward, int32_t out[4]) {
     if (check_dims(d)) return -1;
     ODPD_CHECK(out != nullptr, "out is NULL");
     out[0] = 1; out[1] = d->T; out[2] = 0; out[3] = -1;
-    if (d->B == 0 || d->T == 0 || d->cell == ODPD_CELL_GMP || d->cell == ODPD_CELL_RVTDCNN || d->cell == ODPD_CELL_BOJANET || d->cell == ODPD_CELL_APNRRU || d->cell == ODPD_CELL_MCLDNN || d->cell == ODPD_CELL_DELTAJANET || is_tcn(d->cell) || is_wide(d->cell, d->H, d->K)) return 0;
+    if (d->B == 0 || d->T == 0 || d->cell == ODPD_CELL_GMP || d->cell == ODPD_CELL_RVTDCNN || d->cell == ODPD_CELL_BOJANET || d->cell == ODPD_CELL_APNRRU || d->cell == ODPD_CELL_MCLDNN || d->cell == ODPD_CELL_DELTAJANET || d->cell == ODPD_CELL_TRES_QAT || is_tcn(d->cell) || is_wide(d->cell, d->H, d->K)) return 0;
     int info[4];
     if (!is_gru_family(d->cell)) {
         const int rc = other_plan(d, backward, info);

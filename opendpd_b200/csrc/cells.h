@@ -106,6 +106,12 @@ int64_t deltajanet_saved_floats(int B, int T, int H);
 int64_t deltajanet_workspace_floats(int B, int T, int H);
 int deltajanet_run(const GruArgs &a, int dir, bool dw, cudaStream_t st, int *rows_out);
 
+// tres_qat.cu : fake-quantised TRes-DeltaGRU (QAT)
+int64_t tresq_nparams(int H);
+int64_t tresq_saved_floats(int B, int T);
+int64_t tresq_workspace_floats(int B, int T, int H);
+int tresq_run(const GruArgs &a, int dir, bool dw, cudaStream_t st, int *rows_out);
+
 // remaining families (lstm.cu, delta.cu, janet.cu, gmp.cu) behind one dispatcher in others.cu
 int64_t other_nparams(int cell, int H, int K);
 int64_t other_saved_bytes(const OdpdDims *d);

@@ -25,6 +25,24 @@ def _load_pretrained(qbb, path):
             p.copy_(sd[k])
 
 
+def _load_pretrained_tres(qbb, path):
+    """`--pretrained_model` for the TRes-DeltaGRU (OpenDPDv2.sh:84-111: the float DPD trained in the previous stage).  This backbone has no
+    nn.GRU to swap, so the checkpoint is simply the float model's state_dict and all five weight tensors come from it
+    (quant_envs.py:173-182 loads it before the layers are wrapped; the wrapping keeps the weights)."""
+    import torch
+    sd = torch.load(path, map_location="cpu")
+    want = {"backbone.rnn.x2h.weight": qbb.rnn.x2h.weight, "backbone.rnn.h2h.weight": qbb.rnn.h2h.weight, "backbone.fc_out.weight": qbb.fc_out.weight,
+            "backbone.tcn.0.weight": qbb.tcn[0].weight, "backbone.tcn.2.weight": qbb.tcn[2].weight}
+    if set(sd) != set(want):
+        raise ValueError(f"--pretrained_model {path}: expected the state_dict of the float deltagru_tcnskip model (keys {sorted(want)}), got "
+                         f"{sorted(sd)[:6]}...; the reference would silently continue with the float model here")
+    with torch.no_grad():
+        for k, p in want.items():
+            if tuple(sd[k].shape) != tuple(p.shape):
+                raise ValueError(f"--pretrained_model {path}: {k} has shape {tuple(sd[k].shape)}, model wants {tuple(p.shape)}")
+            p.copy_(sd[k])
+
+
 def get_quant_model(proj, model):
     """If proj.quant is truthy return a CoreModel whose backbone is the fake-quantised QGRU built from `model`'s float QGRU
     (n_bits_w / n_bits_a from proj, default 8; proj.pretrained_model honoured); otherwise return `model` unchanged.  Unlike the reference this does NOT
@@ -32,13 +50,20 @@ def get_quant_model(proj, model):
     if not getattr(proj, "quant", False):
         return model
     bb = model.backbone
-    if getattr(bb, "cell", None) not in ("qgru", "qgru_amp1"):
-        raise ValueError("native QAT is available for the qgru / qgru_amp1 backbones (the ones the reference's QAT scripts use)")
+    if getattr(bb, "cell", None) not in ("qgru", "qgru_amp1", "deltagru_tcnskip"):
+        raise ValueError("native QAT is available for the qgru / qgru_amp1 / deltagru_tcnskip backbones (the ones the reference's QAT scripts use: "
+                         "quant_qgru_dpd_regr.sh, quant_mp_dpd.sh, OpenDPDv2.sh)")
     dev = next(bb.parameters()).device
-    qbb = QGRUQuant.from_float(bb, getattr(proj, "n_bits_w", 8), getattr(proj, "n_bits_a", 8))
     pretrained = getattr(proj, "pretrained_model", "")
-    if pretrained:
-        _load_pretrained(qbb, pretrained)
+    if bb.cell == "deltagru_tcnskip":
+        from .backbones.tres_quant import TResQuant
+        qbb = TResQuant.from_float(bb, getattr(proj, "n_bits_w", 8), getattr(proj, "n_bits_a", 8))
+        if pretrained:
+            _load_pretrained_tres(qbb, pretrained)
+    else:
+        qbb = QGRUQuant.from_float(bb, getattr(proj, "n_bits_w", 8), getattr(proj, "n_bits_a", 8))
+        if pretrained:
+            _load_pretrained(qbb, pretrained)
     qbb = qbb.to(dev)
     import copy
     qmodel = copy.copy(model)

@@ -51,12 +51,12 @@ def build(kind, H, seed, thx=0.0, thh=0.0, K=3, L=1):
     if kind.endswith("_qat"):
         # config 5: the reference's own QAT environment (quant/__init__.py:20-37 -> quant_envs.py Base_GRUQuantEnv) around the float QGRU
         from quant import get_quant_model
-        float_net = models.CoreModel(input_size=2, hidden_size=H, num_layers=1, backbone_type=kind[:-4])
+        float_net = models.CoreModel(input_size=2, hidden_size=H, num_layers=1, backbone_type=kind[:-4], thx=thx, thh=thh)
 
         class _Proj:
             quant, n_bits_w, n_bits_a, pretrained_model, quant_dir_label = True, K & 255, (K >> 8) & 255, "", ""
         qnet = get_quant_model(_Proj(), float_net)
-        assert type(qnet.backbone.rnn).__name__ == "GRU" and qnet is not float_net, "quant env fell back to the float model"
+        assert qnet is not float_net and type(qnet.backbone.fc_out).__name__ == "INT_Linear", "quant env fell back to the float model"
         qnet.train()
         return qnet
     if kind == "pgjanet":
@@ -196,6 +196,9 @@ CASES = [
     ("deltajanet_h10_b3_t50",      "deltajanet", 10, 3, 50, 68, 0.01, 0.05),     # thx / thh are accepted and ignored by the reference (deltajanet.py:22-26)
     ("deltajanet_h16_b2_t70",      "deltajanet", 16, 2, 70, 69, 0, 0),
     ("deltajanet_h3_b2_t2",        "deltajanet", 3, 2, 2, 70, 0, 0),
+    # the W16A16 stage of bash_scripts/OpenDPDv2.sh:47-49: the reference's QAT env around TRes-DeltaGRU (K packs bits_w | bits_a<<8)
+    ("tresqat_w16a16_h15_b3_t60",  "deltagru_tcnskip_qat", 15, 3, 60, 71, 0.01, 0.05, 16 | (16 << 8)),
+    ("tresqat_w8a8_h10_b2_t40",    "deltagru_tcnskip_qat", 10, 2, 40, 72, 0.02, 0.05, 8 | (8 << 8)),
     # hidden sizes above the fused tiers and stacked layers (arguments.py:51,60 -> nn.GRU/nn.LSTM num_layers): 10th field = num_layers
     ("wide_gru_h48_b3_t70",        "gru",  48, 3, 70, 40, 0, 0, 3, 1),
     ("wide_gru_h16_l2_b3_t40",     "gru",  16, 3, 40, 41, 0, 0, 3, 2),
@@ -224,7 +227,7 @@ def main():
         tap_cls = None
         if kind == "deltagru":
             from backbones.deltagru import DeltaGRULayer as tap_cls
-        elif kind == "deltagru_tcnskip":
+        elif kind in ("deltagru_tcnskip", "deltagru_tcnskip_qat"):
             from backbones.deltagru_tcnskip import DeltaGRULayer as tap_cls
         params = flat_params(net)
         r32 = run(net, x, y, torch.float32, tap_cls)

@@ -54,7 +54,7 @@
 #endif
 
 enum { CELL_GRU = 0, CELL_LSTM = 1, CELL_DGRU = 2, CELL_DELTAGRU = 3, CELL_TRES = 4, CELL_PGJANET = 5,
-       CELL_DVRJANET = 6, CELL_GMP = 7, CELL_QGRU = 8, CELL_QGRU_AMP1 = 9, CELL_QGRU_QAT = 10, CELL_QGRU_AMP1_QAT = 11, CELL_RVTDCNN = 13, CELL_BOJANET = 14, CELL_TCNN = 15, CELL_NEURALTX = 16, CELL_APNRRU = 17, CELL_MCLDNN = 18, CELL_DELTAJANET = 19 };
+       CELL_DVRJANET = 6, CELL_GMP = 7, CELL_QGRU = 8, CELL_QGRU_AMP1 = 9, CELL_QGRU_QAT = 10, CELL_QGRU_AMP1_QAT = 11, CELL_RVTDCNN = 13, CELL_BOJANET = 14, CELL_TCNN = 15, CELL_NEURALTX = 16, CELL_APNRRU = 17, CELL_MCLDNN = 18, CELL_DELTAJANET = 19, CELL_TRES_QAT = 20 };
 
 typedef struct {
     int cell, B, T, H, K;
@@ -1412,6 +1412,155 @@ static void seq_deltajanet(const Ctx *c, const REAL *x, const REAL *gout, REAL *
     free(ft); free(act);
 }
 
+/* ================================================================ fake-quantised TRes-DeltaGRU (the W16A16 stage of bash_scripts/OpenDPDv2.sh:47-49)
+ * quant/quant_envs.py:286-305 applied to backbones/deltagru_tcnskip.py: x2h / h2h / fc_out become INT_Linear (weight and input each fake-quantised,
+ * quant_layers.py:70-82; 16-bit output quantiser on fc_out in eval only), the layer's add / mul / sigmoid / tanh modules become Quant_add / Quant_mult /
+ * Quant_sigmoid / Quant_tanh (quant_ops.py:14-66).  The delta logic itself stays in float (deltagru_tcnskip.py:266-291):
+ *   dx, dh thresholded as in the float cell (masks, counters on the UNquantised deltas);  mac_x = x2h(Q(dx)) + M, mac_h = h2h(Q(dh));  M and M_nh accumulate
+ *   as before;  r = Qs(sigm(M_r)), z = Qs(sigm(M_z));  n = Qt(tanh(Qa(M_n + Qm(r M_nh))));  h = Qa(Qm(Qa(1 - z) n) + Qm(z h));  out = fc_out(Q(h)) + tcn(x).
+ * Quantiser and STE as in seq_qgru_qat.  params (named_parameters order): x2h.W(3H,6) + 3 scales | h2h.W(3H,H) + 3 scales | add, mul, sigmoid, tanh scales |
+ * fc_out.W(2,H) + 3 scales | tcn.0.W(3,2,3) tcn.2.W(2,3,1).   K packs bits_w | bits_a<<8 | eval<<16. */
+static void seq_tres_qat(const Ctx *c, const REAL *x, const REAL *gout, REAL *out, REAL *gx, REAL *gp, int phase,
+                         uint64_t *mask_x, uint64_t *mask_h, int64_t *stats) {
+    const int H = c->H, T = c->T, F = 6, bw = c->K & 255, ba = (c->K >> 8) & 255, eval = (c->K >> 16) & 1;
+    const REAL *p = c->params;
+    const REAL *Wx = p, *sx = Wx + 3 * H * F, *Wh = sx + 3, *sh = Wh + 3 * H * H, *sop = sh + 3, *Wo = sop + 4, *so = Wo + 2 * H, *w0 = so + 3, *w2 = w0 + 18;
+    const Quant qxw = mkq(sx[0], bw), qxa = mkq(sx[1], ba), qhw = mkq(sh[0], bw), qha = mkq(sh[1], ba), qadd = mkq(sop[0], ba), qmul = mkq(sop[1], ba),
+                qsig = mkq(sop[2], ba), qtanh = mkq(sop[3], ba), qow = mkq(so[0], bw), qoa = mkq(so[1], ba), qoo = mkq(so[2], 16);
+    /* saved per step: f(6) qdx(6) cdx(6) | per unit 16 values: qdh cdh r z n sr sz tn mn omz hs hq flags(packed) - - - | cv(5) */
+    const int S = 18 + 16 * H + 5;
+    static __thread REAL *sv = NULL; static __thread size_t sv_n = 0;
+    static __thread uint64_t *mk = NULL; static __thread size_t mk_n = 0;
+    if (sv_n < (size_t)T * S) { free(sv); sv = (REAL *)malloc((size_t)T * S * sizeof(REAL)); sv_n = (size_t)T * S; }
+    if (mk_n < (size_t)2 * T) { free(mk); mk = (uint64_t *)malloc(sizeof(uint64_t) * 2 * T); mk_n = 2 * T; }
+    REAL Wxq[192 * 6], Whq[192 * 64], Woq[128]; int cWx[192 * 6], cWh[192 * 64], cWo[128];
+    for (int i = 0; i < 3 * H * F; ++i) Wxq[i] = qf(&qxw, Wx[i], &cWx[i]);
+    for (int i = 0; i < 3 * H * H; ++i) Whq[i] = qf(&qhw, Wh[i], &cWh[i]);
+    for (int i = 0; i < 2 * H; ++i) Woq[i] = qf(&qow, Wo[i], &cWo[i]);
+    if (phase == 0) {
+        REAL h[64] = {0}, hp[64] = {0}, xp[6] = {0}, M[192] = {0}, Mnh[64] = {0};
+        int64_t zx = 0, zh = 0;
+        for (int t = 0; t < T; ++t) {
+            REAL *s = sv + (size_t)t * S, *f = s, *qdx = s + 6, *cdx = s + 12, *u = s + 18, *cv = u + 16 * H;
+            features_fwd(CELL_TRES, x, T, t, f);
+            uint64_t mx = 0, mh = 0;
+            for (int k = 0; k < F; ++k) {
+                REAL d = f[k] - xp[k], a = R_FABS(d);
+                if (a < c->thx) d = 0;
+                if (a >= c->thx) { xp[k] = f[k]; mx |= (uint64_t)1 << k; }
+                zx += (d == 0);
+                int in; qdx[k] = qf(&qxa, d, &in); cdx[k] = (REAL)in;
+            }
+            REAL qdh[64];
+            for (int j = 0; j < H; ++j) {
+                REAL d = h[j] - hp[j], a = R_FABS(d);
+                if (a < c->thh) d = 0;
+                if (a >= c->thh) { hp[j] = h[j]; mh |= (uint64_t)1 << j; }
+                zh += (d == 0);
+                int in; qdh[j] = qf(&qha, d, &in); u[16 * j] = qdh[j]; u[16 * j + 1] = (REAL)in;
+            }
+            mk[2 * t] = mx; mk[2 * t + 1] = mh;
+            if (mask_x) mask_x[t] = mx;
+            if (mask_h) mask_h[t] = mh;
+            REAL hn[64], o0 = 0, o1 = 0;
+            for (int j = 0; j < H; ++j) {
+                REAL *uj = u + 16 * j;
+                const REAL mxr = dotv(Wxq + (size_t)j * F, qdx, F) + M[j], mxz = dotv(Wxq + (size_t)(H + j) * F, qdx, F) + M[H + j],
+                           mxn = dotv(Wxq + (size_t)(2 * H + j) * F, qdx, F) + M[2 * H + j];
+                M[j] = mxr + dotv(Whq + (size_t)j * H, qdh, H);
+                M[H + j] = mxz + dotv(Whq + (size_t)(H + j) * H, qdh, H);
+                M[2 * H + j] = mxn;
+                Mnh[j] = dotv(Whq + (size_t)(2 * H + j) * H, qdh, H) + Mnh[j];
+                int c_r, c_z, c_m1, c_an, c_n, c_omz, c_m3, c_m2, c_h, c_oa;
+                const REAL sr = sigm(M[j]), sz = sigm(M[H + j]);
+                const REAL r = qf(&qsig, sr, &c_r), z = qf(&qsig, sz, &c_z);
+                const REAL m1 = qf(&qmul, r * Mnh[j], &c_m1);
+                const REAL an = qf(&qadd, M[2 * H + j] + m1, &c_an);
+                const REAL tn = R_TANH(an), n = qf(&qtanh, tn, &c_n);
+                const REAL omz = qf(&qadd, (REAL)1 + (-z), &c_omz);
+                const REAL m3 = qf(&qmul, omz * n, &c_m3), m2 = qf(&qmul, z * h[j], &c_m2);
+                hn[j] = qf(&qadd, m3 + m2, &c_h);
+                const REAL hq = qf(&qoa, hn[j], &c_oa);
+                uj[2] = r; uj[3] = z; uj[4] = n; uj[5] = sr; uj[6] = sz; uj[7] = tn; uj[8] = Mnh[j]; uj[9] = omz; uj[10] = hn[j]; uj[11] = hq;
+                uj[12] = (REAL)(c_r | c_z << 1 | c_m1 << 2 | c_an << 3 | c_n << 4 | c_omz << 5 | c_m3 << 6 | c_m2 << 7 | c_h << 8 | c_oa << 9);
+                o0 += Woq[j] * hq; o1 += Woq[H + j] * hq;
+            }
+            memcpy(h, hn, sizeof(REAL) * H);
+            if (eval) { o0 = qf(&qoo, o0, NULL); o1 = qf(&qoo, o1, NULL); }
+            for (int co = 0; co < 3; ++co) {
+                REAL a = 0;
+                for (int ci = 0; ci < 2; ++ci)
+                    for (int k = 0; k < 3; ++k) { int tt = t + (k - 1) * 16; if (tt >= 0 && tt < T) a += w0[(co * 2 + ci) * 3 + k] * x[2 * tt + ci]; }
+                cv[co] = a;
+            }
+            for (int o = 0; o < 2; ++o) { REAL a = 0; for (int ch = 0; ch < 3; ++ch) a += w2[o * 3 + ch] * hardswish(cv[ch]); cv[3 + o] = a; }
+            out[2 * t] = o0 + hardswish(cv[3]); out[2 * t + 1] = o1 + hardswish(cv[4]);
+        }
+        if (stats) { stats[0] = zx; stats[1] = (int64_t)T * F; stats[2] = zh; stats[3] = (int64_t)T * H; }
+        return;
+    }
+    REAL *gWx = gp, *gWh = gWx + 3 * H * F + 3, *gWo = gWh + 3 * H * H + 3 + 4, *gw0 = gWo + 2 * H + 3, *gw2 = gw0 + 18;
+    REAL gH[64] = {0}, gM[192] = {0}, gMnh[64] = {0}, gxp[6] = {0}, ghp[64] = {0};
+    for (int t = T - 1; t >= 0; --t) {
+        REAL *s = sv + (size_t)t * S, *f = s, *qdx = s + 6, *cdx = s + 12, *u = s + 18, *cv = u + 16 * H;
+        const REAL *up = t ? sv + (size_t)(t - 1) * S + 18 : NULL;
+        (void)f;
+        const REAL go0 = gout[2 * t], go1 = gout[2 * t + 1];
+        {
+            REAL g2[2] = {go0 * hardswish_grad(cv[3]), go1 * hardswish_grad(cv[4])}, ga1[3] = {0, 0, 0};
+            for (int o = 0; o < 2; ++o)
+                for (int ch = 0; ch < 3; ++ch) { gw2[o * 3 + ch] += g2[o] * hardswish(cv[ch]); ga1[ch] += w2[o * 3 + ch] * g2[o]; }
+            for (int co = 0; co < 3; ++co) {
+                const REAL gc1 = ga1[co] * hardswish_grad(cv[co]);
+                for (int ci = 0; ci < 2; ++ci)
+                    for (int k = 0; k < 3; ++k) {
+                        int tt = t + (k - 1) * 16;
+                        if (tt >= 0 && tt < T) { gw0[(co * 2 + ci) * 3 + k] += gc1 * x[2 * tt + ci]; if (gx) gx[2 * tt + ci] += w0[(co * 2 + ci) * 3 + k] * gc1; }
+                    }
+            }
+        }
+        REAL ghprev[64], qdh[64];
+        for (int j = 0; j < H; ++j) {
+            const REAL *uj = u + 16 * j;
+            qdh[j] = uj[0];
+            const int fl = (int)uj[12];
+            const REAL r = uj[2], z = uj[3], n = uj[4], sr = uj[5], sz = uj[6], tn = uj[7], mn = uj[8], omz = uj[9], hq = uj[11];
+            const REAL hpj = up ? up[16 * j + 10] : 0;
+            if (cWo[j]) gWo[j] += go0 * hq;
+            if (cWo[H + j]) gWo[H + j] += go1 * hq;
+            REAL g = gH[j] + (((fl >> 9) & 1) ? Woq[j] * go0 + Woq[H + j] * go1 : 0);
+            g = ((fl >> 8) & 1) ? g : 0;                                   /* h = Qa(m3 + m2) */
+            const REAL gm2 = ((fl >> 7) & 1) ? g : 0, gm3 = ((fl >> 6) & 1) ? g : 0;
+            REAL gz = gm2 * hpj;
+            ghprev[j] = gm2 * z;
+            const REAL gomz = ((fl >> 5) & 1) ? gm3 * n : 0;
+            gz -= gomz;
+            const REAL gn = ((fl >> 4) & 1) ? gm3 * omz : 0;
+            const REAL gan = ((fl >> 3) & 1) ? gn * ((REAL)1 - tn * tn) : 0;
+            const REAL gm1 = ((fl >> 2) & 1) ? gan : 0;
+            const REAL gr = (fl & 1) ? gm1 * mn : 0;
+            gM[j] += gr * sr * ((REAL)1 - sr);
+            gM[H + j] += (((fl >> 1) & 1) ? gz : 0) * sz * ((REAL)1 - sz);
+            gM[2 * H + j] += gan;
+            gMnh[j] += gm1 * r;
+        }
+        REAL gdx[6] = {0}, gdh[64] = {0};
+        for (int k = 0; k < 3 * H; ++k) {
+            const REAL gk = gM[k], gk_h = (k < 2 * H) ? gM[k] : gMnh[k - 2 * H];
+            for (int q = 0; q < F; ++q) { if (cWx[k * F + q]) gWx[k * F + q] += gk * qdx[q]; gdx[q] += Wxq[k * F + q] * gk; }
+            for (int q = 0; q < H; ++q) { if (cWh[k * H + q]) gWh[k * H + q] += gk_h * qdh[q]; gdh[q] += Whq[k * H + q] * gk_h; }
+        }
+        for (int q = 0; q < F; ++q) if (cdx[q] == 0) gdx[q] = 0;
+        for (int q = 0; q < H; ++q) if (u[16 * q + 1] == 0) gdh[q] = 0;
+        const uint64_t mx = mk[2 * t], mh = mk[2 * t + 1];
+        REAL gf[6];
+        for (int k = 0; k < F; ++k) { if ((mx >> k) & 1) { gf[k] = gxp[k] + gdx[k]; gxp[k] = -gdx[k]; } else gf[k] = 0; }
+        for (int j = 0; j < H; ++j) if ((mh >> j) & 1) { ghprev[j] += ghp[j] + gdh[j]; ghp[j] = -gdh[j]; }
+        memcpy(gH, ghprev, sizeof(REAL) * H);
+        if (gx) features_bwd(CELL_TRES, x, T, t, gf, gx);
+    }
+}
+
 static size_t n_params(int cell, int H, int K) {
     switch (cell) {
     case CELL_GRU: return (size_t)3 * H * 2 + 3 * H * H + 6 * H + 2 * H + 2;
@@ -1430,6 +1579,7 @@ static size_t n_params(int cell, int H, int K) {
     case CELL_APNRRU: return (size_t)241 + 34 * (2 * H + 3) + 2 * H;
     case CELL_MCLDNN: return (size_t)190 * H + 589;
     case CELL_DELTAJANET: return (size_t)2 * H * H + 18 * H + 2;
+    case CELL_TRES_QAT: return (size_t)3 * H * H + 20 * H + 37;
     case CELL_QGRU_QAT: case CELL_QGRU_AMP1_QAT: return (size_t)3 * H * 4 + 3 * H * H + 6 * H + 2 * H + 2 + 13;
     }
     return 0;
@@ -1450,6 +1600,7 @@ static void seq_dispatch(const Ctx *c, const REAL *x, const REAL *gout, REAL *ou
     case CELL_APNRRU: seq_apnrru(c, x, gout, out, gx, gp, phase); break;
     case CELL_MCLDNN: seq_mcldnn(c, x, gout, out, gx, gp, phase); break;
     case CELL_DELTAJANET: seq_deltajanet(c, x, gout, out, gx, gp, phase); break;
+    case CELL_TRES_QAT: seq_tres_qat(c, x, gout, out, gx, gp, phase, mx, mh, st); break;
     case CELL_QGRU_QAT: case CELL_QGRU_AMP1_QAT: seq_qgru_qat(c, x, gout, out, gx, gp, phase); break;
     }
 }

@@ -4,7 +4,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CELLS = {"gru": 0, "lstm": 1, "dgru": 2, "deltagru": 3, "deltagru_tcnskip": 4, "tres": 4, "pgjanet": 5,
-         "dvrjanet": 6, "gmp": 7, "qgru": 8, "qgru_amp1": 9, "qgru_qat": 10, "qgru_amp1_qat": 11, "rvtdcnn": 13, "bojanet": 14, "tcnn": 15, "neuraltx": 16, "apnrru": 17, "mcldnn": 18, "deltajanet": 19}
+         "dvrjanet": 6, "gmp": 7, "qgru": 8, "qgru_amp1": 9, "qgru_qat": 10, "qgru_amp1_qat": 11, "rvtdcnn": 13, "bojanet": 14, "tcnn": 15, "neuraltx": 16, "apnrru": 17, "mcldnn": 18, "deltajanet": 19, "deltagru_tcnskip_qat": 20, "tres_qat": 20}
 _lib = None
 
 

@@ -20,14 +20,20 @@ CASES = [  # kind, H, B, T, tchunks (fwd,bwd), twarm
     ("vdlstm", 9, 2, 100, (1, 1), 0), ("vdlstm", 9, 2, 256, (2, 2), 64), ("dgru", 23, 2, 130, (1, 1), 0), ("gru", 8, 2, 70, (1, 1), 0),
     ("dgru", 23, 2, 256, (2, 2), 64), ("gru", 32, 2, 100, (1, 1), 0),                      # lane-per-timestep forward helpers (tiers above 16)
     ("gru", 40, 2, 70, (1, 1), 0, 1), ("dgru", 12, 2, 70, (1, 1), 0, 2), ("lstm", 36, 2, 45, (1, 1), 0, 2),   # layered path (7th field = num_layers)
-    ("rvtdcnn", 6, 2, 100, (1, 1), 0), ("bojanet", 10, 2, 100, (1, 1), 0), ("tcnn", 8, 2, 150, (1, 1), 0), ("neuraltx", 8, 2, 150, (1, 1), 0), ("apnrru", 8, 2, 100, (1, 1), 0), ("mcldnn", 8, 2, 100, (1, 1), 0), ("deltajanet", 10, 2, 100, (1, 1), 0),
+    ("rvtdcnn", 6, 2, 100, (1, 1), 0), ("bojanet", 10, 2, 100, (1, 1), 0), ("tcnn", 8, 2, 150, (1, 1), 0), ("neuraltx", 8, 2, 150, (1, 1), 0), ("apnrru", 8, 2, 100, (1, 1), 0), ("mcldnn", 8, 2, 100, (1, 1), 0), ("deltajanet", 10, 2, 100, (1, 1), 0), ("tres_qat", 15, 3, 70, (1, 1), 0),
 ]
 for case in CASES:
     kind, H, B, T, tch, tw = case[:6]
     layers = case[6] if len(case) > 6 else 1
     if only and kind not in only:
         continue
-    if kind == "qgru_qat":
+    if kind == "tres_qat":
+        from opendpd_b200.quant import get_quant_model
+
+        class _Proj:
+            quant, n_bits_w, n_bits_a, pretrained_model = True, 16, 16, ""
+        net = get_quant_model(_Proj(), models.CoreModel(2, H, 1, "deltagru_tcnskip", thx=0.01, thh=0.05)).cuda().train()
+    elif kind == "qgru_qat":
         from opendpd_b200.quant import get_quant_model
 
         class _Proj:

@@ -8,7 +8,7 @@ from tests.util import GOLDEN, golden_cases, load_golden, rel_err, tol_for, asse
 
 pytestmark = pytest.mark.gpu
 
-IMPLEMENTED = ("gru", "dgru", "qgru", "lstm", "deltagru", "tres", "pgjanet", "dvrjanet", "gmp", "qgruqat", "qgruamp1qat", "rvtdcnn", "bojanet", "tcnn", "neuraltx", "apnrru", "mcldnn", "deltajanet")
+IMPLEMENTED = ("gru", "dgru", "qgru", "lstm", "deltagru", "tres", "pgjanet", "dvrjanet", "gmp", "qgruqat", "qgruamp1qat", "rvtdcnn", "bojanet", "tcnn", "neuraltx", "apnrru", "mcldnn", "deltajanet", "tresqat")
 
 
 def _native_kinds():
@@ -19,7 +19,7 @@ def _native_kinds():
     have = set()
     for k, cell in (("gru", "gru"), ("dgru", "dgru"), ("qgru", "qgru"), ("lstm", "lstm"), ("deltagru", "deltagru"),
                     ("tres", "deltagru_tcnskip"), ("pgjanet", "pgjanet"), ("dvrjanet", "dvrjanet"), ("gmp", "gmp"),
-                    ("qgruqat", "qgru_qat"), ("qgruamp1qat", "qgru_amp1_qat"), ("rvtdcnn", "rvtdcnn"), ("bojanet", "bojanet"), ("tcnn", "tcnn"), ("neuraltx", "neuraltx"), ("apnrru", "apnrru"), ("mcldnn", "mcldnn"), ("deltajanet", "deltajanet")):
+                    ("qgruqat", "qgru_qat"), ("qgruamp1qat", "qgru_amp1_qat"), ("rvtdcnn", "rvtdcnn"), ("bojanet", "bojanet"), ("tcnn", "tcnn"), ("neuraltx", "neuraltx"), ("apnrru", "apnrru"), ("mcldnn", "mcldnn"), ("deltajanet", "deltajanet"), ("tresqat", "deltagru_tcnskip_qat")):
         d = _ffi.OdpdDims(_ffi.CELLS[cell], 1, 1, 10, 3, 0, 0.0, 0.0)
         if L.odpd_saved_bytes(ctypes.byref(d)) >= 0:
             have.add(k)
@@ -45,7 +45,7 @@ def build_native(g, device="cuda"):
 
         class _Proj:
             quant, n_bits_w, n_bits_a, pretrained_model = True, g["K"] & 255, (g["K"] >> 8) & 255, ""
-        net = get_quant_model(_Proj(), models.CoreModel(2, g["H"], 1, g["kind"][:-4]))
+        net = get_quant_model(_Proj(), models.CoreModel(2, g["H"], 1, g["kind"][:-4], thx=g["thx"], thh=g["thh"]))
         net.train()
     else:
         net = models.CoreModel(2, max(g["H"], 1), 1, g["kind"], num_dvr_units=g["K"], thx=g["thx"], thh=g["thh"])
@@ -485,3 +485,53 @@ def test_f4_cells_inference_and_dx_only(kind, H):
     x2 = xc.cuda().requires_grad_(True)
     torch.nn.MSELoss()(net(x2), yc.cuda()).backward()
     assert torch.equal(x2.grad, gx_full)
+
+
+@pytest.mark.parametrize("bits", [16, 8])
+def test_tres_qat_oracle_parity_with_flip_accounting(bits):
+    """Fake-quantised TRes-DeltaGRU at the OpenDPDv2.sh shape (H=15, B=64, T=200, thx .01 / thh .05).  As for the QAT GRU, a value within
+    rounding of a quantisation boundary can round the other way than on the CPU (libm vs libdevice); here a flipped h can in turn flip a
+    delta-h keep decision, after which that sequence diverges.  Such sequences are counted, must be few, and are excluded; the others must
+    agree within a few quanta (forward) and closely in the gradients."""
+    from oracle import oracle
+    from opendpd_b200 import models
+    from opendpd_b200.quant import get_quant_model
+    torch.manual_seed(77)
+
+    class _Proj:
+        quant, n_bits_w, n_bits_a, pretrained_model = True, bits, bits, ""
+    net = get_quant_model(_Proj(), models.CoreModel(2, 15, 1, "deltagru_tcnskip", thx=0.01, thh=0.05)).cuda().train()
+    net.backbone.keep_masks = True
+    B, T = 64, 200
+    gen = torch.Generator().manual_seed(5)
+    xc = (0.25 * torch.randn(B, T, 2, generator=gen)).clamp(-0.8, 0.8)
+    yc = xc * (1 - 0.2 * (xc ** 2).sum(-1, keepdim=True))
+    x = xc.cuda().requires_grad_(True)
+    out, loss = net.forward_mse(x, yc.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    params = np.concatenate([p.detach().cpu().numpy().ravel() for _, p in net.backbone.named_parameters()])
+    K = bits | (bits << 8)
+    r = oracle.run("deltagru_tcnskip_qat", xc.numpy(), params, target=yc.numpy(), H=15, K=K, thx=0.01, thh=0.05, dtype=np.float32, nthreads=8,
+                   want_masks=True)
+    o = out.detach().cpu().numpy()
+    quantum = 2.0 ** (2 - bits)
+    mx, mh = net.backbone.last_masks()
+    assert np.array_equal(mx, r["mask_x"])                    # delta-x masks do not depend on the quantised path: bit exact
+    dev = np.abs(o - r["out"]).reshape(B, -1).max(1)
+    bad = np.nonzero((dev > 8 * quantum) | (mh != r["mask_h"]).any(1))[0]
+    note_achieved(f"tres_qat w{bits}a{bits}", bad_sequences=int(len(bad)), worst_good=float(np.delete(dev, bad).max() / quantum) if len(bad) < B else None)
+    assert len(bad) <= B // 4, f"{len(bad)} of {B} sequences diverged after a quantisation / mask flip"
+    good = np.setdiff1d(np.arange(B), bad)
+    assert np.abs(o[good] - r["out"][good]).mean() <= quantum
+    gxm, gxr = x.grad.cpu().numpy()[good], r["gx"][good]
+    assert np.linalg.norm(gxm - gxr) <= 2e-2 * np.linalg.norm(gxr)
+    if len(bad) == 0:
+        gm, gr = grads_flat(net), r["gparams"]
+        assert np.linalg.norm(gm - gr) <= 2e-2 * np.linalg.norm(gr)
+    net.eval()
+    with torch.no_grad():
+        oe = net(xc.cuda()).cpu().numpy()
+    re = oracle.run("deltagru_tcnskip_qat", xc.numpy(), params, H=15, K=K | (1 << 16), thx=0.01, thh=0.05, dtype=np.float32, nthreads=8, want_grads=False)
+    dev_e = np.abs(oe - re["out"]).reshape(B, -1).max(1)
+    assert int((dev_e > 8 * quantum).sum()) <= B // 4
