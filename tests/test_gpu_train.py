@@ -34,17 +34,18 @@ def _flat(net):
 
 
 @pytest.mark.parametrize("kind,H", [("dgru", 13), ("gru", 32), ("deltagru_tcnskip", 15), ("pgjanet", 10), ("gmp", 1), ("lstm", 9),
-                                    ("dvrjanet", 10), ("qgru_qat", 10), ("vdlstm", 9), ("rvtdcnn", 6), ("bojanet", 10), ("tcnn", 8), ("neuraltx", 8), ("apnrru", 8), ("mcldnn", 8), ("deltajanet", 10)])
+                                    ("dvrjanet", 10), ("qgru_qat", 10), ("vdlstm", 9), ("rvtdcnn", 6), ("bojanet", 10), ("tcnn", 8), ("neuraltx", 8), ("apnrru", 8), ("mcldnn", 8), ("deltajanet", 10), ("tres_qat", 15)])
 def test_fused_step_equals_stock_loop(kind, H):
     from opendpd_b200 import models
     from opendpd_b200.train import NativeTrainStep
     torch.manual_seed(0)
-    if kind == "qgru_qat":
+    if kind in ("qgru_qat", "tres_qat"):
         from opendpd_b200.quant import get_quant_model
 
         class _Proj:
             quant, n_bits_w, n_bits_a, pretrained_model = True, 16, 16, ""
-        a = get_quant_model(_Proj(), models.CoreModel(2, H, 1, "qgru")).cuda().train()
+        base = models.CoreModel(2, H, 1, "qgru") if kind == "qgru_qat" else models.CoreModel(2, H, 1, "deltagru_tcnskip", thx=0.01, thh=0.05)
+        a = get_quant_model(_Proj(), base).cuda().train()
     else:
         a = models.CoreModel(2, H, 1, kind, num_dvr_units=3, thx=0.01, thh=0.05).cuda()
     b = copy.deepcopy(a)
