@@ -49,10 +49,12 @@ WORKLOADS = {
     "f4_rvtdcnn": dict(name="RVTDCNN H=6", kind="rvtdcnn", H=6, B=64, T=2048, dataset="APA_200MHz"),
     "f4_tcnn": dict(name="TCNN C=8", kind="tcnn", H=8, B=64, T=2048, dataset="APA_200MHz"),
     "f4_neuraltx": dict(name="NeuralTX C=8", kind="neuraltx", H=8, B=64, T=2048, dataset="APA_200MHz"),
+    "qat_tres": dict(name="fake-quantised W16A16 TRes-DeltaGRU H=15 DPD -> frozen DGRU H=23 PA, B=64 x T=200 (OpenDPDv2.sh QAT stage)", kind="tres_qat",
+                     H=15, B=64, T=200, pa=("dgru", 23), dataset="APA_200MHz"),
     "wide_dgru64": dict(name="DGRU H=64 (layered path)", kind="dgru", H=64, B=64, T=2048, dataset="APA_200MHz"),
     "wide_gru32x2": dict(name="GRU H=32, 2 layers (layered path)", kind="gru", H=32, L=2, B=64, T=2048, dataset="APA_200MHz"),
 }
-OTHER_BACKBONES = ("f4_vdlstm", "f4_bojanet", "f4_apnrru", "f4_deltajanet", "f4_mcldnn", "f4_rvtdcnn", "f4_tcnn", "f4_neuraltx", "wide_dgru64",
+OTHER_BACKBONES = ("qat_tres", "f4_vdlstm", "f4_bojanet", "f4_apnrru", "f4_deltajanet", "f4_mcldnn", "f4_rvtdcnn", "f4_tcnn", "f4_neuraltx", "wide_dgru64",
                    "wide_gru32x2")   # 1-GPU lines only: coverage, ms per whole train step
 SECONDARY = ("c2a", "c3", "c4p", "c4d", "c5g", "c5q")   # extra keys of the line: fixed GLOBAL batch split over the ranks (strong scaling)
 ALGO_BYTES_PER_SAMPLE_PER_KERNEL = 16  # fwd reads x(8)+target(8); bwd re-reads x(8)+target/dout(8)  => 32 B/sample/step
@@ -286,12 +288,14 @@ def build_trainer(wl, dev, pg, world):
     from opendpd_b200 import models
     from opendpd_b200.train import NativeTrainStep
     torch.manual_seed(0)                               # same initial weights on every rank
-    if wl["kind"] == "qgru_qat":
+    if wl["kind"] in ("qgru_qat", "tres_qat"):
         from opendpd_b200.quant import get_quant_model
+        bits = 8 if wl["kind"] == "qgru_qat" else 16
 
         class _Proj:
-            quant, n_bits_w, n_bits_a, pretrained_model = True, 8, 8, ""
-        net = get_quant_model(_Proj(), models.CoreModel(2, wl["H"], 1, "qgru")).to(dev).train()
+            quant, n_bits_w, n_bits_a, pretrained_model = True, bits, bits, ""
+        base = models.CoreModel(2, wl["H"], 1, "qgru") if wl["kind"] == "qgru_qat" else models.CoreModel(2, wl["H"], 1, "deltagru_tcnskip", thx=0.01, thh=0.05)
+        net = get_quant_model(_Proj(), base).to(dev).train()
     else:
         net = models.CoreModel(2, wl["H"], wl.get("L", 1), wl["kind"], num_dvr_units=3, thx=0.01, thh=0.05).to(dev)
     if "pa" in wl:                                      # train_dpd: DPD in front of a frozen PA (steps/train_dpd.py:60-63)
@@ -693,8 +697,8 @@ def main():
                 torch.cuda.empty_cache()
             except Exception as e:
                 others[name] = {"error": repr(e)[:300]}
-        secondary["other_backbones"] = {"what": "train_pa step (fwd + MSE + bwd + clip + AdamW), B=64 x T=2048 real APA_200MHz frames, 40 settle + 10 timed "
-                                                "steps; these cells are not time-chunked (DESIGN.md 4.3/4.4)", "unit": "IQ samples/s", **others}
+        secondary["other_backbones"] = {"what": "whole train step (fwd + MSE + bwd + clip + AdamW) on real APA_200MHz frames, B=64 x T=2048 (qat_tres: the script's "
+                                                "B=64 x T=200 cascade), 40 settle + 10 timed steps; these cells are not time-chunked (DESIGN.md 4.3/4.4)", "unit": "IQ samples/s", **others}
 
     if rank == 0:
         peaks, traffic = {}, {}
