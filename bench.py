@@ -56,7 +56,7 @@ WORKLOADS = {
 }
 OTHER_BACKBONES = ("qat_tres", "f4_vdlstm", "f4_bojanet", "f4_apnrru", "f4_deltajanet", "f4_mcldnn", "f4_rvtdcnn", "f4_tcnn", "f4_neuraltx", "wide_dgru64",
                    "wide_gru32x2")   # 1-GPU lines only: coverage, ms per whole train step
-SECONDARY = ("c2a", "c3", "c4p", "c4d", "c5g", "c5q")   # extra keys of the line: fixed GLOBAL batch split over the ranks (strong scaling)
+SECONDARY = ("c2a", "c3", "c3b", "c4p", "c4d", "c5g", "c5q")   # extra keys of the line: fixed GLOBAL batch split over the ranks (strong scaling)
 ALGO_BYTES_PER_SAMPLE_PER_KERNEL = 16  # fwd reads x(8)+target(8); bwd re-reads x(8)+target/dout(8)  => 32 B/sample/step
 STREAMS = os.path.join(ROOT, "tests", "golden", "iq_streams.npz")
 
@@ -172,28 +172,30 @@ def cpu_port_leg(wl, B, seconds=10.0, threads=None):
     import torch
     from oracle import oracle
     kind, H, T = wl["kind"], wl["H"], wl["T"]
-    if "pa" in wl or kind == "qgru_qat":
-        return {}          # cascades / QAT: no single-call CPU arm (secondary workloads)
+    if kind in ("qgru_qat", "tres_qat"):
+        return {}          # QAT flows: no single-call CPU arm
     cores = threads or os.cpu_count() or 1
     feed = Feed(wl, None, 0, 1, B, B)
     xs, ys = feed.frames(feed.table(0, 1))
     xt, yt = xs[0].float(), ys[0].float()
-    x, y = xt.numpy(), yt.numpy()
-    rng = np.random.default_rng(0)
-    P = oracle.n_params(kind, H)
-    params = (0.3 * rng.standard_normal(P)).astype(np.float32)
-    nthr = min(cores, B)
-    oracle.run(kind, x, params, target=y, H=H, nthreads=nthr)
-    t0, n = time.perf_counter(), 0
-    while time.perf_counter() - t0 < seconds / 2 or n < 3:
+    res = {}
+    if "pa" not in wl:     # the C port is one backbone per call; the cascade is timed on the PyTorch-op restatement only
+        x, y = xt.numpy(), yt.numpy()
+        rng = np.random.default_rng(0)
+        P = oracle.n_params(kind, H)
+        params = (0.3 * rng.standard_normal(P)).astype(np.float32)
+        nthr = min(cores, B)
         oracle.run(kind, x, params, target=y, H=H, nthreads=nthr)
-        n += 1
-    c_dt = (time.perf_counter() - t0) / n
-    res = {"c_port": {"value": B * T / c_dt, "unit": "IQ samples/s", "cores": nthr, "s_per_step": c_dt,
-                      "sample": f"{n} x (fwd+MSE+bwd) of the full {B}x{T} batch of real frames, C/OpenMP over sequences"}}
+        t0, n = time.perf_counter(), 0
+        while time.perf_counter() - t0 < seconds / 2 or n < 3:
+            oracle.run(kind, x, params, target=y, H=H, nthreads=nthr)
+            n += 1
+        c_dt = (time.perf_counter() - t0) / n
+        res["c_port"] = {"value": B * T / c_dt, "unit": "IQ samples/s", "cores": nthr, "s_per_step": c_dt,
+                         "sample": f"{n} x (fwd+MSE+bwd) of the full {B}x{T} batch of real frames, C/OpenMP over sequences"}
     try:
         from oracle import torch_port
-        step = torch_port.make_train_step(kind, H, seed=0, thx=0.01, thh=0.05)
+        step = torch_port.make_train_step(kind, H, seed=0, thx=0.01, thh=0.05, pa=wl.get("pa"))
         # PyTorch's intra-op pool degrades badly when oversubscribed on these ~1e3-element ops: use all host threads it can
         # USE — scan a few pool sizes (one step each) and keep the fastest; the count is reported in `cores`.
         best = None
@@ -206,7 +208,7 @@ def cpu_port_leg(wl, B, seconds=10.0, threads=None):
                 break                     # larger pools only get slower from here (measured: 128 threads = 17x slower than 4)
         torch.set_num_threads(best[0])
         t0, n = time.perf_counter(), 0
-        while time.perf_counter() - t0 < seconds / 2 or n < 3:
+        while time.perf_counter() - t0 < seconds / 2 or n < (3 if "pa" not in wl else 2):
             step(xt, yt)
             n += 1
         dt = (time.perf_counter() - t0) / n
@@ -494,14 +496,17 @@ def main():
             return
         GB = wl["B"] * n_decl                     # the native arm's global batch (weak scaling): same config on both arms
         r = cpu_port_leg(wl, GB, seconds=max(args.cpu_seconds, 6.0))
-        main_leg = r.get("torch_port") or r["c_port"]
+        main_leg = r.get("torch_port") or r.get("c_port")
+        if main_leg is None:
+            emit({"impl": "reference", "unavailable": f"no CPU arm for workload {args.workload}: {r.get('torch_port_error', 'QAT flow')}"})
+            return
         line = {"impl": "reference", "metric": "IQ samples/sec/train-step", "value": main_leg["value"], "unit": "IQ samples/s",
                 "n_gpus": n_decl, "steps": K, "warmup": W, "ms_per_step": main_leg["s_per_step"] * 1e3,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": wl["dataset"],
                 "config": config_of(wl, n_decl, True),
                 "cpu_baseline": {"value": main_leg["value"], "unit": "IQ samples/s", "cores": main_leg["cores"], "kind": "port",
                                  "sample": main_leg["sample"]},
-                "cpu_c_port": r["c_port"],
+                "cpu_c_port": r.get("c_port"),
                 "e2e": {"value": main_leg["value"], "unit": "IQ samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         if "torch_port_error" in r:
             line["torch_port_error"] = r["torch_port_error"]
@@ -781,6 +786,11 @@ def main():
             line["cpu_c_port"] = r["c_port"]
             if "torch_port_error" in r:
                 line["torch_port_error"] = r["torch_port_error"]
+            if "c3" in secondary and "error" not in secondary["c3"]:      # BASELINE configs[2]: the cascade's own CPU arm
+                r3 = cpu_port_leg(WORKLOADS["c3"], 256, seconds=4.0).get("torch_port")
+                if r3:
+                    secondary["c3"]["cpu_baseline"] = {"value": r3["value"], "unit": "IQ samples/s", "cores": r3["cores"], "kind": "port",
+                                                       "sample": r3["sample"], "native_over_cpu": secondary["c3"]["value"] / r3["value"]}
         emit(line)
     if world > 1:
         dist.barrier()

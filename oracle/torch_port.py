@@ -309,9 +309,10 @@ def forward(kind, x, flat, H, K=3, thx=0.0, thh=0.0, L=1):
     raise ValueError(kind)
 
 
-def make_train_step(kind, H, seed=0, K=3, thx=0.0, thh=0.0, lr=5e-4, clip=200.0):
+def make_train_step(kind, H, seed=0, K=3, thx=0.0, thh=0.0, lr=5e-4, clip=200.0, pa=None):
     """The net_train body (train_funcs.py:33-48) on the PyTorch-CPU restatement: zero_grad, forward, MSELoss, backward,
-    clip_grad_norm_, AdamW step, loss.item()."""
+    clip_grad_norm_, AdamW step, loss.item().  pa=(kind, H): the train_dpd cascade (models.py CascadedModel — the DPD feeds a
+    frozen PA model, steps/train_dpd.py:60-66)."""
     import sys, os
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     from oracle import oracle
@@ -320,10 +321,16 @@ def make_train_step(kind, H, seed=0, K=3, thx=0.0, thh=0.0, lr=5e-4, clip=200.0)
     flat = torch.nn.Parameter(0.3 * torch.randn(P, generator=g))
     opt = torch.optim.AdamW([flat], lr=lr)
     crit = torch.nn.MSELoss()
+    pa_flat = None
+    if pa is not None:
+        pa_flat = 0.3 * torch.randn(oracle.n_params(pa[0], pa[1], 3), generator=g)     # frozen: no grad, not in the optimiser
 
     def step(x, y):
         opt.zero_grad()
-        loss = crit(forward(kind, x, flat, H, K, thx, thh), y)
+        out = forward(kind, x, flat, H, K, thx, thh)
+        if pa_flat is not None:
+            out = forward(pa[0], out, pa_flat, pa[1])
+        loss = crit(out, y)
         loss.backward()
         torch.nn.utils.clip_grad_norm_([flat], clip)
         opt.step()
