@@ -37,7 +37,7 @@ struct ApLayout {
     __host__ __device__ int row() const { return 3 * S + 16 + 2 * H; }
 };
 // saved:  FR [B][T][12] = fir_I(3) fir_Q(3) rr ri mag - - -   |  XP [B][T][16]  |  ST [B][T][row]
-// workspace: partials | GV [B][T][S] | GA1 [B][T][16] | GRR [B][T][2] | DFIR [B][T][6] | GXD [B][T][2]
+// workspace: partials (4-aligned) | GXD [B][T][2] (float2 accesses: kept at the aligned front) | GV [B][T][S] | GA1 [B][T][16] | GRR [B][T][2] | DFIR [B][T][6]
 struct ApBufs { float *fr, *xp, *st, *gv, *ga1, *grr, *dfir, *gxd, *partials; };
 
 __device__ __forceinline__ void ap_tile(int tile, int nts, int tid, int &b, int &t) {
@@ -540,7 +540,8 @@ int apnrru_run(const GruArgs &a, int dir, bool dw, cudaStream_t st, int *rows_ou
     if (!a.partials) { set_error("APNRRU backward needs the workspace (odpd_bwd_workspace_bytes)"); return -1; }
     if (a.need_dx && !a.gx) { set_error("APNRRU backward: ODPD_F_NEED_DX without gx"); return -1; }
     const int64_t poff = ((int64_t)grid * L.P + 3) & ~(int64_t)3;
-    u.partials = a.partials; u.gv = a.partials + poff; u.ga1 = u.gv + bt * L.S; u.grr = u.ga1 + bt * 16; u.dfir = u.grr + bt * 2; u.gxd = u.dfir + bt * 6;
+    // gxd is read and written as float2: it sits first, at a 4-float-aligned offset (behind the odd-sized sections it would be misaligned whenever B*T is odd)
+    u.partials = a.partials; u.gxd = a.partials + poff; u.gv = u.gxd + bt * 2; u.ga1 = u.gv + bt * L.S; u.grr = u.ga1 + bt * 16; u.dfir = u.grr + bt * 2;
     launch_pdl(apn_chain_bwd_kernel, dim3(cgrid), dim3(32 * wpc), 0, st, a, u);
     const size_t bsm = (size_t)(96 + 128 + 32 + AP_TT * (17 + (L.U | 1) + (L.S | 1) + 17 + (L.S | 1) + 1 + ((2 * a.H) | 1) + 3 + 7) + 2 * (AP_TT + AP_M - 1)) * sizeof(float);
     if (dw) {

@@ -619,7 +619,7 @@ int64_t lstm_workspace_floats(int B, int T, int H, int64_t P, int tchunks_req, b
 }
 int lstm_run(const GruArgs &a, int dir, bool dw, cudaStream_t st, int *info) {
     const bool vd = a.cell == ODPD_CELL_VDLSTM;
-    if (vd && a.T < VW) { set_error("VDLSTM needs frame_length >= %d (window with wrap-around padding, vdlstm.py:65-73)", VW); return -1; }
+    if (vd && a.T < VW - 1) { set_error("VDLSTM needs frame_length >= %d (the window wraps over the last %d samples, vdlstm.py:65-73; got %d)", VW - 1, VW - 1, a.T); return -1; }
 #define X(HTV) if (a.H <= HTV) return vd ? lstm_launch<HTV, true>(a, dir, dw, st, info) : lstm_launch<HTV, false>(a, dir, dw, st, info);
     ODPD_LSTM_TIERS(X)
 #undef X
