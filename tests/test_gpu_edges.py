@@ -159,3 +159,25 @@ def test_layered_path_short_frames(kind, H, L):
                                 ("gparams", grads_flat(net), flat.grad.numpy())):
             assert_close(mine, want, 1e-5, f"{kind} H{H} L{L} T={T} {key}")
         assert abs(loss.item() - float(rl.detach())) <= 1e-5 * abs(float(rl.detach())) + 1e-12
+
+
+@pytest.mark.parametrize("kind,H", [("bojanet", 9), ("apnrru", 7), ("mcldnn", 7), ("deltajanet", 11), ("dgru", 13), ("pgjanet", 13), ("tcnn", 7)])
+def test_more_sequences_than_resident_ctas(kind, H):
+    """B = 301 sequences (> 2 x 148 SMs): BOJANET / APNRRU / MCLDNN / DeltaJANET switch their chain kernels from one warp per CTA to
+    four (the last CTA is partly empty), and every cell's tile loops run past the grid cap."""
+    from oracle import oracle
+    net, thx, thh = _model(kind, H)
+    params = np.concatenate([p.detach().cpu().numpy().ravel() for _, p in net.backbone.named_parameters()])
+    gen = torch.Generator().manual_seed(23)
+    B, T = 301, 40
+    xc = (0.2 * torch.randn(B, T, 2, generator=gen)).clamp(-0.7, 0.7)
+    yc = xc * (1 - 0.2 * (xc ** 2).sum(-1, keepdim=True))
+    x = xc.cuda().requires_grad_(True)
+    out, loss = net.forward_mse(x, yc.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    r64 = oracle.run(kind, xc.numpy(), params, target=yc.numpy(), H=H, thx=thx, thh=thh, dtype=np.float64, nthreads=8)
+    r32 = oracle.run(kind, xc.numpy(), params, target=yc.numpy(), H=H, thx=thx, thh=thh, dtype=np.float32, nthreads=8)
+    for key, mine in (("out", out.detach().cpu().numpy()), ("gx", x.grad.cpu().numpy()), ("gparams", grads_flat(net))):
+        assert_close(mine, r64[key], max(1e-5, 3 * _q_err(r32[key], r64[key])), f"{kind} B={B} {key}")
+    assert abs(loss.item() - r64["loss"]) <= 1e-5 * abs(r64["loss"])

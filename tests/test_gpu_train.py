@@ -141,7 +141,9 @@ def test_state_dict_roundtrip_after_training():
     assert torch.equal(net2(x), net(x))
 
 
-@pytest.mark.parametrize("kind,H,B,T", [("dgru", 13, 2, 19662), ("deltagru_tcnskip", 15, 1, 19662), ("gru", 32, 3, 2560)])
+@pytest.mark.parametrize("kind,H,B,T", [("dgru", 13, 2, 19662), ("deltagru_tcnskip", 15, 1, 19662), ("gru", 32, 3, 2560), ("lstm", 9, 1, 19662),
+                                        ("pgjanet", 15, 1, 19662), ("rvtdcnn", 6, 2, 19662), ("bojanet", 10, 1, 19662), ("tcnn", 8, 2, 19662),
+                                        ("neuraltx", 8, 1, 19662), ("apnrru", 8, 2, 19662), ("mcldnn", 8, 1, 19662), ("deltajanet", 10, 1, 19662)])
 def test_eval_path_whole_segments(kind, H, B, T):
     """net_eval / run_dpd run forward-only over whole segments (T = nperseg up to 19 662, B = 1..6)."""
     from oracle import oracle
