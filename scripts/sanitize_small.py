@@ -51,6 +51,6 @@ for case in CASES:
     out, loss, saved = backbone_forward_raw(spec, x, flat, y, 1.0 / x.numel(), True, stats, fb)
     gx, g = backbone_backward_raw(spec, x, flat, saved, True, True, out=out, target=y, gscale=2.0 / x.numel(), bufs=bbuf)
     torch.cuda.synchronize()
-    print(kind, H, (B, T), "plan", spec.chunk_plan(B, T, False), spec.chunk_plan(B, T, True), "loss", float(loss.item()), "|g|", float(g.abs().sum()),
+    print(kind, H, (B, T), "plan", spec.chunk_plan(B, T, False), spec.chunk_plan(B, T, True), "loss", float(loss.item()), "|g|", float(g[:bb.flat_layout()[1]].abs().sum()),      # (the flat buffer is padded to 4 floats: the tail is never written)
           "|gx|", float(gx.abs().sum()), flush=True)
 print("sanitize ok")
