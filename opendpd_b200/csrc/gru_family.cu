@@ -1283,11 +1283,11 @@ __global__ void __launch_bounds__(128, 1) gru_bwdw_kernel(GruArgs a) {
             const int sc = s - 1;
             if (sc >= 0) {
                 if constexpr (DW) {
-                    const float *Ap = sG + (sc % 3) * SM::G + TR * rg;
+                    const float *Ap = sG + (sc % 3) * SM::G + (TR * rg < 4 * HP ? TR * rg : 0);      // lanes whose rows lie past the tile (their sums are discarded below) re-read row group 0 instead of running off the row
                     const float *Bp = spre + (sc & 1) * SM::PRE + TC * cg;
                     const float *ac = sact + (sc % 3) * SM::ACT;
                     const float *pr = spre + (sc & 1) * SM::PRE;
-                    const float *A3 = sdp + (sc & 1) * SM::DP + TR3 * rg3;
+                    const float *A3 = sdp + (sc & 1) * SM::DP + (TR3 * rg3 < HP ? TR3 * rg3 : 0);
                     const float *B3 = ac + ROW + 4 * HP + TC3 * cg3;                      // row tl+1 = step t: h_t
                     const float *hcol = ac + ROW + (HEAD ? 5 : 4) * HP + lp;             // g_t (DGRU) or h_t feeds fc_out
 #pragma unroll 4
@@ -1653,6 +1653,8 @@ __global__ void __launch_bounds__(160, 1) gru_bwdf_kernel(GruArgs a) {
         constexpr int NC = (F + 1 + 3) & ~3;
         constexpr int LC = NC / 4, LR = 32 / LC, TR = (4 * HP + LR - 1) / LR, TC = 4;
         constexpr int TR3 = (HP + 7) / 8, TC3 = HP / 4;
+        static_assert((4 * HP) % TR == 0 || TR <= 4, "a lane's rows must end inside the padded G row (GS = 4*HP + 4)");
+        static_assert(HP % TR3 == 0, "a lane's rows of the head tile must end inside the row");
         const int rg = lane / LC, cg = lane % LC;
         const int rg3 = lane >> 2, cg3 = lane & 3;
         float acc[DW ? TR * TC : 1], acc3[(DW && HEAD) ? TR3 * TC3 : 1];
@@ -1669,11 +1671,11 @@ __global__ void __launch_bounds__(160, 1) gru_bwdf_kernel(GruArgs a) {
             const int sc = s - 2;
             if (sc >= 0 && ce - 1 - sc < ce_emit) {
                 if constexpr (DW) {
-                    const float *Ap = sG + (sc & 1) * SM::G + TR * rg;
+                    const float *Ap = sG + (sc & 1) * SM::G + (TR * rg < 4 * HP ? TR * rg : 0);      // lanes whose rows lie past the tile (their sums are discarded below) re-read row group 0 instead of running off the row
                     const float *pr = spre + (sc % 3) * SM::PRE;
                     const float *Bp = pr + TC * cg;
                     const float *ac = sact + (sc % 3) * SM::ACT;
-                    const float *A3 = sdp + (sc % 3) * SM::DH + TR3 * rg3;
+                    const float *A3 = sdp + (sc % 3) * SM::DH + (TR3 * rg3 < HP ? TR3 * rg3 : 0);
                     const float *B3 = ac + ROW + 4 * HP + TC3 * cg3;                      // row tl+1 = step t: h_t
                     const float *hcol = ac + ROW + (HEAD ? 5 : 4) * HP + lp;             // g_t (DGRU) or h_t feeds fc_out
 #pragma unroll 4

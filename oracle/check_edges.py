@@ -16,7 +16,7 @@ import make_golden as mg          # imports the reference
 from oracle import oracle
 
 # kind, H, shortest frame the reference accepts
-CELLS = [("gru", 9, 1), ("dgru", 13, 1), ("qgru", 11, 1), ("qgru_amp1", 10, 1), ("lstm", 9, 1), ("deltagru", 15, 1), ("deltagru_tcnskip", 15, 1),
+CELLS = [("gru", 9, 1), ("dgru", 13, 1), ("dgru", 10, 1), ("qgru", 11, 1), ("qgru_amp1", 10, 1), ("lstm", 9, 1), ("deltagru", 15, 1), ("deltagru_tcnskip", 15, 1),
          ("pgjanet", 13, 1), ("dvrjanet", 11, 1), ("gmp", 0, 1), ("tcnn", 7, 1), ("neuraltx", 9, 1), ("deltajanet", 11, 1),
          ("rvtdcnn", 7, 3), ("mcldnn", 7, 4), ("bojanet", 9, 15), ("apnrru", 7, 15)]
 LENGTHS = (1, 2, 3, 4, 5, 15, 16, 31, 32, 33, 65)

@@ -13,7 +13,7 @@ from tests.util import assert_close, note_achieved
 pytestmark = pytest.mark.gpu
 
 # kind, hidden size, shortest frame length the reference accepts
-CELLS = [("gru", 9, 1), ("dgru", 13, 1), ("qgru", 11, 1), ("qgru_amp1", 10, 1), ("lstm", 9, 1), ("deltagru", 15, 1), ("deltagru_tcnskip", 15, 1),
+CELLS = [("gru", 9, 1), ("dgru", 13, 1), ("dgru", 10, 1), ("qgru", 11, 1), ("qgru_amp1", 10, 1), ("lstm", 9, 1), ("deltagru", 15, 1), ("deltagru_tcnskip", 15, 1),
          ("pgjanet", 13, 1), ("dvrjanet", 11, 1), ("gmp", 0, 1), ("tcnn", 7, 1), ("neuraltx", 9, 1), ("deltajanet", 11, 1),
          ("rvtdcnn", 7, 3), ("mcldnn", 7, 4), ("bojanet", 9, 15), ("apnrru", 7, 15)]      # odd sizes and B*T odd: nothing may lean on alignment
 LENGTHS = (1, 2, 3, 4, 5, 15, 16, 31, 32, 33, 65)

@@ -487,9 +487,9 @@ def test_f4_cells_inference_and_dx_only(kind, H):
     assert torch.equal(x2.grad, gx_full)
 
 
-@pytest.mark.parametrize("bits", [16, 8])
-def test_tres_qat_oracle_parity_with_flip_accounting(bits):
-    """Fake-quantised TRes-DeltaGRU at the OpenDPDv2.sh shape (H=15, B=64, T=200, thx .01 / thh .05).  As for the QAT GRU, a value within
+@pytest.mark.parametrize("bits,H,B,T", [(16, 15, 64, 200), (8, 15, 64, 200), (16, 8, 16, 33), (16, 16, 16, 65), (8, 12, 16, 31)])
+def test_tres_qat_oracle_parity_with_flip_accounting(bits, H, B, T):
+    """Fake-quantised TRes-DeltaGRU at the OpenDPDv2.sh shape (H=15, B=64, T=200, thx .01 / thh .05) and at other hidden sizes / odd frame lengths.  As for the QAT GRU, a value within
     rounding of a quantisation boundary can round the other way than on the CPU (libm vs libdevice); here a flipped h can in turn flip a
     delta-h keep decision, after which that sequence diverges.  Such sequences are counted, must be few, and are excluded; the others must
     agree within a few quanta (forward) and closely in the gradients."""
@@ -500,9 +500,8 @@ def test_tres_qat_oracle_parity_with_flip_accounting(bits):
 
     class _Proj:
         quant, n_bits_w, n_bits_a, pretrained_model = True, bits, bits, ""
-    net = get_quant_model(_Proj(), models.CoreModel(2, 15, 1, "deltagru_tcnskip", thx=0.01, thh=0.05)).cuda().train()
+    net = get_quant_model(_Proj(), models.CoreModel(2, H, 1, "deltagru_tcnskip", thx=0.01, thh=0.05)).cuda().train()
     net.backbone.keep_masks = True
-    B, T = 64, 200
     gen = torch.Generator().manual_seed(5)
     xc = (0.25 * torch.randn(B, T, 2, generator=gen)).clamp(-0.8, 0.8)
     yc = xc * (1 - 0.2 * (xc ** 2).sum(-1, keepdim=True))
@@ -512,7 +511,7 @@ def test_tres_qat_oracle_parity_with_flip_accounting(bits):
     torch.cuda.synchronize()
     params = np.concatenate([p.detach().cpu().numpy().ravel() for _, p in net.backbone.named_parameters()])
     K = bits | (bits << 8)
-    r = oracle.run("deltagru_tcnskip_qat", xc.numpy(), params, target=yc.numpy(), H=15, K=K, thx=0.01, thh=0.05, dtype=np.float32, nthreads=8,
+    r = oracle.run("deltagru_tcnskip_qat", xc.numpy(), params, target=yc.numpy(), H=H, K=K, thx=0.01, thh=0.05, dtype=np.float32, nthreads=8,
                    want_masks=True)
     o = out.detach().cpu().numpy()
     quantum = 2.0 ** (2 - bits)
@@ -520,7 +519,7 @@ def test_tres_qat_oracle_parity_with_flip_accounting(bits):
     assert np.array_equal(mx, r["mask_x"])                    # delta-x masks do not depend on the quantised path: bit exact
     dev = np.abs(o - r["out"]).reshape(B, -1).max(1)
     bad = np.nonzero((dev > 8 * quantum) | (mh != r["mask_h"]).any(1))[0]
-    note_achieved(f"tres_qat w{bits}a{bits}", bad_sequences=int(len(bad)), worst_good=float(np.delete(dev, bad).max() / quantum) if len(bad) < B else None)
+    note_achieved(f"tres_qat w{bits}a{bits} H{H} B{B} T{T}", bad_sequences=int(len(bad)), worst_good=float(np.delete(dev, bad).max() / quantum) if len(bad) < B else None)
     assert len(bad) <= B // 4, f"{len(bad)} of {B} sequences diverged after a quantisation / mask flip"
     good = np.setdiff1d(np.arange(B), bad)
     assert np.abs(o[good] - r["out"][good]).mean() <= quantum
@@ -532,6 +531,6 @@ def test_tres_qat_oracle_parity_with_flip_accounting(bits):
     net.eval()
     with torch.no_grad():
         oe = net(xc.cuda()).cpu().numpy()
-    re = oracle.run("deltagru_tcnskip_qat", xc.numpy(), params, H=15, K=K | (1 << 16), thx=0.01, thh=0.05, dtype=np.float32, nthreads=8, want_grads=False)
+    re = oracle.run("deltagru_tcnskip_qat", xc.numpy(), params, H=H, K=K | (1 << 16), thx=0.01, thh=0.05, dtype=np.float32, nthreads=8, want_grads=False)
     dev_e = np.abs(oe - re["out"]).reshape(B, -1).max(1)
     assert int((dev_e > 8 * quantum).sum()) <= B // 4

@@ -11,7 +11,7 @@ def test_oracle_equals_reference_at_short_and_block_edge_frames():
     p = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "check_edges.py")], capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert p.returncode == 0, p.stderr[-2000:]
     r = json.loads([l for l in p.stdout.splitlines() if l.startswith("{")][-1])
-    assert r["cases"] == 172
+    assert r["cases"] == 183
     assert max(r["worst_rel_err"].values()) < 1e-11, r["worst_rel_err"]
     # the windowed backbones reject frames shorter than their window minus one (their padding is a slice of the frame itself);
     # the library raises for the same lengths (tests/test_gpu_edges.py::test_frames_the_reference_rejects_raise)
