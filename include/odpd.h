@@ -80,12 +80,12 @@ enum {
     ODPD_CELL_QGRU_AMP1 = 9, /* backbones/qgru_amp1.py:59-76 */
     ODPD_CELL_QGRU_QAT = 10, /* qgru.py under --quant: quant/modules/gru.py:32-124 + quant/qmodules (fake-quant QAT) */
     ODPD_CELL_QGRU_AMP1_QAT = 11, /* qgru_amp1.py under --quant */
-    ODPD_CELL_VDLSTM = 12,   /* backbones/vdlstm.py:58-82 */
+    ODPD_CELL_VDLSTM = 12,   /* backbones/vdlstm.py:58-82; frame_length >= 3 (the window wraps over the last 3 samples) */
     ODPD_CELL_RVTDCNN = 13,  /* backbones/rvtdcnn.py:36-62 (row f-4): H = fc_hid_size (1..64); frame_length >= 3 */
-    ODPD_CELL_BOJANET = 14,  /* backbones/bojanet.py:54-106 (row f-4): hidden_size 1..18 (the reference's pr_block covers 3 x 6 units) */
+    ODPD_CELL_BOJANET = 14,  /* backbones/bojanet.py:54-106 (row f-4): hidden_size 1..18 (the reference's pr_block covers 3 x 6 units); frame_length >= 15 */
     ODPD_CELL_TCNN = 15,     /* backbones/tcnn.py:83-97 (row f-4): H = hidden_channels (1..64) */
     ODPD_CELL_NEURALTX = 16, /* backbones/neuraltx.py:107-124 (row f-4): H = hidden_channels (1..64) */
-    ODPD_CELL_APNRRU = 17,   /* backbones/apnrru.py:52-135 (row f-4): hidden_size 1..14 (2H+3 state values, one per warp lane) */
+    ODPD_CELL_APNRRU = 17,   /* backbones/apnrru.py:52-135 (row f-4): hidden_size 1..14 (2H+3 state values, one per warp lane); frame_length >= 15 */
     ODPD_CELL_MCLDNN = 18,   /* backbones/mcldnn.py:83-113 (row f-4): H = conv channels (1..12); the LSTM inside is always 8 wide; frame_length >= 4 */
     ODPD_CELL_DELTAJANET = 19, /* backbones/deltajanet.py:49-60, 203-262 (row f-4): hidden_size 1..16; thx / thh are ignored like in the reference (:22-26) */
     ODPD_CELL_TRES_QAT = 20, /* deltagru_tcnskip.py under --quant (quant/quant_envs.py:286-305; bash_scripts/OpenDPDv2.sh:47-49): hidden_size 1..16,
